@@ -1,0 +1,397 @@
+"""Python mirror of the reference's user-facing interface for the scoring path, over the C ABI
+of libhibag_b200.so (include/hibag_b200.h).
+
+Names and argument meaning follow the reference's R front end where one exists:
+  hlaAttrBagging(hla, snp, nclassifier, mtry, prune, ...)   reference R/HIBAG.R:48-275
+  hlaPredict(model, snp, type=...)                            reference R/HIBAG.R:481-818
+  hlaModelToObj / hlaModelFromObj                             reference R/HIBAG.R:1041-1178
+  hlaSetKernelTarget is not mirrored: there is one target here, the B200.
+
+The product path needs the CUDA extension: importing works anywhere (so the CPU test-suite can
+check the ABI), but every compute call raises if the library or a CUDA device is missing --
+there is no CPU fallback.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhibag_b200.so")
+NA_INTEGER = -2147483648
+
+# binary layouts of include/hibag_b200.h (== reference LibHLA_ext.h:261-352)
+HAPLO_DT = np.dtype([("packed", "<u8", (2,)), ("freq", "<f8"), ("freq_f32", "<f4"),
+                     ("hla", "<i4")], align=True)
+GENO_DT = np.dtype([("s1", "<u8", (2,)), ("s2", "<u8", (2,)), ("boot", "<i4"),
+                    ("a1", "<i4"), ("a2", "<i4"), ("tmp", "<i4")], align=True)
+
+
+class TrainOpts(C.Structure):
+    _fields_ = [("nclassifier", C.c_int), ("mtry", C.c_int), ("prune", C.c_int),
+                ("n_threads", C.c_int), ("seed", C.c_int64), ("per_classifier_seed", C.c_int),
+                ("first_index", C.c_int), ("index_stride", C.c_int),
+                ("use_legacy_hooks", C.c_int), ("verbose", C.c_int)]
+
+
+class TrainStats(C.Structure):
+    _fields_ = [("seconds_total", C.c_double), ("seconds_em", C.c_double),
+                ("seconds_gpu_wait", C.c_double), ("gpu_kernel_ms", C.c_double),
+                ("pair_evals", C.c_uint64), ("popc32_issued", C.c_uint64),
+                ("n_oob_evals", C.c_uint64), ("n_ib_evals", C.c_uint64), ("n_em", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+
+class PredictOut(C.Structure):
+    _fields_ = [("h1", C.c_void_p), ("h2", C.c_void_p), ("max_prob", C.c_void_p),
+                ("matching", C.c_void_p), ("dosage", C.c_void_p), ("post_prob", C.c_void_p)]
+
+
+class PredictStats(C.Structure):
+    _fields_ = [("gpu_kernel_ms", C.c_double), ("cell_kernel_ms", C.c_double),
+                ("pair_evals", C.c_uint64), ("popc32_issued", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("cell_kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+# every symbol include/hibag_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "hibag_b200_version", "hibag_b200_last_error", "hibag_b200_device_count",
+    "hibag_b200_set_device", "hibag_b200_device_info", "hibag_b200_get_procs",
+    "hibag_b200_best_guess", "hibag_b200_post_prob", "hibag_b200_post_prob2",
+    "hibag_b200_model_new", "hibag_b200_model_free", "hibag_b200_model_set_training",
+    "hibag_b200_model_train", "hibag_b200_model_train_stats",
+    "hibag_b200_model_num_classifiers", "hibag_b200_model_clear",
+    "hibag_b200_model_classifier_info", "hibag_b200_model_classifier_get",
+    "hibag_b200_model_add_classifier", "hibag_b200_model_predict",
+    "hibag_b200_model_predict_device", "hibag_b200_model_predict_stats",
+    "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
+    "hibag_b200_model_snp_weights", "hibag_b200_pipe_peak",
+    "hibag_b200_host_unif_rand", "hibag_b200_host_build_tasks",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libhibag_b200.so (built in-tree by `make -C hibag_b200/csrc` / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("hibag_b200: %s is missing -- build it with __graft_entry__.build(); "
+                           "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.hibag_b200_version.restype = C.c_char_p
+    L.hibag_b200_last_error.restype = C.c_char_p
+    L.hibag_b200_get_procs.restype = C.c_void_p
+    L.hibag_b200_device_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for f in (L.hibag_b200_best_guess,):
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.hibag_b200_post_prob.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.hibag_b200_post_prob2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p]
+    L.hibag_b200_model_new.restype = C.c_void_p
+    L.hibag_b200_model_new.argtypes = [C.c_int, C.c_int]
+    L.hibag_b200_model_free.argtypes = [C.c_void_p]
+    L.hibag_b200_model_set_training.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hibag_b200_model_train.argtypes = [C.c_void_p, C.POINTER(TrainOpts)]
+    L.hibag_b200_model_train_stats.argtypes = [C.c_void_p, C.POINTER(TrainStats)]
+    L.hibag_b200_model_num_classifiers.argtypes = [C.c_void_p]
+    L.hibag_b200_model_clear.argtypes = [C.c_void_p]
+    L.hibag_b200_model_classifier_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                                   C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.hibag_b200_model_classifier_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    L.hibag_b200_model_add_classifier.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    L.hibag_b200_model_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PredictOut)]
+    L.hibag_b200_model_predict_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PredictOut),
+                                                  C.c_void_p, C.c_int]
+    L.hibag_b200_model_predict_stats.argtypes = [C.c_void_p, C.POINTER(PredictStats)]
+    L.hibag_b200_model_predict_partial_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                          C.c_void_p, C.c_void_p, C.c_int]
+    L.hibag_b200_predict_finalize_device.argtypes = [C.c_int, C.c_int, C.c_void_p, C.POINTER(PredictOut),
+                                                     C.c_void_p, C.c_int]
+    L.hibag_b200_model_snp_weights.argtypes = [C.c_void_p, C.c_void_p]
+    L.hibag_b200_host_unif_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+    L.hibag_b200_host_build_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    L.hibag_b200_pipe_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise RuntimeError("hibag_b200: " + lib().hibag_b200_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().hibag_b200_device_count()
+
+
+def set_device(i):
+    _chk(lib().hibag_b200_set_device(i))
+
+
+def device_info():
+    name = C.create_string_buffer(128)
+    sm, khz = C.c_int(), C.c_int()
+    _chk(lib().hibag_b200_device_info(name, 128, C.byref(sm), C.byref(khz)))
+    return dict(name=name.value.decode(), sm_count=sm.value, clock_khz=khz.value)
+
+
+def get_procs():
+    """Address of the TypeGPUExtProc-compatible hook struct (reference LibHLA_ext.h:358-388)."""
+    return lib().hibag_b200_get_procs()
+
+
+def pipe_peak(which):
+    ops, ms = C.c_double(), C.c_double()
+    _chk(lib().hibag_b200_pipe_peak(which, C.byref(ops), C.byref(ms)))
+    return ops.value, ms.value
+
+
+def host_unif_rand(seed, n):
+    out = np.zeros(n)
+    _chk(lib().hibag_b200_host_unif_rand(seed, n, _p(out)))
+    return out
+
+
+def host_build_tasks(haplo, n_hla, n_snp, target_chunks=512):
+    nc = n_hla * (n_hla + 1) // 2
+    cells = np.zeros((nc, 8), dtype=np.int32); chunks = np.zeros((nc, 2), dtype=np.int32)
+    n, pairs = C.c_int(), C.c_uint64()
+    _chk(lib().hibag_b200_host_build_tasks(_p(haplo), len(haplo), n_hla, n_snp, target_chunks, _p(cells),
+                                           _p(chunks), C.byref(n), C.byref(pairs)))
+    return cells, chunks[:n.value], pairs.value
+
+
+# ---- kernel-level batched scoring -----------------------------------------------------------
+
+def best_guess(haplo, n_hla, n_snp, geno):
+    a1 = np.zeros(len(geno), dtype=np.int32); a2 = np.zeros(len(geno), dtype=np.int32)
+    _chk(lib().hibag_b200_best_guess(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno), _p(a1), _p(a2)))
+    return a1, a2
+
+
+def post_prob(haplo, n_hla, n_snp, geno):
+    out = np.zeros(len(geno))
+    _chk(lib().hibag_b200_post_prob(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno), _p(out)))
+    return out
+
+
+def post_prob2(haplo, n_hla, n_snp, geno):
+    nc = n_hla * (n_hla + 1) // 2
+    prob = np.zeros((len(geno), nc)); s = np.zeros(len(geno))
+    _chk(lib().hibag_b200_post_prob2(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno), _p(prob), _p(s)))
+    return prob, s
+
+
+# ---- model ----------------------------------------------------------------------------------
+
+class HLAModel:
+    """An attribute-bagging model (reference class "hlaAttrBagClass", R/HIBAG.R:236-247)."""
+
+    def __init__(self, n_snp, n_hla, hla_allele=None, snp_id=None):
+        self.n_snp, self.n_hla = int(n_snp), int(n_hla)
+        self.hla_allele = list(hla_allele) if hla_allele is not None else [str(i) for i in range(n_hla)]
+        self.snp_id = list(snp_id) if snp_id is not None else None
+        self.n_samp = 0
+        self._h = C.c_void_p(lib().hibag_b200_model_new(self.n_snp, self.n_hla))
+        if not self._h:
+            raise RuntimeError("hibag_b200: " + lib().hibag_b200_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hibag_b200_model_free(self._h)
+            self._h = None
+
+    @property
+    def n_cells(self):
+        return self.n_hla * (self.n_hla + 1) // 2
+
+    def set_training(self, geno, h1, h2):
+        g = np.ascontiguousarray(geno, dtype=np.int8)
+        assert g.ndim == 2 and g.shape[1] == self.n_snp
+        self.n_samp = g.shape[0]
+        a = np.ascontiguousarray(h1, dtype=np.int32); b = np.ascontiguousarray(h2, dtype=np.int32)
+        _chk(lib().hibag_b200_model_set_training(self._h, self.n_samp, _p(g), _p(a), _p(b)))
+
+    def train(self, nclassifier, mtry, prune=True, seed=100, n_threads=0, per_classifier_seed=False,
+              first_index=0, index_stride=1, use_legacy_hooks=False, verbose=0):
+        o = TrainOpts(nclassifier, mtry, int(prune), n_threads, seed, int(per_classifier_seed),
+                      first_index, index_stride, int(use_legacy_hooks), verbose)
+        _chk(lib().hibag_b200_model_train(self._h, C.byref(o)))
+
+    def train_stats(self):
+        s = TrainStats()
+        _chk(lib().hibag_b200_model_train_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in TrainStats._fields_}
+
+    def predict_stats(self):
+        s = PredictStats()
+        _chk(lib().hibag_b200_model_predict_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in PredictStats._fields_}
+
+    def num_classifiers(self):
+        return lib().hibag_b200_model_num_classifiers(self._h)
+
+    def clear(self):
+        _chk(lib().hibag_b200_model_clear(self._h))
+
+    def classifier(self, k):
+        ns, nh, acc = C.c_int(), C.c_int(), C.c_double()
+        _chk(lib().hibag_b200_model_classifier_info(self._h, k, C.byref(ns), C.byref(nh), C.byref(acc)))
+        snpidx = np.zeros(ns.value, dtype=np.int32)
+        samp = np.zeros(max(self.n_samp, 1), dtype=np.int32)
+        freq = np.zeros(nh.value); hla = np.zeros(nh.value, dtype=np.int32)
+        packed = np.zeros((nh.value, 2), dtype=np.uint64)
+        _chk(lib().hibag_b200_model_classifier_get(self._h, k, _p(snpidx), _p(samp), _p(freq), _p(hla), _p(packed)))
+        return dict(snpidx=snpidx, samp_num=samp[:self.n_samp], freq=freq, hla=hla, packed=packed,
+                    oob_acc=acc.value)
+
+    def add_classifier(self, snpidx, freq, hla, packed, samp_num=None, oob_acc=0.0):
+        s = np.ascontiguousarray(snpidx, dtype=np.int32)
+        f = np.ascontiguousarray(freq, dtype=np.float64)
+        h = np.ascontiguousarray(hla, dtype=np.int32)
+        p = np.ascontiguousarray(packed, dtype=np.uint64)
+        sn = None if samp_num is None else np.ascontiguousarray(samp_num, dtype=np.int32)
+        _chk(lib().hibag_b200_model_add_classifier(self._h, len(s), _p(s), _p(sn),
+                                                  0 if sn is None else len(sn), len(f), _p(f), _p(h), _p(p),
+                                                  oob_acc))
+
+    def snp_weights(self):
+        w = np.zeros(self.n_snp, dtype=np.int32)
+        _chk(lib().hibag_b200_model_snp_weights(self._h, _p(w)))
+        return w
+
+    def predict(self, geno, want_prob=True, want_dosage=True):
+        """Host-buffer prediction: H2D of the raw genotypes and D2H of the results inside."""
+        g = np.ascontiguousarray(geno, dtype=np.int8)
+        assert g.ndim == 2 and g.shape[1] == self.n_snp
+        n = g.shape[0]
+        h1 = np.zeros(n, dtype=np.int32); h2 = np.zeros(n, dtype=np.int32)
+        mp = np.zeros(n); mt = np.zeros(n)
+        ds = np.zeros((n, self.n_hla)) if want_dosage else None
+        pr = np.zeros((n, self.n_cells)) if want_prob else None
+        out = PredictOut(_p(h1).value, _p(h2).value, _p(mp).value, _p(mt).value,
+                         None if ds is None else _p(ds).value, None if pr is None else _p(pr).value)
+        _chk(lib().hibag_b200_model_predict(self._h, _p(g), n, C.byref(out)))
+        return dict(h1=h1, h2=h2, prob=mp, matching=mt, dosage=ds, postprob=pr)
+
+    def predict_device(self, geno_ptr, n_samp, h1=0, h2=0, max_prob=0, matching=0, dosage=0,
+                       post_prob=0, stream=0, sync=True):
+        """Device-resident prediction; all arguments are raw device pointers (ints)."""
+        out = PredictOut(h1 or None, h2 or None, max_prob or None, matching or None,
+                         dosage or None, post_prob or None)
+        _chk(lib().hibag_b200_model_predict_device(self._h, C.c_void_p(geno_ptr), n_samp, C.byref(out),
+                                                  C.c_void_p(stream) if stream else None, int(sync)))
+
+    def predict_partial_device(self, geno_ptr, n_samp, snp_weight_ptr, acc_ptr, stream=0, sync=True):
+        _chk(lib().hibag_b200_model_predict_partial_device(
+            self._h, C.c_void_p(geno_ptr), n_samp, C.c_void_p(snp_weight_ptr) if snp_weight_ptr else None,
+            C.c_void_p(acc_ptr), C.c_void_p(stream) if stream else None, int(sync)))
+
+    # reference hlaModelToObj / hlaModelFromObj (R/HIBAG.R:1041-1178): the interchange format
+    def to_obj(self):
+        cls = []
+        for k in range(self.num_classifiers()):
+            c = self.classifier(k)
+            cls.append(dict(samp_num=c["samp_num"], snpidx=c["snpidx"] + 1,
+                            haplos=dict(freq=c["freq"], hla=[self.hla_allele[i] for i in c["hla"]],
+                                        haplo=[_bits(p, len(c["snpidx"])) for p in c["packed"]]),
+                            outofbag_acc=c["oob_acc"]))
+        return dict(n_samp=self.n_samp, n_snp=self.n_snp, hla_allele=self.hla_allele,
+                    snp_id=self.snp_id, classifiers=cls)
+
+    @staticmethod
+    def from_obj(obj):
+        m = HLAModel(obj["n_snp"], len(obj["hla_allele"]), obj["hla_allele"], obj.get("snp_id"))
+        m.n_samp = int(obj.get("n_samp", 0))
+        for c in obj["classifiers"]:
+            hla = [obj["hla_allele"].index(x) for x in c["haplos"]["hla"]]
+            packed = np.array([_unbits(s) for s in c["haplos"]["haplo"]], dtype=np.uint64).reshape(-1, 2)
+            m.add_classifier(np.asarray(c["snpidx"]) - 1, c["haplos"]["freq"], hla, packed,
+                             samp_num=c.get("samp_num"), oob_acc=float(c.get("outofbag_acc", 0)))
+        return m
+
+
+def _bits(p, n):
+    return "".join("1" if (int(p[j >> 6]) >> (j & 63)) & 1 else "0" for j in range(n))
+
+
+def _unbits(s):
+    w = [0, 0]
+    for j, ch in enumerate(s):
+        if ch == "1":
+            w[j >> 6] |= 1 << (j & 63)
+    return w
+
+
+def default_mtry(n_snp, mtry="sqrt"):
+    """reference R/HIBAG.R:180-208"""
+    if mtry == "sqrt":
+        v = math.ceil(math.sqrt(n_snp))
+    elif mtry == "all":
+        v = n_snp
+    elif mtry == "one":
+        v = 1
+    else:
+        v = float(mtry)
+        if 0 < v < 1:
+            v = n_snp * v
+        v = min(math.ceil(v), n_snp)
+    return max(int(v), 1)
+
+
+def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=True, seed=100,
+                   nthread=0, per_classifier_seed=False, use_legacy_hooks=False, verbose=False,
+                   hla_allele=None):
+    """Train a model. hla = (h1, h2) integer allele indices (or labels with hla_allele given),
+    snp = int matrix [n_samp, n_snp] with 0/1/2 and anything else missing.
+    Mirrors reference hlaAttrBagging (R/HIBAG.R:48-275): monomorphic SNPs are removed when mono_rm,
+    mtry rule, then HIBAG_Training + HIBAG_NewClassifiers."""
+    h1, h2 = (np.asarray(x) for x in hla)
+    g = np.asarray(snp)
+    assert g.ndim == 2 and len(h1) == g.shape[0] == len(h2)
+    if hla_allele is None:
+        n_hla = int(max(h1.max(), h2.max())) + 1
+    else:
+        n_hla = len(hla_allele)
+    keep = np.arange(g.shape[1])
+    if mono_rm:                                   # R/HIBAG.R:117-155
+        valid = (g >= 0) & (g <= 2)
+        cnt = valid.sum(axis=0)
+        mf = np.where(cnt > 0, (g * valid).sum(axis=0) / np.maximum(cnt, 1) * 0.5, 0.0)
+        mf = np.minimum(mf, 1 - mf)
+        keep = np.nonzero(mf > 0)[0]
+        g = g[:, keep]
+    model = HLAModel(g.shape[1], n_hla, hla_allele)
+    model.snp_sel = keep
+    model.set_training(g, h1, h2)
+    model.train(nclassifier, default_mtry(g.shape[1], mtry), prune=prune, seed=seed, n_threads=nthread,
+                per_classifier_seed=per_classifier_seed, use_legacy_hooks=use_legacy_hooks,
+                verbose=int(verbose))
+    return model
+
+
+def hlaPredict(model, snp, type="response+prob"):
+    """Predict HLA types (reference hlaPredict, R/HIBAG.R:481-818, vote = "prob").
+    type: "response" (best guess, prob, matching), "dosage", "prob", "response+dosage",
+    "response+prob"."""
+    g = np.asarray(snp)
+    if getattr(model, "snp_sel", None) is not None and g.shape[1] != model.n_snp:
+        g = g[:, model.snp_sel]
+    want_prob = type in ("prob", "response+prob")
+    want_dosage = type in ("dosage", "response+dosage", "response+prob")
+    r = model.predict(g, want_prob=want_prob, want_dosage=want_dosage)
+    r["allele1"] = [model.hla_allele[i] if i != NA_INTEGER else None for i in r["h1"]]
+    r["allele2"] = [model.hla_allele[i] if i != NA_INTEGER else None for i in r["h2"]]
+    return r

@@ -1,0 +1,107 @@
+// common.h -- error handling and RAII device / pinned buffers (internal)
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/hibag_b200.h"
+
+namespace hb {
+
+#define HB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+	throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + \
+		" at " __FILE__ ":" + std::to_string(__LINE__)); } while (0)
+
+/// selected device + its properties; throws when no CUDA device is usable (there is no CPU
+/// fallback in this library)
+struct DeviceInfo
+{
+	int device;
+	int sm_count;
+	int clock_khz;
+	char name[128];
+};
+const DeviceInfo &current_device();
+void select_device(int device);
+
+/// growable device buffer (contents are NOT preserved on growth)
+template <typename T>
+class DevBuf
+{
+public:
+	DevBuf() : p_(nullptr), cap_(0) {}
+	~DevBuf() { if (p_) cudaFree(p_); }
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	T *ensure(size_t n)
+	{
+		if (n > cap_)
+		{
+			if (p_) { cudaFree(p_); p_ = nullptr; cap_ = 0; }
+			size_t want = n + n / 4 + 64;
+			HB_CUDA(cudaMalloc((void **)&p_, want * sizeof(T)));
+			cap_ = want;
+		}
+		return p_;
+	}
+	T *get() const { return p_; }
+	size_t capacity() const { return cap_; }
+	void release() { if (p_) { cudaFree(p_); p_ = nullptr; cap_ = 0; } }
+private:
+	T *p_;
+	size_t cap_;
+};
+
+/// growable page-locked host buffer
+template <typename T>
+class PinBuf
+{
+public:
+	PinBuf() : p_(nullptr), cap_(0) {}
+	~PinBuf() { if (p_) cudaFreeHost(p_); }
+	PinBuf(const PinBuf &) = delete;
+	PinBuf &operator=(const PinBuf &) = delete;
+	T *ensure(size_t n)
+	{
+		if (n > cap_)
+		{
+			if (p_) { cudaFreeHost(p_); p_ = nullptr; cap_ = 0; }
+			size_t want = n + n / 4 + 64;
+			HB_CUDA(cudaMallocHost((void **)&p_, want * sizeof(T)));
+			cap_ = want;
+		}
+		return p_;
+	}
+	T *get() const { return p_; }
+	void release() { if (p_) { cudaFreeHost(p_); p_ = nullptr; cap_ = 0; } }
+private:
+	T *p_;
+	size_t cap_;
+};
+
+struct Stream
+{
+	cudaStream_t s = nullptr;
+	Stream() { HB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+	~Stream() { if (s) cudaStreamDestroy(s); }
+	Stream(const Stream &) = delete;
+	Stream &operator=(const Stream &) = delete;
+};
+
+struct Event
+{
+	cudaEvent_t e = nullptr;
+	explicit Event(bool timing = true)
+	{
+		HB_CUDA(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+	}
+	~Event() { if (e) cudaEventDestroy(e); }
+	Event(const Event &) = delete;
+	Event &operator=(const Event &) = delete;
+};
+
+}  // namespace hb

@@ -1,0 +1,125 @@
+// kernels.h -- launch interface of the sm_100a scoring kernels (internal to libhibag_b200.so)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+/// One allele-pair cell (a,b), a <= b, of the posterior matrix: haplotype ranges of the two
+/// alleles inside the list and the position of the cell in the upper-triangular vector
+/// (reference src/LibHLA.cpp:1520-1530).
+struct CellTask
+{
+	int a_start, a_n;    // haplotypes of allele a: [a_start, a_start + a_n)
+	int b_start, b_n;    // haplotypes of allele b
+	int out_idx;         // H2 + H1*(2*n_hla-H1-1)/2
+	int diag;            // 1 when a == b (upper triangle of pairs, first term f*f)
+	int pad0, pad1;      // 32-byte records: two aligned vector loads in the kernel
+};
+
+/// A run of consecutive cells [cell_begin, cell_end) processed by one warp for one group of
+/// samples; chunks are sorted by decreasing cost so the long fp64 chains start first.
+struct Chunk
+{
+	int cell_begin, cell_end;
+};
+
+/// Device-side description of one scoring pass: all cells of one haplotype list against a
+/// list of samples.
+struct CellPass
+{
+	// haplotype records in kernel layout (see pack_hap_records): 16 B (<=64 SNPs) or 32 B each
+	const void *hap;
+	int n_hap;
+	int n_snp;
+	// rare-frequency table EXP_LOG_MIN_RARE_FREQ[257] (host-computed, src/LibHLA.cpp:166-183)
+	const double *table;
+	int n_dist;              // table entries the kernel stages (distances are clamped to n_dist-1)
+	// packed genotypes, SoA 32-bit words: s1[w * geno_stride + sample], same for s2
+	const uint32_t *s1, *s2;
+	int geno_stride;
+	// optional candidate SNP patched in at bit `cand_bit`: raw genotype column int8 [sample]
+	const int8_t *cand_col;
+	int cand_bit;
+	// samples to score: sample index = samp_list ? samp_list[pos] : pos, pos in [0, n_pos)
+	const int *samp_list;
+	int n_pos;
+	// work list
+	const CellTask *cells;
+	const Chunk *chunks;
+	int n_chunks;
+	unsigned int *task_counter;   // zeroed before launch
+	// output: P[out_idx * p_stride + pos] = raw cell sum
+	double *P;
+	size_t p_stride;
+};
+
+/// bytes of one haplotype record in kernel layout for a classifier of n_snp SNPs
+inline int hap_record_bytes(int n_snp) { return (n_snp <= 64) ? 16 : 32; }
+/// number of 32-bit genotype words the kernels use for n_snp SNPs (1, 2 or 4)
+inline int geno_words(int n_snp) { return (n_snp <= 32) ? 1 : ((n_snp <= 64) ? 2 : 4); }
+
+/// Launch the pair-scoring kernel. samples_per_lane in {1,2,4}. Returns the number of POPC.32
+/// issued per pair evaluation by the chosen instantiation (1, 2 or 4) for accounting.
+int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cudaStream_t st);
+
+/// AoS TGenotype[n] (48 B) -> SoA words + true alleles + bootstrap counts
+void launch_unpack_genotypes(const void *geno_aos, int n, uint32_t *s1, uint32_t *s2,
+	int stride, int *a1, int *a2, int *boot, cudaStream_t st);
+
+/// out-of-bag accuracy: per position argmax over cells (strict '<', first wins), compare with
+/// the true type (src/LibHLA.cpp:912-924), integer sum into *out_count (zeroed by the caller)
+void launch_reduce_oob(const double *P, size_t p_stride, int n_hla, const int *samp_list,
+	int n_pos, const int *a1, const int *a2, int *out_count, cudaStream_t st);
+
+/// in-bag: per position P_true / sum_cells (sequential sum in cell order)
+void launch_reduce_ib(const double *P, size_t p_stride, int n_hla, const int *samp_list,
+	int n_pos, const int *a1, const int *a2, double *out_ratio, cudaStream_t st);
+
+/// best guess per position written as allele pair (for hibag_b200_best_guess)
+void launch_reduce_best_guess(const double *P, size_t p_stride, int n_hla, int n_pos,
+	int *out_a1, int *out_a2, cudaStream_t st);
+
+/// PostProb2 normalisation in place + raw sum per position
+void launch_normalize(double *P, size_t p_stride, int n_hla, int n_pos, double *out_sum,
+	cudaStream_t st);
+
+/// transpose P[cell][pos] -> out[pos][cell]
+void launch_transpose(const double *P, size_t p_stride, int n_cells, int n_pos, double *out,
+	cudaStream_t st);
+
+// ---- prediction --------------------------------------------------------------------------
+
+/// int8 matrix transpose: in[rows][cols] -> out[cols][rows]
+void launch_transpose_i8(const int8_t *in, int rows, int cols, int8_t *out, cudaStream_t st);
+
+/// pack raw int8 genotypes for one classifier's SNP order into SoA words for a tile of samples
+/// and compute the classifier's weight per sample (src/LibHLA.cpp:667-706 and 2418-2431).
+/// geno_t is SNP-major: int8 [n_snp_total][n_samp_total]
+void launch_pack_classifier(const int8_t *geno_t, size_t n_samp_total, int samp_begin,
+	int n_tile, const int *snpidx, int n_snp, const int *snp_weight, uint32_t *s1,
+	uint32_t *s2, int stride, double *weight, cudaStream_t st);
+
+/// per sample of the tile: s = sum_cells P (sequential); acc[cell] += (P[cell]/s... ) see .cu
+/// acc layout: acc[cell * acc_stride + pos]; aux[0..2][pos] = sum_w, sum_w*match, n_used
+void launch_predict_accumulate(const double *P, size_t p_stride, int n_cells, int n_tile,
+	const double *weight, double *acc, size_t acc_stride, double *aux, cudaStream_t st);
+
+/// finalisation of a tile: normalise by sum_w, matching, best guess, max prob, dosage,
+/// posterior rows. Outputs are indexed by global sample (samp_begin + pos); any may be NULL.
+void launch_predict_finalize(double *acc, size_t acc_stride, const double *aux, int n_hla,
+	int samp_begin, int n_tile, int *h1, int *h2, double *max_prob, double *matching,
+	double *dosage, double *post_prob, cudaStream_t st);
+
+/// classifier-sharded path: export / import the accumulators as [sample][n_cells + 3]
+void launch_export_partial(const double *acc, size_t acc_stride, const double *aux,
+	int n_cells, int samp_begin, int n_tile, double *out, cudaStream_t st);
+void launch_finalize_from_partial(const double *partial, int n_hla, int n_samp, int *h1,
+	int *h2, double *max_prob, double *matching, double *dosage, double *post_prob,
+	cudaStream_t st);
+
+// ---- microbenchmarks ---------------------------------------------------------------------
+double run_pipe_peak(int which, int sm_count, double *out_ms);
+
+}  // namespace hb

@@ -1,0 +1,353 @@
+// plugin.cu -- the drop-in boundary: HIBAG's ten TypeGPUExtProc hooks
+// (reference inst/include/LibHLA_ext.h:357-388) implemented on the sm_100a kernels, plus the
+// stateless batched scoring entry points of include/hibag_b200.h.
+//
+// Hook contract (call sites in the reference, src/LibHLA.cpp):
+//   build_init :2256-2260 | build_done :2262-2266 | build_set_bootstrap :2290-2293
+//   build_set_haplo_geno :1913-1921 | build_acc_oob :1938-1941 | build_acc_ib :1961-1964
+//   predict_init :2498-2523 | predict_done :2525-2531 | predict_avg_prob :2433-2441
+// The hooks are process-global state (one model at a time), called from one thread, and
+// report failure by throwing std::exception like any other plugin of the reference would.
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "scorer.h"
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------------
+// training hooks
+// ---------------------------------------------------------------------------------------------
+struct BuildState
+{
+	int n_hla = 0, n_samp = 0, n_snp = 0;
+	GenoSet geno;
+	PinBuf<unsigned char> h_aos;
+	DevBuf<unsigned char> d_aos;
+	std::vector<int> boot;            // bootstrap multiplicities currently on the device
+	std::vector<int> oob, ib;         // ascending sample indices (src/LibHLA.cpp:1858-1874)
+	DevBuf<int> d_oob, d_ib;
+	bool have_lists = false;
+	bool have_list_staged = false;
+	EvalSlot slot;
+	ScoreStats total;
+
+	void set_bootstrap(const int *cnt)
+	{
+		boot.assign(cnt, cnt + n_samp);
+		oob.clear(); ib.clear();
+		for (int i = 0; i < n_samp; i++)
+			(cnt[i] > 0 ? ib : oob).push_back(i);
+		d_oob.ensure(n_samp); d_ib.ensure(n_samp);
+		// pageable -> device copies are synchronous with respect to the host buffer
+		if (!oob.empty())
+			HB_CUDA(cudaMemcpyAsync(d_oob.get(), oob.data(), sizeof(int) * oob.size(),
+				cudaMemcpyHostToDevice, slot.stream()));
+		if (!ib.empty())
+			HB_CUDA(cudaMemcpyAsync(d_ib.get(), ib.data(), sizeof(int) * ib.size(),
+				cudaMemcpyHostToDevice, slot.stream()));
+		HB_CUDA(cudaStreamSynchronize(slot.stream()));
+		slot.stats.h2d_bytes += sizeof(int) * (size_t)n_samp;
+		have_lists = true;
+	}
+
+	GenoView view() const
+	{
+		GenoView v;
+		v.s1 = geno.s1.get(); v.s2 = geno.s2.get(); v.stride = n_samp;
+		v.a1 = geno.a1.get(); v.a2 = geno.a2.get();
+		return v;
+	}
+};
+
+static std::unique_ptr<BuildState> g_build;
+
+static void hook_build_init(int n_hla, int n_sample)
+{
+	if (n_hla <= 0 || n_sample <= 0) throw std::runtime_error("build_init: invalid sizes");
+	current_device();
+	g_build.reset(new BuildState());
+	g_build->n_hla = n_hla;
+	g_build->n_samp = n_sample;
+	g_build->geno.ensure(n_sample);
+	g_build->h_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
+	g_build->d_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
+}
+
+static void hook_build_done()
+{
+	g_build.reset();
+}
+
+static void hook_build_set_bootstrap(const int cnt[])
+{
+	if (!g_build) throw std::runtime_error("build_set_bootstrap called before build_init");
+	g_build->set_bootstrap(cnt);
+}
+
+static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo,
+	const hibag_genotype geno[], int n_snp)
+{
+	BuildState *b = g_build.get();
+	if (!b) throw std::runtime_error("build_set_haplo_geno called before build_init");
+	// the genotype array carries the bootstrap counts too; (re)build the sample lists when the
+	// host did not call build_set_bootstrap or the counts changed
+	bool same = b->have_lists;
+	if (same)
+		for (int i = 0; i < b->n_samp; i++)
+			if (geno[i].bootstrap_count != b->boot[i]) { same = false; break; }
+	if (!same)
+	{
+		std::vector<int> cnt(b->n_samp);
+		for (int i = 0; i < b->n_samp; i++) cnt[i] = geno[i].bootstrap_count;
+		b->set_bootstrap(cnt.data());
+	}
+	b->n_snp = n_snp;
+	const size_t bytes = sizeof(hibag_genotype) * (size_t)b->n_samp;
+	// the previous evaluation has been synchronised (acc_* return values), so the pinned
+	// staging buffers are free to overwrite
+	memcpy(b->h_aos.get(), geno, bytes);
+	HB_CUDA(cudaMemcpyAsync(b->d_aos.get(), b->h_aos.get(), bytes, cudaMemcpyHostToDevice,
+		b->slot.stream()));
+	b->slot.stats.h2d_bytes += bytes;
+	launch_unpack_genotypes(b->d_aos.get(), b->n_samp, b->geno.s1.get(), b->geno.s2.get(),
+		b->n_samp, b->geno.a1.get(), b->geno.a2.get(), b->geno.boot.get(), b->slot.stream());
+	b->slot.stats.launches++;
+	b->slot.stage_list(haplo, n_haplo, b->n_hla, n_snp);
+	b->have_list_staged = true;
+}
+
+static int hook_build_acc_oob()
+{
+	BuildState *b = g_build.get();
+	if (!b || !b->have_list_staged)
+		throw std::runtime_error("build_acc_oob called before build_set_haplo_geno");
+	const int n = (int)b->oob.size();
+	if (n == 0) return 0;
+	const GenoView v = b->view();
+	b->slot.enqueue_cells(v, b->d_oob.get(), n);
+	b->slot.enqueue_reduce_oob(v, b->d_oob.get(), n);
+	b->slot.sync();
+	return b->slot.oob_count();
+}
+
+static double hook_build_acc_ib()
+{
+	BuildState *b = g_build.get();
+	if (!b || !b->have_list_staged)
+		throw std::runtime_error("build_acc_ib called before build_set_haplo_geno");
+	const int n = (int)b->ib.size();
+	const GenoView v = b->view();
+	b->slot.enqueue_cells(v, b->d_ib.get(), n);
+	b->slot.enqueue_reduce_ib(v, b->d_ib.get(), n);
+	b->slot.sync();
+	// log() and the in-bag-order sum stay on the host (glibc log, sequential order of
+	// src/LibHLA.cpp:1966-1977)
+	const double *ratio = b->slot.ib_ratios();
+	double loglik = 0;
+	for (int i = 0; i < n; i++)
+		loglik += b->boot[b->ib[i]] * std::log(ratio[i]);
+	return loglik * -2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prediction hooks (one sample per call: the granularity the reference imposes, :2433-2441)
+// ---------------------------------------------------------------------------------------------
+struct PredictHookState
+{
+	int n_hla = 0, n_cls = 0, n_cells = 0;
+	std::vector<ListBlob> blobs;
+	std::vector<size_t> blob_off;
+	DevBuf<unsigned char> d_blobs;
+	GenoSet geno;                       // "sample" c = the genotype packed for classifier c
+	PinBuf<unsigned char> h_aos;
+	DevBuf<unsigned char> d_aos;
+	PinBuf<double> h_w;
+	DevBuf<double> d_w;
+	DevBuf<int> d_idx;
+	DevBuf<double> P, acc, aux, d_match;
+	PinBuf<double> h_out;
+	DevBuf<unsigned int> counters;
+	Stream st;
+	ScoreStats stats;
+};
+
+static std::unique_ptr<PredictHookState> g_pred;
+
+static void hook_predict_init(int n_hla, int n_classifier,
+	const hibag_haplotype *const p_haplo[], const int n_haplo[], const int n_snp[])
+{
+	if (n_hla <= 0 || n_classifier < 0) throw std::runtime_error("predict_init: invalid sizes");
+	current_device();
+	std::unique_ptr<PredictHookState> s(new PredictHookState());
+	s->n_hla = n_hla; s->n_cls = n_classifier;
+	s->n_cells = n_hla * (n_hla + 1) / 2;
+	size_t total = 0;
+	s->blob_off.resize(n_classifier);
+	for (int c = 0; c < n_classifier; c++)
+	{
+		s->blob_off[c] = total;
+		total += (list_blob_capacity(n_haplo[c], n_snp[c], n_hla) + 255) & ~(size_t)255;
+	}
+	std::vector<unsigned char> host(total + 256);
+	unsigned char *hbase = (unsigned char *)(((uintptr_t)host.data() + 15) & ~(uintptr_t)15);
+	s->blobs.resize(n_classifier);
+	for (int c = 0; c < n_classifier; c++)
+		s->blobs[c] = build_list_blob(p_haplo[c], n_haplo[c], n_hla, n_snp[c],
+			hbase + s->blob_off[c], 64);
+	s->d_blobs.ensure(total + 256);
+	if (total) HB_CUDA(cudaMemcpy(s->d_blobs.get(), hbase, total, cudaMemcpyHostToDevice));
+	const int nc = n_classifier > 0 ? n_classifier : 1;
+	s->geno.ensure(nc);
+	s->h_aos.ensure(sizeof(hibag_genotype) * (size_t)nc);
+	s->d_aos.ensure(sizeof(hibag_genotype) * (size_t)nc);
+	s->h_w.ensure(nc); s->d_w.ensure(nc);
+	std::vector<int> idx(nc);
+	for (int c = 0; c < nc; c++) idx[c] = c;
+	s->d_idx.ensure(nc);
+	HB_CUDA(cudaMemcpy(s->d_idx.get(), idx.data(), sizeof(int) * nc, cudaMemcpyHostToDevice));
+	s->P.ensure((size_t)s->n_cells * 32);
+	s->acc.ensure((size_t)s->n_cells); s->aux.ensure(4); s->d_match.ensure(1);
+	s->h_out.ensure((size_t)s->n_cells + 1);
+	s->counters.ensure(nc);
+	device_rare_freq_table();
+	g_pred = std::move(s);
+}
+
+static void hook_predict_done()
+{
+	g_pred.reset();
+}
+
+static void hook_predict_avg_prob(const hibag_genotype geno[], const double weight[],
+	double out_prob[], double out_match[])
+{
+	PredictHookState *s = g_pred.get();
+	if (!s) throw std::runtime_error("predict_avg_prob called before predict_init");
+	const DeviceInfo &di = current_device();
+	cudaStream_t st = s->st.s;
+	const int nc = s->n_cls;
+	memcpy(s->h_aos.get(), geno, sizeof(hibag_genotype) * (size_t)nc);
+	memcpy(s->h_w.get(), weight, sizeof(double) * (size_t)nc);
+	HB_CUDA(cudaMemcpyAsync(s->d_aos.get(), s->h_aos.get(), sizeof(hibag_genotype) * (size_t)nc,
+		cudaMemcpyHostToDevice, st));
+	HB_CUDA(cudaMemcpyAsync(s->d_w.get(), s->h_w.get(), sizeof(double) * (size_t)nc,
+		cudaMemcpyHostToDevice, st));
+	launch_unpack_genotypes(s->d_aos.get(), nc, s->geno.s1.get(), s->geno.s2.get(), nc,
+		s->geno.a1.get(), s->geno.a2.get(), s->geno.boot.get(), st);
+	HB_CUDA(cudaMemsetAsync(s->acc.get(), 0, sizeof(double) * (size_t)s->n_cells, st));
+	HB_CUDA(cudaMemsetAsync(s->aux.get(), 0, sizeof(double) * 4, st));
+	HB_CUDA(cudaMemsetAsync(s->counters.get(), 0, sizeof(unsigned int) * (size_t)nc, st));
+	const double *tbl = device_rare_freq_table();
+	for (int c = 0; c < nc; c++)
+	{
+		if (!(weight[c] > 0)) continue;             // src/LibHLA.cpp:2451
+		CellPass p;
+		memset(&p, 0, sizeof(p));
+		bind_list(s->blobs[c], s->d_blobs.get() + s->blob_off[c], tbl, p);
+		p.s1 = s->geno.s1.get(); p.s2 = s->geno.s2.get(); p.geno_stride = nc;
+		p.samp_list = s->d_idx.get() + c; p.n_pos = 1;
+		p.task_counter = s->counters.get() + c;
+		p.P = s->P.get(); p.p_stride = 32;
+		const int nw = launch_cell_pass(p, 1, di.sm_count, st);
+		launch_predict_accumulate(s->P.get(), 32, s->n_cells, 1, s->d_w.get() + c,
+			s->acc.get(), 1, s->aux.get(), st);
+		s->stats.pair_evals += s->blobs[c].pairs_per_sample;
+		s->stats.popc32 += s->blobs[c].pairs_per_sample * nw;
+		s->stats.launches += 2; s->stats.cell_launches++;
+	}
+	// aux layout for n_tile = 1: [0] = sum_w, [1] = sum_w*match, [2] = n_used
+	launch_predict_finalize(s->acc.get(), 1, s->aux.get(), s->n_hla, 0, 1, nullptr, nullptr,
+		nullptr, s->d_match.get(), nullptr, nullptr, st);
+	HB_CUDA(cudaMemcpyAsync(s->h_out.get(), s->acc.get(), sizeof(double) * (size_t)s->n_cells,
+		cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaMemcpyAsync(s->h_out.get() + s->n_cells, s->d_match.get(), sizeof(double),
+		cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaStreamSynchronize(st));
+	memcpy(out_prob, s->h_out.get(), sizeof(double) * (size_t)s->n_cells);
+	out_match[0] = s->h_out.get()[s->n_cells];
+	s->stats.launches++;
+}
+
+static hibag_gpu_ext_proc g_procs = {
+	hook_build_init, hook_build_done, hook_build_set_bootstrap,
+	nullptr,   // build_haplomatch: optional; the host keeps its CPU search (src/LibHLA.cpp:1074)
+	hook_build_set_haplo_geno, hook_build_acc_oob, hook_build_acc_ib,
+	hook_predict_init, hook_predict_done, hook_predict_avg_prob
+};
+
+hibag_gpu_ext_proc *plugin_procs() { return &g_procs; }
+
+ScoreStats plugin_build_stats()
+{
+	ScoreStats s;
+	if (g_build) s = g_build->slot.stats;
+	return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stateless batched scoring on host arrays
+// ---------------------------------------------------------------------------------------------
+enum ScoreKind { SCORE_BEST_GUESS, SCORE_POST_PROB, SCORE_POST_PROB2 };
+
+void score_host_arrays(int kind, const hibag_haplotype *haplo, int n_haplo, int n_hla,
+	int n_snp, const hibag_genotype *geno, int n_geno, int32_t *out_a1, int32_t *out_a2,
+	double *out_d, double *out_sum)
+{
+	if (n_geno <= 0) return;
+	current_device();
+	EvalSlot slot;
+	slot.stage_list(haplo, n_haplo, n_hla, n_snp);
+	const int n_cells = n_hla * (n_hla + 1) / 2;
+	const int tile = 16384;
+	GenoSet gs;
+	gs.ensure(tile);
+	DevBuf<unsigned char> d_aos;
+	d_aos.ensure(sizeof(hibag_genotype) * (size_t)tile);
+	DevBuf<int> d_a1, d_a2;
+	DevBuf<double> d_out, d_sum;
+	d_a1.ensure(tile); d_a2.ensure(tile);
+	d_sum.ensure(tile);
+	if (kind == SCORE_POST_PROB2) d_out.ensure((size_t)tile * n_cells);
+	cudaStream_t st = slot.stream();
+	for (int begin = 0; begin < n_geno; begin += tile)
+	{
+		const int n = (n_geno - begin < tile) ? (n_geno - begin) : tile;
+		HB_CUDA(cudaMemcpyAsync(d_aos.get(), geno + begin, sizeof(hibag_genotype) * (size_t)n,
+			cudaMemcpyHostToDevice, st));
+		launch_unpack_genotypes(d_aos.get(), n, gs.s1.get(), gs.s2.get(), tile, gs.a1.get(),
+			gs.a2.get(), gs.boot.get(), st);
+		GenoView v;
+		v.s1 = gs.s1.get(); v.s2 = gs.s2.get(); v.stride = tile;
+		v.a1 = gs.a1.get(); v.a2 = gs.a2.get();
+		slot.enqueue_cells(v, nullptr, n);
+		if (kind == SCORE_BEST_GUESS)
+		{
+			launch_reduce_best_guess(slot.cell_matrix(), slot.cell_stride(), n_hla, n,
+				d_a1.get(), d_a2.get(), st);
+			HB_CUDA(cudaMemcpyAsync(out_a1 + begin, d_a1.get(), sizeof(int) * (size_t)n,
+				cudaMemcpyDeviceToHost, st));
+			HB_CUDA(cudaMemcpyAsync(out_a2 + begin, d_a2.get(), sizeof(int) * (size_t)n,
+				cudaMemcpyDeviceToHost, st));
+		} else if (kind == SCORE_POST_PROB)
+		{
+			launch_reduce_ib(slot.cell_matrix(), slot.cell_stride(), n_hla, nullptr, n,
+				gs.a1.get(), gs.a2.get(), d_sum.get(), st);
+			HB_CUDA(cudaMemcpyAsync(out_d + begin, d_sum.get(), sizeof(double) * (size_t)n,
+				cudaMemcpyDeviceToHost, st));
+		} else {
+			launch_normalize(slot.cell_matrix(), slot.cell_stride(), n_hla, n, d_sum.get(), st);
+			launch_transpose(slot.cell_matrix(), slot.cell_stride(), n_cells, n, d_out.get(), st);
+			HB_CUDA(cudaMemcpyAsync(out_d + (size_t)begin * n_cells, d_out.get(),
+				sizeof(double) * (size_t)n * n_cells, cudaMemcpyDeviceToHost, st));
+			HB_CUDA(cudaMemcpyAsync(out_sum + begin, d_sum.get(), sizeof(double) * (size_t)n,
+				cudaMemcpyDeviceToHost, st));
+		}
+		slot.sync();
+	}
+}
+
+}  // namespace hb

@@ -1,0 +1,99 @@
+// scorer.h -- device-side state for scoring one haplotype list against lists of samples
+// (the body of build_set_haplo_geno / build_acc_oob / build_acc_ib) (internal)
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+#include "tasks.h"
+
+namespace hb {
+
+/// device copy of EXP_LOG_MIN_RARE_FREQ for the current device (uploaded once per device)
+const double *device_rare_freq_table();
+
+/// counters shared by the training / prediction drivers
+struct ScoreStats
+{
+	uint64_t pair_evals = 0, popc32 = 0, launches = 0, cell_launches = 0;
+	uint64_t h2d_bytes = 0, d2h_bytes = 0;
+	double kernel_ms = 0, cell_ms = 0;
+	void add(const ScoreStats &o)
+	{
+		pair_evals += o.pair_evals; popc32 += o.popc32; launches += o.launches;
+		cell_launches += o.cell_launches; h2d_bytes += o.h2d_bytes; d2h_bytes += o.d2h_bytes;
+		kernel_ms += o.kernel_ms; cell_ms += o.cell_ms;
+	}
+};
+
+/// packed genotypes of a cohort on the device, SoA 32-bit words, plus true HLA types
+struct GenoSet
+{
+	int n = 0;
+	DevBuf<uint32_t> s1, s2;     // [4][n]
+	DevBuf<int> a1, a2, boot;    // [n]
+	void ensure(int n_samp)
+	{
+		n = n_samp;
+		s1.ensure((size_t)4 * n_samp); s2.ensure((size_t)4 * n_samp);
+		a1.ensure(n_samp); a2.ensure(n_samp); boot.ensure(n_samp);
+	}
+};
+
+struct GenoView
+{
+	const uint32_t *s1 = nullptr, *s2 = nullptr;
+	int stride = 0;
+	const int *a1 = nullptr, *a2 = nullptr;
+	const int8_t *cand_col = nullptr;    // optional candidate SNP column, int8 [n]
+	int cand_bit = 0;
+};
+
+/// One in-flight evaluation: its own stream, pinned staging, device list, cell matrix and
+/// result buffers. Not thread-safe; use one slot per host thread.
+class EvalSlot
+{
+public:
+	EvalSlot();
+	/// pack + cut + async upload of a haplotype list (tags must be filled, see tasks.h)
+	void stage_list(const hibag_haplotype *haplo, int n_hap, int n_hla, int n_snp);
+	/// all cells for the positions in pos_list (device int[n_pos], may be null = identity)
+	void enqueue_cells(const GenoView &g, const int *pos_list, int n_pos);
+	/// out-of-bag accuracy over the last enqueue_cells (src/LibHLA.cpp:1934-1955)
+	void enqueue_reduce_oob(const GenoView &g, const int *pos_list, int n_pos);
+	/// in-bag P_true/sum ratios over the last enqueue_cells (src/LibHLA.cpp:1957-1979)
+	void enqueue_reduce_ib(const GenoView &g, const int *pos_list, int n_pos);
+	/// wait for everything enqueued on this slot; folds event timings into stats
+	void sync();
+	int oob_count() const { return *h_count_.get(); }
+	const double *ib_ratios() const { return h_ratio_.get(); }
+
+	cudaStream_t stream() const { return st_.s; }
+	const ListBlob &list() const { return blob_; }
+	double *cell_matrix() const { return P_.get(); }
+	size_t cell_stride() const { return p_stride_; }
+	const void *dev_blob() const { return d_blob_.get(); }
+	ScoreStats stats;
+
+private:
+	Stream st_;
+	Event ev0_, ev1_, ev2_;
+	bool timing_pending_ = false;
+	PinBuf<unsigned char> h_blob_;
+	DevBuf<unsigned char> d_blob_;
+	ListBlob blob_;
+	DevBuf<double> P_;
+	size_t p_stride_ = 0;
+	DevBuf<unsigned int> counter_;
+	DevBuf<int> d_count_;
+	PinBuf<int> h_count_;
+	DevBuf<double> d_ratio_;
+	PinBuf<double> h_ratio_;
+};
+
+/// samples per lane for a pass over n_pos samples with n_chunks chunks
+int choose_samples_per_lane(int n_pos, int n_chunks, int n_snp, int sm_count);
+
+}  // namespace hb

@@ -241,3 +241,115 @@ class RefModel:
         self.ref._chk(self.L.ref_model_predict(self.h, _p(g), n, vote, _p(h1), _p(h2), _p(mp),
                                                _p(mt), _p(ds), _p(pr)))
         return dict(h1=h1, h2=h2, prob=mp, matching=mt, dosage=ds, postprob=pr)
+
+
+class OracleLib:
+    """This repo's C restatement of the scoring path (oracle/hibag_oracle.c)."""
+
+    def __init__(self, path=ORACLE_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle oracle`)")
+        L = self.lib = C.CDLL(path)
+        common = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.hibag_oracle_table.argtypes = [C.c_void_p]
+        L.hibag_oracle_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hibag_oracle_best_guess.argtypes = common + [C.c_void_p, C.c_void_p]
+        L.hibag_oracle_post_prob.argtypes = common + [C.c_void_p]
+        L.hibag_oracle_post_prob2.argtypes = common + [C.c_void_p, C.c_void_p]
+        L.hibag_oracle_acc_oob.argtypes = common
+        L.hibag_oracle_acc_ib.argtypes = common
+        L.hibag_oracle_acc_ib.restype = C.c_double
+        L.hibag_oracle_predict_avg.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hibag_oracle_best_guess_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hibag_oracle_dosage.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hibag_oracle_int_to_snp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hibag_oracle_classifier_weights.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                      C.c_void_p, C.c_void_p]
+
+    def table(self):
+        t = np.zeros(257)
+        self.lib.hibag_oracle_table(_p(t))
+        return t
+
+    def hamming(self, geno1, h1, h2, n_snp):
+        return self.lib.hibag_oracle_hamming(_p(geno1), _p(h1), _p(h2), n_snp)
+
+    def best_guess(self, haplo, n_hla, n_snp, geno):
+        a1 = np.zeros(len(geno), dtype=np.int32); a2 = np.zeros(len(geno), dtype=np.int32)
+        self.lib.hibag_oracle_best_guess(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno),
+                                         _p(a1), _p(a2))
+        return a1, a2
+
+    def post_prob(self, haplo, n_hla, n_snp, geno):
+        out = np.zeros(len(geno))
+        self.lib.hibag_oracle_post_prob(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno), _p(out))
+        return out
+
+    def post_prob2(self, haplo, n_hla, n_snp, geno):
+        nc = n_hla * (n_hla + 1) // 2
+        prob = np.zeros((len(geno), nc)); s = np.zeros(len(geno))
+        self.lib.hibag_oracle_post_prob2(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno),
+                                         _p(prob), _p(s))
+        return prob, s
+
+    def acc_oob(self, haplo, n_hla, n_snp, geno):
+        return self.lib.hibag_oracle_acc_oob(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno))
+
+    def acc_ib(self, haplo, n_hla, n_snp, geno):
+        return self.lib.hibag_oracle_acc_ib(_p(haplo), len(haplo), n_hla, n_snp, _p(geno), len(geno))
+
+    def int_to_snp(self, geno_row, index):
+        out = np.zeros(1, dtype=GENO_DT)
+        g = np.ascontiguousarray(geno_row, dtype=np.int32)
+        ix = np.ascontiguousarray(index, dtype=np.int32)
+        self.lib.hibag_oracle_int_to_snp(_p(out), len(ix), _p(g), _p(ix))
+        return out
+
+    def best_guess_cells(self, prob, n_hla):
+        a1, a2 = C.c_int32(), C.c_int32()
+        p = np.ascontiguousarray(prob, dtype=np.float64)
+        self.lib.hibag_oracle_best_guess_cells(_p(p), n_hla, C.byref(a1), C.byref(a2))
+        return a1.value, a2.value
+
+    def dosage(self, prob, n_hla):
+        p = np.ascontiguousarray(prob, dtype=np.float64)
+        d = np.zeros(n_hla)
+        self.lib.hibag_oracle_dosage(_p(p), n_hla, _p(d))
+        return d
+
+    def predict(self, classifiers, n_hla, n_total_snp, geno_rows):
+        """Ensemble prediction of int genotype rows [n][n_total_snp] with a list of classifier
+        dicts (snpidx, freq, hla, packed): the CPU branch of _PredictHLA + PredictHLA's outputs."""
+        nc = n_hla * (n_hla + 1) // 2
+        n_cls = len(classifiers)
+        haplos = [make_haplo(c["packed"], c["freq"], c["hla"]) for c in classifiers]
+        hp = (C.c_void_p * n_cls)(*[h.ctypes.data for h in haplos])
+        nh = np.array([len(h) for h in haplos], dtype=np.int32)
+        ns = np.array([len(c["snpidx"]) for c in classifiers], dtype=np.int32)
+        idx = [np.ascontiguousarray(c["snpidx"], dtype=np.int32) for c in classifiers]
+        ip = (C.c_void_p * n_cls)(*[x.ctypes.data for x in idx])
+        g = np.ascontiguousarray(geno_rows, dtype=np.int32)
+        n = g.shape[0]
+        out = dict(h1=np.zeros(n, dtype=np.int32), h2=np.zeros(n, dtype=np.int32), prob=np.zeros(n),
+                   matching=np.zeros(n), dosage=np.zeros((n, n_hla)), postprob=np.zeros((n, nc)))
+        w = np.zeros(n_cls)
+        packed = np.zeros(n_cls, dtype=GENO_DT)
+        for s in range(n):
+            row = g[s]
+            self.lib.hibag_oracle_classifier_weights(n_cls, _p(ns), ip, n_total_snp, _p(row), _p(w))
+            for c in range(n_cls):
+                self.lib.hibag_oracle_int_to_snp(C.c_void_p(packed.ctypes.data + 48 * c), int(ns[c]),
+                                                 _p(row), _p(idx[c]))
+            m = C.c_double()
+            pr = out["postprob"][s]
+            self.lib.hibag_oracle_predict_avg(n_hla, n_cls, hp, _p(nh), _p(ns), _p(packed), _p(w),
+                                              _p(pr), C.byref(m))
+            out["matching"][s] = m.value
+            a1, a2 = self.best_guess_cells(pr, n_hla)
+            out["h1"][s], out["h2"][s] = a1, a2
+            if a1 != NA_INTEGER:
+                lo, hi = min(a1, a2), max(a1, a2)
+                out["prob"][s] = pr[hi + lo * (2 * n_hla - lo - 1) // 2]
+            out["dosage"][s] = self.dosage(pr, n_hla)
+        return out

@@ -1,0 +1,280 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the oracle,
+the compiled reference and the reference's golden model. Integers are bit-exact; fp64 outputs
+are required to agree within 1e-10 relative (north_star) and in practice are bit-identical, which
+is asserted too where the operation order is the reference's."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import refpy
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+SNP_COUNTS = [1, 7, 31, 32, 33, 64, 65, 96, 128]
+RTOL = 1e-10      # tolerance stated by BASELINE.json north_star for fp64 outputs
+
+
+def rel_close(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if not np.array_equal(np.isnan(a), np.isnan(b)):
+        return False
+    m = ~np.isnan(a)
+    return np.all(np.abs(a[m] - b[m]) <= RTOL * np.maximum(np.abs(a[m]), np.abs(b[m])))
+
+
+# ---- kernel level -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n_snp", SNP_COUNTS)
+def test_scoring_matches_oracle(gpu, orc, n_snp):
+    rng = np.random.default_rng(2000 + n_snp)
+    h, n_hla, _ = helpers.random_haplo_list(rng, 13, n_snp)
+    g = helpers.random_genotypes(rng, 777, n_snp, n_hla, haplo=h)
+    a1, a2 = gpu.best_guess(h, n_hla, n_snp, g)
+    o1, o2 = orc.best_guess(h, n_hla, n_snp, g)
+    assert np.array_equal(a1, o1) and np.array_equal(a2, o2)
+    assert np.array_equal(gpu.post_prob(h, n_hla, n_snp, g), orc.post_prob(h, n_hla, n_snp, g),
+                          equal_nan=True)
+    p, s = gpu.post_prob2(h, n_hla, n_snp, g)
+    q, t = orc.post_prob2(h, n_hla, n_snp, g)
+    assert np.array_equal(s, t) and np.array_equal(p, q, equal_nan=True)
+
+
+def test_scoring_edge_cases(gpu, orc):
+    rng = np.random.default_rng(9)
+    # a single genotype, a single allele, a single haplotype
+    h = refpy.make_haplo(np.array([[5, 0]], dtype=np.uint64), [1.0], [0])
+    g = helpers.random_genotypes(rng, 1, 3, 1)
+    assert np.array_equal(gpu.post_prob2(h, 1, 3, g)[0], orc.post_prob2(h, 1, 3, g)[0])
+    # all SNPs missing
+    h, n_hla, n_snp = helpers.random_haplo_list(rng, 6, 20)
+    g = refpy.pack_geno(np.full((40, 20), -1), boot=np.zeros(40), a1=np.zeros(40, int), a2=np.ones(40, int))
+    p, s = gpu.post_prob2(h, n_hla, n_snp, g)
+    q, t = orc.post_prob2(h, n_hla, n_snp, g)
+    assert np.array_equal(p, q) and np.array_equal(s, t)
+    # everything scores exactly zero -> (NA, NA) and NaN ratio
+    h0 = refpy.make_haplo(np.zeros((2, 2), dtype=np.uint64), [0.5, 0.5], [0, 1])
+    g0 = refpy.pack_geno(np.full((5, 128), 2), boot=np.zeros(5), a1=np.zeros(5, int), a2=np.ones(5, int))
+    a1, a2 = gpu.best_guess(h0, 2, 128, g0)
+    assert np.all(a1 == refpy.NA_INTEGER) and np.all(a2 == refpy.NA_INTEGER)
+    assert np.all(np.isnan(gpu.post_prob(h0, 2, 128, g0)))
+    # denormal products are honoured (distances 62..64)
+    g1 = refpy.pack_geno(np.concatenate([np.full((1, 32), 2), np.full((1, 96), -1)], axis=1),
+                         boot=[0], a1=[0], a2=[1])
+    assert np.array_equal(gpu.post_prob2(h0, 2, 128, g1)[1], orc.post_prob2(h0, 2, 128, g1)[1])
+
+
+def test_scoring_large_list_many_alleles(gpu, orc):
+    """DRB1-like shape: 60 alleles, 2 words, long list (global-memory operand path when the list
+    exceeds shared memory is exercised by the 9000-haplotype case)"""
+    rng = np.random.default_rng(31)
+    h, n_hla, n_snp = helpers.random_haplo_list(rng, 60, 100, max_per_allele=12, empty_frac=0.1)
+    g = helpers.random_genotypes(rng, 300, n_snp, n_hla, haplo=h)
+    a1, a2 = gpu.best_guess(h, n_hla, n_snp, g)
+    o1, o2 = orc.best_guess(h, n_hla, n_snp, g)
+    assert np.array_equal(a1, o1) and np.array_equal(a2, o2)
+    h, n_hla, n_snp = helpers.random_haplo_list(rng, 3, 70, max_per_allele=4000, empty_frac=0.0)
+    g = helpers.random_genotypes(rng, 40, n_snp, n_hla, haplo=h)
+    assert np.array_equal(gpu.post_prob(h, n_hla, n_snp, g), orc.post_prob(h, n_hla, n_snp, g),
+                          equal_nan=True)
+
+
+# ---- the drop-in plugin driven by the reference's own host code -------------------------------------
+
+def test_reference_host_with_gpu_hooks_reproduces_golden(gpu, ref):
+    """the reference's BuildClassifiers (compiled, unmodified) calling OUR ten hooks:
+    set.seed(100) -> the first 30 classifiers of inst/extdata/ModelList.RData bit for bit"""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = ref.new_model()
+    m.init_training(geno, h1, h2, len(al))
+    ref.set_seed(int(ml["seed"]))
+    ref.set_gpu_procs(gpu.get_procs())
+    try:
+        m.build(30, int(ml["mtry"]))
+    finally:
+        ref.set_gpu_procs(None)
+    for k in range(30):
+        helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+
+
+def test_reference_predict_with_gpu_hook_matches_cpu(gpu, ref):
+    """the reference's PredictHLA calling predict_init / predict_avg_prob / predict_done"""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = ref.new_model()
+    m.init_predict(geno.shape[1], geno.shape[0], len(al))
+    for k in range(100):
+        c = helpers.golden_classifier(ml, k)
+        m.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"], acc=c["oob_acc"])
+    test = geno.astype(np.int32).copy()
+    rng = np.random.default_rng(8)
+    test[rng.random(test.shape) < 0.04] = -1
+    test[5, :] = -1
+    cpu = m.predict(test)
+    ref.set_gpu_procs(gpu.get_procs())
+    try:
+        dev = m.predict(test)
+    finally:
+        ref.set_gpu_procs(None)
+    assert np.array_equal(cpu["h1"], dev["h1"]) and np.array_equal(cpu["h2"], dev["h2"])
+    for key in ("prob", "matching", "dosage", "postprob"):
+        assert rel_close(cpu[key], dev[key]), key
+        assert np.array_equal(cpu[key], dev[key], equal_nan=True), key + " (bit-exact)"
+
+
+# ---- own host driver ------------------------------------------------------------------------------
+
+def test_trainer_reproduces_reference_golden_model(gpu):
+    """own C++ driver + CUDA scoring, set.seed(100), 100 classifiers: every bootstrap sample, SNP
+    set, haplotype list, frequency and OOB accuracy of ModelList.RData bit for bit"""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = gpu.HLAModel(geno.shape[1], len(al), al)
+    m.set_training(geno, h1, h2)
+    m.train(100, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), n_threads=8)
+    assert m.num_classifiers() == 100
+    for k in range(100):
+        helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+    st = m.train_stats()
+    assert st["pair_evals"] > 0 and st["kernel_launches"] > 0
+
+
+def test_trainer_legacy_hook_mode_and_thread_count_invariance(gpu):
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    for kwargs in (dict(use_legacy_hooks=True, n_threads=3), dict(n_threads=1)):
+        m = gpu.HLAModel(geno.shape[1], len(al), al)
+        m.set_training(geno, h1, h2)
+        m.train(8, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), **kwargs)
+        for k in range(8):
+            helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+
+
+def _synthetic():
+    from hibag_b200 import synth
+    return synth.make_cohort(400, 120, 12, seed=3)
+
+
+def test_trainer_matches_reference_on_synthetic(gpu, ref):
+    """per-classifier seeding (the multi-GPU convention), prune on and off, vs reference 'base'"""
+    coh = _synthetic()
+    mtry = gpu.default_mtry(coh.n_snp)
+    for prune in (True, False):
+        r = ref.new_model()
+        r.init_training(coh.geno, coh.h1, coh.h2, coh.n_hla)
+        r.build(3, mtry, prune=prune, reseed_base=500, first_index=0)
+        m = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        m.set_training(coh.geno, coh.h1, coh.h2)
+        m.train(3, mtry, prune=prune, seed=500, per_classifier_seed=True, n_threads=6)
+        for k in range(3):
+            d = helpers.classifier_diff(m.classifier(k), r.classifier(k))
+            assert d == "", (prune, k, d)
+    # sharding: classifiers {1, 3} built as a strided shard equal classifiers 1 and 3 of a full run
+    full = gpu.HLAModel(coh.n_snp, coh.n_hla); full.set_training(coh.geno, coh.h1, coh.h2)
+    full.train(4, mtry, seed=500, per_classifier_seed=True)
+    shard = gpu.HLAModel(coh.n_snp, coh.n_hla); shard.set_training(coh.geno, coh.h1, coh.h2)
+    shard.train(2, mtry, seed=500, per_classifier_seed=True, first_index=1, index_stride=2)
+    for j, k in enumerate((1, 3)):
+        assert helpers.classifier_diff(shard.classifier(j), full.classifier(k)) == ""
+
+
+def _golden_model(gpu, ref, n_cls=100):
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = gpu.HLAModel(geno.shape[1], len(al), al)
+    r = ref.new_model()
+    r.init_predict(geno.shape[1], geno.shape[0], len(al))
+    for k in range(n_cls):
+        c = helpers.golden_classifier(ml, k)
+        m.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"], oob_acc=c["oob_acc"])
+        r.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"], acc=c["oob_acc"])
+    return m, r, geno
+
+
+def test_batched_predict_matches_reference(gpu, ref):
+    m, r, geno = _golden_model(gpu, ref)
+    rng = np.random.default_rng(21)
+    test = np.tile(geno, (5, 1)).astype(np.int8)
+    test[rng.random(test.shape) < 0.05] = -1
+    test[7, :] = -1                                    # no usable SNP: (NA, NA), prob 0, NaN matching
+    test[11, ::2] = 3                                  # out-of-range codes are missing too
+    want = r.predict(test.astype(np.int32))
+    got = gpu.hlaPredict(m, test, type="response+prob")
+    assert np.array_equal(want["h1"], got["h1"]) and np.array_equal(want["h2"], got["h2"])
+    assert got["h1"][7] == refpy.NA_INTEGER and got["prob"][7] == 0 and np.isnan(got["matching"][7])
+    for key in ("prob", "matching", "dosage", "postprob"):
+        assert rel_close(want[key], got[key]), key
+        assert np.array_equal(want[key], got[key], equal_nan=True), key + " (bit-exact)"
+
+
+def test_predict_on_synthetic_model_matches_reference(gpu, ref):
+    from hibag_b200 import synth
+    coh = _synthetic()
+    mtry = gpu.default_mtry(coh.n_snp)
+    m = gpu.HLAModel(coh.n_snp, coh.n_hla); m.set_training(coh.geno, coh.h1, coh.h2)
+    m.train(6, mtry, seed=900, per_classifier_seed=True)
+    r = ref.new_model(); r.init_predict(coh.n_snp, coh.n_samp, coh.n_hla)
+    for k in range(6):
+        c = m.classifier(k)
+        r.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"], acc=c["oob_acc"])
+    new = synth.draw_more(coh, 3000, seed=77)
+    want = r.predict(new.geno.astype(np.int32))
+    got = m.predict(new.geno)
+    assert np.array_equal(want["h1"], got["h1"]) and np.array_equal(want["h2"], got["h2"])
+    for key in ("prob", "matching", "dosage", "postprob"):
+        assert np.array_equal(want[key], got[key], equal_nan=True), key
+    acc = np.mean((np.minimum(got["h1"], got["h2"]) == np.minimum(new.h1, new.h2)) &
+                  (np.maximum(got["h1"], got["h2"]) == np.maximum(new.h1, new.h2)))
+    assert acc > 0.5          # sanity: the ensemble actually predicts
+
+
+def test_classifier_sharded_predict_agrees_within_tolerance(gpu, ref):
+    """classifiers split over two 'ranks', partial sums added (what the NCCL all-reduce does), then
+    finalised: calls equal, posteriors within 1e-10 of the single-rank result"""
+    import torch
+    m, r, geno = _golden_model(gpu, ref, n_cls=40)
+    geno_t = torch.from_numpy(np.tile(geno, (3, 1)).astype(np.int8)).cuda()
+    n = geno_t.shape[0]
+    n_cells = m.n_cells
+    full = gpu.hlaPredict(m, geno_t.cpu().numpy(), type="response+prob")
+    wts = torch.from_numpy(m.snp_weights()).cuda()
+    parts = []
+    for rank in range(2):
+        sub = gpu.HLAModel(m.n_snp, m.n_hla)
+        for k in range(rank, 40, 2):
+            c = m.classifier(k)
+            sub.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"])
+        acc = torch.zeros((n, n_cells + 3), dtype=torch.float64, device="cuda")
+        sub.predict_partial_device(geno_t.data_ptr(), n, wts.data_ptr(), acc.data_ptr())
+        parts.append(acc)
+    total = parts[0] + parts[1]
+    h1 = torch.zeros(n, dtype=torch.int32, device="cuda"); h2 = torch.zeros_like(h1)
+    pp = torch.zeros((n, n_cells), dtype=torch.float64, device="cuda")
+    mt = torch.zeros(n, dtype=torch.float64, device="cuda")
+    out = gpu.PredictOut(h1.data_ptr(), h2.data_ptr(), None, mt.data_ptr(), None, pp.data_ptr())
+    rc = gpu.lib().hibag_b200_predict_finalize_device(m.n_hla, n, C.c_void_p(total.data_ptr()),
+                                                      C.byref(out), None, 1)
+    assert rc == 0
+    assert np.array_equal(h1.cpu().numpy(), full["h1"]) and np.array_equal(h2.cpu().numpy(), full["h2"])
+    assert rel_close(pp.cpu().numpy(), full["postprob"]) and rel_close(mt.cpu().numpy(), full["matching"])
+
+
+def test_round_trip_properties_at_scale(gpu):
+    """size-independent properties on a larger batch: posterior rows sum to 1, dosages to 2,
+    best guess = argmax of the posterior row, a sample equal to two model haplotypes is called
+    with those alleles' pair among the top, and prediction is invariant to batch splitting"""
+    from hibag_b200 import synth
+    coh = synth.make_cohort(1500, 200, 20, seed=5)
+    m = gpu.HLAModel(coh.n_snp, coh.n_hla); m.set_training(coh.geno, coh.h1, coh.h2)
+    m.train(4, gpu.default_mtry(coh.n_snp), seed=1, per_classifier_seed=True)
+    new = synth.draw_more(coh, 70000, seed=9)
+    got = m.predict(new.geno)
+    ok = got["h1"] != refpy.NA_INTEGER
+    assert ok.mean() > 0.99
+    assert np.allclose(got["postprob"][ok].sum(axis=1), 1.0, rtol=0, atol=1e-12)
+    assert np.allclose(got["dosage"][ok].sum(axis=1), 2.0, rtol=0, atol=1e-12)
+    am = got["postprob"].argmax(axis=1)
+    n_hla = m.n_hla
+    idx = got["h2"] + got["h1"] * (2 * n_hla - got["h1"] - 1) // 2
+    assert np.array_equal(am[ok], idx[ok])
+    assert np.array_equal(got["prob"][ok], got["postprob"][ok, am[ok]])
+    part = m.predict(new.geno[12345:23456])
+    for key in ("h1", "h2", "prob", "matching", "dosage", "postprob"):
+        assert np.array_equal(part[key], got[key][12345:23456], equal_nan=True), key

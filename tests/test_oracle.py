@@ -1,0 +1,105 @@
+"""CPU tests: the oracle (oracle/hibag_oracle.c) against the compiled reference and the
+reference's own golden model; the compiled reference against the golden fixture."""
+import numpy as np
+import pytest
+
+from oracle import refpy
+from tests import helpers
+
+SNP_COUNTS = [1, 2, 7, 31, 32, 33, 63, 64, 65, 100, 128]
+
+
+def test_table_matches_reference(ref, orc):
+    t = orc.table()
+    assert np.array_equal(t, ref.table())
+    assert t[0] == 1.0 and t[64] > 0 and t[65] == 0 and t[256] == 0      # denormal tail, then 0
+    assert t[62] < 2.3e-308                                              # entries 62..64 are denormal
+
+
+@pytest.mark.parametrize("n_snp", SNP_COUNTS)
+def test_scoring_functions_match_reference(ref, orc, n_snp):
+    rng = np.random.default_rng(1000 + n_snp)
+    h, n_hla, _ = helpers.random_haplo_list(rng, 12, n_snp)
+    g = helpers.random_genotypes(rng, 150, n_snp, n_hla, haplo=h)
+    for i in range(0, 150, 37):
+        for j in (0, len(h) - 1):
+            assert orc.hamming(g[i:i + 1], h[j:j + 1], h[0:1], n_snp) == \
+                ref.hamming(g[i:i + 1], h[j:j + 1], h[0:1], n_snp)
+    a, b = ref.best_guess(h, n_hla, n_snp, g), orc.best_guess(h, n_hla, n_snp, g)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(ref.post_prob(h, n_hla, n_snp, g), orc.post_prob(h, n_hla, n_snp, g),
+                          equal_nan=True)
+    p, s = ref.post_prob2(h, n_hla, n_snp, g)
+    q, t = orc.post_prob2(h, n_hla, n_snp, g)
+    assert np.array_equal(p, q, equal_nan=True) and np.array_equal(s, t)
+    assert ref.acc_oob(h, n_hla, n_snp, g) == orc.acc_oob(h, n_hla, n_snp, g)
+    x, y = ref.acc_ib(h, n_hla, n_snp, g), orc.acc_ib(h, n_hla, n_snp, g)
+    assert x == y or (np.isnan(x) and np.isnan(y))
+
+
+def test_all_missing_genotype_gives_prior(orc, ref):
+    """every SNP missing: distance 0 everywhere, posterior = frequency products; BestGuess picks
+    the first maximum"""
+    rng = np.random.default_rng(5)
+    h, n_hla, n_snp = helpers.random_haplo_list(rng, 6, 20)
+    g = refpy.pack_geno(np.full((3, 20), -1), boot=[0, 1, 2], a1=[0, 1, 2], a2=[1, 2, 3])
+    p, s = orc.post_prob2(h, n_hla, n_snp, g)
+    assert np.allclose(s, 1.0, rtol=1e-12)       # sum over all pairs of (sum f)^2 = 1
+    pr, sr = ref.post_prob2(h, n_hla, n_snp, g)
+    assert np.array_equal(p, pr) and np.array_equal(s, sr)
+
+
+def test_zero_posterior_is_na(orc, ref):
+    """a genotype at distance >= 65 from every pair scores exactly 0 everywhere -> (NA, NA)"""
+    n_snp = 128
+    packed = np.zeros((2, 2), dtype=np.uint64)                  # two all-zero haplotypes
+    h = refpy.make_haplo(packed, [0.5, 0.5], [0, 1])
+    g = refpy.pack_geno(np.full((1, n_snp), 2), boot=[0], a1=[0], a2=[1])   # distance 256
+    a1, a2 = orc.best_guess(h, 2, n_snp, g)
+    assert a1[0] == refpy.NA_INTEGER and a2[0] == refpy.NA_INTEGER
+    r1, r2 = ref.best_guess(h, 2, n_snp, g)
+    assert r1[0] == a1[0] and r2[0] == a2[0]
+    assert np.isnan(orc.post_prob(h, 2, n_snp, g)[0])
+
+
+def test_int_to_snp_matches_reference(orc, ref):
+    rng = np.random.default_rng(11)
+    row = rng.integers(-1, 4, size=400).astype(np.int32)        # 3 and -1 are both "missing"
+    for length in (0, 1, 7, 8, 9, 63, 64, 65, 127, 128):
+        idx = rng.choice(400, size=length, replace=False).astype(np.int32)
+        a, b = orc.int_to_snp(row, idx), ref.int_to_snp(row, idx)
+        for f in ("s1", "s2"):
+            assert np.array_equal(a[f], b[f]), (length, f)
+
+
+def test_reference_reproduces_golden_model(ref):
+    """the compiled reference, target base, set.seed(100): first 12 classifiers of
+    inst/extdata/ModelList.RData bit for bit (all 100 are checked on the GPU box against the CUDA
+    path; 12 keep the CPU suite short)"""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = ref.new_model()
+    m.init_training(geno, h1, h2, len(al))
+    ref.set_seed(int(ml["seed"]))
+    m.build(12, int(ml["mtry"]))
+    for k in range(12):
+        helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+
+
+def test_oracle_predict_matches_reference_on_golden_model(ref, orc):
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    n_hla = len(al)
+    cls = [helpers.golden_classifier(ml, k) for k in range(25)]
+    m = ref.new_model()
+    m.init_predict(geno.shape[1], geno.shape[0], n_hla)
+    for c in cls:
+        m.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"], acc=c["oob_acc"])
+    test = geno.astype(np.int32).copy()
+    rng = np.random.default_rng(2)
+    test[rng.random(test.shape) < 0.05] = -1
+    test[3, :] = -1                                   # a sample with every SNP missing
+    r = m.predict(test)
+    o = orc.predict(cls, n_hla, geno.shape[1], test)
+    assert np.array_equal(r["h1"], o["h1"]) and np.array_equal(r["h2"], o["h2"])
+    for key in ("prob", "matching", "dosage", "postprob"):
+        assert np.array_equal(r[key], o[key], equal_nan=True), key
+    assert r["h1"][3] == refpy.NA_INTEGER and np.isnan(r["matching"][3])
