@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 scoring path (driver contract in the task statement).
+
+Workload (BASELINE.json configs[1]): synthetic HLA-A training, 5,000 samples x 500 flanking SNPs,
+seed-fixed, mtry = ceil(sqrt(500)) = 23, prune on.  A STEP = growing one classifier per GPU
+(bootstrap, greedy SNP search: host EM + GPU pair scoring).  Weak scaling: every rank builds its
+own classifiers (classifier-sharded ensemble, no data-path collective).
+
+  value  classifiers/min with the cohort resident in HBM (own host driver, device-resident
+         genotype bit planes; per candidate only the haplotype list crosses PCIe)
+  e2e    classifiers/min through the reference-facing plugin: the ten TypeGPUExtProc hooks with
+         full host buffers per candidate (hlaAttrBagging(..., use_legacy_hooks=True))
+  predict.* (secondary, configs[2]): samples/s of a 100-classifier model on 200,000 samples
+
+`--impl reference` times the reference's own CPU implementation (compiled unmodified sources,
+oracle/_ref, kernel target "max") on the box's host cores, on bounded prefixes of the same
+classifiers, extrapolated with the workload's pair-evaluation counts (profiles/c2_workload.json).
+"""
+import argparse
+import json
+import math
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
+TRAIN_SEED = 2024
+MTRY = 23
+N_PREDICT = 200000
+N_PREDICT_CLS = 100
+WORKLOAD_JSON = os.path.join(ROOT, "profiles", "c2_workload.json")
+PEAKS_JSON = os.path.join(ROOT, "profiles", "pipe_peaks.json")
+
+
+def make_cohort():
+    from hibag_b200 import synth
+    return synth.make_cohort(N_SAMP, N_SNP, N_HLA_REQ, seed=COHORT_SEED)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, recipe in B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()          # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            out["samples"] = len(sm)
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nm in enumerate(names):
+                if any(r[5 + k].strip().lower().startswith("active") for r in rows):
+                    out["reasons"].append(nm)
+        except Exception as e:          # never let telemetry break the benchmark
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref): bounded prefixes of the same classifiers
+# ---------------------------------------------------------------------------------------------
+def load_workload():
+    if os.path.exists(WORKLOAD_JSON):
+        return json.load(open(WORKLOAD_JSON))
+    return None
+
+
+def _ref_train_worker(args):
+    """One host process: the reference's BuildClassifiers (target 'max') on classifier `k` of the
+    workload until `budget` seconds have passed (checked at accepted SNPs); returns (k, accepted
+    SNPs, seconds, finished)."""
+    k, budget = args
+    from oracle import refpy
+    ref = refpy.RefLib()
+    info = ref.set_target("max")
+    ref.set_gpu_procs(None)
+    coh = make_cohort()
+    m = ref.new_model()
+    m.init_training(coh.geno, coh.h1, coh.h2, coh.n_hla)
+    ref.set_interrupt(seconds=budget)
+    t0 = time.time()
+    rc = m.build(1, MTRY, prune=True, reseed_base=TRAIN_SEED, first_index=k, allow_interrupt=True)
+    dt = time.time() - t0
+    accepted = int(ref.lib.ref_interrupt_checks())
+    ref.set_interrupt(0.0, -1)
+    return k, accepted, dt, rc == 0, info
+
+
+def _ref_predict_worker(args):
+    """reference PredictHLA (target 'max') on successive 4-sample chunks for `budget` seconds"""
+    p, budget = args
+    from oracle import refpy
+    from hibag_b200 import synth
+    ref = refpy.RefLib()
+    ref.set_target("max")
+    ref.set_gpu_procs(None)
+    wl = np.load(os.path.join(ROOT, "tests", "golden", "c2_model.npz"))
+    coh = make_cohort()
+    new = synth.draw_more(coh, 64 * (p + 1), seed=4242).geno[64 * p:].astype(np.int32)
+    m = ref.new_model()
+    m.init_predict(N_SNP, 1, int(wl["n_hla"]))
+    n_src = len(wl["snp_off"]) - 1
+    for c in range(N_PREDICT_CLS):
+        k = c % n_src
+        a, b = wl["snp_off"][k:k + 2]; q, r = wl["hap_off"][k:k + 2]
+        m.add_classifier(wl["snpidx"][a:b], wl["freq"][q:r], wl["hla"][q:r], wl["packed"][q:r])
+    done, t0 = 0, time.time()
+    while time.time() - t0 < budget and done + 4 <= len(new):
+        m.predict(new[done:done + 4])
+        done += 4
+    return done, time.time() - t0
+
+
+def reference_train_rate(step, procs, budget, wl):
+    """classifiers/min of the reference CPU path with `procs` worker processes"""
+    n_tr = len(wl["classifiers"]) if wl else 0
+    ks = [(step * procs + p) % max(n_tr, 1) for p in range(procs)]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map(_ref_train_worker, [(k, budget) for k in ks])
+    rate, detail = 0.0, []
+    for k, accepted, dt, finished, info in res:
+        if finished or not wl:
+            est = dt
+        else:
+            tr = wl["classifiers"][k]
+            cum = {a: p for a, p in tr["accepted_pairs"]}
+            part = cum.get(accepted) or cum.get(max(x for x in cum if x <= accepted), None)
+            est = dt * tr["total_pairs"] / part if part else float("nan")
+        rate += 60.0 / est
+        detail.append(dict(classifier=k, accepted_snps=accepted, seconds=round(dt, 2),
+                           est_seconds_per_classifier=round(est, 1)))
+    return rate, detail, res[0][4]
+
+
+def cpu_baseline(procs, budget, wl, with_predict=True):
+    rate, detail, info = reference_train_rate(0, procs, budget, wl)
+    out = {"value": rate, "unit": "classifiers/min", "cores": procs, "kind": "reference",
+           "target": info,
+           "sample": "reference BuildClassifiers, kernel target max, %d worker processes x one classifier "
+                     "each for %.0f s (until the next accepted SNP), extrapolated by pair evaluations "
+                     "done / pair evaluations of the whole classifier (profiles/c2_workload.json)"
+                     % (procs, budget),
+           "per_process": detail[:4]}
+    if with_predict and os.path.exists(os.path.join(ROOT, "tests", "golden", "c2_model.npz")):
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_ref_predict_worker, [(p, budget / 2) for p in range(procs)])
+        out["predict_value"] = sum(d / t for d, t in res)
+        out["predict_unit"] = "samples/s"
+        out["predict_sample"] = "%d samples over %d processes, 100-classifier model" % (
+            sum(d for d, _ in res), procs)
+    return out
+
+
+def run_reference_arm(args):
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), 0, int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    wl = load_workload()
+    procs = args.cpu_procs or os.cpu_count() or 1
+    rates, detail, info = [], None, ""
+    t0 = time.time()
+    for s in range(args.warmup):
+        reference_train_rate(s, procs, min(args.cpu_seconds, 5.0), wl)
+    tw = time.time()
+    for s in range(args.steps):
+        r, detail, info = reference_train_rate(args.warmup + s, procs, args.cpu_seconds, wl)
+        rates.append(r)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "classifiers/min trained (HLA-A 5k x 500 SNP)", "value": value,
+        "unit": "classifiers/min", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 60000.0 / value * procs if value > 0 else None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "classifiers/min", "cores": procs, "kind": "reference",
+                         "target": info,
+                         "sample": "per step: %d worker processes x one classifier each for %.0f s of the "
+                                   "reference BuildClassifiers (target max), extrapolated by pair "
+                                   "evaluations" % (procs, args.cpu_seconds),
+                         "per_process": (detail or [])[:4]},
+        "e2e": {"value": value, "unit": "classifiers/min", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": round(time.time() - t0, 1), "timed_wall_s": round(time.time() - tw, 1),
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "synthetic HLA-A training: 5000 samples x 500 SNPs, 34 alleles (40 drawn), "
+                        "cohort seed 1, mtry 23, prune, one classifier per GPU per step "
+                        "(per-classifier seed %d + index)" % TRAIN_SEED,
+            "n_samp": N_SAMP, "n_snp": N_SNP, "mtry": MTRY, "parallelism": "classifier-sharded x%d" % n_gpus,
+            "l2": "operands are KB-scale and rebuilt per candidate; the cell matrix written per launch "
+                  "(15-20 MB) plus 24 concurrent slots exceeds L2 reuse between timed launches"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    from hibag_b200 import api, dist as hd, synth
+    rank, local_rank, world = hd.init()
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    api.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    info = api.device_info()
+    n_threads = args.threads or max(1, (os.cpu_count() or 1) // max(world, 1))
+
+    coh = make_cohort()
+    geno = np.ascontiguousarray(coh.geno, dtype=np.int8)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        hd.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident path --------------------------------------------------------------------------
+    model = api.HLAModel(N_SNP, coh.n_hla)
+    model.set_training(geno, coh.h1, coh.h2)
+
+    def step_resident(step):
+        model.train(1, MTRY, prune=True, seed=TRAIN_SEED, per_classifier_seed=True,
+                    first_index=rank + world * step, n_threads=n_threads)
+
+    for s in range(args.warmup):
+        step_resident(s)
+    st0 = model.train_stats()
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.time()
+    for s in range(args.steps):
+        step_resident(args.warmup + s)
+    e1.record()
+    sync_all()
+    wall = time.time() - t0
+    ms = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = model.train_stats()
+    d = {k: st1[k] - st0[k] for k in st1}
+    value = world * args.steps / (ms / 60000.0)
+
+    # ---- reference-facing plugin path (host buffers per candidate) ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def step_hooks(step):
+            m = api.hlaAttrBagging((coh.h1, coh.h2), geno, nclassifier=1, mtry=MTRY, prune=True,
+                                   mono_rm=False, seed=TRAIN_SEED, nthread=n_threads,
+                                   per_classifier_seed=True, use_legacy_hooks=True,
+                                   first_index=rank + world * step)
+            return m.train_stats()
+        step_hooks(0)
+        sync_all()
+        e0.record()
+        h2d = d2h = 0
+        for s in range(args.steps):
+            stt = step_hooks(args.warmup + s)
+            h2d += stt["h2d_bytes"]; d2h += stt["d2h_bytes"]
+        e1.record()
+        sync_all()
+        ms2 = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+        e2e = {"value": world * args.steps / (ms2 / 60000.0), "unit": "classifiers/min",
+               "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+               "api": "hlaAttrBagging(hla, snp, nclassifier=1, use_legacy_hooks=True): ten TypeGPUExtProc "
+                      "hooks, TGenotype[5000] + haplotype list from host memory per candidate SNP"}
+
+    # ---- roofline of the dominant kernel (pair scoring), training region ---------------------------
+    peaks = json.load(open(PEAKS_JSON)) if os.path.exists(PEAKS_JSON) else None
+    popc_peak = (peaks or {}).get("popc32_per_s", 148 * 16 * 1.965e9)
+    peak_src = "measured (profiles/pipe_peaks.json, POPC.32 microbenchmark on this pool's B200)" if peaks \
+        else "nominal 148 SM x 16 POPC/clk x 1.965 GHz (no measured file)"
+    n_l = max(d["cell_kernel_launches"], 1)
+    avg_ms = d["cell_kernel_ms"] / n_l
+    pair_rate = d["pair_evals"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
+    roofline = {
+        "bound": "popc", "kernel": "cell_pass_kernel",
+        "achieved": pair_rate * 4 / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s",
+        "frac": pair_rate * 4 / popc_peak,
+        "achieved_issued": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / 1e9,
+        "frac_issued": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / popc_peak,
+        "pair_evals_per_s": pair_rate, "avg_launch_ms": avg_ms, "launches": int(d["cell_kernel_launches"]),
+        "pair_evals_per_launch": d["pair_evals"] / n_l,
+        "note": "algorithmic POPC.32 = 4 per pair evaluation (reference formulation, <=64 SNPs); the "
+                "kernel's one-popcount form issues 1 per 32 SNPs (frac_issued). Launches of up to 23 "
+                "candidates overlap on separate streams, so per-launch durations include sharing.",
+        "peak_source": peak_src, "traffic": None,
+        "fp64_frac": pair_rate * 3 / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9),
+    }
+
+    # ---- secondary metric: prediction (configs[2]) ---------------------------------------------------
+    predict = None
+    if not args.no_predict:
+        predict = bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args)
+        if predict and peaks:
+            predict["roofline"]["peak"] = popc_peak / 1e9
+            predict["roofline"]["frac"] = predict["roofline"]["achieved"] * 1e9 / popc_peak
+            predict["roofline"]["frac_issued"] = predict["roofline"]["achieved_issued"] * 1e9 / popc_peak
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline(args.cpu_procs or os.cpu_count() or 1, args.cpu_seconds, load_workload())
+        except Exception as ex:        # the checker library may be absent on some boxes
+            cpu = {"value": None, "unit": "classifiers/min", "cores": 0, "kind": "reference",
+                   "sample": "unavailable: %s" % ex}
+
+    if rank == 0:
+        line = {
+            "metric": "classifiers/min trained (HLA-A 5k x 500 SNP)", "value": value,
+            "unit": "classifiers/min", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": e2e, "gpu_launches": int(d["kernel_launches"]),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "predict": predict,
+            "train_detail": {
+                "host_threads": n_threads, "seconds_em_sum": d["seconds_em"],
+                "seconds_gpu_wait_sum": d["seconds_gpu_wait"], "gpu_kernel_span_ms": d["gpu_kernel_ms"],
+                "pair_evals": int(d["pair_evals"]), "oob_evals": int(d["n_oob_evals"]),
+                "ib_evals": int(d["n_ib_evals"]), "em_runs": int(d["n_em"]),
+                "h2d_bytes_per_step": int(d["h2d_bytes"] / args.steps),
+                "d2h_bytes_per_step": int(d["d2h_bytes"] / args.steps), "wall_s": wall,
+                "classifiers": [dict(zip(("n_snp", "n_haplo"), (len(model.classifier(k)["snpidx"]),
+                                                                 len(model.classifier(k)["freq"]))))
+                                for k in range(model.num_classifiers())]},
+            "device": info,
+        }
+        print(json.dumps(line))
+
+
+def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
+    """samples/s of a 100-classifier model on 200,000 fresh samples, sample-sharded over ranks"""
+    n_src = model.num_classifiers()
+    big = api.HLAModel(N_SNP, coh.n_hla)
+    for c in range(N_PREDICT_CLS):
+        k = model.classifier(c % n_src)
+        big.add_classifier(k["snpidx"], k["freq"], k["hla"], k["packed"])
+    n_total = args.predict_samples
+    b, e = hd.shard_range(n_total, rank, world)
+    n = e - b
+    host = np.ascontiguousarray(synth.draw_more(coh, n_total, seed=99).geno[b:e], dtype=np.int8)
+    pinned = torch.from_numpy(host).pin_memory()
+    g = pinned.to(dev, non_blocking=False)
+    nc = big.n_cells
+    h1 = torch.empty(n, dtype=torch.int32, device=dev); h2 = torch.empty_like(h1)
+    mp_ = torch.empty(n, dtype=torch.float64, device=dev); mt = torch.empty_like(mp_)
+    ds = torch.empty((n, coh.n_hla), dtype=torch.float64, device=dev)
+    pp = torch.empty((n, nc), dtype=torch.float64, device=dev)
+
+    def run():
+        big.predict_device(g.data_ptr(), n, h1.data_ptr(), h2.data_ptr(), mp_.data_ptr(), mt.data_ptr(),
+                           ds.data_ptr(), pp.data_ptr(), stream=torch.cuda.current_stream().cuda_stream,
+                           sync=True)
+    warm = min(n, 8192)
+    big.predict_device(g.data_ptr(), warm, h1.data_ptr(), h2.data_ptr(), mp_.data_ptr(), mt.data_ptr(),
+                       ds.data_ptr(), pp.data_ptr(), stream=torch.cuda.current_stream().cuda_stream, sync=True)
+    s0 = big.predict_stats()
+    torch.cuda.synchronize(); hd.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize(); hd.barrier()
+    ms = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+    s1 = big.predict_stats()
+    d = {k: s1[k] - s0[k] for k in s1}
+    # end to end with host buffers (H2D of raw genotypes, D2H of every output inside)
+    t0 = time.time()
+    res = big.predict(host, want_prob=True, want_dosage=True)
+    torch.cuda.synchronize(); hd.barrier()
+    ms2 = hd.max_over_ranks((time.time() - t0) * 1e3, dev)
+    same = bool(np.array_equal(res["h1"], h1.cpu().numpy()))
+    rate = d["pair_evals"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
+    out = {
+        "metric": "samples/s predicted (100 classifiers, type=response+prob)", "value": n_total / (ms * 1e-3),
+        "unit": "samples/s", "samples": n_total, "ms": ms,
+        "e2e": {"value": n_total / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes": int(host.nbytes),
+                "d2h_bytes": int(n * (8 + 16 + 8 * coh.n_hla + 8 * nc)), "api": "HLAModel.predict (host numpy)"},
+        "model": "100 classifiers = the %d classifiers trained above, cycled" % n_src,
+        "calls_equal_between_paths": same,
+        "roofline": {"bound": "popc", "kernel": "cell_pass_kernel", "achieved": rate * 4 / 1e9,
+                     "achieved_issued": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / 1e9,
+                     "peak": 148 * 16 * 1.965, "unit": "Gpopc32/s", "frac": rate * 4 / (148 * 16 * 1.965e9),
+                     "pair_evals_per_s": rate, "launches": int(d["cell_kernel_launches"]),
+                     "avg_launch_ms": d["cell_kernel_ms"] / max(d["cell_kernel_launches"], 1),
+                     "cell_kernel_share_of_step": d["cell_kernel_ms"] / max(d["gpu_kernel_ms"], 1e-9)},
+        "gpu_launches": int(d["kernel_launches"]),
+    }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default cores/ranks)")
+    ap.add_argument("--predict-samples", type=int, default=N_PREDICT)
+    ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,9 @@ class TrainStats(C.Structure):
                 ("pair_evals", C.c_uint64), ("popc32_issued", C.c_uint64),
                 ("n_oob_evals", C.c_uint64), ("n_ib_evals", C.c_uint64), ("n_em", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("cell_kernel_ms", C.c_double),
+                ("cell_kernel_launches", C.c_uint64), ("seconds_prepare", C.c_double),
+                ("seconds_phase_oob", C.c_double), ("seconds_phase_ib", C.c_double)]
 
 
 class PredictOut(C.Structure):
@@ -62,7 +64,7 @@ EXPORTS = [
     "hibag_b200_set_device", "hibag_b200_device_info", "hibag_b200_get_procs",
     "hibag_b200_best_guess", "hibag_b200_post_prob", "hibag_b200_post_prob2",
     "hibag_b200_model_new", "hibag_b200_model_free", "hibag_b200_model_set_training",
-    "hibag_b200_model_train", "hibag_b200_model_train_stats",
+    "hibag_b200_model_train", "hibag_b200_model_train_stats", "hibag_b200_model_train_trace",
     "hibag_b200_model_num_classifiers", "hibag_b200_model_clear",
     "hibag_b200_model_classifier_info", "hibag_b200_model_classifier_get",
     "hibag_b200_model_add_classifier", "hibag_b200_model_predict",
@@ -99,6 +101,7 @@ def lib():
     L.hibag_b200_model_set_training.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hibag_b200_model_train.argtypes = [C.c_void_p, C.POINTER(TrainOpts)]
     L.hibag_b200_model_train_stats.argtypes = [C.c_void_p, C.POINTER(TrainStats)]
+    L.hibag_b200_model_train_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.hibag_b200_model_num_classifiers.argtypes = [C.c_void_p]
     L.hibag_b200_model_clear.argtypes = [C.c_void_p]
     L.hibag_b200_model_classifier_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
@@ -235,6 +238,14 @@ class HLAModel:
         _chk(lib().hibag_b200_model_train_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in TrainStats._fields_}
 
+    def train_trace(self):
+        """rows {classifier, accepted SNPs (-1 = classifier finished), cumulative pair evaluations,
+        cumulative candidate EM runs}"""
+        n = lib().hibag_b200_model_train_trace(self._h, None, 0)
+        out = np.zeros((max(n, 1), 4), dtype=np.int64)
+        lib().hibag_b200_model_train_trace(self._h, _p(out), n)
+        return out[:n]
+
     def predict_stats(self):
         s = PredictStats()
         _chk(lib().hibag_b200_model_predict_stats(self._h, C.byref(s)))
@@ -353,7 +364,7 @@ def default_mtry(n_snp, mtry="sqrt"):
 
 def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=True, seed=100,
                    nthread=0, per_classifier_seed=False, use_legacy_hooks=False, verbose=False,
-                   hla_allele=None):
+                   hla_allele=None, first_index=0, index_stride=1):
     """Train a model. hla = (h1, h2) integer allele indices (or labels with hla_allele given),
     snp = int matrix [n_samp, n_snp] with 0/1/2 and anything else missing.
     Mirrors reference hlaAttrBagging (R/HIBAG.R:48-275): monomorphic SNPs are removed when mono_rm,
@@ -377,8 +388,8 @@ def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=T
     model.snp_sel = keep
     model.set_training(g, h1, h2)
     model.train(nclassifier, default_mtry(g.shape[1], mtry), prune=prune, seed=seed, n_threads=nthread,
-                per_classifier_seed=per_classifier_seed, use_legacy_hooks=use_legacy_hooks,
-                verbose=int(verbose))
+                per_classifier_seed=per_classifier_seed, first_index=first_index,
+                index_stride=index_stride, use_legacy_hooks=use_legacy_hooks, verbose=int(verbose))
     return model
 
 

@@ -138,6 +138,16 @@ int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_sta
 	return guarded([&]() { require(m && out, "null argument"); *out = m->train_stats; });
 }
 
+int hibag_b200_model_train_trace(const hibag_b200_model *m, int64_t *out, int max_rows)
+{
+	if (!m) return -1;
+	const int rows = (int)(m->train_trace.size() / 4);
+	if (out)
+		for (int i = 0; i < rows && i < max_rows; i++)
+			for (int j = 0; j < 4; j++) out[4 * i + j] = m->train_trace[4 * (size_t)i + j];
+	return rows;
+}
+
 int hibag_b200_model_num_classifiers(const hibag_b200_model *m)
 {
 	return m ? (int)m->cls.size() : -1;
@@ -147,7 +157,7 @@ int hibag_b200_model_clear(hibag_b200_model *m)
 {
 	return guarded([&]() {
 		require(m != nullptr, "null argument");
-		m->cls.clear(); m->pcache.reset();
+		m->cls.clear(); m->pcache.reset(); m->train_trace.clear();
 		memset(&m->train_stats, 0, sizeof(m->train_stats));
 		memset(&m->predict_stats, 0, sizeof(m->predict_stats));
 	});

@@ -276,7 +276,6 @@ bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *
 	const int n_entry = (int)rp.samp.size();
 	const int n_cur = rp.n_cur;
 	const int n2 = 2 * n_cur;
-	const size_t n_pair = rp.p1.size();
 
 	// allele frequency of the new SNP in the bootstrap sample (:1136-1151)
 	int allele_cnt = 0, valid_cnt = 0;
@@ -293,8 +292,6 @@ bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *
 
 	// doubled list, initial frequencies (:444-459)
 	scr.freq.resize(n2); scr.old.resize(n2);
-	scr.flag.resize(n_pair); scr.gf.resize(n_pair);
-	scr.logbuf.resize(n_entry);
 	double *freq = scr.freq.data(), *old = scr.old.data();
 	{
 		const double af = double(allele_cnt) / valid_cnt;
@@ -305,55 +302,62 @@ bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *
 			freq[2 * k + 1] = p1 * cur.h[k].freq + EM_INIT_VAL_FRAC;
 		}
 	}
-	// which pairs are compatible with the new genotype (:1157-1180)
+	// which pairs are compatible with the new genotype (:1157-1180). The flags never change
+	// during EM, so the compatible pairs are compacted once; the loops below then visit exactly
+	// the pairs the reference visits with Flag == true, in the same order.
 	const int *P1 = rp.p1.data(), *P2 = rp.p2.data();
-	unsigned char *flag = scr.flag.data();
+	scr.cp1.clear(); scr.cp2.clear();
+	scr.coff.resize(n_entry + 1);
+	size_t max_pairs = 0;
 	for (int k = 0; k < n_entry; k++)
 	{
 		const int g = snp_col[rp.samp[k]];
 		const size_t b = rp.off[k], e = rp.off[k + 1];
+		scr.coff[k] = scr.cp1.size();
 		if (0 <= g && g <= 2)
-			for (size_t t = b; t < e; t++) flag[t] = (((P1[t] & 1) + (P2[t] & 1)) == g);
-		else
-			for (size_t t = b; t < e; t++) flag[t] = 1;
+		{
+			for (size_t t = b; t < e; t++)
+				if (((P1[t] & 1) + (P2[t] & 1)) == g) { scr.cp1.push_back(P1[t]); scr.cp2.push_back(P2[t]); }
+		} else {
+			for (size_t t = b; t < e; t++) { scr.cp1.push_back(P1[t]); scr.cp2.push_back(P2[t]); }
+		}
+		max_pairs = std::max(max_pairs, scr.cp1.size() - scr.coff[k]);
 	}
+	scr.coff[n_entry] = scr.cp1.size();
+	scr.gf.resize(max_pairs + 1);
+	const int *C1 = scr.cp1.data(), *C2 = scr.cp2.data();
+	const size_t *coff = scr.coff.data();
+	const int *boot = rp.boot.data();
 
-	// EM (:1185-1255)
+	// EM (:1185-1255). The reference runs the E-step over all samples and then accumulates the
+	// new frequencies sample by sample; the two loops are fused per sample here, which leaves the
+	// sequence of additions into LogLik and into every Freq unchanged.
 	double *gf = scr.gf.data();
-	double *logbuf = scr.logbuf.data();
 	double conv_tol = 0, loglik = -1e+30;
 	const double scale = 0.5 / n_samp_total;
 	for (int iter = 0; iter <= EM_MAX_ITER; iter++)
 	{
 		const double old_loglik = loglik;
 		for (int i = 0; i < n2; i++) { old[i] = freq[i]; freq[i] = 0; }
-		for (int k = 0; k < n_entry; k++)
-		{
-			const size_t b = rp.off[k], e = rp.off[k + 1];
-			double psum = 0;
-			for (size_t t = b; t < e; t++)
-				if (flag[t])
-				{
-					const int u = P1[t], v = P2[t];
-					gf[t] = (u != v) ? (2 * old[u] * old[v]) : (old[u] * old[v]);
-					psum += gf[t];
-				}
-			logbuf[k] = rp.boot[k] * std::log(psum);
-			psum = rp.boot[k] / psum;
-			for (size_t t = b; t < e; t++)
-				if (flag[t]) gf[t] *= psum;
-		}
 		loglik = 0;
 		for (int k = 0; k < n_entry; k++)
 		{
-			loglik += logbuf[k];
-			const size_t b = rp.off[k], e = rp.off[k + 1];
+			const size_t b = coff[k], e = coff[k + 1];
+			double psum = 0;
 			for (size_t t = b; t < e; t++)
-				if (flag[t])
-				{
-					const double r = gf[t];
-					freq[P1[t]] += r; freq[P2[t]] += r;
-				}
+			{
+				const int u = C1[t], v = C2[t];
+				const double x = (u != v) ? (2 * old[u] * old[v]) : (old[u] * old[v]);
+				gf[t - b] = x;
+				psum += x;
+			}
+			loglik += boot[k] * std::log(psum);
+			psum = boot[k] / psum;
+			for (size_t t = b; t < e; t++)
+			{
+				const double r = gf[t - b] * psum;
+				freq[C1[t]] += r; freq[C2[t]] += r;
+			}
 		}
 		for (int i = 0; i < n2; i++) freq[i] *= scale;
 		if (iter > 0)

@@ -81,9 +81,9 @@ struct RoundPairs
 struct EmScratch
 {
 	std::vector<double> freq, old;       // doubled list frequencies
-	std::vector<unsigned char> flag;     // per pair
-	std::vector<double> gf;              // per pair GenoFreq
-	std::vector<double> logbuf;          // per in-bag entry
+	std::vector<int> cp1, cp2;           // pairs compatible with the candidate SNP (compacted)
+	std::vector<size_t> coff;            // their range per in-bag entry
+	std::vector<double> gf;              // GenoFreq of one sample's pairs
 };
 
 /// pairs at minimum distance for every in-bag sample on the current SNP set

@@ -32,6 +32,7 @@ struct hibag_b200_model
 	std::vector<hb::Classifier> cls;
 	hibag_b200_train_stats train_stats;
 	hibag_b200_predict_stats predict_stats;
+	std::vector<int64_t> train_trace;   // rows of 4, see hibag_b200_model_train_trace
 	std::shared_ptr<hb::PredictCache> pcache;
 	hibag_b200_model();
 };

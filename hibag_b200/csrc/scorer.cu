@@ -120,8 +120,9 @@ void EvalSlot::enqueue_cells(const GenoView &g, const int *pos_list, int n_pos)
 	p.P = P_.get(); p.p_stride = p_stride_;
 	HB_CUDA(cudaMemsetAsync(counter_.get(), 0, sizeof(unsigned int), st_.s));
 	const int R = choose_samples_per_lane(n_pos, blob_.n_chunks, blob_.n_snp, di.sm_count);
-	if (!timing_pending_) HB_CUDA(cudaEventRecord(ev0_.e, st_.s));
+	HB_CUDA(cudaEventRecord(ev0_.e, st_.s));
 	const int nw = launch_cell_pass(p, R, di.sm_count, st_.s);
+	HB_CUDA(cudaEventRecord(evc_.e, st_.s));
 	stats.launches++; stats.cell_launches++;
 	stats.pair_evals += blob_.pairs_per_sample * (uint64_t)n_pos;
 	stats.popc32 += blob_.pairs_per_sample * (uint64_t)n_pos * (uint64_t)nw;
@@ -155,6 +156,8 @@ void EvalSlot::sync()
 		float ms = 0;
 		HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 		stats.kernel_ms += ms;
+		HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, evc_.e));
+		stats.cell_ms += ms;
 		timing_pending_ = false;
 	}
 }

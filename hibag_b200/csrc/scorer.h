@@ -79,7 +79,7 @@ public:
 
 private:
 	Stream st_;
-	Event ev0_, ev1_, ev2_;
+	Event ev0_, ev1_, evc_;      // slot span begin / end, end of the pair-scoring kernel
 	bool timing_pending_ = false;
 	PinBuf<unsigned char> h_blob_;
 	DevBuf<unsigned char> d_blob_;

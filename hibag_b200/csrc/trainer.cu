@@ -198,6 +198,7 @@ private:
 	std::vector<EmScratch> scratch_;                  // one per worker
 	std::vector<double> em_seconds_, wait_seconds_;   // per worker
 
+	int64_t cl_global_index_ = 0;
 	hibag_gpu_ext_proc *procs_ = nullptr;    // legacy-hook mode
 	ScoreStats stats_;
 };
@@ -212,7 +213,13 @@ Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o) : m_(m), o
 	int nt = o_.n_threads;
 	if (nt <= 0) nt = (int)std::thread::hardware_concurrency();
 	if (nt < 1) nt = 1;
-	if (nt > o_.mtry && o_.mtry >= 1) nt = std::max(1, std::min(nt, std::max(o_.mtry, 4)));
+	if (o_.n_threads <= 0)
+	{
+		// one worker per candidate of a round when that is a modest over-subscription: 23
+		// equal EM jobs on 16 cores finish in ~1.4 job-times instead of 2
+		if (o_.mtry > nt && o_.mtry <= 2 * nt) nt = o_.mtry;
+		if (nt > std::max(o_.mtry, 4)) nt = std::max(o_.mtry, 4);
+	}
 	pool_.reset(new ThreadPool(nt, dev_->device));
 	scratch_.resize(pool_->size());
 	em_seconds_.assign(pool_->size(), 0.0);
@@ -336,6 +343,7 @@ void Trainer::run()
 			}
 		} while (n_unique >= n_samp_);
 
+		cl_global_index_ = global_k;
 		m_.cls.emplace_back();
 		Classifier &cl = m_.cls.back();
 		cl.samp_num = boot_;
@@ -362,6 +370,8 @@ void Trainer::run()
 	ts.pair_evals += stats_.pair_evals;
 	ts.popc32_issued += stats_.popc32;
 	ts.kernel_launches += stats_.launches;
+	ts.cell_kernel_ms += stats_.cell_ms;
+	ts.cell_kernel_launches += stats_.cell_launches;
 	ts.h2d_bytes += stats_.h2d_bytes;
 	ts.d2h_bytes += stats_.d2h_bytes;
 }
@@ -427,6 +437,19 @@ void Trainer::grow(Classifier &cl)
 	int global_max_acc = 0;
 	double global_min_loss = 1e+30;
 
+	const int global_k = (int)cl_global_index_;
+	int64_t cum_pairs = 0, cum_em = 0;
+	auto list_pairs = [](const HapList &l) {
+		int64_t tot = 0, rest = 0;
+		for (int a = (int)l.len.size() - 1; a >= 0; a--)
+		{
+			const int64_t n = l.len[a];
+			tot += n * (n + 1) / 2 + n * rest;
+			rest += n;
+		}
+		return tot;
+	};
+
 	SnpPool pool;
 	pool.init(n_snp_);
 	RoundPairs rp;
@@ -439,7 +462,9 @@ void Trainer::grow(Classifier &cl)
 
 	while (pool.total() > 0 && (int)cl.snpidx.size() < HIBAG_B200_MAX_SNP)
 	{
+		const double t_prep = now_s();
 		prepare_round(cur, geno_, a1_, a2_, boot_, inbag_, rp, pool_parallel_for, &pf);
+		ts.seconds_prepare += now_s() - t_prep;
 
 		pool.random_select(o_.mtry, rng_);
 		const int m = pool.n_selected();
@@ -448,6 +473,7 @@ void Trainer::grow(Classifier &cl)
 		const int bit = cur.n_snp;
 
 		// ---- phase 1: EM for every candidate, out-of-bag accuracy as soon as it is ready ----
+		const double t_p1 = now_s();
 		pool_->run(m, [&](int i, int w) {
 			Candidate &cd = cand[i];
 			cd.snp = pool.at(i);
@@ -470,6 +496,8 @@ void Trainer::grow(Classifier &cl)
 			cd.acc = sl.oob_count();
 		});
 		for (int i = 0; i < m; i++) if (cand[i].valid) { ts.n_em++; }
+		ts.seconds_phase_oob += now_s() - t_p1;
+		const double t_p2 = now_s();
 
 		if (!procs_)
 		{
@@ -535,6 +563,21 @@ void Trainer::grow(Classifier &cl)
 			}
 		}
 
+		ts.seconds_phase_ib += now_s() - t_p2;
+		// workload accounting (independent of scheduling): what the reference would evaluate
+		{
+			int running = global_max_acc;
+			for (int i = 0; i < m; i++)
+			{
+				if (!cand[i].valid) continue;
+				const int64_t lp = list_pairs(cand[i].list);
+				cum_em++;
+				cum_pairs += lp * n_oob;
+				if (cand[i].acc >= running) cum_pairs += lp * (int64_t)inbag_.size();
+				if (cand[i].acc > running) running = cand[i].acc;
+			}
+		}
+
 		// ---- phase 3: the reference's decisions in candidate order (:2041-2067) -------------
 		int max_acc = global_max_acc;
 		double min_loss = global_min_loss;
@@ -595,6 +638,10 @@ void Trainer::grow(Classifier &cl)
 			} else {
 				pool.remove(min_i);
 			}
+			{
+				const int64_t row[4] = { global_k, (int64_t)cl.snpidx.size(), cum_pairs, cum_em };
+				m_.train_trace.insert(m_.train_trace.end(), row, row + 4);
+			}
 			if (o_.verbose > 1)
 				fprintf(stderr, "    %2d, SNP: %d, loss: %g, oob acc: %0.2f%%, # of haplo: %d\n",
 					(int)cl.snpidx.size(), snp + 1, global_min_loss,
@@ -615,6 +662,10 @@ void Trainer::grow(Classifier &cl)
 		}
 	}
 
+	{
+		const int64_t row[4] = { global_k, -1, cum_pairs, cum_em };
+		m_.train_trace.insert(m_.train_trace.end(), row, row + 4);
+	}
 	cl.haplo = cur;
 	cl.oob_acc = 0.5 * global_max_acc / n_oob;                       // :2121
 }

@@ -143,8 +143,19 @@ typedef struct hibag_b200_train_stats {
 	uint64_t n_oob_evals, n_ib_evals, n_em;
 	uint64_t kernel_launches;
 	uint64_t h2d_bytes, d2h_bytes;
+	double   cell_kernel_ms;      /* summed CUDA-event durations of the pair-scoring kernel */
+	uint64_t cell_kernel_launches;
+	double   seconds_prepare;     /* wall: haplotype-pair preparation per round */
+	double   seconds_phase_oob;   /* wall: candidate EM + out-of-bag scoring */
+	double   seconds_phase_ib;    /* wall: in-bag scoring of the candidates that need it */
 } hibag_b200_train_stats;
 int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_stats *out);
+
+/* search trace of the classifiers built so far: rows of 4 int64 = {global classifier index,
+ * SNPs accepted so far, pair evaluations since the classifier started, candidate EM runs since
+ * the classifier started}, one row per accepted SNP plus a final row per classifier (accepted
+ * = -1). Returns the number of rows (copies at most max_rows). */
+int hibag_b200_model_train_trace(const hibag_b200_model *m, int64_t *out, int max_rows);
 
 int hibag_b200_model_num_classifiers(const hibag_b200_model *m);
 int hibag_b200_model_clear(hibag_b200_model *m);
