@@ -114,6 +114,7 @@ int hibag_b200_model_set_training(hibag_b200_model *m, int n_samp, const int8_t 
 {
 	return guarded([&]() {
 		require(m && geno && h1 && h2 && n_samp > 0, "set_training: invalid argument");
+		m->tsession.reset();
 		m->n_samp = n_samp;
 		m->geno_t.resize((size_t)m->n_snp * n_samp);
 		for (int s = 0; s < n_samp; s++)

@@ -95,9 +95,11 @@ struct Stream
 struct Event
 {
 	cudaEvent_t e = nullptr;
-	explicit Event(bool timing = true)
+	explicit Event(bool timing = true, bool blocking = false)
 	{
-		HB_CUDA(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+		unsigned flags = timing ? cudaEventDefault : cudaEventDisableTiming;
+		if (blocking) flags |= cudaEventBlockingSync;    // waiting host thread sleeps instead of spinning
+		HB_CUDA(cudaEventCreateWithFlags(&e, flags));
 	}
 	~Event() { if (e) cudaEventDestroy(e); }
 	Event(const Event &) = delete;

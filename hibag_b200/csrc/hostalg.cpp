@@ -159,63 +159,105 @@ void SnpPool::remove_flagged()
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+const int PREP_GRAIN = 32;     // in-bag entries per work item
+
+struct PrepBlock               // pairs found for entries [b*PREP_GRAIN, ...), concatenated
+{
+	std::vector<int> p1, p2;
+	std::vector<int> count;    // pairs per entry of the block
+};
+
 struct PrepJob
 {
 	const HapList *cur;
 	const std::vector<HostGeno> *geno;
 	const std::vector<int> *a1, *a2, *inbag;
 	std::vector<int> start;                          // first haplotype of each allele in cur
-	std::vector<std::vector<std::pair<int, int> > > *per_entry;
+	std::vector<PrepBlock> *blocks;
+	RoundPairs *out;
 };
 
-void prep_range(void *arg, int begin, int end)
+void prep_range(void *arg, int bbegin, int bend)
 {
 	PrepJob &J = *(PrepJob *)arg;
 	const HapList &cur = *J.cur;
 	const int n_snp = cur.n_snp;
+	const int n_ib = (int)J.inbag->size();
 	std::vector<short> dist;
-	for (int k = begin; k < end; k++)
+	for (int b = bbegin; b < bend; b++)
 	{
-		const int s = (*J.inbag)[k];
-		const HostGeno &g = (*J.geno)[s];
-		const int A1 = (*J.a1)[s], A2 = (*J.a2)[s];
-		const int st1 = J.start[A1], m1 = cur.len[A1];
-		const int st2 = J.start[A2], m2 = cur.len[A2];
-		std::vector<std::pair<int, int> > &out = (*J.per_entry)[k];
-		out.clear();
-		int min_d = n_snp * 4;
-		// the doubled list holds haplotype k as entries 2k (new allele 0) and 2k+1 (1); on the
-		// current SNPs both copies are at the same distance, so distances are taken on `cur`
-		if (st1 != st2)
+		PrepBlock &blk = (*J.blocks)[b];
+		blk.p1.clear(); blk.p2.clear(); blk.count.clear();
+		const int kend = std::min(n_ib, (b + 1) * PREP_GRAIN);
+		for (int k = b * PREP_GRAIN; k < kend; k++)
 		{
-			dist.resize((size_t)m1 * m2);
-			for (int i = 0; i < m1; i++)
-				for (int j = 0; j < m2; j++)
+			const int s = (*J.inbag)[k];
+			const HostGeno &g = (*J.geno)[s];
+			const int A1 = (*J.a1)[s], A2 = (*J.a2)[s];
+			const int st1 = J.start[A1], m1 = cur.len[A1];
+			const int st2 = J.start[A2], m2 = cur.len[A2];
+			const size_t before = blk.p1.size();
+			int min_d = n_snp * 4;
+			// the doubled list holds haplotype k as entries 2k (new allele 0) and 2k+1 (1); on
+			// the current SNPs both copies are at the same distance: distances are taken on `cur`
+			if (st1 != st2)
+			{
+				dist.resize((size_t)m1 * m2);
+				for (int i = 0; i < m1; i++)
+					for (int j = 0; j < m2; j++)
+					{
+						const int d = hamming(g, cur.h[st1 + i].packed, cur.h[st2 + j].packed, n_snp);
+						dist[(size_t)i * m2 + j] = (short)d;
+						if (d < min_d) min_d = d;
+					}
+				// scan order of the doubled ranges: first index outer, second inner (:1578-1604);
+				// with minimum 0 the zero-distance pairs are exactly the pairs at the minimum
+				for (int i = 0; i < 2 * m1; i++)
 				{
-					const int d = hamming(g, cur.h[st1 + i].packed, cur.h[st2 + j].packed, n_snp);
-					dist[(size_t)i * m2 + j] = (short)d;
-					if (d < min_d) min_d = d;
+					const short *row = &dist[(size_t)(i >> 1) * m2];
+					for (int j = 0; j < 2 * m2; j++)
+						if (row[j >> 1] == min_d)
+						{
+							blk.p1.push_back(2 * st1 + i); blk.p2.push_back(2 * st2 + j);
+						}
 				}
-			// scan order of the doubled ranges: first index outer, second inner (:1578-1604);
-			// when the minimum is 0 the zero-distance pairs are exactly the pairs at the minimum
-			for (int i = 0; i < 2 * m1; i++)
-				for (int j = 0; j < 2 * m2; j++)
-					if (dist[(size_t)(i >> 1) * m2 + (j >> 1)] == min_d)
-						out.push_back(std::make_pair(2 * st1 + i, 2 * st2 + j));
-		} else {
-			// same start => same allele range: upper triangle including i == j (:1608-1634)
-			dist.resize((size_t)m1 * m1);
-			for (int i = 0; i < m1; i++)
-				for (int j = i; j < m1; j++)
+			} else {
+				// same start => same allele range: upper triangle including i == j (:1608-1634)
+				dist.resize((size_t)m1 * m1);
+				for (int i = 0; i < m1; i++)
+					for (int j = i; j < m1; j++)
+					{
+						const int d = hamming(g, cur.h[st1 + i].packed, cur.h[st1 + j].packed, n_snp);
+						dist[(size_t)i * m1 + j] = (short)d;
+						if (d < min_d) min_d = d;
+					}
+				for (int i = 0; i < 2 * m1; i++)
 				{
-					const int d = hamming(g, cur.h[st1 + i].packed, cur.h[st1 + j].packed, n_snp);
-					dist[(size_t)i * m1 + j] = (short)d;
-					if (d < min_d) min_d = d;
+					const short *row = &dist[(size_t)(i >> 1) * m1];
+					for (int j = i; j < 2 * m1; j++)
+						if (row[j >> 1] == min_d)
+						{
+							blk.p1.push_back(2 * st1 + i); blk.p2.push_back(2 * st1 + j);
+						}
 				}
-			for (int i = 0; i < 2 * m1; i++)
-				for (int j = i; j < 2 * m1; j++)
-					if (dist[(size_t)(i >> 1) * m1 + (j >> 1)] == min_d)
-						out.push_back(std::make_pair(2 * st1 + i, 2 * st1 + j));
+			}
+			blk.count.push_back((int)(blk.p1.size() - before));
+		}
+	}
+}
+
+void prep_copy(void *arg, int bbegin, int bend)
+{
+	PrepJob &J = *(PrepJob *)arg;
+	RoundPairs &out = *J.out;
+	for (int b = bbegin; b < bend; b++)
+	{
+		const PrepBlock &blk = (*J.blocks)[b];
+		const size_t o = out.off[(size_t)b * PREP_GRAIN];
+		if (!blk.p1.empty())
+		{
+			memcpy(&out.p1[o], blk.p1.data(), sizeof(int) * blk.p1.size());
+			memcpy(&out.p2[o], blk.p2.data(), sizeof(int) * blk.p2.size());
 		}
 	}
 }
@@ -231,35 +273,35 @@ void prepare_round(const HapList &cur, const std::vector<HostGeno> &geno,
 	if (cur.n_snp >= HIBAG_B200_MAX_SNP)
 		throw std::runtime_error("prepare_round: too many SNP markers in the classifier");
 	const int n_ib = (int)inbag.size();
-	std::vector<std::vector<std::pair<int, int> > > per_entry(n_ib);
+	const int n_blocks = (n_ib + PREP_GRAIN - 1) / PREP_GRAIN;
+	static thread_local std::vector<PrepBlock> blocks;     // reused across rounds (one trainer thread)
+	if ((int)blocks.size() < n_blocks) blocks.resize(n_blocks);
 	PrepJob J;
 	J.cur = &cur; J.geno = &geno; J.a1 = &a1; J.a2 = &a2; J.inbag = &inbag;
 	J.start.assign(cur.len.size() + 1, 0);
 	for (size_t a = 0; a < cur.len.size(); a++) J.start[a + 1] = J.start[a] + cur.len[a];
-	J.per_entry = &per_entry;
-	parallel_for(pf_ctx, n_ib, prep_range, &J);
+	J.blocks = &blocks;
+	J.out = &out;
+	parallel_for(pf_ctx, n_blocks, prep_range, &J);
 
 	out.n_cur = (int)cur.h.size();
 	out.samp.resize(n_ib); out.boot.resize(n_ib); out.off.resize(n_ib + 1);
 	size_t total = 0;
-	for (int k = 0; k < n_ib; k++)
+	for (int b = 0; b < n_blocks; b++)
 	{
-		out.samp[k] = inbag[k];
-		out.boot[k] = boot[inbag[k]];
-		out.off[k] = total;
-		total += per_entry[k].size();
+		const PrepBlock &blk = blocks[b];
+		for (size_t t = 0; t < blk.count.size(); t++)
+		{
+			const int k = b * PREP_GRAIN + (int)t;
+			out.samp[k] = inbag[k];
+			out.boot[k] = boot[inbag[k]];
+			out.off[k] = total;
+			total += blk.count[t];
+		}
 	}
 	out.off[n_ib] = total;
 	out.p1.resize(total); out.p2.resize(total);
-	for (int k = 0; k < n_ib; k++)
-	{
-		size_t o = out.off[k];
-		for (size_t t = 0; t < per_entry[k].size(); t++, o++)
-		{
-			out.p1[o] = per_entry[k][t].first;
-			out.p2[o] = per_entry[k][t].second;
-		}
-	}
+	parallel_for(pf_ctx, n_blocks, prep_copy, &J);
 }
 
 // ---------------------------------------------------------------------------------------------

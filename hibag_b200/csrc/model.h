@@ -22,6 +22,13 @@ struct Classifier
 
 struct PredictCache;   // device-resident copy of all classifiers (predictor.cu)
 
+/// training state kept between hibag_b200_model_train calls (thread pool, streams, device
+/// buffers); defined in trainer.cu
+struct TrainSession
+{
+	virtual ~TrainSession() {}
+};
+
 }  // namespace hb
 
 struct hibag_b200_model
@@ -34,6 +41,7 @@ struct hibag_b200_model
 	hibag_b200_predict_stats predict_stats;
 	std::vector<int64_t> train_trace;   // rows of 4, see hibag_b200_model_train_trace
 	std::shared_ptr<hb::PredictCache> pcache;
+	std::shared_ptr<hb::TrainSession> tsession;
 	hibag_b200_model();
 };
 

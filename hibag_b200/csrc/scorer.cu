@@ -149,8 +149,8 @@ void EvalSlot::enqueue_reduce_ib(const GenoView &g, const int *pos_list, int n_p
 
 void EvalSlot::sync()
 {
-	if (timing_pending_) HB_CUDA(cudaEventRecord(ev1_.e, st_.s));
-	HB_CUDA(cudaStreamSynchronize(st_.s));
+	HB_CUDA(cudaEventRecord(ev1_.e, st_.s));
+	HB_CUDA(cudaEventSynchronize(ev1_.e));
 	if (timing_pending_)
 	{
 		float ms = 0;

@@ -79,7 +79,8 @@ public:
 
 private:
 	Stream st_;
-	Event ev0_, ev1_, evc_;      // slot span begin / end, end of the pair-scoring kernel
+	Event ev0_, evc_;            // slot span begin, end of the pair-scoring kernel
+	Event ev1_{true, true};      // slot span end; blocking sync so waiting workers free their core
 	bool timing_pending_ = false;
 	PinBuf<unsigned char> h_blob_;
 	DevBuf<unsigned char> d_blob_;

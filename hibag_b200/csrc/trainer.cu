@@ -142,13 +142,7 @@ struct PfCtx { ThreadPool *pool; };
 void pool_parallel_for(void *ctx, int n, void (*fn)(void *, int, int), void *arg)
 {
 	ThreadPool *pool = ((PfCtx *)ctx)->pool;
-	const int grain = 16;
-	const int n_blocks = (n + grain - 1) / grain;
-	pool->run(n_blocks, [&](int b, int) {
-		const int begin = b * grain;
-		const int end = std::min(n, begin + grain);
-		fn(arg, begin, end);
-	});
+	pool->run(n, [&](int b, int) { fn(arg, b, b + 1); });
 }
 
 /// per-candidate state of one selection round
@@ -161,12 +155,23 @@ struct Candidate
 	HapList list;
 };
 
-class Trainer
+class Trainer : public TrainSession
 {
 public:
 	Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o);
-	~Trainer();
+	~Trainer() override;
 	void run();
+	/// can this session (threads, scoring mode) serve a call with these options?
+	bool compatible(const hibag_b200_train_opts &o) const
+	{
+		return (o.use_legacy_hooks != 0) == (procs_ != nullptr) && o.n_threads == requested_threads_ &&
+			(o.mtry <= 0 ? 1 : o.mtry) == o_.mtry;
+	}
+	void configure(const hibag_b200_train_opts &o)
+	{
+		o_ = o;
+		if (o_.mtry <= 0) o_.mtry = 1;
+	}
 
 private:
 	void grow(Classifier &c);
@@ -199,6 +204,7 @@ private:
 	std::vector<double> em_seconds_, wait_seconds_;   // per worker
 
 	int64_t cl_global_index_ = 0;
+	int requested_threads_ = 0;
 	hibag_gpu_ext_proc *procs_ = nullptr;    // legacy-hook mode
 	ScoreStats stats_;
 };
@@ -210,6 +216,7 @@ Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o) : m_(m), o
 	if (n_samp_ <= 0 || m.geno_t.empty())
 		throw std::runtime_error("train: no training data (call hibag_b200_model_set_training)");
 	if (o_.mtry <= 0) o_.mtry = 1;
+	requested_threads_ = o.n_threads;
 	int nt = o_.n_threads;
 	if (nt <= 0) nt = (int)std::thread::hardware_concurrency();
 	if (nt < 1) nt = 1;
@@ -323,6 +330,12 @@ double Trainer::ib_loss(const double *ratio) const
 void Trainer::run()
 {
 	const double t0 = now_s();
+	// the session outlives a call: start this call's counters from zero
+	stats_ = ScoreStats();
+	for (auto &sl : slots_) if (sl) sl->stats = ScoreStats();
+	const ScoreStats plugin_before = procs_ ? plugin_build_stats() : ScoreStats();
+	std::fill(em_seconds_.begin(), em_seconds_.end(), 0.0);
+	std::fill(wait_seconds_.begin(), wait_seconds_.end(), 0.0);
 	if (!o_.per_classifier_seed) rng_.set_seed((uint32_t)o_.seed);
 	const int stride = o_.index_stride > 0 ? o_.index_stride : 1;
 	for (int c = 0; c < o_.nclassifier; c++)
@@ -361,7 +374,15 @@ void Trainer::run()
 	}
 	// fold the counters
 	for (auto &s : slots_) if (s) stats_.add(s->stats);
-	if (procs_) stats_.add(plugin_build_stats());
+	if (procs_)
+	{
+		ScoreStats now = plugin_build_stats();
+		now.pair_evals -= plugin_before.pair_evals; now.popc32 -= plugin_before.popc32;
+		now.launches -= plugin_before.launches; now.cell_launches -= plugin_before.cell_launches;
+		now.h2d_bytes -= plugin_before.h2d_bytes; now.d2h_bytes -= plugin_before.d2h_bytes;
+		now.kernel_ms -= plugin_before.kernel_ms; now.cell_ms -= plugin_before.cell_ms;
+		stats_.add(now);
+	}
 	hibag_b200_train_stats &ts = m_.train_stats;
 	ts.seconds_total += now_s() - t0;
 	for (double v : em_seconds_) ts.seconds_em += v;
@@ -472,8 +493,16 @@ void Trainer::grow(Classifier &cl)
 		while ((int)slots_.size() < m && !procs_) slots_.emplace_back(new EvalSlot());
 		const int bit = cur.n_snp;
 
-		// ---- phase 1: EM for every candidate, out-of-bag accuracy as soon as it is ready ----
+		// ---- candidates in parallel: EM, out-of-bag accuracy, and -- speculatively -- the in-bag
+		// loss. The reference computes the loss only when acc >= the running maximum over the
+		// earlier candidates (:2033). A worker that finishes candidate i knows the accuracies of
+		// the earlier candidates that are already done; their maximum is a lower bound of the true
+		// threshold, so "acc >= that bound" never misses a loss the reference would compute. Losses
+		// computed in excess are discarded below (the reference keeps loss = 0 for them).
 		const double t_p1 = now_s();
+		std::vector<std::atomic<int> > pub(m);          // published accuracy, -1 = not yet, -2 = skipped
+		for (int i = 0; i < m; i++) pub[i].store(-1, std::memory_order_relaxed);
+		std::vector<unsigned char> have_loss(m, 0);
 		pool_->run(m, [&](int i, int w) {
 			Candidate &cd = cand[i];
 			cd.snp = pool.at(i);
@@ -482,7 +511,8 @@ void Trainer::grow(Classifier &cl)
 			cd.valid = estimate_candidate(cur, rp, m_.geno_t.data() + (size_t)cd.snp * n_samp_,
 				n_samp_, rare_prob, scratch_[w], cd.list);
 			em_seconds_[w] += now_s() - t_em;
-			if (!cd.valid || procs_) return;
+			if (!cd.valid) { pub[i].store(-2, std::memory_order_release); return; }
+			if (procs_) return;
 			EvalSlot &sl = *slots_[i];
 			sl.stage_list(cd.list.h.data(), (int)cd.list.h.size(), n_hla_, cd.list.n_snp);
 			GenoView v = view;
@@ -490,10 +520,27 @@ void Trainer::grow(Classifier &cl)
 			v.cand_bit = bit;
 			sl.enqueue_cells(v, d_oob_.get(), n_oob);
 			sl.enqueue_reduce_oob(v, d_oob_.get(), n_oob);
-			const double t_w = now_s();
+			double t_w = now_s();
 			sl.sync();
 			wait_seconds_[w] += now_s() - t_w;
 			cd.acc = sl.oob_count();
+			pub[i].store(cd.acc, std::memory_order_release);
+			int bound = global_max_acc;
+			for (int j = 0; j < i; j++)
+			{
+				const int a = pub[j].load(std::memory_order_acquire);
+				if (a > bound) bound = a;
+			}
+			if (cd.acc >= bound)
+			{
+				sl.enqueue_cells(v, d_ib_.get(), (int)inbag_.size());
+				sl.enqueue_reduce_ib(v, d_ib_.get(), (int)inbag_.size());
+				t_w = now_s();
+				sl.sync();
+				wait_seconds_[w] += now_s() - t_w;
+				cd.loss = ib_loss(sl.ib_ratios());
+				have_loss[i] = 1;
+			}
 		});
 		for (int i = 0; i < m; i++) if (cand[i].valid) { ts.n_em++; }
 		ts.seconds_phase_oob += now_s() - t_p1;
@@ -501,30 +548,20 @@ void Trainer::grow(Classifier &cl)
 
 		if (!procs_)
 		{
-			// ---- phase 2: which candidates need the in-bag loss (acc >= running max, :2033) ----
-			std::vector<int> need;
+			// ---- exact rule in candidate order: keep a loss only where the reference has one ------
 			int running = global_max_acc;
 			for (int i = 0; i < m; i++)
 			{
-				if (!cand[i].valid) continue;
+				Candidate &cd = cand[i];
+				if (!cd.valid) continue;
 				ts.n_oob_evals++;
-				if (cand[i].acc >= running) need.push_back(i);
-				if (cand[i].acc > running) running = cand[i].acc;
+				const bool need = cd.acc >= running;
+				if (need && !have_loss[i])
+					throw std::runtime_error("internal error: in-bag loss missing for a candidate");
+				if (!need) cd.loss = 0;
+				else ts.n_ib_evals++;
+				if (cd.acc > running) running = cd.acc;
 			}
-			pool_->run((int)need.size(), [&](int k, int w) {
-				Candidate &cd = cand[need[k]];
-				EvalSlot &sl = *slots_[need[k]];
-				GenoView v = view;
-				v.cand_col = d_geno_t_.get() + (size_t)cd.snp * n_samp_;
-				v.cand_bit = bit;
-				sl.enqueue_cells(v, d_ib_.get(), (int)inbag_.size());
-				sl.enqueue_reduce_ib(v, d_ib_.get(), (int)inbag_.size());
-				const double t_w = now_s();
-				sl.sync();
-				wait_seconds_[w] += now_s() - t_w;
-				cd.loss = ib_loss(sl.ib_ratios());
-			});
-			ts.n_ib_evals += need.size();
 		} else {
 			// ---- legacy hooks: sequential, exactly the reference's call sequence -------------
 			int running = global_max_acc;
@@ -675,8 +712,22 @@ void Trainer::grow(Classifier &cl)
 void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 {
 	current_device();      // fails here, loudly, when no CUDA device is usable
-	Trainer t(m, opts);
-	t.run();
+	Trainer *t = dynamic_cast<Trainer *>(m.tsession.get());
+	if (!t || !t->compatible(opts))
+	{
+		m.tsession.reset();
+		t = new Trainer(m, opts);
+		m.tsession.reset(t);
+	}
+	t->configure(opts);
+	try
+	{
+		t->run();
+	} catch (...)
+	{
+		m.tsession.reset();
+		throw;
+	}
 	m.pcache.reset();
 }
 
