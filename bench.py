@@ -408,7 +408,7 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
         big.predict_device(g.data_ptr(), n, h1.data_ptr(), h2.data_ptr(), mp_.data_ptr(), mt.data_ptr(),
                            ds.data_ptr(), pp.data_ptr(), stream=torch.cuda.current_stream().cuda_stream,
                            sync=True)
-    warm = min(n, 8192)
+    warm = n        # full-size warm-up: every tile buffer is allocated before the timed pass
     big.predict_device(g.data_ptr(), warm, h1.data_ptr(), h2.data_ptr(), mp_.data_ptr(), mt.data_ptr(),
                        ds.data_ptr(), pp.data_ptr(), stream=torch.cuda.current_stream().cuda_stream, sync=True)
     s0 = big.predict_stats()
