@@ -32,7 +32,8 @@ class TrainOpts(C.Structure):
     _fields_ = [("nclassifier", C.c_int), ("mtry", C.c_int), ("prune", C.c_int),
                 ("n_threads", C.c_int), ("seed", C.c_int64), ("per_classifier_seed", C.c_int),
                 ("first_index", C.c_int), ("index_stride", C.c_int),
-                ("use_legacy_hooks", C.c_int), ("verbose", C.c_int)]
+                ("use_legacy_hooks", C.c_int), ("verbose", C.c_int), ("n_concurrent", C.c_int),
+                ("em_on_device", C.c_int)]
 
 
 class TrainStats(C.Structure):
@@ -43,7 +44,8 @@ class TrainStats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("cell_kernel_ms", C.c_double),
                 ("cell_kernel_launches", C.c_uint64), ("seconds_prepare", C.c_double),
-                ("seconds_phase_oob", C.c_double), ("seconds_phase_ib", C.c_double)]
+                ("seconds_phase_oob", C.c_double), ("seconds_phase_ib", C.c_double),
+                ("em_kernel_ms", C.c_double), ("n_em_host_fallback", C.c_uint64)]
 
 
 class PredictOut(C.Structure):
@@ -228,9 +230,11 @@ class HLAModel:
         _chk(lib().hibag_b200_model_set_training(self._h, self.n_samp, _p(g), _p(a), _p(b)))
 
     def train(self, nclassifier, mtry, prune=True, seed=100, n_threads=0, per_classifier_seed=False,
-              first_index=0, index_stride=1, use_legacy_hooks=False, verbose=0):
+              first_index=0, index_stride=1, use_legacy_hooks=False, verbose=0, n_concurrent=1,
+              em_on_device=True):
         o = TrainOpts(nclassifier, mtry, int(prune), n_threads, seed, int(per_classifier_seed),
-                      first_index, index_stride, int(use_legacy_hooks), verbose)
+                      first_index, index_stride, int(use_legacy_hooks), verbose, int(n_concurrent),
+                      int(em_on_device))
         _chk(lib().hibag_b200_model_train(self._h, C.byref(o)))
 
     def train_stats(self):
@@ -364,7 +368,7 @@ def default_mtry(n_snp, mtry="sqrt"):
 
 def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=True, seed=100,
                    nthread=0, per_classifier_seed=False, use_legacy_hooks=False, verbose=False,
-                   hla_allele=None, first_index=0, index_stride=1):
+                   hla_allele=None, first_index=0, index_stride=1, n_concurrent=1, em_on_device=True):
     """Train a model. hla = (h1, h2) integer allele indices (or labels with hla_allele given),
     snp = int matrix [n_samp, n_snp] with 0/1/2 and anything else missing.
     Mirrors reference hlaAttrBagging (R/HIBAG.R:48-275): monomorphic SNPs are removed when mono_rm,
@@ -389,7 +393,8 @@ def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=T
     model.set_training(g, h1, h2)
     model.train(nclassifier, default_mtry(g.shape[1], mtry), prune=prune, seed=seed, n_threads=nthread,
                 per_classifier_seed=per_classifier_seed, first_index=first_index,
-                index_stride=index_stride, use_legacy_hooks=use_legacy_hooks, verbose=int(verbose))
+                index_stride=index_stride, use_legacy_hooks=use_legacy_hooks, verbose=int(verbose),
+                n_concurrent=n_concurrent, em_on_device=em_on_device)
     return model
 
 

@@ -1,0 +1,850 @@
+// em.cu -- see em.h
+#include "em.h"
+
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace hb {
+
+namespace {
+
+constexpr int EM_THREADS = 1024;
+constexpr int EM_MAX_ITER = 500;                 // src/LibHLA.cpp:98
+constexpr double EM_INIT_VAL_FRAC = 0.001;       // :100
+// Half-width of the band around the stopping tolerance inside which the device does not decide,
+// relative to |LL|: device log and glibc log are both within 1 ulp (2.2e-16 per term) and the
+// host's sequential sum of n same-sign terms carries at most n*u/2 relative error (u = 1.1e-16),
+// the device's tree sum far less; the difference of two such sums at most twice that. The band is
+// twice the bound. It is ~1e-4 of the tolerance sqrt(eps)*|LL| at n = 5000.
+__host__ __device__ inline double em_guard_rel(int n_entry) { return 2.0 * (n_entry * 1.2e-16 + 1e-15); }
+
+// ---------------------------------------------------------------------------------------------
+// haplotype-pair matching
+// ---------------------------------------------------------------------------------------------
+
+/// reference hamm_d, generic form (src/LibHLA.cpp:802-817)
+__device__ __forceinline__ int hamm_ref(const uint64_t S1[2], const uint64_t S2[2],
+	const uint64_t *__restrict__ A, const uint64_t *__restrict__ B, int words)
+{
+	int d = 0;
+	for (int w = 0; w < words; w++)
+	{
+		const uint64_t a = A[w], b = B[w];
+		const uint64_t miss = S2[w] & ~S1[w];
+		const uint64_t mask = ((a ^ S2[w]) | (b ^ S1[w])) & ~miss;
+		d += __popcll((a ^ S1[w]) & mask) + __popcll((b ^ S2[w]) & mask);
+	}
+	return d;
+}
+
+struct MatchArgs
+{
+	const uint64_t *hap;          // [n_cur][2]
+	const int *start;             // [n_hla + 1]
+	const uint32_t *s1, *s2;      // SoA planes [4][stride]
+	int stride;
+	const int *a1, *a2;           // true types per sample, a1 <= a2
+	const int *ib;                // in-bag sample per entry
+	int n_entry, n_snp;
+	int *cnt;                     // per entry: pairs (doubled) or records
+	int *mind;                    // per entry: minimum distance
+	const int *off;               // exclusive scan of cnt
+	int *p1, *p2;                 // doubled pairs
+	uint32_t *rec;                // records (entry, (i2 << 16) | i1)
+};
+
+/// MODE 0: minimum distance + number of doubled pairs; 1: emit the doubled pairs in the
+/// reference's scan order (first index outer, second inner over the doubled ranges, :1578-1634);
+/// 2: number of records; 3: emit records (i1 outer, i2 inner)
+template <int MODE>
+__global__ void __launch_bounds__(128) haplomatch_kernel(const MatchArgs p)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= p.n_entry) return;
+	const int s = p.ib[k];
+	uint64_t S1[2], S2[2];
+	{
+		const size_t st = (size_t)p.stride;
+		S1[0] = (uint64_t)p.s1[s] | ((uint64_t)p.s1[st + s] << 32);
+		S1[1] = (uint64_t)p.s1[2 * st + s] | ((uint64_t)p.s1[3 * st + s] << 32);
+		S2[0] = (uint64_t)p.s2[s] | ((uint64_t)p.s2[st + s] << 32);
+		S2[1] = (uint64_t)p.s2[2 * st + s] | ((uint64_t)p.s2[3 * st + s] << 32);
+	}
+	const int words = (p.n_snp <= 64) ? 1 : 2;
+	const int A1 = p.a1[s], A2 = p.a2[s];
+	const int st1 = p.start[A1], m1 = p.start[A1 + 1] - st1;
+	const int st2 = p.start[A2], m2 = p.start[A2 + 1] - st2;
+	const bool same = (st1 == st2);
+
+	if (MODE == 0 || MODE == 2)
+	{
+		int min_d = p.n_snp * 4, n = 0;
+		for (int i = 0; i < m1; i++)
+		{
+			const uint64_t *hi = p.hap + 2 * (size_t)(st1 + i);
+			for (int j = same ? i : 0; j < m2; j++)
+			{
+				const int d = hamm_ref(S1, S2, hi, p.hap + 2 * (size_t)(st2 + j), words);
+				if (d < min_d) { min_d = d; n = 0; }
+				if (d == min_d) n += (MODE == 2) ? 1 : ((same && i == j) ? 3 : 4);
+			}
+		}
+		p.cnt[k] = n;
+		p.mind[k] = min_d;
+		return;
+	}
+
+	const int min_d = p.mind[k];
+	int o = p.off[k];
+	if (MODE == 3)
+	{
+		for (int i = 0; i < m1; i++)
+		{
+			const uint64_t *hi = p.hap + 2 * (size_t)(st1 + i);
+			for (int j = same ? i : 0; j < m2; j++)
+				if (hamm_ref(S1, S2, hi, p.hap + 2 * (size_t)(st2 + j), words) == min_d)
+				{
+					p.rec[2 * (size_t)o] = (uint32_t)k;
+					p.rec[2 * (size_t)o + 1] = ((uint32_t)j << 16) | (uint32_t)i;
+					o++;
+				}
+		}
+		return;
+	}
+	for (int i = 0; i < m1; i++)
+	{
+		const uint64_t *hi = p.hap + 2 * (size_t)(st1 + i);
+		for (int a = 0; a < 2; a++)
+		{
+			const int i2 = 2 * (st1 + i) + a;
+			for (int j = same ? i : 0; j < m2; j++)
+				if (hamm_ref(S1, S2, hi, p.hap + 2 * (size_t)(st2 + j), words) == min_d)
+				{
+					for (int b = 0; b < 2; b++)
+					{
+						const int j2 = 2 * (st2 + j) + b;
+						if (!same || j2 >= i2)
+						{
+							p.p1[o] = i2; p.p2[o] = j2;
+							o++;
+						}
+					}
+				}
+		}
+	}
+}
+
+/// keys[2t + side] = haplotype of that side of pair t, vals = 2t + side
+__global__ void incidence_fill_kernel(const int *__restrict__ p1, const int *__restrict__ p2,
+	int n_pairs, int *key, int *val)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_pairs) return;
+	key[2 * t] = p1[t]; key[2 * t + 1] = p2[t];
+	val[2 * t] = 2 * t; val[2 * t + 1] = 2 * t + 1;
+}
+
+/// after the stable sort by haplotype: inc_off[u] = first sorted slot of haplotype u
+/// (u in [0, n2]) and len[u] = number of contributions of u
+__global__ void incidence_offsets_kernel(const int *__restrict__ key_sorted, int n, int n2,
+	int *inc_off)
+{
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q > n2) return;
+	int lo = 0, hi = n;                // lower_bound(key_sorted, q)
+	while (lo < hi)
+	{
+		const int mid = (lo + hi) >> 1;
+		if (key_sorted[mid] < q) lo = mid + 1; else hi = mid;
+	}
+	inc_off[q] = lo;
+}
+
+__global__ void incidence_len_kernel(const int *__restrict__ inc_off, int n2, int *len, int *hap)
+{
+	const int u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= n2) return;
+	len[u] = inc_off[u + 1] - inc_off[u];
+	hap[u] = u;
+}
+
+/// Haplotypes sorted by decreasing contribution count are cut into groups of 32 (one per lane
+/// of a warp); group g stores its contributions interleaved ("ELL"): slot (i, lane) at
+/// group_base[g] + 64*(i/2) + 2*lane + (i&1), i < group_len[g] = the longest chain of the group
+/// (two consecutive rows of a lane are 16 contiguous bytes: one cp.async.cg per lane), so the M
+/// step reads 512 contiguous bytes per warp step and every lane still adds its own chain in order.
+/// Single block; group_base[n_groups] = total slots.
+__global__ void incidence_groups_kernel(const int *__restrict__ len_sorted,
+	const int *__restrict__ hap_sorted, int n2, int *rank_of, int *group_len, int *group_base)
+{
+	const int n_groups = (n2 + 31) / 32;
+	for (int r = threadIdx.x; r < n2; r += blockDim.x) rank_of[hap_sorted[r]] = r;
+	// rows padded to a multiple of 8: padding slots stay 0.0 and the M step runs guard-free
+	for (int g = threadIdx.x; g < n_groups; g += blockDim.x) group_len[g] = (len_sorted[32 * g] + 7) & ~7;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		int base = 0;
+		for (int g = 0; g < n_groups; g++) { group_base[g] = base; base += 32 * group_len[g]; }
+		group_base[n_groups] = base;
+	}
+}
+
+/// pairs4[t] = {u | v << 16, entry of the pair, slot of the contribution to u, slot of the
+/// contribution to v}
+__global__ void incidence_slots_kernel(const int *__restrict__ key_sorted,
+	const int *__restrict__ val_sorted, int n, const int *__restrict__ inc_off,
+	const int *__restrict__ rank_of, const int *__restrict__ group_base, int *pairs4)
+{
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n) return;
+	const int u = key_sorted[q], e = val_sorted[q];
+	const int r = rank_of[u];
+	const int i = q - inc_off[u];
+	const int slot = group_base[r >> 5] + 64 * (i >> 1) + 2 * (r & 31) + (i & 1);
+	pairs4[4 * (size_t)(e >> 1) + 2 + (e & 1)] = slot;
+}
+
+__global__ void pairs_pack_kernel(const int *__restrict__ p1, const int *__restrict__ p2,
+	const int *__restrict__ off, int n_entry, int *pairs4)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_entry) return;
+	for (int t = off[k]; t < off[k + 1]; t++)
+	{
+		pairs4[4 * (size_t)t] = p1[t] | (p2[t] << 16);
+		pairs4[4 * (size_t)t + 1] = k;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// EM of the candidates of a round: one CTA per candidate
+// ---------------------------------------------------------------------------------------------
+struct EmArgs
+{
+	int n_entry, n_cur, n_samp;
+	const int *ib, *boot;             // in-bag sample per entry; bootstrap count per sample
+	const int *off;                   // pair range per entry
+	const int4 *pairs4;               // {u, v, slot_u, slot_v} per pair
+	const int *hap_sorted, *group_len, *group_base;   // ELL incidence layout
+	const double *cur_freq;
+	size_t n_slots;                   // ELL slots per candidate
+	const int8_t *geno_t;             // raw genotypes, SNP-major [n_snp][n_samp]
+	const int *cand_snp;              // [m]
+	double *rinc;                     // [m][n_slots] contributions in ELL incidence order, zeroed
+	double *xbuf;                     // [m][total_pairs] GenoFreq of every pair
+	int total_pairs;
+	int m_warps;                      // warps that run the M step, each with a RING_ROWS-row ring
+	double *out_freq;                 // [m][2 * n_cur]
+	int *out_status;                  // [m][4] = status, iterations, 0, 0
+	double scale;                     // 0.5 / n_samp
+	double em_reltol;                 // sqrt(DBL_EPSILON)
+};
+
+constexpr int RING_ROWS = 64;      // ELL rows (256 B each) a warp keeps in flight in the M step
+constexpr int MAX_CLUSTER = 8;
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void *src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+	asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+	double2 v;
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ double block_sum_f64(double v, double *scratch)
+{
+	// fixed-shape tree: lanes, then warps -- deterministic for a given block size
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+	const int w = threadIdx.x >> 5;
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) scratch[w] = v;
+	__syncthreads();
+	if (w == 0)
+	{
+		double x = (threadIdx.x < (blockDim.x >> 5)) ? scratch[threadIdx.x] : 0.0;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+		if (threadIdx.x == 0) scratch[32] = x;
+	}
+	__syncthreads();
+	return scratch[32];
+}
+
+/// A cluster of C CTAs (C SMs) estimates one candidate. The pairs -- whole in-bag entries -- are
+/// split evenly over the CTAs for the E step; the groups of haplotype chains are dealt round-robin
+/// for the M step. Every CTA keeps the full frequency vector in shared memory; new frequencies
+/// and the partial log-likelihoods are written into all CTAs through distributed shared memory,
+/// so two cluster barriers per iteration are the only synchronisation.
+__global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
+{
+	cg::cluster_group cluster = cg::this_cluster();
+	const int C = (int)cluster.num_blocks();
+	const int rank = (int)cluster.block_rank();
+
+	extern __shared__ double em_smem[];
+	double *fr = em_smem;                      // [2 * n_cur] frequencies (old, then new in place)
+	double *scratch = fr + 2 * (size_t)p.n_cur;        // [40]
+	double *llp = scratch + 40;                // [2][MAX_CLUSTER] partial log-likelihoods
+	double *bck = llp + 2 * MAX_CLUSTER;       // [n_entry] bootstrap count of the entry
+	double *sck = bck + p.n_entry;             // [n_entry] count / sum of the entry's GenoFreq
+	double *rings = sck + p.n_entry;           // [m_warps][RING_ROWS][32] M-step rings
+	int *gk = (int *)(rings + (size_t)p.m_warps * RING_ROWS * 32);   // [n_entry] candidate genotype, 3 = missing
+	__shared__ int sh_i[4];
+
+	const int c = blockIdx.x / C;
+	const int tid = threadIdx.x;
+	const int n2 = 2 * p.n_cur;
+	const int8_t *col = p.geno_t + (size_t)p.cand_snp[c] * p.n_samp;
+	double *rinc = p.rinc + (size_t)c * p.n_slots;
+	double *xbuf = p.xbuf + (size_t)c * p.total_pairs;
+	int *status = p.out_status + 4 * c;
+
+	// allele frequency of the new SNP in the bootstrap sample (:1136-1151), integers; every CTA
+	// of the cluster computes the same numbers
+	{
+		int ac = 0, vc = 0;
+		for (int k = tid; k < p.n_entry; k += EM_THREADS)
+		{
+			const int s = p.ib[k];
+			const int g = col[s];
+			const int b = p.boot[s];
+			bck[k] = (double)b;
+			gk[k] = (0 <= g && g <= 2) ? g : 3;
+			if (0 <= g && g <= 2) { ac += g * b; vc += 2 * b; }
+		}
+		if (tid < 4) sh_i[tid] = 0;
+		__syncthreads();
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			ac += __shfl_xor_sync(0xffffffffu, ac, o);
+			vc += __shfl_xor_sync(0xffffffffu, vc, o);
+		}
+		if ((tid & 31) == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); }
+		__syncthreads();
+	}
+	const int allele_cnt = sh_i[0], valid_cnt = sh_i[1];
+	if (allele_cnt == 0 || allele_cnt == valid_cnt)
+	{
+		if (tid == 0 && rank == 0) { status[0] = EM_INVALID; status[1] = 0; }
+		return;                                 // uniform over the cluster
+	}
+
+	// doubled list, initial frequencies (:444-459)
+	{
+		const double af = __ddiv_rn((double)allele_cnt, (double)valid_cnt);
+		const double q0 = __dsub_rn(1.0, af), q1 = af;
+		for (int k = tid; k < p.n_cur; k += EM_THREADS)
+		{
+			const double f = p.cur_freq[k];
+			fr[2 * k] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
+			fr[2 * k + 1] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
+		}
+	}
+	// this CTA's slice: entries [k_lo, k_hi) and exactly their pairs [t_lo, t_hi)
+	int k_lo, k_hi;
+	{
+		auto first_entry_at = [&](long long target) {      // first k with off[k] >= target
+			int lo = 0, hi = p.n_entry;
+			while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.off[mid] < target) lo = mid + 1; else hi = mid; }
+			return lo;
+		};
+		k_lo = (rank == 0) ? 0 : first_entry_at((long long)p.total_pairs * rank / C);
+		k_hi = (rank == C - 1) ? p.n_entry : first_entry_at((long long)p.total_pairs * (rank + 1) / C);
+	}
+	const int t_lo = p.off[k_lo], t_hi = p.off[k_hi];
+	const int n_groups = (n2 + 31) >> 5;
+	cluster.sync();                             // all CTAs are running: remote shared memory is live
+
+	double conv_tol = 0, loglik = -1e+30;
+	int result = EM_OK, iters = 0;
+	for (int iter = 0; iter <= EM_MAX_ITER; iter++)
+	{
+		const double old_loglik = loglik;
+		// ---- E step (:1204-1222) in three passes; loads are issued in batches of 8 so that the
+		// L2 round trips of a thread overlap -----------------------------------------------------
+		// (1) one thread per pair, coalesced: GenoFreq x of the pairs compatible with the new
+		//     genotype, 0.0 for the others (s + 0.0 == s, so they leave every sum untouched)
+		for (int t0 = t_lo + tid; t0 < t_hi; t0 += EM_THREADS * 8)
+		{
+			int4 pr[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int t = t0 + j * EM_THREADS;
+				pr[j] = (t < t_hi) ? __ldg(p.pairs4 + t) : make_int4(0, 0, 0, 0);
+			}
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int t = t0 + j * EM_THREADS;
+				if (t < t_hi)
+				{
+					const int u = pr[j].x & 0xffff, v = (int)((unsigned)pr[j].x >> 16);
+					const int g = gk[pr[j].y];
+					double x = 0.0;
+					if (g == 3 || ((u & 1) + (v & 1)) == g)
+						x = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v]) : __dmul_rn(fr[u], fr[v]);
+					xbuf[t] = x;
+				}
+			}
+		}
+		if (tid == 0) sh_i[2] = 0;                 // group counter of the M step
+		__syncthreads();
+		// (2) one thread per in-bag entry: sum of its pairs in list order, log-likelihood term
+		double ll = 0;
+		for (int k = k_lo + tid; k < k_hi; k += EM_THREADS)
+		{
+			const int b = p.off[k], e = p.off[k + 1];
+			double psum = 0;
+			int t = b;
+			for (; t + 8 <= e; t += 8)
+			{
+				double x[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++) x[j] = xbuf[t + j];
+#pragma unroll
+				for (int j = 0; j < 8; j++) psum = __dadd_rn(psum, x[j]);
+			}
+			for (; t < e; t++) psum = __dadd_rn(psum, xbuf[t]);
+			const double bc = bck[k];
+			ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
+			sck[k] = __ddiv_rn(bc, psum);
+		}
+		ll = block_sum_f64(ll, scratch);           // (its barriers also publish sck)
+		if (tid < C) cluster.map_shared_rank(llp, tid)[(iter & 1) * MAX_CLUSTER + rank] = ll;
+		// (3) one thread per pair: the pair's contribution into the incidence slots of its two
+		//     haplotypes (slots of incompatible pairs were zeroed before the launch)
+		for (int t0 = t_lo + tid; t0 < t_hi; t0 += EM_THREADS * 8)
+		{
+			int4 pr[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int t = t0 + j * EM_THREADS;
+				pr[j] = (t < t_hi) ? __ldg(p.pairs4 + t) : make_int4(0, 0, 0, 0);
+			}
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int t = t0 + j * EM_THREADS;
+				if (t < t_hi)
+				{
+					const int u = pr[j].x & 0xffff, v = (int)((unsigned)pr[j].x >> 16);
+					const int g = gk[pr[j].y];
+					if (g == 3 || ((u & 1) + (v & 1)) == g)
+					{
+						const double x = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v])
+						                          : __dmul_rn(fr[u], fr[v]);
+						const double r = __dmul_rn(x, sck[pr[j].y]);
+						rinc[pr[j].z] = r; rinc[pr[j].w] = r;
+					}
+				}
+			}
+		}
+		cluster.sync();        // every contribution of every CTA is in place (and fr is free to overwrite)
+		// ---- M step: one lane per haplotype, contributions in the reference's order. A warp
+		// takes the next-longest group of 32 chains dealt to this CTA and streams its ELL rows
+		// through a private shared-memory ring with cp.async (L2 -> shared, no L1: other CTAs of
+		// the cluster wrote them), RING_ROWS rows ahead of the fp64 add chain. ------------------
+		if ((tid >> 5) < p.m_warps)
+		{
+			const int lane = tid & 31;
+			const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(
+				rings + (size_t)(tid >> 5) * RING_ROWS * 32) + (uint32_t)lane * 16u;
+			constexpr int NB = RING_ROWS / 8;      // batches of 8 rows (4 row pairs) in flight
+			for (;;)
+			{
+				int gi = 0;
+				if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
+				gi = __shfl_sync(0xffffffffu, gi, 0) * C + rank;
+				if (gi >= n_groups) break;
+				const int nb = p.group_len[gi] >> 3;
+				const char *src = (const char *)(rinc + p.group_base[gi]) + lane * 16;   // + 512 per row pair
+				for (int b = 0; b < NB - 1; b++)
+				{
+					if (b < nb)
+					{
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							cp_async16_cg(ring_s + (uint32_t)(b * 4 + k) * 512u, src + (size_t)(b * 4 + k) * 512);
+					}
+					cp_async_commit();
+				}
+				double acc = 0;
+				int rb = 0;                         // b mod NB
+				for (int b = 0; b < nb; b++)
+				{
+					const int bn = b + NB - 1;
+					if (bn < nb)
+					{
+						const int rbn = (rb + NB - 1) & (NB - 1);
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							cp_async16_cg(ring_s + (uint32_t)(rbn * 4 + k) * 512u, src + (size_t)(bn * 4 + k) * 512);
+					}
+					cp_async_commit();
+					cp_async_wait<NB - 1>();
+					double2 r[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++) r[k] = lds_f64x2(ring_s + (uint32_t)(rb * 4 + k) * 512u);
+#pragma unroll
+					for (int k = 0; k < 4; k++) { acc = __dadd_rn(acc, r[k].x); acc = __dadd_rn(acc, r[k].y); }
+					rb = (rb + 1) & (NB - 1);
+				}
+				cp_async_wait<0>();
+				const int r = 32 * gi + lane;
+				if (r < n2)
+				{
+					const double f = __dmul_rn(acc, p.scale);
+					const int u = p.hap_sorted[r];
+					for (int q = 0; q < C; q++) cluster.map_shared_rank(fr, q)[u] = f;
+				}
+			}
+		}
+		cluster.sync();        // new frequencies and all partial log-likelihoods have landed
+		iters = iter + 1;
+		// ---- stopping rule (:1236-1250) with the guard band of em.h; every CTA evaluates the
+		// same numbers in the same order ---------------------------------------------------------
+		loglik = 0;
+		for (int q = 0; q < C; q++) loglik = __dadd_rn(loglik, llp[(iter & 1) * MAX_CLUSTER + q]);
+		int f = 0;
+		if (iter > 0)
+		{
+			const double diff = fabs(__dsub_rn(loglik, old_loglik));
+			if (fabs(__dsub_rn(diff, conv_tol)) <= em_guard_rel(p.n_entry) * fabs(loglik)) f = 2;
+			else if (diff <= conv_tol) f = 1;
+		} else {
+			conv_tol = __dmul_rn(p.em_reltol, __dadd_rn(fabs(loglik), p.em_reltol));
+			if (conv_tol < 0) conv_tol = 0;
+		}
+		if (f == 2) { result = EM_AMBIGUOUS; break; }
+		if (f == 1) break;
+	}
+	if (rank == 0)
+	{
+		double *out = p.out_freq + (size_t)c * n2;
+		for (int u = tid; u < n2; u += EM_THREADS) out[u] = fr[u];
+		if (tid == 0) { status[0] = result; status[1] = iters; }
+	}
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+RoundEM::RoundEM() { current_device(); h_total_.ensure(4); }
+RoundEM::~RoundEM() {}
+
+void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2, int stride,
+	const int *a1, const int *a2, const int *ib, int n_entry, const int *boot, cudaStream_t st)
+{
+	if (cur.n_snp >= HIBAG_B200_MAX_SNP)
+		throw std::runtime_error("prepare: too many SNP markers in the classifier");
+	if (!supports((int)cur.h.size(), n_entry))
+		throw std::runtime_error("prepare: list too large for the device EM");
+	n_entry_ = n_entry; n_cur_ = (int)cur.h.size(); n2_ = 2 * n_cur_; n_snp_ = cur.n_snp;
+	ib_ = ib; boot_ = boot;
+	const int n_hla = (int)cur.len.size();
+	// stage: packed haplotypes, frequencies, allele starts -> one pinned block, three copies
+	const size_t b_hap = sizeof(uint64_t) * 2 * (size_t)n_cur_, b_fr = sizeof(double) * (size_t)n_cur_;
+	const size_t b_st = sizeof(int) * (size_t)(n_hla + 1);
+	unsigned char *h = h_stage_.ensure(b_hap + b_fr + b_st + 64);
+	uint64_t *hh = (uint64_t *)h;
+	double *hf = (double *)(h + b_hap);
+	int *hs = (int *)(h + b_hap + b_fr);
+	for (int k = 0; k < n_cur_; k++)
+	{
+		hh[2 * k] = (uint64_t)cur.h[k].packed[0]; hh[2 * k + 1] = (uint64_t)cur.h[k].packed[1];
+		hf[k] = cur.h[k].freq;
+	}
+	hs[0] = 0;
+	for (int a = 0; a < n_hla; a++) hs[a + 1] = hs[a] + cur.len[a];
+	d_hap_.ensure(2 * (size_t)n_cur_ + 2); d_curfreq_.ensure(n_cur_ + 1); d_start_.ensure(n_hla + 1);
+	HB_CUDA(cudaMemcpyAsync(d_hap_.get(), hh, b_hap, cudaMemcpyHostToDevice, st));
+	HB_CUDA(cudaMemcpyAsync(d_curfreq_.get(), hf, b_fr, cudaMemcpyHostToDevice, st));
+	HB_CUDA(cudaMemcpyAsync(d_start_.get(), hs, b_st, cudaMemcpyHostToDevice, st));
+	h2d_bytes += b_hap + b_fr + b_st;
+
+	d_cnt_.ensure(n_entry + 1); d_off_.ensure(n_entry + 1); d_mind_.ensure(n_entry + 1);
+	MatchArgs m;
+	memset(&m, 0, sizeof(m));
+	m.hap = d_hap_.get(); m.start = d_start_.get();
+	m.s1 = s1; m.s2 = s2; m.stride = stride; m.a1 = a1; m.a2 = a2; m.ib = ib;
+	m.n_entry = n_entry; m.n_snp = cur.n_snp;
+	m.cnt = d_cnt_.get(); m.mind = d_mind_.get(); m.off = d_off_.get();
+	if (n_entry <= 0) throw std::runtime_error("prepare: no in-bag samples");
+	const int blocks = (n_entry + 127) / 128;
+	HB_CUDA(cudaMemsetAsync(d_cnt_.get() + n_entry, 0, sizeof(int), st));
+	haplomatch_kernel<0><<<blocks, 128, 0, st>>>(m);
+	HB_CUDA(cudaGetLastError());
+	size_t tmp_bytes = 0;
+	HB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt_.get(), d_off_.get(), n_entry + 1, st));
+	d_tmp_.ensure(tmp_bytes + 16);
+	HB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp_.get(), tmp_bytes, d_cnt_.get(), d_off_.get(), n_entry + 1, st));
+	HB_CUDA(cudaMemcpyAsync(h_total_.get(), d_off_.get() + n_entry, sizeof(int), cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaStreamSynchronize(st));
+	total_pairs_ = (size_t)h_total_.get()[0];
+	d2h_bytes += sizeof(int);
+	launches += 2;
+	if (total_pairs_ == 0) return;
+	if (total_pairs_ > (size_t)500000000)
+		throw std::runtime_error("prepare: too many haplotype pairs");
+
+	d_p1_.ensure(total_pairs_); d_p2_.ensure(total_pairs_);
+	m.p1 = d_p1_.get(); m.p2 = d_p2_.get();
+	haplomatch_kernel<1><<<blocks, 128, 0, st>>>(m);
+	HB_CUDA(cudaGetLastError());
+
+	// incidence lists: stable sort of (haplotype, contribution) keeps every haplotype's
+	// contributions in (sample, pair, H1-before-H2) order
+	const int n_inc = (int)(2 * total_pairs_);
+	d_key_.ensure(n_inc); d_val_.ensure(n_inc); d_key2_.ensure(n_inc); d_val2_.ensure(n_inc);
+	d_inc_off_.ensure(n2_ + 2);
+	incidence_fill_kernel<<<((int)total_pairs_ + 255) / 256, 256, 0, st>>>(d_p1_.get(), d_p2_.get(),
+		(int)total_pairs_, d_key_.get(), d_val_.get());
+	HB_CUDA(cudaGetLastError());
+	int end_bit = 1;
+	while ((1 << end_bit) < n2_ + 1) end_bit++;
+	tmp_bytes = 0;
+	HB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key_.get(), d_key2_.get(),
+		d_val_.get(), d_val2_.get(), n_inc, 0, end_bit, st));
+	d_tmp_.ensure(tmp_bytes + 16);
+	HB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp_.get(), tmp_bytes, d_key_.get(), d_key2_.get(),
+		d_val_.get(), d_val2_.get(), n_inc, 0, end_bit, st));
+	incidence_offsets_kernel<<<(n2_ + 1 + 255) / 256, 256, 0, st>>>(d_key2_.get(), n_inc, n2_,
+		d_inc_off_.get());
+	HB_CUDA(cudaGetLastError());
+	// ELL layout: haplotypes by decreasing chain length, groups of 32
+	const int n_groups = (n2_ + 31) / 32;
+	d_len_.ensure(n2_ + 1); d_hapid_.ensure(n2_ + 1); d_len2_.ensure(n2_ + 1); d_hap_sorted_.ensure(n2_ + 1);
+	d_rank_.ensure(n2_ + 1); d_group_len_.ensure(n_groups + 1); d_group_base_.ensure(n_groups + 2);
+	incidence_len_kernel<<<(n2_ + 255) / 256, 256, 0, st>>>(d_inc_off_.get(), n2_, d_len_.get(), d_hapid_.get());
+	HB_CUDA(cudaGetLastError());
+	tmp_bytes = 0;
+	HB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_len_.get(), d_len2_.get(),
+		d_hapid_.get(), d_hap_sorted_.get(), n2_, 0, 32, st));
+	d_tmp_.ensure(tmp_bytes + 16);
+	HB_CUDA(cub::DeviceRadixSort::SortPairsDescending(d_tmp_.get(), tmp_bytes, d_len_.get(), d_len2_.get(),
+		d_hapid_.get(), d_hap_sorted_.get(), n2_, 0, 32, st));
+	incidence_groups_kernel<<<1, 1024, 0, st>>>(d_len2_.get(), d_hap_sorted_.get(), n2_, d_rank_.get(),
+		d_group_len_.get(), d_group_base_.get());
+	HB_CUDA(cudaGetLastError());
+	d_pairs4_.ensure(4 * total_pairs_ + 4);
+	pairs_pack_kernel<<<blocks, 128, 0, st>>>(d_p1_.get(), d_p2_.get(), d_off_.get(), n_entry,
+		d_pairs4_.get());
+	HB_CUDA(cudaGetLastError());
+	incidence_slots_kernel<<<(n_inc + 255) / 256, 256, 0, st>>>(d_key2_.get(), d_val2_.get(), n_inc,
+		d_inc_off_.get(), d_rank_.get(), d_group_base_.get(), d_pairs4_.get());
+	HB_CUDA(cudaGetLastError());
+	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 1, d_group_base_.get() + n_groups, sizeof(int),
+		cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 2, d_group_len_.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaStreamSynchronize(st));
+	n_slots_ = (size_t)h_total_.get()[1];
+	max_chain_ = h_total_.get()[2];
+	if (getenv("HIBAG_B200_EM_DEBUG"))
+	{
+		std::vector<int> c(n_entry);
+		HB_CUDA(cudaMemcpy(c.data(), d_cnt_.get(), sizeof(int) * (size_t)n_entry, cudaMemcpyDeviceToHost));
+		std::sort(c.begin(), c.end());
+		fprintf(stderr, "pairs/entry: median %d p90 %d p99 %d max %d\n", c[n_entry / 2],
+			c[(size_t)n_entry * 9 / 10], c[(size_t)n_entry * 99 / 100], c[n_entry - 1]);
+	}
+	d2h_bytes += 2 * sizeof(int);
+	launches += 8;
+}
+
+void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_samp, cudaStream_t st)
+{
+	if (m <= 0) return;
+	int *hc = h_cand_.ensure(m);
+	for (int i = 0; i < m; i++) hc[i] = cand_snp[i];
+	d_cand_.ensure(m);
+	HB_CUDA(cudaMemcpyAsync(d_cand_.get(), hc, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, st));
+	d_rinc_.ensure((size_t)m * n_slots_ + 2);
+	HB_CUDA(cudaMemsetAsync(d_rinc_.get(), 0, sizeof(double) * (size_t)m * n_slots_, st));
+	d_xbuf_.ensure((size_t)m * total_pairs_ + 2);
+	d_freq_.ensure((size_t)m * n2_ + 2);
+	d_status_.ensure(4 * (size_t)m);
+	h_freq_.ensure((size_t)m * n2_ + 2);
+	h_status_.ensure(4 * (size_t)m);
+	EmArgs a;
+	memset(&a, 0, sizeof(a));
+	a.n_entry = n_entry_; a.n_cur = n_cur_; a.n_samp = n_samp;
+	a.ib = ib_; a.boot = boot_;
+	a.off = d_off_.get(); a.pairs4 = (const int4 *)d_pairs4_.get();
+	a.hap_sorted = d_hap_sorted_.get(); a.group_len = d_group_len_.get(); a.group_base = d_group_base_.get();
+	a.cur_freq = d_curfreq_.get();
+	a.n_slots = n_slots_;
+	a.xbuf = d_xbuf_.get(); a.total_pairs = (int)total_pairs_;
+	a.geno_t = geno_t; a.cand_snp = d_cand_.get();
+	a.rinc = d_rinc_.get(); a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
+	a.scale = 0.5 / n_samp;
+	a.em_reltol = std::sqrt(DBL_EPSILON);
+	const size_t smem_base = sizeof(double) * ((size_t)n2_ + 40 + 2 * MAX_CLUSTER + 2 * (size_t)n_entry_) +
+		sizeof(int) * (size_t)n_entry_ + 16;
+	int m_warps = (int)((220 * 1024 - smem_base) / (sizeof(double) * RING_ROWS * 32));
+	if (m_warps > 8) m_warps = 8;
+	if (m_warps < 1) throw std::runtime_error("run_em: list too large for the device EM");
+	a.m_warps = m_warps;
+	const size_t smem = smem_base + sizeof(double) * RING_ROWS * 32 * (size_t)m_warps;
+	// SMs per candidate: enough pairs per CTA to pay for the cluster barriers, and the whole
+	// round resident at once
+	int cluster = 1;
+	while (cluster < MAX_CLUSTER && total_pairs_ / (2 * (size_t)cluster) >= 6000 &&
+		(size_t)m * 2 * cluster <= (size_t)current_device().sm_count) cluster *= 2;
+	if (const char *e = getenv("HIBAG_B200_EM_CLUSTER")) cluster = std::max(1, std::min(MAX_CLUSTER, atoi(e)));
+	HB_CUDA(cudaFuncSetAttribute(em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+	HB_CUDA(cudaEventRecord(ev0_.e, st));
+	{
+		cudaLaunchConfig_t cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cfg.gridDim = dim3((unsigned)(m * cluster)); cfg.blockDim = dim3(EM_THREADS);
+		cfg.dynamicSmemBytes = smem; cfg.stream = st;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+		cfg.attrs = attr; cfg.numAttrs = 1;
+		HB_CUDA(cudaLaunchKernelEx(&cfg, em_kernel, a));
+	}
+	HB_CUDA(cudaGetLastError());
+	HB_CUDA(cudaEventRecord(ev1_.e, st));
+	HB_CUDA(cudaMemcpyAsync(h_freq_.get(), d_freq_.get(), sizeof(double) * (size_t)m * n2_,
+		cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaMemcpyAsync(h_status_.get(), d_status_.get(), sizeof(int) * 4 * (size_t)m,
+		cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaEventRecord(ev_done_.e, st));
+	HB_CUDA(cudaEventSynchronize(ev_done_.e));
+	float ms = 0;
+	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+	kernel_ms += ms;
+	launches++;
+	h2d_bytes += sizeof(int) * (size_t)m;
+	d2h_bytes += sizeof(double) * (size_t)m * n2_ + sizeof(int) * 4 * (size_t)m;
+}
+
+void RoundEM::fetch_pairs(RoundPairs &out, const std::vector<int> &inbag,
+	const std::vector<int> &boot, cudaStream_t st)
+{
+	const int n = n_entry_;
+	out.n_cur = n_cur_;
+	out.samp.resize(n); out.boot.resize(n); out.off.resize(n + 1);
+	std::vector<int> off(n + 1);
+	out.p1.resize(total_pairs_); out.p2.resize(total_pairs_);
+	HB_CUDA(cudaMemcpyAsync(off.data(), d_off_.get(), sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+	if (total_pairs_)
+	{
+		HB_CUDA(cudaMemcpyAsync(out.p1.data(), d_p1_.get(), sizeof(int) * total_pairs_, cudaMemcpyDeviceToHost, st));
+		HB_CUDA(cudaMemcpyAsync(out.p2.data(), d_p2_.get(), sizeof(int) * total_pairs_, cudaMemcpyDeviceToHost, st));
+	}
+	HB_CUDA(cudaStreamSynchronize(st));
+	for (int k = 0; k < n; k++)
+	{
+		out.samp[k] = inbag[k];
+		out.boot[k] = boot[inbag[k]];
+		out.off[k] = (size_t)off[k];
+	}
+	out.off[n] = (size_t)off[n];
+	d2h_bytes += sizeof(int) * ((size_t)(n + 1) + 2 * total_pairs_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// build_haplomatch hook body
+// ---------------------------------------------------------------------------------------------
+uint32_t *haplomatch_records(const hibag_haplotype *haplo, const size_t *n_haplo, int n_hla,
+	int n_snp, const hibag_genotype *geno, int n_samp, const std::vector<int> &ib, size_t *out_n)
+{
+	current_device();
+	Stream st;
+	std::vector<int> start(n_hla + 1, 0);
+	for (int a = 0; a < n_hla; a++)
+	{
+		if (n_haplo[a] > 65535)
+			throw std::runtime_error("There are too many HLA allele-specific haplotypes (# > 65535).");
+		start[a + 1] = start[a] + (int)n_haplo[a];
+	}
+	const int n_cur = start[n_hla];
+	const int n_entry = (int)ib.size();
+	std::vector<uint64_t> hh(2 * (size_t)n_cur + 2);
+	for (int k = 0; k < n_cur; k++)
+	{
+		hh[2 * k] = (uint64_t)haplo[k].packed[0]; hh[2 * k + 1] = (uint64_t)haplo[k].packed[1];
+	}
+	DevBuf<uint64_t> d_hap; DevBuf<int> d_start, d_ib, d_cnt, d_off, d_mind, d_a1, d_a2, d_boot;
+	DevBuf<uint32_t> d_s1, d_s2, d_rec;
+	DevBuf<unsigned char> d_aos, d_tmp;
+	d_hap.ensure(hh.size()); d_start.ensure(n_hla + 1); d_ib.ensure(n_entry + 1);
+	d_cnt.ensure(n_entry + 1); d_off.ensure(n_entry + 1); d_mind.ensure(n_entry + 1);
+	d_a1.ensure(n_samp); d_a2.ensure(n_samp); d_boot.ensure(n_samp);
+	d_s1.ensure(4 * (size_t)n_samp); d_s2.ensure(4 * (size_t)n_samp);
+	d_aos.ensure(sizeof(hibag_genotype) * (size_t)n_samp);
+	HB_CUDA(cudaMemcpyAsync(d_hap.get(), hh.data(), sizeof(uint64_t) * 2 * (size_t)n_cur, cudaMemcpyHostToDevice, st.s));
+	HB_CUDA(cudaMemcpyAsync(d_start.get(), start.data(), sizeof(int) * (size_t)(n_hla + 1), cudaMemcpyHostToDevice, st.s));
+	HB_CUDA(cudaMemcpyAsync(d_ib.get(), ib.data(), sizeof(int) * (size_t)n_entry, cudaMemcpyHostToDevice, st.s));
+	HB_CUDA(cudaMemcpyAsync(d_aos.get(), geno, sizeof(hibag_genotype) * (size_t)n_samp, cudaMemcpyHostToDevice, st.s));
+	launch_unpack_genotypes(d_aos.get(), n_samp, d_s1.get(), d_s2.get(), n_samp, d_a1.get(),
+		d_a2.get(), d_boot.get(), st.s);
+	MatchArgs m;
+	memset(&m, 0, sizeof(m));
+	m.hap = d_hap.get(); m.start = d_start.get();
+	m.s1 = d_s1.get(); m.s2 = d_s2.get(); m.stride = n_samp;
+	m.a1 = d_a1.get(); m.a2 = d_a2.get(); m.ib = d_ib.get();
+	m.n_entry = n_entry; m.n_snp = n_snp;
+	m.cnt = d_cnt.get(); m.mind = d_mind.get(); m.off = d_off.get();
+	const int blocks = (n_entry + 127) / 128;
+	HB_CUDA(cudaMemsetAsync(d_cnt.get() + n_entry, 0, sizeof(int), st.s));
+	if (n_entry > 0)
+	{
+		haplomatch_kernel<2><<<blocks, 128, 0, st.s>>>(m);
+		HB_CUDA(cudaGetLastError());
+	}
+	size_t tmp_bytes = 0;
+	HB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt.get(), d_off.get(), n_entry + 1, st.s));
+	d_tmp.ensure(tmp_bytes + 16);
+	HB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.get(), tmp_bytes, d_cnt.get(), d_off.get(), n_entry + 1, st.s));
+	int total = 0;
+	HB_CUDA(cudaMemcpyAsync(&total, d_off.get() + n_entry, sizeof(int), cudaMemcpyDeviceToHost, st.s));
+	HB_CUDA(cudaStreamSynchronize(st.s));
+	uint32_t *buf = (uint32_t *)malloc(sizeof(uint32_t) * (1 + 2 * (size_t)total));
+	if (!buf) throw std::runtime_error("build_haplomatch: out of memory");
+	buf[0] = (uint32_t)(2 * total);
+	if (total > 0)
+	{
+		d_rec.ensure(2 * (size_t)total);
+		m.rec = d_rec.get();
+		haplomatch_kernel<3><<<blocks, 128, 0, st.s>>>(m);
+		HB_CUDA(cudaGetLastError());
+		HB_CUDA(cudaMemcpyAsync(buf + 1, d_rec.get(), sizeof(uint32_t) * 2 * (size_t)total,
+			cudaMemcpyDeviceToHost, st.s));
+		HB_CUDA(cudaStreamSynchronize(st.s));
+	}
+	if (out_n) *out_n = 1 + 2 * (size_t)total;
+	return buf;
+}
+
+}  // namespace hb

@@ -313,8 +313,6 @@ bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *
 	static const double EM_INIT_VAL_FRAC = 0.001;          // src/LibHLA.cpp:100
 	static const int EM_MAX_ITER = 500;                    // :98
 	const double EM_RELTOL = std::sqrt(DBL_EPSILON);       // :102
-	static const double MIN_RARE_FREQ = 1e-5;              // LibHLA_ext.h:230
-
 	const int n_entry = (int)rp.samp.size();
 	const int n_cur = rp.n_cur;
 	const int n2 = 2 * n_cur;
@@ -411,6 +409,13 @@ bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *
 		}
 	}
 
+	finish_candidate(cur, freq, rare_prob, out);
+	return true;
+}
+
+void finish_candidate(const HapList &cur, const double *freq, double rare_prob, HapList &out)
+{
+	static const double MIN_RARE_FREQ = 1e-5;              // LibHLA_ext.h:230
 	// drop / merge rare members of each doubled pair (:461-515)
 	out.n_snp = cur.n_snp + 1;
 	out.h.clear();
@@ -453,7 +458,6 @@ bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *
 	const double sc = 1 / sum;
 	for (size_t i = 0; i < out.h.size(); i++) out.h[i].freq *= sc;
 	out.set_tags();
-	return true;
 }
 
 }  // namespace hb

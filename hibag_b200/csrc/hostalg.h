@@ -101,4 +101,8 @@ void prepare_round(const HapList &cur, const std::vector<HostGeno> &geno,
 bool estimate_candidate(const HapList &cur, const RoundPairs &rp, const int8_t *snp_col,
 	int n_samp_total, double rare_prob, EmScratch &scr, HapList &out);
 
+/// EraseDoubleHaplos (:461-515) + renormalisation of a doubled list with frequencies
+/// freq[2 * n_cur] (from the host or the device EM) into the candidate's haplotype list
+void finish_candidate(const HapList &cur, const double *freq, double rare_prob, HapList &out);
+
 }  // namespace hb

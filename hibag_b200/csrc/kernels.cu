@@ -25,6 +25,7 @@
 #include "kernels.h"
 
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -137,12 +138,13 @@ struct HapRec
 
 template <int NW, int R, bool CLAMP, bool SMEM>
 __global__ void __launch_bounds__(CELL_THREADS)
-cell_pass_kernel(const CellPass p)
+cell_pass_kernel(const __grid_constant__ CellBatch p)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	// [0,16): mbarrier | table: n_dist x 32 lanes x 8 B | haplotype records
+	// [0,16): mbarrier | [16,24): list-has-work flags | table: n_dist x 32 lanes x 8 B | records
 	const uint32_t smem_base = smem_u32(smem_raw);
 	const uint32_t bar = smem_base;
+	volatile int *sh_flag = (volatile int *)(smem_raw + 16);
 	const uint32_t tbl_base = smem_base + 128;
 	const uint32_t hap_base = tbl_base + (uint32_t)p.n_dist * 256u;
 	constexpr int REC = (NW <= 2) ? 16 : 32;
@@ -150,28 +152,10 @@ cell_pass_kernel(const CellPass p)
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 
-	if (SMEM)
+	if (SMEM && tid == 0)
 	{
-		if (tid == 0)
-		{
-			mbar_init(bar, 1);
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		}
-		__syncthreads();
-		if (tid == 0)
-		{
-			const uint32_t total = (uint32_t)p.n_hap * REC;
-			mbar_expect_tx(bar, total);
-			const char *src = (const char *)p.hap;
-			uint32_t off = 0;
-			while (off < total)            // pieces of <= 64 KB, all multiples of 16 B
-			{
-				uint32_t n = total - off;
-				if (n > 65536u) n = 65536u;
-				tma_bulk_g2s(hap_base + off, src + off, n, bar);
-				off += n;
-			}
-		}
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	// lane-replicated rare-frequency table: tbl[d][lane]
 	{
@@ -180,163 +164,206 @@ cell_pass_kernel(const CellPass p)
 		for (int k = tid; k < n; k += CELL_THREADS)
 			tbl[k] = __ldg(p.table + (k >> 5));
 	}
-	if (SMEM) mbar_wait(bar, 0);
 	__syncthreads();
 
 	const uint32_t tbl_lane = tbl_base + lane * 8;
-	const char *hap_g = (const char *)p.hap;
 	const int n_groups = (p.n_pos + 32 * R - 1) / (32 * R);
-	const unsigned n_tasks = (unsigned)n_groups * (unsigned)p.n_chunks;
 	const int dmax = p.n_dist - 1;
+	uint32_t phase = 0;
 
-	unsigned task = 0;
-	if (lane == 0) task = atomicAdd(p.task_counter, 1u);
-	task = __shfl_sync(0xffffffffu, task, 0);
-
-	while (task < n_tasks)
+	// A CTA starts on list (blockIdx mod n_lists) and moves on to the next list when the current
+	// one has no tasks left, so all CTAs converge on whatever work remains.
+	for (int k = 0; k < p.n_lists; k++)
 	{
-		unsigned next_task = 0;
-		if (lane == 0) next_task = atomicAdd(p.task_counter, 1u);
+		int l = (int)(blockIdx.x % (unsigned)p.n_lists) + k;
+		if (l >= p.n_lists) l -= p.n_lists;
+		const ListDesc &L = p.lists[l];
+		const unsigned n_tasks = (unsigned)n_groups * (unsigned)L.n_chunks;
+		unsigned int *counter = p.task_counters + l;
 
-		const int chunk_id = task / n_groups;
-		const int group = task - chunk_id * n_groups;
-
-		// ---- genotype bit planes of this lane's R samples -----------------------------
-		uint32_t S1[R][NW], S2[R][NW], V[R][NW];
-		int pos[R];
-#pragma unroll
-		for (int r = 0; r < R; r++)
+		if (p.n_lists > 1)
 		{
-			pos[r] = group * (32 * R) + r * 32 + lane;
-			const bool ok = pos[r] < p.n_pos;
-			int samp = 0;
-			if (ok) samp = p.samp_list ? __ldg(p.samp_list + pos[r]) : pos[r];
-#pragma unroll
-			for (int w = 0; w < NW; w++)
+			if (tid == 0) sh_flag[k & 1] = (*(volatile unsigned int *)counter < n_tasks) ? 1 : 0;
+			__syncthreads();
+			if (!sh_flag[k & 1]) continue;
+		}
+		if (SMEM)
+		{
+			if (tid == 0)
 			{
-				S1[r][w] = ok ? __ldg(p.s1 + (size_t)w * p.geno_stride + samp) : 0u;
-				S2[r][w] = ok ? __ldg(p.s2 + (size_t)w * p.geno_stride + samp) : 0xffffffffu;
+				const uint32_t total = (uint32_t)L.n_hap * REC;
+				mbar_expect_tx(bar, total);
+				const char *src = (const char *)L.hap;
+				uint32_t off = 0;
+				while (off < total)            // pieces of <= 64 KB, all multiples of 16 B
+				{
+					uint32_t n = total - off;
+					if (n > 65536u) n = 65536u;
+					tma_bulk_g2s(hap_base + off, src + off, n, bar);
+					off += n;
+				}
 			}
-			if (p.cand_col != nullptr && ok)
+			mbar_wait(bar, phase);
+			phase ^= 1u;
+		}
+
+		const char *hap_g = (const char *)L.hap;
+		const int8_t *cand_col = L.cand_col;
+		const int cand_bit = L.cand_bit;
+		double *Pl = L.P;
+
+		unsigned task = 0;
+		if (lane == 0) task = atomicAdd(counter, 1u);
+		task = __shfl_sync(0xffffffffu, task, 0);
+
+		while (task < n_tasks)
+		{
+			unsigned next_task = 0;
+			if (lane == 0) next_task = atomicAdd(counter, 1u);
+
+			const int chunk_id = task / n_groups;
+			const int group = task - chunk_id * n_groups;
+
+			// ---- genotype bit planes of this lane's R samples ---------------------------
+			uint32_t S1[R][NW], S2[R][NW], V[R][NW];
+			int pos[R];
+#pragma unroll
+			for (int r = 0; r < R; r++)
 			{
-				// CGenotypeList::AddSNP of the candidate column (src/LibHLA.cpp:609-622, 860-874)
-				const int g = __ldg(p.cand_col + samp);
-				const int cw = p.cand_bit >> 5;
-				const uint32_t bit = 1u << (p.cand_bit & 31);
+				pos[r] = group * (32 * R) + r * 32 + lane;
+				const bool ok = pos[r] < p.n_pos;
+				int samp = 0;
+				if (ok) samp = p.samp_list ? __ldg(p.samp_list + pos[r]) : pos[r];
 #pragma unroll
 				for (int w = 0; w < NW; w++)
 				{
-					if (w == cw)
-					{
-						if (g == 1 || g == 2) S1[r][w] |= bit; else S1[r][w] &= ~bit;
-						if (g == 0 || g == 1) S2[r][w] &= ~bit; else S2[r][w] |= bit;
-					}
+					S1[r][w] = ok ? __ldg(p.s1 + (size_t)w * p.geno_stride + samp) : 0u;
+					S2[r][w] = ok ? __ldg(p.s2 + (size_t)w * p.geno_stride + samp) : 0xffffffffu;
 				}
-			}
-#pragma unroll
-			for (int w = 0; w < NW; w++) V[r][w] = S1[r][w] | ~S2[r][w];
-		}
-
-		const int2 ch = __ldg((const int2 *)p.chunks + chunk_id);    // cell_begin, cell_end
-
-		for (int c = ch.x; c < ch.y; c++)
-		{
-			const int4 ca = __ldg((const int4 *)(p.cells + c));           // a_start,a_n,b_start,b_n
-			const int2 cb = __ldg((const int2 *)((const char *)(p.cells + c) + 16));  // out_idx, diag
-			const int a_start = ca.x, a_n = ca.y, b_start = ca.z, b_n = ca.w;
-			const bool diag = cb.y != 0;
-
-			double sum[R];
-#pragma unroll
-			for (int r = 0; r < R; r++) sum[r] = 0.0;
-
-			for (int ii = 0; ii < a_n; ii++)
-			{
-				HapRec<NW, SMEM> hi;
-				hi.load(hap_base, hap_g, a_start + ii);
-
-				uint32_t K[R][NW];
-				uint32_t tb[R];     // shared address of T[c_i][lane]   (no clamp)
-				int ci[R];          // c_i                                 (clamp)
-#pragma unroll
-				for (int r = 0; r < R; r++)
+				if (cand_col != nullptr && ok)
 				{
-					int c0 = 0;
+					// CGenotypeList::AddSNP of the candidate column (src/LibHLA.cpp:609-622, 860-874)
+					const int g = __ldg(cand_col + samp);
+					const int cw = cand_bit >> 5;
+					const uint32_t bit = 1u << (cand_bit & 31);
 #pragma unroll
 					for (int w = 0; w < NW; w++)
 					{
-						K[r][w] = S1[r][w] & (S2[r][w] | ~hi.h[w]);
-						c0 += __popc((hi.h[w] ^ (S1[r][w] & S2[r][w])) & ~(S1[r][w] ^ S2[r][w]));
-					}
-					ci[r] = c0;
-					tb[r] = tbl_lane + (uint32_t)c0 * 256u;
-				}
-
-				int j0 = 0;
-				double ff;
-				if (diag)
-				{
-					// i2 == i1: (f*f) * T[d(i,i)]   (src/LibHLA.cpp:1658-1659)
-					const double p2 = __dmul_rn(hi.f, hi.f);
-#pragma unroll
-					for (int r = 0; r < R; r++)
-					{
-						int pc = 0;
-#pragma unroll
-						for (int w = 0; w < NW; w++)
-							pc += __popc((hi.h[w] ^ K[r][w]) & V[r][w]);
-						double t;
-						if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
-						else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
-						sum[r] = __dadd_rn(sum[r], __dmul_rn(p2, t));
-					}
-					j0 = ii + 1;
-				}
-				ff = __dmul_rn(2.0, hi.f);    // exact
-
-#pragma unroll 2
-				for (int j = j0; j < b_n; j++)
-				{
-					HapRec<NW, SMEM> hj;
-					hj.load(hap_base, hap_g, b_start + j);
-					const double pf = __dmul_rn(ff, hj.f);
-#pragma unroll
-					for (int r = 0; r < R; r++)
-					{
-						int pc = 0;
-#pragma unroll
-						for (int w = 0; w < NW; w++)
-							pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
-						double t;
-						if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
-						else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
-						sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
+						if (w == cw)
+						{
+							if (g == 1 || g == 2) S1[r][w] |= bit; else S1[r][w] &= ~bit;
+							if (g == 0 || g == 1) S2[r][w] &= ~bit; else S2[r][w] |= bit;
+						}
 					}
 				}
+#pragma unroll
+				for (int w = 0; w < NW; w++) V[r][w] = S1[r][w] | ~S2[r][w];
 			}
 
-#pragma unroll
-			for (int r = 0; r < R; r++)
-				if (pos[r] < p.n_pos)
-					p.P[(size_t)cb.x * p.p_stride + pos[r]] = sum[r];
-		}
+			const int2 ch = __ldg((const int2 *)L.chunks + chunk_id);    // cell_begin, cell_end
 
-		task = __shfl_sync(0xffffffffu, next_task, 0);
+			for (int c = ch.x; c < ch.y; c++)
+			{
+				const int4 ca = __ldg((const int4 *)(L.cells + c));           // a_start,a_n,b_start,b_n
+				const int2 cb = __ldg((const int2 *)((const char *)(L.cells + c) + 16));  // out_idx, diag
+				const int a_start = ca.x, a_n = ca.y, b_start = ca.z, b_n = ca.w;
+				const bool diag = cb.y != 0;
+
+				double sum[R];
+#pragma unroll
+				for (int r = 0; r < R; r++) sum[r] = 0.0;
+
+				for (int ii = 0; ii < a_n; ii++)
+				{
+					HapRec<NW, SMEM> hi;
+					hi.load(hap_base, hap_g, a_start + ii);
+
+					uint32_t K[R][NW];
+					uint32_t tb[R];     // shared address of T[c_i][lane]   (no clamp)
+					int ci[R];          // c_i                                 (clamp)
+#pragma unroll
+					for (int r = 0; r < R; r++)
+					{
+						int c0 = 0;
+#pragma unroll
+						for (int w = 0; w < NW; w++)
+						{
+							K[r][w] = S1[r][w] & (S2[r][w] | ~hi.h[w]);
+							c0 += __popc((hi.h[w] ^ (S1[r][w] & S2[r][w])) & ~(S1[r][w] ^ S2[r][w]));
+						}
+						ci[r] = c0;
+						tb[r] = tbl_lane + (uint32_t)c0 * 256u;
+					}
+
+					int j0 = 0;
+					double ff;
+					if (diag)
+					{
+						// i2 == i1: (f*f) * T[d(i,i)]   (src/LibHLA.cpp:1658-1659)
+						const double p2 = __dmul_rn(hi.f, hi.f);
+#pragma unroll
+						for (int r = 0; r < R; r++)
+						{
+							int pc = 0;
+#pragma unroll
+							for (int w = 0; w < NW; w++)
+								pc += __popc((hi.h[w] ^ K[r][w]) & V[r][w]);
+							double t;
+							if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
+							else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
+							sum[r] = __dadd_rn(sum[r], __dmul_rn(p2, t));
+						}
+						j0 = ii + 1;
+					}
+					ff = __dmul_rn(2.0, hi.f);    // exact
+
+#pragma unroll 2
+					for (int j = j0; j < b_n; j++)
+					{
+						HapRec<NW, SMEM> hj;
+						hj.load(hap_base, hap_g, b_start + j);
+						const double pf = __dmul_rn(ff, hj.f);
+#pragma unroll
+						for (int r = 0; r < R; r++)
+						{
+							int pc = 0;
+#pragma unroll
+							for (int w = 0; w < NW; w++)
+								pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
+							double t;
+							if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
+							else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
+							sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
+						}
+					}
+				}
+
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					if (pos[r] < p.n_pos)
+						Pl[(size_t)cb.x * p.p_stride + pos[r]] = sum[r];
+			}
+
+			task = __shfl_sync(0xffffffffu, next_task, 0);
+		}
+		// every warp is done with this list's records before the next list overwrites them
+		if (p.n_lists > 1) __syncthreads();
 	}
 }
 
 template <int NW, int R, bool CLAMP>
-static void launch_cell_variant(const CellPass &p, int sm_count, cudaStream_t st)
+static void launch_cell_variant(const CellBatch &p, int sm_count, cudaStream_t st)
 {
 	const size_t rec = (NW <= 2) ? 16 : 32;
 	const size_t fixed = 128 + (size_t)p.n_dist * 256;
-	const size_t with_hap = fixed + (size_t)p.n_hap * rec;
+	const size_t with_hap = fixed + (size_t)p.max_hap * rec;
 	const size_t smem_limit = 227 * 1024;
 	const bool in_smem = with_hap <= smem_limit;
 	const size_t smem = in_smem ? with_hap : fixed;
 
 	const int n_groups = (p.n_pos + 32 * R - 1) / (32 * R);
-	const long long n_tasks = (long long)n_groups * p.n_chunks;
+	long long n_tasks = 0;
+	for (int l = 0; l < p.n_lists; l++) n_tasks += (long long)n_groups * p.lists[l].n_chunks;
 	if (n_tasks <= 0) return;
 	const int warps_per_cta = CELL_THREADS / 32;
 	// persistent CTAs: as many as fit by shared memory (<= 8 per SM), never more than needed
@@ -346,6 +373,7 @@ static void launch_cell_variant(const CellPass &p, int sm_count, cudaStream_t st
 	long long grid = (long long)sm_count * cta_per_sm;
 	const long long need = (n_tasks + warps_per_cta - 1) / warps_per_cta;
 	if (grid > need) grid = need;
+	if (grid < p.n_lists) grid = p.n_lists;
 
 	if (in_smem)
 	{
@@ -360,8 +388,10 @@ static void launch_cell_variant(const CellPass &p, int sm_count, cudaStream_t st
 	CUDA_CHECK(cudaGetLastError());
 }
 
-int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cudaStream_t st)
+int launch_cell_batch(const CellBatch &p, int samples_per_lane, int sm_count, cudaStream_t st)
 {
+	if (p.n_lists < 1 || p.n_lists > MAX_BATCH_LISTS)
+		throw std::runtime_error("launch_cell_batch: invalid number of lists");
 	const int nw = geno_words(p.n_snp);
 	const bool clamp = (2 * p.n_snp) > (p.n_dist - 1);
 	int R = samples_per_lane;
@@ -375,7 +405,21 @@ int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cuda
 	HB_CASE(2, 1) HB_CASE(2, 2) HB_CASE(2, 4)
 	HB_CASE(4, 1) HB_CASE(4, 2)
 #undef HB_CASE
-	throw std::runtime_error("launch_cell_pass: unsupported configuration");
+	throw std::runtime_error("launch_cell_batch: unsupported configuration");
+}
+
+int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cudaStream_t st)
+{
+	CellBatch b;
+	memset(&b, 0, sizeof(b));
+	b.table = p.table; b.s1 = p.s1; b.s2 = p.s2; b.samp_list = p.samp_list;
+	b.task_counters = p.task_counter; b.p_stride = p.p_stride;
+	b.n_dist = p.n_dist; b.n_snp = p.n_snp; b.geno_stride = p.geno_stride; b.n_pos = p.n_pos;
+	b.n_lists = 1; b.max_hap = p.n_hap;
+	ListDesc &L = b.lists[0];
+	L.hap = p.hap; L.cells = p.cells; L.chunks = p.chunks; L.cand_col = p.cand_col; L.P = p.P;
+	L.n_hap = p.n_hap; L.n_chunks = p.n_chunks; L.cand_bit = p.cand_bit;
+	return launch_cell_batch(b, samples_per_lane, sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -457,11 +501,13 @@ __device__ __forceinline__ double seqsum_cells(const double *P, size_t stride, i
 	return s;
 }
 
-__global__ void reduce_oob_kernel(const double *__restrict__ P, size_t p_stride, int n_hla,
-	const int *__restrict__ samp_list, int n_pos, const int *__restrict__ a1,
+__global__ void reduce_oob_kernel(const double *__restrict__ P, size_t p_stride, size_t list_stride,
+	int n_hla, const int *__restrict__ samp_list, int n_pos, const int *__restrict__ a1,
 	const int *__restrict__ a2, int *out_count)
 {
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	P += (size_t)blockIdx.y * list_stride;        // one haplotype list per blockIdx.y
+	out_count += blockIdx.y;
 	int cnt = 0;
 	if (pos < n_pos)
 	{
@@ -483,20 +529,24 @@ __global__ void reduce_oob_kernel(const double *__restrict__ P, size_t p_stride,
 }
 
 void launch_reduce_oob(const double *P, size_t p_stride, int n_hla, const int *samp_list,
-	int n_pos, const int *a1, const int *a2, int *out_count, cudaStream_t st)
+	int n_pos, const int *a1, const int *a2, int *out_count, cudaStream_t st, int n_lists,
+	size_t list_stride)
 {
-	if (n_pos <= 0) return;
-	reduce_oob_kernel<<<(n_pos + 63) / 64, 64, 0, st>>>(P, p_stride, n_hla, samp_list, n_pos,
+	if (n_pos <= 0 || n_lists <= 0) return;
+	dim3 grid((n_pos + 63) / 64, n_lists);
+	reduce_oob_kernel<<<grid, 64, 0, st>>>(P, p_stride, list_stride, n_hla, samp_list, n_pos,
 		a1, a2, out_count);
 	CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void reduce_ib_kernel(const double *__restrict__ P, size_t p_stride, int n_hla,
-	const int *__restrict__ samp_list, int n_pos, const int *__restrict__ a1,
-	const int *__restrict__ a2, double *out_ratio)
+__global__ void reduce_ib_kernel(const double *__restrict__ P, size_t p_stride, size_t list_stride,
+	int n_hla, const int *__restrict__ samp_list, int n_pos, const int *__restrict__ a1,
+	const int *__restrict__ a2, double *out_ratio, size_t out_stride)
 {
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
 	if (pos >= n_pos) return;
+	P += (size_t)blockIdx.y * list_stride;
+	out_ratio += (size_t)blockIdx.y * out_stride;
 	const int n_cells = n_hla * (n_hla + 1) / 2;
 	const double s = seqsum_cells(P + pos, p_stride, n_cells);
 	const int samp = samp_list ? samp_list[pos] : pos;
@@ -507,11 +557,13 @@ __global__ void reduce_ib_kernel(const double *__restrict__ P, size_t p_stride, 
 }
 
 void launch_reduce_ib(const double *P, size_t p_stride, int n_hla, const int *samp_list,
-	int n_pos, const int *a1, const int *a2, double *out_ratio, cudaStream_t st)
+	int n_pos, const int *a1, const int *a2, double *out_ratio, cudaStream_t st, int n_lists,
+	size_t list_stride, size_t out_stride)
 {
-	if (n_pos <= 0) return;
-	reduce_ib_kernel<<<(n_pos + 63) / 64, 64, 0, st>>>(P, p_stride, n_hla, samp_list, n_pos,
-		a1, a2, out_ratio);
+	if (n_pos <= 0 || n_lists <= 0) return;
+	dim3 grid((n_pos + 63) / 64, n_lists);
+	reduce_ib_kernel<<<grid, 64, 0, st>>>(P, p_stride, list_stride, n_hla, samp_list, n_pos,
+		a1, a2, out_ratio, out_stride);
 	CUDA_CHECK(cudaGetLastError());
 }
 

@@ -55,6 +55,35 @@ struct CellPass
 	size_t p_stride;
 };
 
+/// One haplotype list of a batched launch (all lists of a batch share the samples, the SNP
+/// count and the table; each has its own cells/chunks, optional candidate SNP column and
+/// output matrix). Passed by value inside the kernel parameters.
+struct ListDesc
+{
+	const void *hap;
+	const CellTask *cells;
+	const Chunk *chunks;
+	const int8_t *cand_col;       // raw genotype column patched in at bit cand_bit, or null
+	double *P;                    // P[out_idx * p_stride + pos]
+	int n_hap, n_chunks, cand_bit, pad;
+};
+
+static const int MAX_BATCH_LISTS = 32;
+
+/// Device-side description of one launch of the pair-scoring kernel: n_lists haplotype lists
+/// (e.g. the candidate SNPs of one selection round) against one list of samples.
+struct CellBatch
+{
+	const double *table;
+	const uint32_t *s1, *s2;
+	const int *samp_list;
+	unsigned int *task_counters;  // [n_lists], zeroed before launch
+	size_t p_stride;
+	int n_dist, n_snp, geno_stride, n_pos;
+	int n_lists, max_hap;         // max_hap = largest n_hap of the batch (shared-memory sizing)
+	ListDesc lists[MAX_BATCH_LISTS];
+};
+
 /// bytes of one haplotype record in kernel layout for a classifier of n_snp SNPs
 inline int hap_record_bytes(int n_snp) { return (n_snp <= 64) ? 16 : 32; }
 /// number of 32-bit genotype words the kernels use for n_snp SNPs (1, 2 or 4)
@@ -63,6 +92,8 @@ inline int geno_words(int n_snp) { return (n_snp <= 32) ? 1 : ((n_snp <= 64) ? 2
 /// Launch the pair-scoring kernel. samples_per_lane in {1,2,4}. Returns the number of POPC.32
 /// issued per pair evaluation by the chosen instantiation (1, 2 or 4) for accounting.
 int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cudaStream_t st);
+/// the same for a batch of lists (n_lists <= MAX_BATCH_LISTS)
+int launch_cell_batch(const CellBatch &b, int samples_per_lane, int sm_count, cudaStream_t st);
 
 /// AoS TGenotype[n] (48 B) -> SoA words + true alleles + bootstrap counts
 void launch_unpack_genotypes(const void *geno_aos, int n, uint32_t *s1, uint32_t *s2,
@@ -70,12 +101,16 @@ void launch_unpack_genotypes(const void *geno_aos, int n, uint32_t *s1, uint32_t
 
 /// out-of-bag accuracy: per position argmax over cells (strict '<', first wins), compare with
 /// the true type (src/LibHLA.cpp:912-924), integer sum into *out_count (zeroed by the caller)
+/// (n_lists > 1: list l reads P + l*list_stride and adds into out_count[l])
 void launch_reduce_oob(const double *P, size_t p_stride, int n_hla, const int *samp_list,
-	int n_pos, const int *a1, const int *a2, int *out_count, cudaStream_t st);
+	int n_pos, const int *a1, const int *a2, int *out_count, cudaStream_t st, int n_lists = 1,
+	size_t list_stride = 0);
 
 /// in-bag: per position P_true / sum_cells (sequential sum in cell order)
+/// (n_lists > 1: list l reads P + l*list_stride and writes out_ratio + l*out_stride)
 void launch_reduce_ib(const double *P, size_t p_stride, int n_hla, const int *samp_list,
-	int n_pos, const int *a1, const int *a2, double *out_ratio, cudaStream_t st);
+	int n_pos, const int *a1, const int *a2, double *out_ratio, cudaStream_t st, int n_lists = 1,
+	size_t list_stride = 0, size_t out_stride = 0);
 
 /// best guess per position written as allele pair (for hibag_b200_best_guess)
 void launch_reduce_best_guess(const double *P, size_t p_stride, int n_hla, int n_pos,

@@ -1,6 +1,7 @@
 // scorer.cu -- see scorer.h
 #include "scorer.h"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -160,6 +161,172 @@ void EvalSlot::sync()
 		stats.cell_ms += ms;
 		timing_pending_ = false;
 	}
+}
+
+// ---- ScoreQueue / BatchScorer ------------------------------------------------------------------
+static std::mutex g_queue_mutex;
+static std::map<int, ScoreQueue *> g_queues;
+
+ScoreQueue &ScoreQueue::get()
+{
+	const DeviceInfo &di = current_device();
+	std::lock_guard<std::mutex> lk(g_queue_mutex);
+	auto it = g_queues.find(di.device);
+	if (it != g_queues.end()) return *it->second;
+	ScoreQueue *q = new ScoreQueue();       // lives for the process (one stream per device)
+	g_queues[di.device] = q;
+	return *q;
+}
+
+BatchScorer::BatchScorer()
+{
+	current_device();
+}
+
+void BatchScorer::begin_round(int n_lists, int max_hap, int n_snp, int n_hla)
+{
+	n_snp_ = n_snp; n_hla_ = n_hla; n_cells_ = n_hla * (n_hla + 1) / 2;
+	cap_ = (list_blob_capacity(max_hap, n_snp, n_hla) + 255) & ~(size_t)255;
+	h_blobs_.ensure(cap_ * (size_t)n_lists);
+	d_blobs_.ensure(cap_ * (size_t)n_lists);
+	blobs_.assign(n_lists, ListBlob());
+	cols_.assign(n_lists, nullptr);
+	counters_.ensure(n_lists);
+	d_counts_.ensure(n_lists);
+	h_counts_.ensure(n_lists);
+}
+
+void BatchScorer::upload(const std::vector<int> &which)
+{
+	for (int i : which)
+	{
+		HB_CUDA(cudaMemcpyAsync(d_blobs_.get() + (size_t)i * cap_, h_blobs_.get() + (size_t)i * cap_,
+			blobs_[i].bytes, cudaMemcpyHostToDevice, st_.s));
+		stats.h2d_bytes += blobs_[i].bytes;
+	}
+	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+}
+
+void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<int> &which,
+	int first, int count, const int *pos_list, int n_pos)
+{
+	const DeviceInfo &di = current_device();
+	CellBatch b;
+	memset(&b, 0, sizeof(b));
+	b.table = device_rare_freq_table();
+	b.s1 = g.s1; b.s2 = g.s2; b.geno_stride = g.stride;
+	b.samp_list = pos_list; b.n_pos = n_pos;
+	b.task_counters = counters_.get();
+	b.p_stride = p_stride_;
+	b.n_snp = n_snp_;
+	b.n_lists = count;
+	int total_chunks = 0;
+	uint64_t pairs = 0;
+	for (int k = 0; k < count; k++)
+	{
+		const int i = which[first + k];
+		const ListBlob &lb = blobs_[i];
+		const unsigned char *d = d_blobs_.get() + (size_t)i * cap_;
+		ListDesc &L = b.lists[k];
+		L.hap = d;
+		L.cells = (const CellTask *)(d + lb.off_cells);
+		L.chunks = (const Chunk *)(d + lb.off_chunks);
+		L.cand_col = cols_[i];
+		L.cand_bit = cand_bit;
+		L.P = P_.get() + (size_t)(first + k) * n_cells_ * p_stride_;
+		L.n_hap = lb.n_hap; L.n_chunks = lb.n_chunks;
+		b.n_dist = lb.n_dist;
+		if (lb.n_hap > b.max_hap) b.max_hap = lb.n_hap;
+		total_chunks += lb.n_chunks;
+		pairs += lb.pairs_per_sample;
+	}
+	const int R = choose_samples_per_lane(n_pos, total_chunks, n_snp_, di.sm_count);
+	ScoreQueue &q = ScoreQueue::get();
+	int nw;
+	{
+		std::lock_guard<std::mutex> lk(q.mu);
+		HB_CUDA(cudaStreamWaitEvent(q.st.s, ev_up_.e, 0));
+		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * (size_t)count, q.st.s));
+		HB_CUDA(cudaEventRecord(ev0_.e, q.st.s));
+		nw = launch_cell_batch(b, R, di.sm_count, q.st.s);
+		HB_CUDA(cudaEventRecord(ev1_.e, q.st.s));
+	}
+	HB_CUDA(cudaStreamWaitEvent(st_.s, ev1_.e, 0));
+	// the next sub-batch (or pass) reuses the counters: keep its memset behind this kernel
+	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	stats.launches++; stats.cell_launches++;
+	stats.pair_evals += pairs * (uint64_t)n_pos;
+	stats.popc32 += pairs * (uint64_t)n_pos * (uint64_t)nw;
+}
+
+void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<int> &which,
+	const int *pos_list, int n_pos, std::vector<int> &counts)
+{
+	const int n = (int)which.size();
+	counts.assign(n, 0);
+	if (n == 0 || n_pos <= 0) return;
+	p_stride_ = ((size_t)n_pos + 31) & ~(size_t)31;
+	P_.ensure((size_t)n * n_cells_ * p_stride_);
+	HB_CUDA(cudaMemsetAsync(d_counts_.get(), 0, sizeof(int) * (size_t)n, st_.s));
+	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	for (int first = 0; first < n; first += MAX_BATCH_LISTS)
+	{
+		const int count = std::min(MAX_BATCH_LISTS, n - first);
+		run_cells(g, cand_bit, which, first, count, pos_list, n_pos);
+		float ms = 0;
+		if (first + count < n)        // counters are reused by the next sub-batch
+		{
+			HB_CUDA(cudaEventSynchronize(ev1_.e));
+			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+			stats.cell_ms += ms; stats.kernel_ms += ms;
+		}
+	}
+	launch_reduce_oob(P_.get(), p_stride_, n_hla_, pos_list, n_pos, g.a1, g.a2, d_counts_.get(),
+		st_.s, n, (size_t)n_cells_ * p_stride_);
+	HB_CUDA(cudaMemcpyAsync(h_counts_.get(), d_counts_.get(), sizeof(int) * (size_t)n,
+		cudaMemcpyDeviceToHost, st_.s));
+	HB_CUDA(cudaEventRecord(ev_done_.e, st_.s));
+	HB_CUDA(cudaEventSynchronize(ev_done_.e));
+	float ms = 0;
+	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+	stats.cell_ms += ms; stats.kernel_ms += ms;
+	stats.launches++; stats.d2h_bytes += sizeof(int) * (size_t)n;
+	for (int k = 0; k < n; k++) counts[k] = h_counts_.get()[k];
+}
+
+void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<int> &which,
+	const int *pos_list, int n_pos)
+{
+	const int n = (int)which.size();
+	if (n == 0 || n_pos <= 0) return;
+	p_stride_ = ((size_t)n_pos + 31) & ~(size_t)31;
+	ratio_stride_ = p_stride_;
+	P_.ensure((size_t)n * n_cells_ * p_stride_);
+	d_ratio_.ensure((size_t)n * ratio_stride_);
+	h_ratio_.ensure((size_t)n * ratio_stride_);
+	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	for (int first = 0; first < n; first += MAX_BATCH_LISTS)
+	{
+		const int count = std::min(MAX_BATCH_LISTS, n - first);
+		run_cells(g, cand_bit, which, first, count, pos_list, n_pos);
+		if (first + count < n)
+		{
+			float ms = 0;
+			HB_CUDA(cudaEventSynchronize(ev1_.e));
+			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+			stats.cell_ms += ms; stats.kernel_ms += ms;
+		}
+	}
+	launch_reduce_ib(P_.get(), p_stride_, n_hla_, pos_list, n_pos, g.a1, g.a2, d_ratio_.get(),
+		st_.s, n, (size_t)n_cells_ * p_stride_, ratio_stride_);
+	HB_CUDA(cudaMemcpyAsync(h_ratio_.get(), d_ratio_.get(), sizeof(double) * (size_t)n * ratio_stride_,
+		cudaMemcpyDeviceToHost, st_.s));
+	HB_CUDA(cudaEventRecord(ev_done_.e, st_.s));
+	HB_CUDA(cudaEventSynchronize(ev_done_.e));
+	float ms = 0;
+	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+	stats.cell_ms += ms; stats.kernel_ms += ms;
+	stats.launches++; stats.d2h_bytes += sizeof(double) * (size_t)n * ratio_stride_;
 }
 
 }  // namespace hb

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -92,6 +93,62 @@ private:
 	PinBuf<int> h_count_;
 	DevBuf<double> d_ratio_;
 	PinBuf<double> h_ratio_;
+};
+
+/// The one stream per device on which every batched pair-scoring launch of the training path
+/// is enqueued, from however many classifiers are being grown concurrently: launches run one
+/// after the other (each fills the GPU), so the CUDA events around a launch time that launch
+/// alone.
+struct ScoreQueue
+{
+	std::mutex mu;
+	Stream st;
+	static ScoreQueue &get();            // of the current device
+};
+
+/// Scores the candidate haplotype lists of one selection round in ONE launch per pass
+/// (out-of-bag, then in-bag for the candidates that need it). Owned by one trainer lane.
+class BatchScorer
+{
+public:
+	BatchScorer();
+	/// reserve pinned + device staging for n_lists lists of at most max_hap haplotypes
+	void begin_round(int n_lists, int max_hap, int n_snp, int n_hla);
+	/// pinned staging area of list i (capacity list_blob_capacity(max_hap, ...)); thread-safe
+	/// for distinct i
+	unsigned char *host_blob(int i) const { return h_blobs_.get() + (size_t)i * cap_; }
+	void set_list(int i, const ListBlob &b, const int8_t *cand_col) { blobs_[i] = b; cols_[i] = cand_col; }
+	/// async H2D of the lists in `which`
+	void upload(const std::vector<int> &which);
+	/// out-of-bag correct-allele counts of the lists in `which` -> counts[k] (blocks)
+	void score_oob(const GenoView &g, int cand_bit, const std::vector<int> &which,
+		const int *pos_list, int n_pos, std::vector<int> &counts);
+	/// in-bag P_true/sum ratios of the lists in `which`; ratios(k) valid until the next call
+	void score_ib(const GenoView &g, int cand_bit, const std::vector<int> &which,
+		const int *pos_list, int n_pos);
+	const double *ratios(int k) const { return h_ratio_.get() + (size_t)k * ratio_stride_; }
+	ScoreStats stats;
+
+private:
+	void run_cells(const GenoView &g, int cand_bit, const std::vector<int> &which, int first,
+		int count, const int *pos_list, int n_pos);
+	Stream st_;
+	Event ev_up_{false}, ev0_, ev1_;
+	Event ev_done_{false, true};
+	size_t cap_ = 0;
+	int n_snp_ = 0, n_hla_ = 0, n_cells_ = 0;
+	PinBuf<unsigned char> h_blobs_;
+	DevBuf<unsigned char> d_blobs_;
+	std::vector<ListBlob> blobs_;
+	std::vector<const int8_t *> cols_;
+	DevBuf<double> P_;
+	size_t p_stride_ = 0;
+	DevBuf<unsigned int> counters_;
+	DevBuf<int> d_counts_;
+	PinBuf<int> h_counts_;
+	DevBuf<double> d_ratio_;
+	PinBuf<double> h_ratio_;
+	size_t ratio_stride_ = 0;
 };
 
 /// samples per lane for a pass over n_pos samples with n_chunks chunks

@@ -21,11 +21,13 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
 #include <thread>
 
+#include "em.h"
 #include "model.h"
 
 namespace hb {
@@ -153,25 +155,26 @@ struct Candidate
 	int acc = 0;
 	double loss = 0;
 	HapList list;
+	ListBlob blob;
 };
 
 class Trainer : public TrainSession
 {
 public:
-	Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o);
+	Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads);
 	~Trainer() override;
-	void run();
+	/// grow the classifiers with the given global indices into built_ / ts_ / trace_
+	void run(const std::vector<int> &indices);
 	/// can this session (threads, scoring mode) serve a call with these options?
-	bool compatible(const hibag_b200_train_opts &o) const
-	{
-		return (o.use_legacy_hooks != 0) == (procs_ != nullptr) && o.n_threads == requested_threads_ &&
-			(o.mtry <= 0 ? 1 : o.mtry) == o_.mtry;
-	}
 	void configure(const hibag_b200_train_opts &o)
 	{
 		o_ = o;
 		if (o_.mtry <= 0) o_.mtry = 1;
 	}
+	// results of the last run()
+	std::vector<std::pair<int, Classifier> > built_;
+	hibag_b200_train_stats ts_;
+	std::vector<int64_t> trace_;
 
 private:
 	void grow(Classifier &c);
@@ -195,39 +198,30 @@ private:
 
 	// device-resident state
 	DevBuf<int8_t> d_geno_t_;                // raw genotypes, SNP-major
-	DevBuf<int> d_a1_, d_a2_, d_oob_, d_ib_;
+	DevBuf<int> d_a1_, d_a2_, d_oob_, d_ib_, d_boot_;
+	std::unique_ptr<RoundEM> rem_;                    // device-side pair matching + EM
 	DevBuf<uint32_t> d_s1_, d_s2_;           // base bit planes [4][n_samp]
 	PinBuf<uint32_t> h_planes_;
 	Stream main_st_;
-	std::vector<std::unique_ptr<EvalSlot> > slots_;   // one per candidate of a round
+	std::unique_ptr<BatchScorer> scorer_;             // all candidates of a round per launch
 	std::vector<EmScratch> scratch_;                  // one per worker
 	std::vector<double> em_seconds_, wait_seconds_;   // per worker
 
 	int64_t cl_global_index_ = 0;
-	int requested_threads_ = 0;
 	hibag_gpu_ext_proc *procs_ = nullptr;    // legacy-hook mode
 	ScoreStats stats_;
 };
 
-Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o) : m_(m), o_(o)
+Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads)
+	: m_(m), o_(o)
 {
 	dev_ = &current_device();
+	memset(&ts_, 0, sizeof(ts_));
 	n_samp_ = m.n_samp; n_snp_ = m.n_snp; n_hla_ = m.n_hla;
 	if (n_samp_ <= 0 || m.geno_t.empty())
 		throw std::runtime_error("train: no training data (call hibag_b200_model_set_training)");
 	if (o_.mtry <= 0) o_.mtry = 1;
-	requested_threads_ = o.n_threads;
-	int nt = o_.n_threads;
-	if (nt <= 0) nt = (int)std::thread::hardware_concurrency();
-	if (nt < 1) nt = 1;
-	if (o_.n_threads <= 0)
-	{
-		// one worker per candidate of a round when that is a modest over-subscription: 23
-		// equal EM jobs on 16 cores finish in ~1.4 job-times instead of 2
-		if (o_.mtry > nt && o_.mtry <= 2 * nt) nt = o_.mtry;
-		if (nt > std::max(o_.mtry, 4)) nt = std::max(o_.mtry, 4);
-	}
-	pool_.reset(new ThreadPool(nt, dev_->device));
+	pool_.reset(new ThreadPool(n_pool_threads, dev_->device));
 	scratch_.resize(pool_->size());
 	em_seconds_.assign(pool_->size(), 0.0);
 	wait_seconds_.assign(pool_->size(), 0.0);
@@ -256,6 +250,9 @@ Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o) : m_(m), o
 		d_s1_.ensure((size_t)4 * n_samp_); d_s2_.ensure((size_t)4 * n_samp_);
 		h_planes_.ensure((size_t)8 * n_samp_);
 		device_rare_freq_table();
+		scorer_.reset(new BatchScorer());
+		d_boot_.ensure(n_samp_);
+		rem_.reset(new RoundEM());
 	}
 }
 
@@ -327,20 +324,23 @@ double Trainer::ib_loss(const double *ratio) const
 	return loglik * -2;
 }
 
-void Trainer::run()
+void Trainer::run(const std::vector<int> &indices)
 {
 	const double t0 = now_s();
 	// the session outlives a call: start this call's counters from zero
 	stats_ = ScoreStats();
-	for (auto &sl : slots_) if (sl) sl->stats = ScoreStats();
+	memset(&ts_, 0, sizeof(ts_));
+	built_.clear();
+	trace_.clear();
+	if (scorer_) scorer_->stats = ScoreStats();
+	if (rem_) { rem_->kernel_ms = 0; rem_->launches = 0; rem_->h2d_bytes = 0; rem_->d2h_bytes = 0; }
 	const ScoreStats plugin_before = procs_ ? plugin_build_stats() : ScoreStats();
 	std::fill(em_seconds_.begin(), em_seconds_.end(), 0.0);
 	std::fill(wait_seconds_.begin(), wait_seconds_.end(), 0.0);
 	if (!o_.per_classifier_seed) rng_.set_seed((uint32_t)o_.seed);
-	const int stride = o_.index_stride > 0 ? o_.index_stride : 1;
-	for (int c = 0; c < o_.nclassifier; c++)
+	for (size_t c = 0; c < indices.size(); c++)
 	{
-		const int global_k = o_.first_index + c * stride;
+		const int global_k = indices[c];
 		if (o_.per_classifier_seed) rng_.set_seed((uint32_t)(o_.seed + global_k));
 		// bootstrap; redraw the whole sample when nobody is left out of the bag (:2229-2240)
 		boot_.assign(n_samp_, 0);
@@ -357,8 +357,8 @@ void Trainer::run()
 		} while (n_unique >= n_samp_);
 
 		cl_global_index_ = global_k;
-		m_.cls.emplace_back();
-		Classifier &cl = m_.cls.back();
+		built_.emplace_back(global_k, Classifier());
+		Classifier &cl = built_.back().second;
 		cl.samp_num = boot_;
 		if (o_.verbose)
 		{
@@ -373,7 +373,13 @@ void Trainer::run()
 		}
 	}
 	// fold the counters
-	for (auto &s : slots_) if (s) stats_.add(s->stats);
+	if (scorer_) stats_.add(scorer_->stats);
+	if (rem_)
+	{
+		stats_.launches += rem_->launches; stats_.kernel_ms += rem_->kernel_ms;
+		stats_.h2d_bytes += rem_->h2d_bytes; stats_.d2h_bytes += rem_->d2h_bytes;
+		ts_.em_kernel_ms += rem_->kernel_ms;
+	}
 	if (procs_)
 	{
 		ScoreStats now = plugin_build_stats();
@@ -383,7 +389,7 @@ void Trainer::run()
 		now.kernel_ms -= plugin_before.kernel_ms; now.cell_ms -= plugin_before.cell_ms;
 		stats_.add(now);
 	}
-	hibag_b200_train_stats &ts = m_.train_stats;
+	hibag_b200_train_stats &ts = ts_;
 	ts.seconds_total += now_s() - t0;
 	for (double v : em_seconds_) ts.seconds_em += v;
 	for (double v : wait_seconds_) ts.seconds_gpu_wait += v;
@@ -403,7 +409,7 @@ void Trainer::grow(Classifier &cl)
 	static const double MIN_RARE_FREQ = 1e-5;
 	static const double STOP_RELTOL_LOGLIK_ADDSNP = 0.001;     // :114
 	static const double PRUNE_RELTOL_LOGLIK = 0.1;             // :116
-	hibag_b200_train_stats &ts = m_.train_stats;
+	hibag_b200_train_stats &ts = ts_;
 
 	// ---- InitSelection (:1843-1878) ------------------------------------------------------
 	inbag_.clear(); oob_.clear();
@@ -422,7 +428,9 @@ void Trainer::grow(Classifier &cl)
 			cudaMemcpyHostToDevice, main_st_.s));
 		HB_CUDA(cudaMemcpyAsync(d_ib_.get(), inbag_.data(), sizeof(int) * inbag_.size(),
 			cudaMemcpyHostToDevice, main_st_.s));
-		stats_.h2d_bytes += sizeof(int) * (size_t)n_samp_;
+		HB_CUDA(cudaMemcpyAsync(d_boot_.get(), boot_.data(), sizeof(int) * (size_t)n_samp_,
+			cudaMemcpyHostToDevice, main_st_.s));
+		stats_.h2d_bytes += 2 * sizeof(int) * (size_t)n_samp_;
 		upload_base_geno();
 	}
 
@@ -481,87 +489,119 @@ void Trainer::grow(Classifier &cl)
 	view.s1 = d_s1_.get(); view.s2 = d_s2_.get(); view.stride = n_samp_;
 	view.a1 = d_a1_.get(); view.a2 = d_a2_.get();
 
+	const bool dev_em_wanted = (o_.em_on_device != 0) && !procs_;
+	bool dev_em = dev_em_wanted;
+	bool pairs_dirty = true;       // the pair lists depend on `cur` and the accepted SNPs only
+	bool host_rp_valid = false;
+	std::vector<int> cand_snps;
+
 	while (pool.total() > 0 && (int)cl.snpidx.size() < HIBAG_B200_MAX_SNP)
 	{
 		const double t_prep = now_s();
-		prepare_round(cur, geno_, a1_, a2_, boot_, inbag_, rp, pool_parallel_for, &pf);
+		if (pairs_dirty)
+		{
+			dev_em = dev_em_wanted && RoundEM::supports((int)cur.h.size(), (int)inbag_.size());
+			if (dev_em)
+			{
+				rem_->prepare(cur, d_s1_.get(), d_s2_.get(), n_samp_, d_a1_.get(), d_a2_.get(),
+					d_ib_.get(), (int)inbag_.size(), d_boot_.get(), main_st_.s);
+				host_rp_valid = false;
+			} else {
+				prepare_round(cur, geno_, a1_, a2_, boot_, inbag_, rp, pool_parallel_for, &pf);
+			}
+			pairs_dirty = false;
+		}
 		ts.seconds_prepare += now_s() - t_prep;
 
 		pool.random_select(o_.mtry, rng_);
 		const int m = pool.n_selected();
 		if ((int)cand.size() < m) cand.resize(m);
-		while ((int)slots_.size() < m && !procs_) slots_.emplace_back(new EvalSlot());
 		const int bit = cur.n_snp;
+		if (!procs_) scorer_->begin_round(m, 2 * (int)cur.h.size(), bit + 1, n_hla_);
 
-		// ---- candidates in parallel: EM, out-of-bag accuracy, and -- speculatively -- the in-bag
-		// loss. The reference computes the loss only when acc >= the running maximum over the
-		// earlier candidates (:2033). A worker that finishes candidate i knows the accuracies of
-		// the earlier candidates that are already done; their maximum is a lower bound of the true
-		// threshold, so "acc >= that bound" never misses a loss the reference would compute. Losses
-		// computed in excess are discarded below (the reference keeps loss = 0 for them).
+		// ---- phase 1: EM of the candidates. Device: one launch, one CTA per candidate; the host
+		// then only prunes rare haplotypes and packs the lists (in parallel on the pool), and
+		// re-estimates on the host the rare candidate whose stopping test the device could not
+		// decide (em.h). Host: the candidates' EM in parallel on the pool.
 		const double t_p1 = now_s();
-		std::vector<std::atomic<int> > pub(m);          // published accuracy, -1 = not yet, -2 = skipped
-		for (int i = 0; i < m; i++) pub[i].store(-1, std::memory_order_relaxed);
-		std::vector<unsigned char> have_loss(m, 0);
+		if (dev_em)
+		{
+			cand_snps.resize(m);
+			for (int i = 0; i < m; i++) cand_snps[i] = pool.at(i);
+			const double t_w = now_s();
+			rem_->run_em(cand_snps.data(), m, d_geno_t_.get(), n_samp_, main_st_.s);
+			wait_seconds_[0] += now_s() - t_w;
+			if (getenv("HIBAG_B200_EM_DEBUG"))
+			{
+				int it_max = 0, it_sum = 0, nv = 0;
+				for (int i = 0; i < m; i++)
+					if (rem_->status(i) != EM_INVALID)
+					{
+						it_max = std::max(it_max, rem_->iterations(i)); it_sum += rem_->iterations(i); nv++;
+					}
+				fprintf(stderr, "em round: n_snp %d n_cur %d pairs %zu slots %zu maxchain %d m %d valid %d iters max %d mean %.1f wall %.3f ms\n",
+					bit, (int)cur.h.size(), rem_->total_pairs(), rem_->ell_slots(), rem_->max_chain(), m, nv, it_max, nv ? (double)it_sum / nv : 0.0,
+					(now_s() - t_w) * 1e3);
+			}
+			for (int i = 0; i < m; i++)
+				if (rem_->status(i) == EM_AMBIGUOUS && !host_rp_valid)
+				{
+					rem_->fetch_pairs(rp, inbag_, boot_, main_st_.s);
+					host_rp_valid = true;
+				}
+		}
 		pool_->run(m, [&](int i, int w) {
 			Candidate &cd = cand[i];
 			cd.snp = pool.at(i);
 			cd.acc = 0; cd.loss = 0;
 			const double t_em = now_s();
-			cd.valid = estimate_candidate(cur, rp, m_.geno_t.data() + (size_t)cd.snp * n_samp_,
-				n_samp_, rare_prob, scratch_[w], cd.list);
+			if (dev_em && rem_->status(i) != EM_AMBIGUOUS)
+			{
+				cd.valid = rem_->status(i) == EM_OK;
+				if (cd.valid) finish_candidate(cur, rem_->freq(i), rare_prob, cd.list);
+			} else {
+				cd.valid = estimate_candidate(cur, rp, m_.geno_t.data() + (size_t)cd.snp * n_samp_,
+					n_samp_, rare_prob, scratch_[w], cd.list);
+			}
 			em_seconds_[w] += now_s() - t_em;
-			if (!cd.valid) { pub[i].store(-2, std::memory_order_release); return; }
-			if (procs_) return;
-			EvalSlot &sl = *slots_[i];
-			sl.stage_list(cd.list.h.data(), (int)cd.list.h.size(), n_hla_, cd.list.n_snp);
-			GenoView v = view;
-			v.cand_col = d_geno_t_.get() + (size_t)cd.snp * n_samp_;
-			v.cand_bit = bit;
-			sl.enqueue_cells(v, d_oob_.get(), n_oob);
-			sl.enqueue_reduce_oob(v, d_oob_.get(), n_oob);
-			double t_w = now_s();
-			sl.sync();
-			wait_seconds_[w] += now_s() - t_w;
-			cd.acc = sl.oob_count();
-			pub[i].store(cd.acc, std::memory_order_release);
-			int bound = global_max_acc;
-			for (int j = 0; j < i; j++)
-			{
-				const int a = pub[j].load(std::memory_order_acquire);
-				if (a > bound) bound = a;
-			}
-			if (cd.acc >= bound)
-			{
-				sl.enqueue_cells(v, d_ib_.get(), (int)inbag_.size());
-				sl.enqueue_reduce_ib(v, d_ib_.get(), (int)inbag_.size());
-				t_w = now_s();
-				sl.sync();
-				wait_seconds_[w] += now_s() - t_w;
-				cd.loss = ib_loss(sl.ib_ratios());
-				have_loss[i] = 1;
-			}
+			if (!cd.valid || procs_) return;
+			cd.blob = build_list_blob(cd.list.h.data(), (int)cd.list.h.size(), n_hla_, cd.list.n_snp,
+				scorer_->host_blob(i), 256);
+			scorer_->set_list(i, cd.blob, d_geno_t_.get() + (size_t)cd.snp * n_samp_);
 		});
+		if (dev_em)
+			for (int i = 0; i < m; i++) if (rem_->status(i) == EM_AMBIGUOUS) ts.n_em_host_fallback++;
 		for (int i = 0; i < m; i++) if (cand[i].valid) { ts.n_em++; }
 		ts.seconds_phase_oob += now_s() - t_p1;
 		const double t_p2 = now_s();
 
 		if (!procs_)
 		{
-			// ---- exact rule in candidate order: keep a loss only where the reference has one ------
+			// ---- phase 2: ONE launch scores every valid candidate on the out-of-bag samples;
+			// then, with all accuracies known, ONE launch scores exactly the candidates whose
+			// in-bag loss the reference computes (acc >= running maximum in candidate order, :2033)
+			std::vector<int> which, counts;
+			for (int i = 0; i < m; i++) if (cand[i].valid) which.push_back(i);
+			double t_w = now_s();
+			scorer_->upload(which);
+			scorer_->score_oob(view, bit, which, d_oob_.get(), n_oob, counts);
+			wait_seconds_[0] += now_s() - t_w;
+			std::vector<int> need;
 			int running = global_max_acc;
-			for (int i = 0; i < m; i++)
+			for (size_t k = 0; k < which.size(); k++)
 			{
-				Candidate &cd = cand[i];
-				if (!cd.valid) continue;
+				Candidate &cd = cand[which[k]];
+				cd.acc = counts[k];
 				ts.n_oob_evals++;
-				const bool need = cd.acc >= running;
-				if (need && !have_loss[i])
-					throw std::runtime_error("internal error: in-bag loss missing for a candidate");
-				if (!need) cd.loss = 0;
-				else ts.n_ib_evals++;
+				if (cd.acc >= running) { need.push_back(which[k]); ts.n_ib_evals++; }
 				if (cd.acc > running) running = cd.acc;
 			}
+			t_w = now_s();
+			scorer_->score_ib(view, bit, need, d_ib_.get(), (int)inbag_.size());
+			wait_seconds_[0] += now_s() - t_w;
+			pool_->run((int)need.size(), [&](int k, int) {
+				cand[need[k]].loss = ib_loss(scorer_->ratios(k));
+			});
 		} else {
 			// ---- legacy hooks: sequential, exactly the reference's call sequence -------------
 			int running = global_max_acc;
@@ -655,6 +695,7 @@ void Trainer::grow(Classifier &cl)
 			global_min_loss = min_loss;
 			const int snp = cand[min_i].snp;
 			std::swap(cur, cand[min_i].list);
+			pairs_dirty = true;
 			cl.snpidx.push_back(snp);
 			set_snp_bit(bit, snp);
 			if (procs_)
@@ -677,7 +718,7 @@ void Trainer::grow(Classifier &cl)
 			}
 			{
 				const int64_t row[4] = { global_k, (int64_t)cl.snpidx.size(), cum_pairs, cum_em };
-				m_.train_trace.insert(m_.train_trace.end(), row, row + 4);
+				trace_.insert(trace_.end(), row, row + 4);
 			}
 			if (o_.verbose > 1)
 				fprintf(stderr, "    %2d, SNP: %d, loss: %g, oob acc: %0.2f%%, # of haplo: %d\n",
@@ -701,7 +742,7 @@ void Trainer::grow(Classifier &cl)
 
 	{
 		const int64_t row[4] = { global_k, -1, cum_pairs, cum_em };
-		m_.train_trace.insert(m_.train_trace.end(), row, row + 4);
+		trace_.insert(trace_.end(), row, row + 4);
 	}
 	cl.haplo = cur;
 	cl.oob_acc = 0.5 * global_max_acc / n_oob;                       // :2121
@@ -709,24 +750,122 @@ void Trainer::grow(Classifier &cl)
 
 }  // namespace
 
+/// the lanes of one model: each grows its own classifiers (own RNG stream, host pool, device
+/// state); all share the device's scoring stream
+struct LaneGroup : public TrainSession
+{
+	std::vector<std::unique_ptr<Trainer> > lanes;
+	bool legacy = false, dev_em = false;
+	int req_threads = 0, req_concurrent = 0, mtry = 0;
+};
+
 void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 {
-	current_device();      // fails here, loudly, when no CUDA device is usable
-	Trainer *t = dynamic_cast<Trainer *>(m.tsession.get());
-	if (!t || !t->compatible(opts))
+	const DeviceInfo &di = current_device();      // fails here, loudly, when no CUDA device is usable
+	const int mtry = opts.mtry <= 0 ? 1 : opts.mtry;
+	// classifiers in flight on this GPU: independent RNG streams are required for that
+	int n_lanes = 1;
+	if (opts.per_classifier_seed && !opts.use_legacy_hooks && opts.n_concurrent > 1)
+		n_lanes = std::min(opts.n_concurrent, std::max(opts.nclassifier, 1));
+	LaneGroup *g = dynamic_cast<LaneGroup *>(m.tsession.get());
+	if (!g || g->legacy != (opts.use_legacy_hooks != 0) || g->req_threads != opts.n_threads ||
+		g->req_concurrent != opts.n_concurrent || g->mtry != mtry || (int)g->lanes.size() < n_lanes ||
+		g->dev_em != (opts.em_on_device != 0))
 	{
 		m.tsession.reset();
-		t = new Trainer(m, opts);
-		m.tsession.reset(t);
+		g = new LaneGroup();
+		m.tsession.reset(g);
+		g->legacy = opts.use_legacy_hooks != 0;
+		g->req_threads = opts.n_threads; g->req_concurrent = opts.n_concurrent; g->mtry = mtry;
+		g->dev_em = opts.em_on_device != 0;
+		// host threads: all cores by default, split over the lanes; one worker per candidate of
+		// a round when that is a modest over-subscription (23 equal EM jobs on 16 cores finish in
+		// ~1.4 job-times instead of 2)
+		int nt = opts.n_threads;
+		if (nt <= 0)
+		{
+			nt = (int)std::thread::hardware_concurrency();
+			if (nt < 1) nt = 1;
+			if (n_lanes == 1)
+			{
+				if (mtry > nt && mtry <= 2 * nt) nt = mtry;
+				if (nt > std::max(mtry, 4)) nt = std::max(mtry, 4);
+			} else {
+				nt = std::min(mtry, std::max(2, (nt * 3 / 2 + n_lanes - 1) / n_lanes));
+			}
+		} else if (n_lanes > 1)
+		{
+			nt = std::max(1, (nt + n_lanes - 1) / n_lanes);
+		}
+		for (int l = 0; l < n_lanes; l++)
+			g->lanes.emplace_back(new Trainer(m, opts, nt));
 	}
-	t->configure(opts);
-	try
+	(void)di;
+
+	const int stride = opts.index_stride > 0 ? opts.index_stride : 1;
+	std::vector<std::vector<int> > idx(n_lanes);
+	for (int c = 0; c < opts.nclassifier; c++)
+		idx[c % n_lanes].push_back(opts.first_index + c * stride);
+
+	const double t0 = now_s();
+	std::vector<std::string> errors(n_lanes);
+	auto run_lane = [&](int l) {
+		try
+		{
+			cudaSetDevice(di.device);
+			g->lanes[l]->configure(opts);
+			g->lanes[l]->run(idx[l]);
+		} catch (std::exception &e)
+		{
+			errors[l] = e.what();
+			if (errors[l].empty()) errors[l] = "unknown error";
+		}
+	};
+	if (n_lanes == 1)
+		run_lane(0);
+	else {
+		std::vector<std::thread> th;
+		for (int l = 1; l < n_lanes; l++) th.emplace_back(run_lane, l);
+		run_lane(0);
+		for (auto &t : th) t.join();
+	}
+	for (int l = 0; l < n_lanes; l++)
+		if (!errors[l].empty())
+		{
+			const std::string msg = errors[l];
+			m.tsession.reset();
+			throw std::runtime_error(msg);
+		}
+
+	// merge in global classifier order: the model a single lane would have built
+	std::vector<std::pair<int, int> > order;       // (global index, lane)
+	std::vector<size_t> next(n_lanes, 0);
+	for (int l = 0; l < n_lanes; l++)
+		for (size_t k = 0; k < g->lanes[l]->built_.size(); k++)
+			order.emplace_back(g->lanes[l]->built_[k].first, l);
+	std::sort(order.begin(), order.end());
+	for (auto &o : order)
 	{
-		t->run();
-	} catch (...)
+		Trainer &t = *g->lanes[o.second];
+		m.cls.emplace_back(std::move(t.built_[next[o.second]++].second));
+	}
+	hibag_b200_train_stats &ts = m.train_stats;
+	ts.seconds_total += now_s() - t0;
+	for (int l = 0; l < n_lanes; l++)
 	{
-		m.tsession.reset();
-		throw;
+		Trainer &t = *g->lanes[l];
+		const hibag_b200_train_stats &a = t.ts_;
+		ts.seconds_em += a.seconds_em; ts.seconds_gpu_wait += a.seconds_gpu_wait;
+		ts.gpu_kernel_ms += a.gpu_kernel_ms; ts.pair_evals += a.pair_evals;
+		ts.popc32_issued += a.popc32_issued; ts.n_oob_evals += a.n_oob_evals;
+		ts.n_ib_evals += a.n_ib_evals; ts.n_em += a.n_em; ts.kernel_launches += a.kernel_launches;
+		ts.h2d_bytes += a.h2d_bytes; ts.d2h_bytes += a.d2h_bytes;
+		ts.cell_kernel_ms += a.cell_kernel_ms; ts.cell_kernel_launches += a.cell_kernel_launches;
+		ts.seconds_prepare += a.seconds_prepare; ts.seconds_phase_oob += a.seconds_phase_oob;
+		ts.seconds_phase_ib += a.seconds_phase_ib;
+		ts.em_kernel_ms += a.em_kernel_ms; ts.n_em_host_fallback += a.n_em_host_fallback;
+		m.train_trace.insert(m.train_trace.end(), t.trace_.begin(), t.trace_.end());
+		t.built_.clear();
 	}
 	m.pcache.reset();
 }

@@ -127,6 +127,12 @@ typedef struct hibag_b200_train_opts {
 	int      use_legacy_hooks;  /* 1: score through the 10-hook plugin struct with full host
 	                               buffers per candidate (the reference-facing path) */
 	int      verbose;
+	int      n_concurrent;      /* classifiers grown concurrently on this GPU (host EM of one
+	                               overlaps pair scoring of another); needs per_classifier_seed
+	                               = 1 and is ignored with use_legacy_hooks; <= 1: one */
+	int      em_on_device;      /* 1: haplotype-pair matching and the candidates' EM run on the
+	                               GPU (bit-identical results); 0: on the
+	                               host thread pool. Ignored with use_legacy_hooks */
 } hibag_b200_train_opts;
 
 /* reference CAttrBag_Model::BuildClassifiers, src/LibHLA.cpp:2268-2305 */
@@ -148,6 +154,8 @@ typedef struct hibag_b200_train_stats {
 	double   seconds_prepare;     /* wall: haplotype-pair preparation per round */
 	double   seconds_phase_oob;   /* wall: candidate EM + out-of-bag scoring */
 	double   seconds_phase_ib;    /* wall: in-bag scoring of the candidates that need it */
+	double   em_kernel_ms;        /* summed CUDA-event durations of the device EM launches */
+	uint64_t n_em_host_fallback;  /* candidates re-estimated on the host (undecidable stop test) */
 } hibag_b200_train_stats;
 int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_stats *out);
 

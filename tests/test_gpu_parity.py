@@ -130,7 +130,7 @@ def test_trainer_reproduces_reference_golden_model(gpu):
     geno, h1, h2, al, ml = helpers.hapmap_a_training()
     m = gpu.HLAModel(geno.shape[1], len(al), al)
     m.set_training(geno, h1, h2)
-    m.train(100, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), n_threads=8)
+    m.train(100, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), n_threads=8, em_on_device=True)
     assert m.num_classifiers() == 100
     for k in range(100):
         helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
@@ -140,7 +140,8 @@ def test_trainer_reproduces_reference_golden_model(gpu):
 
 def test_trainer_legacy_hook_mode_and_thread_count_invariance(gpu):
     geno, h1, h2, al, ml = helpers.hapmap_a_training()
-    for kwargs in (dict(use_legacy_hooks=True, n_threads=3), dict(n_threads=1)):
+    for kwargs in (dict(use_legacy_hooks=True, n_threads=3), dict(n_threads=1),
+                   dict(n_threads=4, em_on_device=False)):
         m = gpu.HLAModel(geno.shape[1], len(al), al)
         m.set_training(geno, h1, h2)
         m.train(8, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), **kwargs)
@@ -167,6 +168,11 @@ def test_trainer_matches_reference_on_synthetic(gpu, ref):
         for k in range(3):
             d = helpers.classifier_diff(m.classifier(k), r.classifier(k))
             assert d == "", (prune, k, d)
+        h = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        h.set_training(coh.geno, coh.h1, coh.h2)
+        h.train(3, mtry, prune=prune, seed=500, per_classifier_seed=True, n_threads=6, em_on_device=False)
+        for k in range(3):
+            assert helpers.classifier_diff(h.classifier(k), r.classifier(k)) == "", (prune, k, "host EM")
     # sharding: classifiers {1, 3} built as a strided shard equal classifiers 1 and 3 of a full run
     full = gpu.HLAModel(coh.n_snp, coh.n_hla); full.set_training(coh.geno, coh.h1, coh.h2)
     full.train(4, mtry, seed=500, per_classifier_seed=True)
@@ -174,6 +180,15 @@ def test_trainer_matches_reference_on_synthetic(gpu, ref):
     shard.train(2, mtry, seed=500, per_classifier_seed=True, first_index=1, index_stride=2)
     for j, k in enumerate((1, 3)):
         assert helpers.classifier_diff(shard.classifier(j), full.classifier(k)) == ""
+    # several classifiers in flight on one GPU: same model, in global classifier order
+    conc = gpu.HLAModel(coh.n_snp, coh.n_hla); conc.set_training(coh.geno, coh.h1, coh.h2)
+    conc.train(4, mtry, seed=500, per_classifier_seed=True, n_concurrent=3, n_threads=6)
+    assert conc.num_classifiers() == 4
+    for k in range(4):
+        assert helpers.classifier_diff(conc.classifier(k), full.classifier(k)) == ""
+    st = conc.train_stats()
+    assert st["n_oob_evals"] == full.train_stats()["n_oob_evals"]
+    assert st["pair_evals"] == full.train_stats()["pair_evals"]
 
 
 def _golden_model(gpu, ref, n_cls=100):

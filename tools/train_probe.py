@@ -1,4 +1,4 @@
-"""GPU probe: config-2 training, phase breakdown for several host-thread counts."""
+"""GPU probe: config-2 training, phase breakdown for several (host threads, classifiers in flight)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,14 +7,16 @@ from hibag_b200 import api
 api.set_device(0)
 coh = bench.make_cohort()
 g = np.ascontiguousarray(coh.geno, dtype=np.int8)
-for nt in [int(x) for x in (sys.argv[1:] or ["16", "23"])]:
+for spec in (sys.argv[1:] or ["0:1", "0:2", "0:3", "0:4"]):
+    nt, nc, dev = (int(x) for x in (spec + ":1").split(":")[:3])
+    n = max(4, 2 * nc)
     m = api.HLAModel(bench.N_SNP, coh.n_hla); m.set_training(g, coh.h1, coh.h2)
-    m.train(1, bench.MTRY, seed=bench.TRAIN_SEED, per_classifier_seed=True, first_index=0, n_threads=nt)
+    m.train(nc, bench.MTRY, seed=bench.TRAIN_SEED, per_classifier_seed=True, first_index=0, n_threads=nt, n_concurrent=nc, em_on_device=bool(dev))
     s0 = m.train_stats(); t0 = time.time()
-    m.train(4, bench.MTRY, seed=bench.TRAIN_SEED, per_classifier_seed=True, first_index=1, n_threads=nt)
+    m.train(n, bench.MTRY, seed=bench.TRAIN_SEED, per_classifier_seed=True, first_index=nc, n_threads=nt, n_concurrent=nc, em_on_device=bool(dev))
     dt = time.time() - t0; s1 = m.train_stats()
     d = {k: s1[k] - s0[k] for k in s1}
-    print("threads %d: %.3f s/classifier | prepare %.3f oob-phase %.3f ib-phase %.3f other %.3f | em_sum %.2f wait_sum %.2f | cell_ms_sum %.0f launches %d" % (
-        nt, dt / 4, d["seconds_prepare"] / 4, d["seconds_phase_oob"] / 4, d["seconds_phase_ib"] / 4,
-        (dt - d["seconds_prepare"] - d["seconds_phase_oob"] - d["seconds_phase_ib"]) / 4,
-        d["seconds_em"] / 4, d["seconds_gpu_wait"] / 4, d["cell_kernel_ms"] / 4, d["cell_kernel_launches"] / 4), flush=True)
+    print("threads %d lanes %d devEM %d (em kernel %.0f ms, host fallbacks %d): %.3f s/classifier (%.1f /min) | per classifier: prepare %.3f em-phase %.3f score-phase %.3f | em_sum %.2f wait_sum %.2f | cell_ms %.0f launches %d -> %.3e pair-evals/s in kernel" % (
+        nt, nc, dev, d["em_kernel_ms"] / n, d["n_em_host_fallback"], dt / n, 60 * n / dt, d["seconds_prepare"] / n, d["seconds_phase_oob"] / n, d["seconds_phase_ib"] / n,
+        d["seconds_em"] / n, d["seconds_gpu_wait"] / n, d["cell_kernel_ms"] / n, d["cell_kernel_launches"] / n,
+        d["pair_evals"] / (d["cell_kernel_ms"] * 1e-3)), flush=True)
