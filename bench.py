@@ -2,14 +2,18 @@
 """bench.py -- headline benchmark of the B200 scoring path (driver contract in the task statement).
 
 Workload (BASELINE.json configs[1]): synthetic HLA-A training, 5,000 samples x 500 flanking SNPs,
-seed-fixed, mtry = ceil(sqrt(500)) = 23, prune on.  A STEP = growing one classifier per GPU
-(bootstrap, greedy SNP search: host EM + GPU pair scoring).  Weak scaling: every rank builds its
-own classifiers (classifier-sharded ensemble, no data-path collective).
+seed-fixed, mtry = ceil(sqrt(500)) = 23, prune on.  A STEP = growing LANES classifiers per GPU
+(bootstrap, greedy SNP search: pair matching + EM + pair scoring on the GPU, decisions on the
+host), LANES of them in flight at a time.  Weak scaling: every rank builds its own classifiers
+(classifier-sharded ensemble, no data-path collective).
 
-  value  classifiers/min with the cohort resident in HBM (own host driver, device-resident
-         genotype bit planes; per candidate only the haplotype list crosses PCIe)
-  e2e    classifiers/min through the reference-facing plugin: the ten TypeGPUExtProc hooks with
-         full host buffers per candidate (hlaAttrBagging(..., use_legacy_hooks=True))
+  value  classifiers/min with the cohort resident in HBM (persistent training session: genotype
+         matrix and bit planes stay on the device between steps)
+  e2e    classifiers/min through the public call hlaAttrBagging(hla, snp, ...) on HOST arrays:
+         model creation, H2D of the cohort, every per-round list upload and result download inside
+         the timed region
+  e2e_legacy_hooks  the same through the ten TypeGPUExtProc hooks exactly as the reference host
+         calls them (full TGenotype[5000] + haplotype list from host memory per candidate SNP)
   predict.* (secondary, configs[2]): samples/s of a 100-classifier model on 200,000 samples
 
 `--impl reference` times the reference's own CPU implementation (compiled unmodified sources,
@@ -36,6 +40,7 @@ if ROOT not in sys.path:
 N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
+LANES = 6            # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
 WORKLOAD_JSON = os.path.join(ROOT, "profiles", "c2_workload.json")
@@ -231,11 +236,13 @@ def run_reference_arm(args):
 
 def workload_config(n_gpus):
     return {"workload": "synthetic HLA-A training: 5000 samples x 500 SNPs, 34 alleles (40 drawn), "
-                        "cohort seed 1, mtry 23, prune, one classifier per GPU per step "
-                        "(per-classifier seed %d + index)" % TRAIN_SEED,
+                        "cohort seed 1, mtry 23, prune, %d classifiers per GPU per step, all in flight "
+                        "(per-classifier seed %d + index)" % (LANES, TRAIN_SEED),
             "n_samp": N_SAMP, "n_snp": N_SNP, "mtry": MTRY, "parallelism": "classifier-sharded x%d" % n_gpus,
-            "l2": "operands are KB-scale and rebuilt per candidate; the cell matrix written per launch "
-                  "(15-20 MB) plus 24 concurrent slots exceeds L2 reuse between timed launches"}
+            "lanes": LANES,
+            "l2": "inputs larger than L2: every pair-scoring launch writes a fresh 280-480 MB cell matrix "
+                  "(23 candidate lists x 820 cells x 1,840-3,160 samples x 8 B) and its operands are rebuilt "
+                  "per selection round, so nothing is reused from L2 between timed launches"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -252,11 +259,10 @@ def run_b200_arm(args):
     api.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     info = api.device_info()
+    lanes = args.lanes
     n_threads = args.threads
     if not n_threads:
-        n_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
-        if MTRY > n_threads and MTRY <= 2 * n_threads:
-            n_threads = MTRY       # one worker per candidate SNP of a round (modest over-subscription)
+        n_threads = max(2 * lanes, ((os.cpu_count() or 1) // max(world, 1)) * 3 // 2)
 
     coh = make_cohort()
     geno = np.ascontiguousarray(coh.geno, dtype=np.int8)
@@ -269,10 +275,13 @@ def run_b200_arm(args):
     # ---- resident path --------------------------------------------------------------------------
     model = api.HLAModel(N_SNP, coh.n_hla)
     model.set_training(geno, coh.h1, coh.h2)
+    dev_em = not args.host_em
 
     def step_resident(step):
-        model.train(1, MTRY, prune=True, seed=TRAIN_SEED, per_classifier_seed=True,
-                    first_index=rank + world * step, n_threads=n_threads)
+        # classifiers (step*world + rank)*lanes ... + lanes-1 of the global sequence
+        model.train(lanes, MTRY, prune=True, seed=TRAIN_SEED, per_classifier_seed=True,
+                    first_index=(step * world + rank) * lanes, n_threads=n_threads,
+                    n_concurrent=lanes, em_on_device=dev_em)
 
     for s in range(args.warmup):
         step_resident(s)
@@ -293,14 +302,34 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     st1 = model.train_stats()
     d = {k: st1[k] - st0[k] for k in st1}
-    value = world * args.steps / (ms / 60000.0)
+    value = world * args.steps * lanes / (ms / 60000.0)
 
-    # ---- reference-facing plugin path (host buffers per candidate) ---------------------------------
+    # ---- end to end through the public API on host arrays -------------------------------------------
     e2e = None
+    e2e_hooks = None
     if not args.no_e2e:
+        def run_public(first_step, n_steps, **kw):
+            # ONE call of the public API per rank: the cohort goes in as host numpy arrays
+            m = api.hlaAttrBagging((coh.h1, coh.h2), geno, nclassifier=n_steps * lanes, mtry=MTRY, prune=True,
+                                   mono_rm=False, seed=TRAIN_SEED, nthread=n_threads, per_classifier_seed=True,
+                                   first_index=first_step * world * lanes + rank, index_stride=world,
+                                   n_concurrent=lanes, em_on_device=dev_em, **kw)
+            return m.train_stats()
+        run_public(0, 1)
+        sync_all()
+        e0.record()
+        stt = run_public(args.warmup, args.steps)
+        e1.record()
+        sync_all()
+        ms2 = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+        e2e = {"value": world * args.steps * lanes / (ms2 / 60000.0), "unit": "classifiers/min",
+               "h2d_bytes_per_step": int((stt["h2d_bytes"] + geno.nbytes + 8 * N_SAMP) / args.steps),
+               "d2h_bytes_per_step": int(stt["d2h_bytes"] / args.steps),
+               "api": "one hlaAttrBagging(hla, snp, nclassifier=steps*lanes) call on host numpy arrays "
+                      "(new model, cohort H2D, per-round list uploads, accuracy/ratio/frequency downloads)"}
+        # the reference-facing plugin struct, driven with the reference's own call sequence
+        n_hook = max(1, min(3, args.steps))
         def run_hooks(first, count):
-            # ONE call of the public API: the cohort goes in as host arrays, every candidate SNP is
-            # scored through the ten hooks with TGenotype[] + haplotype list copied from host memory
             m = api.hlaAttrBagging((coh.h1, coh.h2), geno, nclassifier=count, mtry=MTRY, prune=True,
                                    mono_rm=False, seed=TRAIN_SEED, nthread=n_threads,
                                    per_classifier_seed=True, use_legacy_hooks=True,
@@ -309,16 +338,17 @@ def run_b200_arm(args):
         run_hooks(0, 1)
         sync_all()
         e0.record()
-        stt = run_hooks(args.warmup, args.steps)
+        sth = run_hooks(1, n_hook)
         e1.record()
         sync_all()
-        ms2 = hd.max_over_ranks(e0.elapsed_time(e1), dev)
-        e2e = {"value": world * args.steps / (ms2 / 60000.0), "unit": "classifiers/min",
-               "h2d_bytes_per_step": int(stt["h2d_bytes"] / args.steps),
-               "d2h_bytes_per_step": int(stt["d2h_bytes"] / args.steps),
-               "api": "one hlaAttrBagging(hla, snp, nclassifier=steps, use_legacy_hooks=True) call: ten "
-                      "TypeGPUExtProc hooks, TGenotype[5000] + haplotype list from host memory per "
-                      "candidate SNP, scalar results back per hook call"}
+        ms3 = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+        e2e_hooks = {"value": world * n_hook / (ms3 / 60000.0), "unit": "classifiers/min",
+                     "classifiers": n_hook * world,
+                     "h2d_bytes_per_classifier": int(sth["h2d_bytes"] / n_hook),
+                     "d2h_bytes_per_classifier": int(sth["d2h_bytes"] / n_hook),
+                     "api": "hlaAttrBagging(..., use_legacy_hooks=True): ten TypeGPUExtProc hooks, "
+                            "TGenotype[5000] + haplotype list from host memory per candidate SNP, scalar "
+                            "results back per hook call, strictly sequential as the reference host calls them"}
 
     # ---- roofline of the dominant kernel (pair scoring), training region ---------------------------
     peaks = json.load(open(PEAKS_JSON)) if os.path.exists(PEAKS_JSON) else None
@@ -328,17 +358,22 @@ def run_b200_arm(args):
     n_l = max(d["cell_kernel_launches"], 1)
     avg_ms = d["cell_kernel_ms"] / n_l
     pair_rate = d["pair_evals"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
+    issued_rate = d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
     roofline = {
         "bound": "popc", "kernel": "cell_pass_kernel",
-        "achieved": pair_rate * 4 / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s",
-        "frac": pair_rate * 4 / popc_peak,
-        "achieved_issued": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / 1e9,
-        "frac_issued": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / popc_peak,
+        "achieved": issued_rate / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s",
+        "frac": issued_rate / popc_peak,
+        "achieved_reference_formulation": pair_rate * 4 / 1e9,
+        "frac_reference_formulation": pair_rate * 4 / popc_peak,
         "pair_evals_per_s": pair_rate, "avg_launch_ms": avg_ms, "launches": int(d["cell_kernel_launches"]),
         "pair_evals_per_launch": d["pair_evals"] / n_l,
-        "note": "algorithmic POPC.32 = 4 per pair evaluation (reference formulation, <=64 SNPs); the "
-                "kernel's one-popcount form issues 1 per 32 SNPs (frac_issued). Launches of up to 23 "
-                "candidates overlap on separate streams, so per-launch durations include sharing.",
+        "note": "achieved = POPC.32 the kernel issues (1 per pair evaluation per 32 SNPs: the one-popcount "
+                "distance) / summed launch durations; POPC (XU pipe) and the lane-private LDS.64 table lookup "
+                "co-bind at the same 16 /clk/SM, so frac is also the fraction of the shared-memory-pipe bound. "
+                "*_reference_formulation counts the 4 POPC.32 per pair evaluation of the reference's hamm_d "
+                "(SURVEY.md 8d) and can exceed 1. One launch scores all candidate lists of a selection round; "
+                "launches of all lanes are serialised on one stream, so a launch's CUDA events time it alone "
+                "(EM clusters of other lanes may hold some of the SMs meanwhile).",
         "peak_source": peak_src, "traffic": None,
         "fp64_frac": pair_rate * 3 / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9),
     }
@@ -350,7 +385,8 @@ def run_b200_arm(args):
         if predict and peaks:
             predict["roofline"]["peak"] = popc_peak / 1e9
             predict["roofline"]["frac"] = predict["roofline"]["achieved"] * 1e9 / popc_peak
-            predict["roofline"]["frac_issued"] = predict["roofline"]["achieved_issued"] * 1e9 / popc_peak
+            predict["roofline"]["frac_reference_formulation"] = \
+                predict["roofline"]["achieved_reference_formulation"] * 1e9 / popc_peak
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -367,10 +403,12 @@ def run_b200_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
-            "e2e": e2e, "gpu_launches": int(d["kernel_launches"]),
+            "e2e": e2e, "e2e_legacy_hooks": e2e_hooks, "gpu_launches": int(d["kernel_launches"]),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "predict": predict,
             "train_detail": {
-                "host_threads": n_threads, "seconds_em_sum": d["seconds_em"],
+                "host_threads": n_threads, "lanes": lanes, "em_on_device": dev_em,
+                "em_kernel_ms": d["em_kernel_ms"], "em_host_fallbacks": int(d["n_em_host_fallback"]),
+                "seconds_em_sum": d["seconds_em"],
                 "seconds_prepare": d["seconds_prepare"], "seconds_candidates": d["seconds_phase_oob"],
                 "seconds_gpu_wait_sum": d["seconds_gpu_wait"], "gpu_kernel_span_ms": d["gpu_kernel_ms"],
                 "pair_evals": int(d["pair_evals"]), "oob_evals": int(d["n_oob_evals"]),
@@ -435,9 +473,11 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
                 "d2h_bytes": int(n * (8 + 16 + 8 * coh.n_hla + 8 * nc)), "api": "HLAModel.predict (host numpy)"},
         "model": "100 classifiers = the %d classifiers trained above, cycled" % n_src,
         "calls_equal_between_paths": same,
-        "roofline": {"bound": "popc", "kernel": "cell_pass_kernel", "achieved": rate * 4 / 1e9,
-                     "achieved_issued": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / 1e9,
-                     "peak": 148 * 16 * 1.965, "unit": "Gpopc32/s", "frac": rate * 4 / (148 * 16 * 1.965e9),
+        "roofline": {"bound": "popc", "kernel": "cell_pass_kernel",
+                     "achieved": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / 1e9,
+                     "achieved_reference_formulation": rate * 4 / 1e9,
+                     "peak": 148 * 16 * 1.965, "unit": "Gpopc32/s",
+                     "frac": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / (148 * 16 * 1.965e9),
                      "pair_evals_per_s": rate, "launches": int(d["cell_kernel_launches"]),
                      "avg_launch_ms": d["cell_kernel_ms"] / max(d["cell_kernel_launches"], 1),
                      "cell_kernel_share_of_step": d["cell_kernel_ms"] / max(d["gpu_kernel_ms"], 1e-9)},
@@ -453,6 +493,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default cores/ranks)")
+    ap.add_argument("--lanes", type=int, default=LANES, help="classifiers in flight per GPU")
+    ap.add_argument("--host-em", action="store_true", help="candidate EM on the host thread pool")
     ap.add_argument("--predict-samples", type=int, default=N_PREDICT)
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
