@@ -231,7 +231,16 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "classifiers/min", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(time.time() - t0, 1), "timed_wall_s": round(time.time() - tw, 1),
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def emit(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def workload_config(n_gpus):
@@ -420,7 +429,7 @@ def run_b200_arm(args):
                                 for k in range(model.num_classifiers())]},
             "device": info,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
 
 
 def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
@@ -487,6 +496,12 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
 
 
 def main():
+    # exactly ONE line on stdout (the JSON): libraries that print to fd 1 (NCCL's version banner)
+    # go to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

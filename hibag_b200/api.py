@@ -74,6 +74,7 @@ EXPORTS = [
     "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
     "hibag_b200_model_snp_weights", "hibag_b200_pipe_peak",
     "hibag_b200_host_unif_rand", "hibag_b200_host_build_tasks",
+    "hibag_b200_get_procs_ex", "hibag_b200_haplomatch", "hibag_b200_free",
 ]
 
 _lib = None
@@ -91,6 +92,11 @@ def lib():
     L.hibag_b200_version.restype = C.c_char_p
     L.hibag_b200_last_error.restype = C.c_char_p
     L.hibag_b200_get_procs.restype = C.c_void_p
+    L.hibag_b200_get_procs_ex.restype = C.c_void_p
+    L.hibag_b200_get_procs_ex.argtypes = [C.c_int]
+    L.hibag_b200_haplomatch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.hibag_b200_free.argtypes = [C.c_void_p]
     L.hibag_b200_device_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for f in (L.hibag_b200_best_guess,):
         f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -152,9 +158,27 @@ def device_info():
     return dict(name=name.value.decode(), sm_count=sm.value, clock_khz=khz.value)
 
 
-def get_procs():
-    """Address of the TypeGPUExtProc-compatible hook struct (reference LibHLA_ext.h:358-388)."""
+def get_procs(with_haplomatch=False):
+    """Address of the TypeGPUExtProc-compatible hook struct (reference LibHLA_ext.h:358-388);
+    with_haplomatch also fills the optional build_haplomatch hook."""
+    if with_haplomatch:
+        return lib().hibag_b200_get_procs_ex(1)
     return lib().hibag_b200_get_procs()
+
+
+def haplomatch(haplo, len_per_hla, n_snp, geno):
+    """GPU body of the build_haplomatch hook on host arrays: uint32 [n][2] records
+    (in-bag index, (i2 << 16) | i1) for every genotype with boot > 0."""
+    lens = np.ascontiguousarray(len_per_hla, dtype=np.uint64)
+    buf, n = C.c_void_p(), C.c_size_t()
+    _chk(lib().hibag_b200_haplomatch(_p(haplo), _p(lens), len(lens), n_snp, _p(geno), len(geno),
+                                     C.byref(buf), C.byref(n)))
+    try:
+        arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint32)), shape=(n.value,)).copy()
+    finally:
+        lib().hibag_b200_free(buf)
+    assert arr[0] == n.value - 1
+    return arr[1:].reshape(-1, 2)
 
 
 def pipe_peak(which):

@@ -4,6 +4,10 @@
 #include <cstring>
 #include <string>
 
+#include <cstdlib>
+#include <vector>
+
+#include "em.h"
 #include "model.h"
 
 namespace {
@@ -65,6 +69,23 @@ int hibag_b200_device_info(char *name, int name_len, int *sm_count, int *clock_k
 }
 
 hibag_gpu_ext_proc *hibag_b200_get_procs(void) { return hb::plugin_procs(); }
+hibag_gpu_ext_proc *hibag_b200_get_procs_ex(int with_haplomatch)
+{
+	return with_haplomatch ? hb::plugin_procs_with_haplomatch() : hb::plugin_procs();
+}
+
+int hibag_b200_haplomatch(const hibag_haplotype *haplo, const size_t *n_haplo, int n_hla, int n_snp,
+	const hibag_genotype *geno, int n_samp, uint32_t **out_buf, size_t *out_n)
+{
+	return guarded([&]() {
+		require(haplo && n_haplo && geno && out_buf && out_n, "haplomatch: null argument");
+		std::vector<int> ib;
+		for (int i = 0; i < n_samp; i++) if (geno[i].bootstrap_count > 0) ib.push_back(i);
+		*out_buf = hb::haplomatch_records(haplo, n_haplo, n_hla, n_snp, geno, n_samp, ib, out_n);
+	});
+}
+
+void hibag_b200_free(void *p) { free(p); }
 
 int hibag_b200_best_guess(const hibag_haplotype *haplo, int n_haplo, int n_hla, int n_snp,
 	const hibag_genotype *geno, int n_geno, int32_t *out_a1, int32_t *out_a2)

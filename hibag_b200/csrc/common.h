@@ -28,32 +28,38 @@ struct DeviceInfo
 const DeviceInfo &current_device();
 void select_device(int device);
 
+/// Process-wide cache of device and page-locked host blocks. cudaMalloc / cudaMallocHost /
+/// cudaFree synchronise the device (and serialise across processes for pinned memory); training
+/// sessions and predict calls come and go, so released blocks are kept and handed out again.
+void *pool_alloc(bool pinned, size_t bytes, size_t *got_bytes);
+void pool_free(bool pinned, void *p, size_t bytes);
+
 /// growable device buffer (contents are NOT preserved on growth)
 template <typename T>
 class DevBuf
 {
 public:
-	DevBuf() : p_(nullptr), cap_(0) {}
-	~DevBuf() { if (p_) cudaFree(p_); }
+	DevBuf() : p_(nullptr), cap_(0), bytes_(0) {}
+	~DevBuf() { release(); }
 	DevBuf(const DevBuf &) = delete;
 	DevBuf &operator=(const DevBuf &) = delete;
 	T *ensure(size_t n)
 	{
 		if (n > cap_)
 		{
-			if (p_) { cudaFree(p_); p_ = nullptr; cap_ = 0; }
-			size_t want = n + n / 4 + 64;
-			HB_CUDA(cudaMalloc((void **)&p_, want * sizeof(T)));
-			cap_ = want;
+			release();
+			const size_t want = n + n / 4 + 64;
+			p_ = (T *)pool_alloc(false, want * sizeof(T), &bytes_);
+			cap_ = bytes_ / sizeof(T);
 		}
 		return p_;
 	}
 	T *get() const { return p_; }
 	size_t capacity() const { return cap_; }
-	void release() { if (p_) { cudaFree(p_); p_ = nullptr; cap_ = 0; } }
+	void release() { if (p_) { pool_free(false, p_, bytes_); p_ = nullptr; cap_ = 0; bytes_ = 0; } }
 private:
 	T *p_;
-	size_t cap_;
+	size_t cap_, bytes_;
 };
 
 /// growable page-locked host buffer
@@ -61,26 +67,26 @@ template <typename T>
 class PinBuf
 {
 public:
-	PinBuf() : p_(nullptr), cap_(0) {}
-	~PinBuf() { if (p_) cudaFreeHost(p_); }
+	PinBuf() : p_(nullptr), cap_(0), bytes_(0) {}
+	~PinBuf() { release(); }
 	PinBuf(const PinBuf &) = delete;
 	PinBuf &operator=(const PinBuf &) = delete;
 	T *ensure(size_t n)
 	{
 		if (n > cap_)
 		{
-			if (p_) { cudaFreeHost(p_); p_ = nullptr; cap_ = 0; }
-			size_t want = n + n / 4 + 64;
-			HB_CUDA(cudaMallocHost((void **)&p_, want * sizeof(T)));
-			cap_ = want;
+			release();
+			const size_t want = n + n / 4 + 64;
+			p_ = (T *)pool_alloc(true, want * sizeof(T), &bytes_);
+			cap_ = bytes_ / sizeof(T);
 		}
 		return p_;
 	}
 	T *get() const { return p_; }
-	void release() { if (p_) { cudaFreeHost(p_); p_ = nullptr; cap_ = 0; } }
+	void release() { if (p_) { pool_free(true, p_, bytes_); p_ = nullptr; cap_ = 0; bytes_ = 0; } }
 private:
 	T *p_;
-	size_t cap_;
+	size_t cap_, bytes_;
 };
 
 struct Stream

@@ -60,6 +60,7 @@ void snp_weights(const hibag_b200_model &m, std::vector<int> &w);
 
 // from plugin.cu
 hibag_gpu_ext_proc *plugin_procs();
+hibag_gpu_ext_proc *plugin_procs_with_haplomatch();
 ScoreStats plugin_build_stats();
 void score_host_arrays(int kind, const hibag_haplotype *haplo, int n_haplo, int n_hla,
 	int n_snp, const hibag_genotype *geno, int n_geno, int32_t *out_a1, int32_t *out_a2,

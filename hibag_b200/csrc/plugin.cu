@@ -14,6 +14,7 @@
 #include <memory>
 #include <vector>
 
+#include "em.h"
 #include "scorer.h"
 
 namespace hb {
@@ -118,6 +119,21 @@ static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo
 	b->slot.stats.launches++;
 	b->slot.stage_list(haplo, n_haplo, b->n_hla, n_snp);
 	b->have_list_staged = true;
+}
+
+/// optional hook (src/LibHLA.cpp:1014-1072): the host expands every record into the 3-4 doubled
+/// pairs itself and free()s the buffer (:1062)
+static uint32_t *hook_build_haplomatch(const hibag_haplotype haplo[], const size_t n_haplo[],
+	int n_snp, const hibag_genotype geno[], size_t *out_n)
+{
+	BuildState *b = g_build.get();
+	if (!b) throw std::runtime_error("build_haplomatch called before build_init");
+	// in-bag list from the genotypes' own bootstrap counts (identical to build_set_bootstrap's)
+	std::vector<int> ib;
+	for (int i = 0; i < b->n_samp; i++)
+		if (geno[i].bootstrap_count > 0) ib.push_back(i);
+	b->slot.stats.launches += 3;
+	return haplomatch_records(haplo, n_haplo, b->n_hla, n_snp, geno, b->n_samp, ib, out_n);
 }
 
 static int hook_build_acc_oob()
@@ -279,7 +295,20 @@ static hibag_gpu_ext_proc g_procs = {
 	hook_predict_init, hook_predict_done, hook_predict_avg_prob
 };
 
+// the same hooks plus build_haplomatch. Kept apart because a host that receives this hook
+// builds its pair lists in record order (4 doubled pairs per record, :1052-1059) instead of its
+// CPU scan order (:1569-1637): EM sums are then accumulated in a different order and its
+// frequencies differ from the CPU path in the last bits -- the reference behaves the same way
+// with any plugin that provides this hook.
+static hibag_gpu_ext_proc g_procs_hm = {
+	hook_build_init, hook_build_done, hook_build_set_bootstrap,
+	hook_build_haplomatch,
+	hook_build_set_haplo_geno, hook_build_acc_oob, hook_build_acc_ib,
+	hook_predict_init, hook_predict_done, hook_predict_avg_prob
+};
+
 hibag_gpu_ext_proc *plugin_procs() { return &g_procs; }
+hibag_gpu_ext_proc *plugin_procs_with_haplomatch() { return &g_procs_hm; }
 
 ScoreStats plugin_build_stats()
 {

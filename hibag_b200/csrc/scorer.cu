@@ -5,6 +5,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace hb {
 
@@ -83,6 +85,90 @@ int choose_samples_per_lane(int n_pos, int n_chunks, int n_snp, int sm_count)
 		R >>= 1;
 	}
 	return R;
+}
+
+// ---- block cache ----------------------------------------------------------------------------------
+namespace {
+struct BlockPool
+{
+	std::mutex mu;
+	std::multimap<size_t, void *> free_blocks;      // size -> block
+	size_t cached_bytes = 0;
+};
+BlockPool g_pool[2];                                 // [0] device (per current device), [1] pinned
+std::map<void *, int> g_block_device;                // device blocks: which device owns them
+const size_t POOL_LIMIT[2] = { (size_t)24 << 30, (size_t)2 << 30 };
+}
+
+void *pool_alloc(bool pinned, size_t bytes, size_t *got_bytes)
+{
+	// size classes: next multiple of 1/8 of the leading power of two (<= 12.5 % slack), >= 512 B
+	size_t cls = 512;
+	while (cls < bytes) cls <<= 1;
+	if (cls > 4096)
+	{
+		const size_t step = cls >> 4;
+		cls = (bytes + step - 1) / step * step;
+	}
+	BlockPool &bp = g_pool[pinned ? 1 : 0];
+	int dev = 0;
+	if (!pinned) cudaGetDevice(&dev);
+	{
+		std::lock_guard<std::mutex> lk(bp.mu);
+		auto range = bp.free_blocks.equal_range(cls);
+		for (auto it = range.first; it != range.second; ++it)
+		{
+			if (!pinned && g_block_device[it->second] != dev) continue;
+			void *p = it->second;
+			bp.free_blocks.erase(it);
+			bp.cached_bytes -= cls;
+			*got_bytes = cls;
+			return p;
+		}
+	}
+	void *p = nullptr;
+	cudaError_t e = pinned ? cudaMallocHost(&p, cls) : cudaMalloc(&p, cls);
+	if (e != cudaSuccess)
+	{
+		// give the cache back and retry once
+		std::vector<void *> drop;
+		{
+			std::lock_guard<std::mutex> lk(bp.mu);
+			for (auto &kv : bp.free_blocks) drop.push_back(kv.second);
+			bp.free_blocks.clear();
+			bp.cached_bytes = 0;
+		}
+		for (void *q : drop) { if (pinned) cudaFreeHost(q); else cudaFree(q); }
+		cudaGetLastError();
+		e = pinned ? cudaMallocHost(&p, cls) : cudaMalloc(&p, cls);
+	}
+	if (e != cudaSuccess)
+		throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " +
+			std::to_string(cls) + " bytes");
+	if (!pinned)
+	{
+		std::lock_guard<std::mutex> lk(bp.mu);
+		g_block_device[p] = dev;
+	}
+	*got_bytes = cls;
+	return p;
+}
+
+void pool_free(bool pinned, void *p, size_t bytes)
+{
+	if (!p) return;
+	BlockPool &bp = g_pool[pinned ? 1 : 0];
+	{
+		std::lock_guard<std::mutex> lk(bp.mu);
+		if (bp.cached_bytes + bytes <= POOL_LIMIT[pinned ? 1 : 0])
+		{
+			bp.free_blocks.emplace(bytes, p);
+			bp.cached_bytes += bytes;
+			return;
+		}
+		if (!pinned) g_block_device.erase(p);
+	}
+	if (pinned) cudaFreeHost(p); else cudaFree(p);
 }
 
 // ---- EvalSlot ---------------------------------------------------------------------------------

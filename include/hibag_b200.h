@@ -86,6 +86,19 @@ int hibag_b200_device_info(char *name, int name_len, int *sm_count, int *clock_k
  * R/HIBAG.R:707). build_haplomatch is NULL (optional hook, the reference then uses its CPU
  * search, src/LibHLA.cpp:1074). */
 hibag_gpu_ext_proc *hibag_b200_get_procs(void);
+/* with_haplomatch != 0: the same hooks plus build_haplomatch (reference src/LibHLA.cpp:1014-1072,
+ * replacing the CPU search _PrepHaploMatch_*, :1569-1637). A host given this hook builds its
+ * haplotype-pair lists in record order rather than in its CPU scan order, so its EM sums -- and
+ * the trained frequencies -- differ from the CPU path in the last bits (true of any plugin
+ * that provides the hook); hibag_b200_get_procs() therefore leaves it NULL. */
+hibag_gpu_ext_proc *hibag_b200_get_procs_ex(int with_haplomatch);
+/* the body of that hook on host arrays: records (in-bag index, (i2 << 16) | i1) of the haplotype
+ * pairs at minimum distance for every sample with bootstrap_count > 0. *out_buf is malloc'd
+ * (release with hibag_b200_free): out_buf[0] = 2 * n_records, then the records; *out_n = number
+ * of uint32 in the buffer. n_haplo[n_hla] = haplotypes per allele (LenPerHLA). */
+int hibag_b200_haplomatch(const hibag_haplotype *haplo, const size_t *n_haplo, int n_hla, int n_snp,
+	const hibag_genotype *geno, int n_samp, uint32_t **out_buf, size_t *out_n);
+void hibag_b200_free(void *p);
 
 /* ---- stateless batched scoring (kernel-level entry points; host buffers) ----------------------
  * haplo[]: n_haplo records grouped by allele (hla_allele non-decreasing), geno[]: n_geno packed

@@ -285,3 +285,46 @@ void hibag_oracle_classifier_weights(int n_classifier, const int *n_snp,
 	}
 	free(snp_weight);
 }
+
+/* The records a build_haplomatch plugin returns (src/LibHLA.cpp:1014-1072): for every in-bag
+ * sample (ascending index k within the in-bag list) the haplotype pairs of its two true alleles
+ * at the minimum Hamming distance on n_snp SNPs -- the selection rule of _PrepHaploMatch_def,
+ * src/LibHLA.cpp:1569-1637, on the list BEFORE doubling -- as (k, (i2 << 16) | i1), i1 outer and
+ * i2 inner, upper triangle when the two alleles are the same. out must hold 2 * max_records
+ * uint32; returns the number of records (or -1 if max_records is too small). */
+long hibag_oracle_haplomatch_records(const oracle_haplo_t *haplo, const int64_t *n_haplo,
+	int n_hla, int n_snp, const oracle_geno_t *geno, int n_samp, uint32_t *out, long max_records)
+{
+	int *st = (int *)malloc(sizeof(int) * (size_t)(n_hla + 1));
+	long n = 0;
+	int k = 0;
+	st[0] = 0;
+	for (int a = 0; a < n_hla; a++) st[a + 1] = st[a] + (int)n_haplo[a];
+	for (int s = 0; s < n_samp; s++)
+	{
+		if (geno[s].boot <= 0) continue;
+		const oracle_geno_t *g = &geno[s];
+		const int st1 = st[g->a1], m1 = st[g->a1 + 1] - st1;
+		const int st2 = st[g->a2], m2 = st[g->a2 + 1] - st2;
+		const int same = (st1 == st2);
+		int min_d = n_snp * 4;
+		for (int i = 0; i < m1; i++)
+			for (int j = same ? i : 0; j < m2; j++)
+			{
+				const int d = hibag_oracle_hamming(g, &haplo[st1 + i], &haplo[st2 + j], n_snp);
+				if (d < min_d) min_d = d;
+			}
+		for (int i = 0; i < m1; i++)
+			for (int j = same ? i : 0; j < m2; j++)
+				if (hibag_oracle_hamming(g, &haplo[st1 + i], &haplo[st2 + j], n_snp) == min_d)
+				{
+					if (n >= max_records) { free(st); return -1; }
+					out[2 * n] = (uint32_t)k;
+					out[2 * n + 1] = ((uint32_t)j << 16) | (uint32_t)i;
+					n++;
+				}
+		k++;
+	}
+	free(st);
+	return n;
+}

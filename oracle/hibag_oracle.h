@@ -78,6 +78,11 @@ void hibag_oracle_int_to_snp(oracle_geno_t *out, int length, const int32_t *geno
 void hibag_oracle_classifier_weights(int n_classifier, const int *n_snp,
 	const int32_t *const *snpidx, int n_total_snp, const int32_t *geno_row, double *weight);
 
+/* records of a build_haplomatch plugin, src/LibHLA.cpp:1014-1072 with the selection rule of
+ * _PrepHaploMatch_def :1569-1637 (see the .c file) */
+long hibag_oracle_haplomatch_records(const oracle_haplo_t *haplo, const int64_t *n_haplo,
+	int n_hla, int n_snp, const oracle_geno_t *geno, int n_samp, uint32_t *out, long max_records);
+
 #ifdef __cplusplus
 }
 #endif

@@ -523,6 +523,26 @@ int ref_hamming(const void *geno, const void *h1, const void *h2, int n_snp)
 		*(const THaplotype *)h2);
 }
 
+/// the reference's own pair matcher (CAlg_Prediction::_PrepHaploMatch_def, LibHLA.cpp:1569-1637)
+/// on two allele ranges [st1, st1+m1), [st2, st2+m2) of a haplotype list; pairs are returned as
+/// offsets (i1, i2) inside the two ranges. Returns the number of pairs (<= max_pairs).
+int ref_prep_haplo_match(const void *geno, const void *haplo, int st1, int m1, int st2, int m2,
+	int n_snp, int *out_i1, int *out_i2, int max_pairs)
+{
+	THaplotype *H = (THaplotype *)haplo;
+	std::vector<CAlg_EM::THaploPair> pl;
+	std::vector<short> diff((size_t)m1 * (size_t)(m2 > m1 ? m2 : m1) + 1);
+	CAlg_Prediction::_PrepHaploMatch_def(*(const TGenotype *)geno, H + st1, (size_t)m1, H + st2,
+		(size_t)m2, (size_t)n_snp, pl, diff.data());
+	int n = 0;
+	for (size_t k = 0; k < pl.size() && n < max_pairs; k++, n++)
+	{
+		out_i1[n] = (int)(pl[k].H1 - (H + st1));
+		out_i2[n] = (int)(pl[k].H2 - (H + st2));
+	}
+	return (int)pl.size();
+}
+
 }  // extern "C"
 
 // CHLATypeList::Compare is declared inline in the reference's .cpp (LibHLA.cpp:912) and is

@@ -169,6 +169,15 @@ class RefLib:
     def hamming(self, geno1, h1, h2, n_snp):
         return self.lib.ref_hamming(_p(geno1), _p(h1), _p(h2), n_snp)
 
+    def prep_haplo_match(self, geno1, haplo, st1, m1, st2, m2, n_snp):
+        """reference _PrepHaploMatch_def on two allele ranges; returns [(i1, i2), ...]"""
+        cap = max(m1 * max(m1, m2), 1)
+        a = np.zeros(cap, dtype=np.int32); b = np.zeros(cap, dtype=np.int32)
+        self.lib.ref_prep_haplo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        n = self.lib.ref_prep_haplo_match(_p(geno1), _p(haplo), st1, m1, st2, m2, n_snp, _p(a), _p(b), cap)
+        return list(zip(a[:n].tolist(), b[:n].tolist()))
+
     def new_model(self):
         return RefModel(self)
 
@@ -271,6 +280,22 @@ class OracleLib:
         t = np.zeros(257)
         self.lib.hibag_oracle_table(_p(t))
         return t
+
+    def haplomatch_records(self, haplo, len_per_hla, n_snp, geno):
+        """records a build_haplomatch plugin returns: uint32 [n][2] = (in-bag index, (i2<<16)|i1)"""
+        L = self.lib
+        L.hibag_oracle_haplomatch_records.restype = C.c_long
+        L.hibag_oracle_haplomatch_records.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                      C.c_int, C.c_void_p, C.c_long]
+        lens = np.ascontiguousarray(len_per_hla, dtype=np.int64)
+        cap = 1 << 16
+        while True:
+            out = np.zeros((cap, 2), dtype=np.uint32)
+            n = L.hibag_oracle_haplomatch_records(_p(haplo), _p(lens), len(lens), n_snp, _p(geno), len(geno),
+                                                  _p(out), cap)
+            if n >= 0:
+                return out[:n]
+            cap *= 4
 
     def hamming(self, geno1, h1, h2, n_snp):
         return self.lib.hibag_oracle_hamming(_p(geno1), _p(h1), _p(h2), n_snp)

@@ -122,6 +122,43 @@ def test_reference_predict_with_gpu_hook_matches_cpu(gpu, ref):
         assert np.array_equal(cpu[key], dev[key], equal_nan=True), key + " (bit-exact)"
 
 
+def test_haplomatch_hook_matches_oracle(gpu, orc):
+    """build_haplomatch body on the GPU == the CPU restatement, record for record"""
+    rng = np.random.default_rng(123)
+    for n_snp, n_hla, per in ((0, 5, 1), (5, 8, 4), (40, 12, 9), (64, 6, 30), (65, 9, 12), (128, 7, 20)):
+        haplo, n_hla, _ = helpers.random_haplo_list(rng, n_hla=n_hla, n_snp=max(n_snp, 1), max_per_allele=per)
+        geno = helpers.random_genotypes(rng, 700, max(n_snp, 1), n_hla, haplo=haplo)
+        if n_snp == 0:
+            geno["s1"][:] = 0; geno["s2"][:] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        a1 = np.minimum(geno["a1"], geno["a2"]); a2 = np.maximum(geno["a1"], geno["a2"])
+        geno["a1"], geno["a2"] = a1, a2
+        lens = np.bincount(haplo["hla"], minlength=n_hla)
+        got = gpu.haplomatch(haplo, lens, n_snp, geno)
+        want = orc.haplomatch_records(haplo, lens, n_snp, geno)
+        assert got.shape == want.shape and np.array_equal(got, want), n_snp
+
+
+def test_reference_host_with_haplomatch_hook(gpu, ref):
+    """the unmodified reference host driven through ALL hooks including build_haplomatch: pair
+    lists arrive in record order, so EM sums differ from the CPU path in the last bits only --
+    same SNPs, same haplotypes, frequencies within 1e-9 relative (see include/hibag_b200.h)"""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    try:
+        ref.set_gpu_procs(gpu.get_procs(with_haplomatch=True))
+        r = ref.new_model()
+        r.init_training(geno, h1, h2, len(al))
+        ref.set_seed(int(ml["seed"]))
+        r.build(6, int(ml["mtry"]), prune=True)
+        got = [r.classifier(k) for k in range(6)]
+    finally:
+        ref.set_gpu_procs(None)
+    for k in range(6):
+        g = helpers.golden_classifier(ml, k)
+        assert np.array_equal(got[k]["snpidx"], g["snpidx"]), k
+        assert np.array_equal(got[k]["packed"], g["packed"]) and np.array_equal(got[k]["hla"], g["hla"]), k
+        assert np.allclose(got[k]["freq"], g["freq"], rtol=1e-9, atol=0), k
+
+
 # ---- own host driver ------------------------------------------------------------------------------
 
 def test_trainer_reproduces_reference_golden_model(gpu):

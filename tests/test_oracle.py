@@ -103,3 +103,27 @@ def test_oracle_predict_matches_reference_on_golden_model(ref, orc):
     for key in ("prob", "matching", "dosage", "postprob"):
         assert np.array_equal(r[key], o[key], equal_nan=True), key
     assert r["h1"][3] == refpy.NA_INTEGER and np.isnan(r["matching"][3])
+
+
+def test_haplomatch_records_follow_reference_pair_matcher(ref, orc):
+    """the oracle's build_haplomatch records == the reference's own _PrepHaploMatch_def
+    (src/LibHLA.cpp:1569-1637) run per in-bag sample on the same (un-doubled) list"""
+    rng = np.random.default_rng(77)
+    for n_snp in (3, 17, 64, 100):
+        haplo, n_hla, _ = helpers.random_haplo_list(rng, n_hla=7, n_snp=n_snp, max_per_allele=5)
+        geno = helpers.random_genotypes(rng, 60, n_snp, n_hla, haplo=haplo)
+        a1 = np.minimum(geno["a1"], geno["a2"]); a2 = np.maximum(geno["a1"], geno["a2"])
+        geno["a1"], geno["a2"] = a1, a2
+        lens = np.bincount(haplo["hla"], minlength=n_hla)
+        start = np.concatenate([[0], np.cumsum(lens)])
+        rec = orc.haplomatch_records(haplo, lens, n_snp, geno)
+        want, k = [], 0
+        for s in range(len(geno)):
+            if geno["boot"][s] <= 0:
+                continue
+            x, y = int(geno["a1"][s]), int(geno["a2"][s])
+            for i1, i2 in ref.prep_haplo_match(geno[s:s + 1], haplo, int(start[x]), int(lens[x]),
+                                               int(start[y]), int(lens[y]), n_snp):
+                want.append((k, (i2 << 16) | i1))
+            k += 1
+        assert [tuple(r) for r in rec.tolist()] == want
