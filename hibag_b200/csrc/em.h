@@ -51,6 +51,8 @@ public:
 	void run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_samp, cudaStream_t st);
 	const double *freq(int i) const { return h_freq_.get() + (size_t)i * n2_; }
 	int status(int i) const { return h_status_.get()[4 * i]; }
+	/// test hook: report candidate i as undecided so that the caller's host fallback runs
+	void force_ambiguous(int i) { if (h_status_.get()[4 * i] == EM_OK) h_status_.get()[4 * i] = EM_AMBIGUOUS; }
 	int iterations(int i) const { return h_status_.get()[4 * i + 1]; }
 
 	/// the pair lists as the host algorithm holds them (for the host fallback / tests)

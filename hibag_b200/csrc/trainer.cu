@@ -531,6 +531,12 @@ void Trainer::grow(Classifier &cl)
 			const double t_w = now_s();
 			rem_->run_em(cand_snps.data(), m, d_geno_t_.get(), n_samp_, main_st_.s);
 			wait_seconds_[0] += now_s() - t_w;
+			if (const char *e = getenv("HIBAG_B200_EM_FORCE_FALLBACK"))
+			{
+				// test hook: every k-th candidate takes the host re-estimation path
+				const int every = std::max(1, atoi(e));
+				for (int i = 0; i < m; i += every) rem_->force_ambiguous(i);
+			}
 			if (getenv("HIBAG_B200_EM_DEBUG"))
 			{
 				int it_max = 0, it_sum = 0, nv = 0;

@@ -186,6 +186,19 @@ def test_trainer_legacy_hook_mode_and_thread_count_invariance(gpu):
             helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
 
 
+def test_device_em_host_fallback_path(gpu, monkeypatch):
+    """candidates whose stopping test the device cannot decide are re-estimated on the host:
+    force that path for every third candidate and require the golden model all the same"""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    monkeypatch.setenv("HIBAG_B200_EM_FORCE_FALLBACK", "3")
+    m = gpu.HLAModel(geno.shape[1], len(al), al)
+    m.set_training(geno, h1, h2)
+    m.train(6, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), n_threads=4, em_on_device=True)
+    for k in range(6):
+        helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+    assert m.train_stats()["n_em_host_fallback"] > 0
+
+
 def _synthetic():
     from hibag_b200 import synth
     return synth.make_cohort(400, 120, 12, seed=3)
