@@ -194,11 +194,14 @@ void predict_host(hibag_b200_model &m, const int8_t *geno, int n_samp,
 	current_device();
 	const int n_hla = m.n_hla;
 	const size_t n_cells = (size_t)n_hla * (n_hla + 1) / 2;
-	Stream st;
+	// Chunks of one tile: chunk c+1 is enqueued on the compute stream before the outputs of
+	// chunk c are copied back on the copy stream, so the device-to-host traffic (1 GB of
+	// posterior rows at 200,000 samples) hides behind the scoring of the next chunk.
+	Stream st, st_copy;
+	const int chunk = pick_tile(n_samp, (int)n_cells);
+	const int n_chunks = (n_samp + chunk - 1) / chunk;
 	DevBuf<int8_t> d_geno;
 	d_geno.ensure((size_t)n_samp * m.n_snp);
-	HB_CUDA(cudaMemcpyAsync(d_geno.get(), geno, (size_t)n_samp * m.n_snp, cudaMemcpyHostToDevice, st.s));
-	m.predict_stats.h2d_bytes += (size_t)n_samp * m.n_snp;
 	DevBuf<int> d_h1, d_h2;
 	DevBuf<double> d_mp, d_mt, d_ds, d_pp;
 	hibag_b200_predict_out dev;
@@ -209,20 +212,49 @@ void predict_host(hibag_b200_model &m, const int8_t *geno, int n_samp,
 	if (out.matching) dev.matching = d_mt.ensure(n_samp);
 	if (out.dosage) dev.dosage = d_ds.ensure((size_t)n_samp * n_hla);
 	if (out.post_prob) dev.post_prob = d_pp.ensure((size_t)n_samp * n_cells);
-	predict_device(m, d_geno.get(), n_samp, dev, nullptr, nullptr, st.s, true);
+	std::vector<std::unique_ptr<Event> > done;
+	for (int c = 0; c < n_chunks; c++) done.emplace_back(new Event(false));
 	size_t d2h = 0;
-	auto back = [&](void *dst, const void *src, size_t bytes) {
-		if (!dst) return;
-		HB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st.s));
-		d2h += bytes;
+	auto enqueue = [&](int c) {
+		const int b = c * chunk, n = std::min(chunk, n_samp - b);
+		HB_CUDA(cudaMemcpyAsync(d_geno.get() + (size_t)b * m.n_snp, geno + (size_t)b * m.n_snp,
+			(size_t)n * m.n_snp, cudaMemcpyHostToDevice, st.s));
+		hibag_b200_predict_out o = dev;
+		if (o.h1) o.h1 += b;
+		if (o.h2) o.h2 += b;
+		if (o.max_prob) o.max_prob += b;
+		if (o.matching) o.matching += b;
+		if (o.dosage) o.dosage += (size_t)b * n_hla;
+		if (o.post_prob) o.post_prob += (size_t)b * n_cells;
+		predict_device(m, d_geno.get() + (size_t)b * m.n_snp, n, o, nullptr, nullptr, st.s, false);
+		HB_CUDA(cudaEventRecord(done[c]->e, st.s));
 	};
-	back(out.h1, dev.h1, sizeof(int) * (size_t)n_samp);
-	back(out.h2, dev.h2, sizeof(int) * (size_t)n_samp);
-	back(out.max_prob, dev.max_prob, sizeof(double) * (size_t)n_samp);
-	back(out.matching, dev.matching, sizeof(double) * (size_t)n_samp);
-	back(out.dosage, dev.dosage, sizeof(double) * (size_t)n_samp * n_hla);
-	back(out.post_prob, dev.post_prob, sizeof(double) * (size_t)n_samp * n_cells);
+	auto fetch = [&](int c) {
+		const int b = c * chunk, n = std::min(chunk, n_samp - b);
+		HB_CUDA(cudaStreamWaitEvent(st_copy.s, done[c]->e, 0));
+		auto back = [&](void *dst, const void *src, size_t bytes) {
+			if (!dst) return;
+			HB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st_copy.s));
+			d2h += bytes;
+		};
+		back(out.h1 ? out.h1 + b : nullptr, dev.h1 + b, sizeof(int) * (size_t)n);
+		back(out.h2 ? out.h2 + b : nullptr, dev.h2 + b, sizeof(int) * (size_t)n);
+		back(out.max_prob ? out.max_prob + b : nullptr, dev.max_prob + b, sizeof(double) * (size_t)n);
+		back(out.matching ? out.matching + b : nullptr, dev.matching + b, sizeof(double) * (size_t)n);
+		back(out.dosage ? out.dosage + (size_t)b * n_hla : nullptr, dev.dosage + (size_t)b * n_hla,
+			sizeof(double) * (size_t)n * n_hla);
+		back(out.post_prob ? out.post_prob + (size_t)b * n_cells : nullptr,
+			dev.post_prob + (size_t)b * n_cells, sizeof(double) * (size_t)n * n_cells);
+	};
+	enqueue(0);
+	for (int c = 0; c < n_chunks; c++)
+	{
+		if (c + 1 < n_chunks) enqueue(c + 1);
+		fetch(c);
+	}
 	HB_CUDA(cudaStreamSynchronize(st.s));
+	HB_CUDA(cudaStreamSynchronize(st_copy.s));
+	m.predict_stats.h2d_bytes += (size_t)n_samp * m.n_snp;
 	m.predict_stats.d2h_bytes += d2h;
 }
 
