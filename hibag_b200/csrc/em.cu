@@ -62,6 +62,7 @@ struct MatchArgs
 	const int *off;               // exclusive scan of cnt
 	int *p1, *p2;                 // doubled pairs
 	uint32_t *rec;                // records (entry, (i2 << 16) | i1)
+	int *empty_flag;              // set when an entry has no pair at all (an allele without haplotypes)
 };
 
 /// MODE 0: minimum distance + number of doubled pairs; 1: emit the doubled pairs in the
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(128) haplomatch_kernel(const MatchArgs p)
 		}
 		p.cnt[k] = n;
 		p.mind[k] = min_d;
+		if (n == 0 && p.empty_flag) *p.empty_flag = 1;
 		return;
 	}
 
@@ -236,16 +238,22 @@ struct EmArgs
 	int n_entry, n_cur, n_samp;
 	const int *ib, *boot;             // in-bag sample per entry; bootstrap count per sample
 	const int *off;                   // pair range per entry
-	const int4 *pairs4;               // {u, v, slot_u, slot_v} per pair
-	const int *hap_sorted, *group_len, *group_base;   // ELL incidence layout
+	const int4 *pairs4;               // {u | v << 16, entry, slot_u, slot_v} per pair (all pairs)
+	const int *hap_sorted, *group_base;   // ELL incidence layout (groups of 32 haplotype chains)
+	const int *inc_off, *inc_val;     // incidence lists sorted by haplotype: (2t + side) in order
 	const double *cur_freq;
 	size_t n_slots;                   // ELL slots per candidate
 	const int8_t *geno_t;             // raw genotypes, SNP-major [n_snp][n_samp]
 	const int *cand_snp;              // [m]
-	double *rinc;                     // [m][n_slots] contributions in ELL incidence order, zeroed
-	double *xbuf;                     // [m][total_pairs] GenoFreq of every pair
 	int total_pairs;
 	int m_warps;                      // warps that run the M step, each with a RING_ROWS-row ring
+	// per-candidate scratch
+	int2 *sp;                         // [m][n_slots] slot -> {u | v << 16, entry}; entry < 0: empty
+	double *rinc;                     // [m][n_slots] contributions in ELL slot order
+	int *cuv;                         // [m][total_pairs] u | v << 16 of the compatible pairs
+	double *xbuf;                     // [m][total_pairs] GenoFreq of the compatible pairs
+	int *coff;                        // [m][n_entry + 1] compact range per entry
+	int *glen;                        // [m][n_groups] ELL rows per group (multiple of 8), zeroed
 	double *out_freq;                 // [m][2 * n_cur]
 	int *out_status;                  // [m][4] = status, iterations, 0, 0
 	double scale;                     // 0.5 / n_samp
@@ -274,6 +282,13 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
 	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
 	return v;
 }
+__device__ __forceinline__ int4 lds_i32x4(uint32_t addr)
+{
+	int4 v;
+	asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+		: "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
 
 __device__ __forceinline__ double block_sum_f64(double v, double *scratch)
 {
@@ -295,11 +310,20 @@ __device__ __forceinline__ double block_sum_f64(double v, double *scratch)
 	return scratch[32];
 }
 
-/// A cluster of C CTAs (C SMs) estimates one candidate. The pairs -- whole in-bag entries -- are
-/// split evenly over the CTAs for the E step; the groups of haplotype chains are dealt round-robin
-/// for the M step. Every CTA keeps the full frequency vector in shared memory; new frequencies
-/// and the partial log-likelihoods are written into all CTAs through distributed shared memory,
-/// so two cluster barriers per iteration are the only synchronisation.
+/// A cluster of C CTAs (C SMs) estimates one candidate. Whole in-bag entries (and their pairs)
+/// are split evenly over the CTAs for the E step; the groups of haplotype chains are dealt
+/// round-robin for the M step. Every CTA keeps the full frequency vector (double-buffered) and
+/// the per-entry scale factors in shared memory; new frequencies, scale factors and partial
+/// log-likelihoods are written into all CTAs through distributed shared memory, so two cluster
+/// barriers per iteration are the only synchronisation.
+///
+/// Only the pairs compatible with the candidate's genotype take part in EM (:1157-1180, about a
+/// third of all pairs). Once per candidate the kernel (A) compacts them in pair order and (B)
+/// assigns every compatible contribution its ELL slot counted among the compatible contributions
+/// of its haplotype only, recording slot -> (pair haplotypes, entry). Per iteration the
+/// contributions are then produced IN SLOT ORDER -- r = (c * f_u * f_v) * (count / sum) rebuilt from
+/// shared memory, bit-identical to the E step's value -- so the writes are coalesced, and the M
+/// step walks chains a half to a third as long.
 __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 {
 	cg::cluster_group cluster = cg::this_cluster();
@@ -307,20 +331,24 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 	const int rank = (int)cluster.block_rank();
 
 	extern __shared__ double em_smem[];
-	double *fr = em_smem;                      // [2 * n_cur] frequencies (old, then new in place)
-	double *scratch = fr + 2 * (size_t)p.n_cur;        // [40]
+	const int n2 = 2 * p.n_cur;
+	double *fr0 = em_smem;                     // [2][n2] frequencies, double-buffered
+	double *scratch = fr0 + 2 * (size_t)n2;    // [40]
 	double *llp = scratch + 40;                // [2][MAX_CLUSTER] partial log-likelihoods
-	double *bck = llp + 2 * MAX_CLUSTER;       // [n_entry] bootstrap count of the entry
-	double *sck = bck + p.n_entry;             // [n_entry] count / sum of the entry's GenoFreq
+	int *tot = (int *)(llp + 2 * MAX_CLUSTER); // [MAX_CLUSTER] compatible pairs per CTA (8 doubles reserved)
+	double *bck = llp + 3 * MAX_CLUSTER;       // [n_entry] bootstrap count of the entry
+	double *sck = bck + p.n_entry;             // [n_entry] count / sum of the entry's GenoFreq (all entries)
 	double *rings = sck + p.n_entry;           // [m_warps][RING_ROWS][32] M-step rings
 	int *gk = (int *)(rings + (size_t)p.m_warps * RING_ROWS * 32);   // [n_entry] candidate genotype, 3 = missing
 	__shared__ int sh_i[4];
 
 	const int c = blockIdx.x / C;
 	const int tid = threadIdx.x;
-	const int n2 = 2 * p.n_cur;
+	const int lane = tid & 31;
 	const int8_t *col = p.geno_t + (size_t)p.cand_snp[c] * p.n_samp;
+	int2 *sp = p.sp + (size_t)c * p.n_slots;
 	double *rinc = p.rinc + (size_t)c * p.n_slots;
+	int *cuv = p.cuv + (size_t)c * p.total_pairs;
 	double *xbuf = p.xbuf + (size_t)c * p.total_pairs;
 	int *status = p.out_status + 4 * c;
 
@@ -345,7 +373,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 			ac += __shfl_xor_sync(0xffffffffu, ac, o);
 			vc += __shfl_xor_sync(0xffffffffu, vc, o);
 		}
-		if ((tid & 31) == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); }
+		if (lane == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); }
 		__syncthreads();
 	}
 	const int allele_cnt = sh_i[0], valid_cnt = sh_i[1];
@@ -362,8 +390,8 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		for (int k = tid; k < p.n_cur; k += EM_THREADS)
 		{
 			const double f = p.cur_freq[k];
-			fr[2 * k] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
-			fr[2 * k + 1] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
+			fr0[2 * k] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
+			fr0[2 * k + 1] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
 		}
 	}
 	// this CTA's slice: entries [k_lo, k_hi) and exactly their pairs [t_lo, t_hi)
@@ -379,102 +407,222 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 	}
 	const int t_lo = p.off[k_lo], t_hi = p.off[k_hi];
 	const int n_groups = (n2 + 31) >> 5;
+	int *coff = p.coff + (size_t)c * (p.n_entry + 1);
+	int *glen = p.glen + (size_t)c * n_groups;
 	cluster.sync();                             // all CTAs are running: remote shared memory is live
+
+	// ---- (A) compact list of the compatible pairs of this CTA's slice, in pair order ------------
+	int jb_lo, jb_hi;
+	{
+		const int n_slice = t_hi - t_lo;
+		const int chunk = (n_slice + EM_THREADS - 1) / EM_THREADS;
+		const int tb = min(t_hi, t_lo + tid * chunk), te = min(t_hi, tb + chunk);
+		int cnt = 0;
+		for (int t = tb; t < te; t++)
+		{
+			const int4 pr = __ldg(p.pairs4 + t);
+			const int u = pr.x & 0xffff, v = (int)((unsigned)pr.x >> 16);
+			const int g = gk[pr.y];
+			cnt += (g == 3 || ((u & 1) + (v & 1)) == g) ? 1 : 0;
+		}
+		// block exclusive scan of cnt (warp shuffles + one pass over the 32 warp totals)
+		int incl = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int y = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += y;
+		}
+		int *wsum = (int *)scratch;             // [32] ints (scratch is 40 doubles)
+		__syncthreads();
+		if (lane == 31) wsum[tid >> 5] = incl;
+		__syncthreads();
+		if (tid < 32)
+		{
+			int w = wsum[tid];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const int y = __shfl_up_sync(0xffffffffu, w, o);
+				if (tid >= o) w += y;
+			}
+			wsum[tid] = w;                       // inclusive over warps
+		}
+		__syncthreads();
+		const int cta_total = wsum[31];
+		const int start = incl - cnt + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0);
+		if (tid < C) cluster.map_shared_rank(tot, tid)[rank] = cta_total;
+		cluster.sync();
+		int base = 0;
+		for (int q = 0; q < rank; q++) base += tot[q];
+		jb_lo = base; jb_hi = base + cta_total;
+		int j = base + start;
+		for (int t = tb; t < te; t++)
+		{
+			const int4 pr = __ldg(p.pairs4 + t);
+			const int u = pr.x & 0xffff, v = (int)((unsigned)pr.x >> 16);
+			const int g = gk[pr.y];
+			if (t == p.off[pr.y]) coff[pr.y] = j;          // first pair of its entry
+			if (g == 3 || ((u & 1) + (v & 1)) == g) cuv[j++] = pr.x;
+		}
+		if (rank == C - 1 && tid == 0) coff[p.n_entry] = jb_hi;
+		if (tid == 0) sh_i[3] = 0;
+		__syncthreads();
+	}
+	// ---- (B) ELL slots of the compatible contributions: a warp takes one haplotype of the groups
+	// dealt to this CTA at a time and walks its incidence list 128 contributions per step ---------
+	{
+		const int n_local_groups = (n_groups > rank) ? (n_groups - rank + C - 1) / C : 0;
+		for (;;)
+		{
+			int idx = 0;
+			if (lane == 0) idx = atomicAdd(&sh_i[3], 1);
+			idx = __shfl_sync(0xffffffffu, idx, 0);
+			if (idx >= n_local_groups * 32) break;
+			const int gi = (idx >> 5) * C + rank, l = idx & 31;
+			const int r = 32 * gi + l;
+			if (r >= n2) continue;
+			const int u = p.hap_sorted[r];
+			const int gbase = p.group_base[gi];
+			const int qb = p.inc_off[u], qe = p.inc_off[u + 1];
+			int n = 0;
+			for (int q0 = qb; q0 < qe; q0 += 128)
+			{
+				int e[4]; int4 pr[4];
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+				{
+					const int q = q0 + w * 32 + lane;
+					e[w] = (q < qe) ? __ldg(p.inc_val + q) : -1;
+				}
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+					pr[w] = (e[w] >= 0) ? __ldg(p.pairs4 + (e[w] >> 1)) : make_int4(0, 0, 0, 0);
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+				{
+					bool ok = false;
+					if (e[w] >= 0)
+					{
+						const int uu = pr[w].x & 0xffff, vv = (int)((unsigned)pr[w].x >> 16);
+						const int g = gk[pr[w].y];
+						ok = (g == 3 || ((uu & 1) + (vv & 1)) == g);
+					}
+					const unsigned m = __ballot_sync(0xffffffffu, ok);
+					if (ok)
+					{
+						const int rk = n + __popc(m & ((1u << lane) - 1u));
+						sp[gbase + 64 * (rk >> 1) + 2 * l + (rk & 1)] = make_int2(pr[w].x, pr[w].y);
+					}
+					n += __popc(m);
+				}
+			}
+			if (lane == 0 && n > 0) atomicMax(&glen[gi], (n + 7) & ~7);
+		}
+	}
+	cluster.sync();        // compact lists, entry ranges, slots and group lengths of every CTA are in place
 
 	double conv_tol = 0, loglik = -1e+30;
 	int result = EM_OK, iters = 0;
 	for (int iter = 0; iter <= EM_MAX_ITER; iter++)
 	{
 		const double old_loglik = loglik;
-		// ---- E step (:1204-1222) in three passes; loads are issued in batches of 8 so that the
-		// L2 round trips of a thread overlap -----------------------------------------------------
-		// (1) one thread per pair, coalesced: GenoFreq x of the pairs compatible with the new
-		//     genotype, 0.0 for the others (s + 0.0 == s, so they leave every sum untouched)
-		for (int t0 = t_lo + tid; t0 < t_hi; t0 += EM_THREADS * 8)
+		const double *fr = fr0 + (size_t)(iter & 1) * n2;          // current frequencies
+		double *fr_new = fr0 + (size_t)((iter & 1) ^ 1) * n2;
+		// ---- E step (:1204-1222) ---------------------------------------------------------------
+		// (1) one thread per compatible pair, coalesced: GenoFreq x. Loads are issued in batches
+		//     of 8 so that a thread's L2 round trips overlap.
+		for (int j0 = jb_lo + tid; j0 < jb_hi; j0 += EM_THREADS * 8)
 		{
-			int4 pr[8];
+			int uv[8];
 #pragma unroll
-			for (int j = 0; j < 8; j++)
+			for (int q = 0; q < 8; q++)
 			{
-				const int t = t0 + j * EM_THREADS;
-				pr[j] = (t < t_hi) ? __ldg(p.pairs4 + t) : make_int4(0, 0, 0, 0);
+				const int j = j0 + q * EM_THREADS;
+				uv[q] = (j < jb_hi) ? cuv[j] : 0;       // written in this kernel: no ld.nc
 			}
 #pragma unroll
-			for (int j = 0; j < 8; j++)
+			for (int q = 0; q < 8; q++)
 			{
-				const int t = t0 + j * EM_THREADS;
-				if (t < t_hi)
+				const int j = j0 + q * EM_THREADS;
+				if (j < jb_hi)
 				{
-					const int u = pr[j].x & 0xffff, v = (int)((unsigned)pr[j].x >> 16);
-					const int g = gk[pr[j].y];
-					double x = 0.0;
-					if (g == 3 || ((u & 1) + (v & 1)) == g)
-						x = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v]) : __dmul_rn(fr[u], fr[v]);
-					xbuf[t] = x;
+					const int u = uv[q] & 0xffff, v = (int)((unsigned)uv[q] >> 16);
+					xbuf[j] = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v]) : __dmul_rn(fr[u], fr[v]);
 				}
 			}
 		}
 		if (tid == 0) sh_i[2] = 0;                 // group counter of the M step
 		__syncthreads();
-		// (2) one thread per in-bag entry: sum of its pairs in list order, log-likelihood term
+		// (2) one thread per in-bag entry: sum of its pairs in list order, log-likelihood term,
+		//     scale factor count / sum into every CTA of the cluster
 		double ll = 0;
 		for (int k = k_lo + tid; k < k_hi; k += EM_THREADS)
 		{
-			const int b = p.off[k], e = p.off[k + 1];
+			const int b = coff[k], e = coff[k + 1];
 			double psum = 0;
 			int t = b;
 			for (; t + 8 <= e; t += 8)
 			{
 				double x[8];
 #pragma unroll
-				for (int j = 0; j < 8; j++) x[j] = xbuf[t + j];
+				for (int q = 0; q < 8; q++) x[q] = xbuf[t + q];
 #pragma unroll
-				for (int j = 0; j < 8; j++) psum = __dadd_rn(psum, x[j]);
+				for (int q = 0; q < 8; q++) psum = __dadd_rn(psum, x[q]);
 			}
 			for (; t < e; t++) psum = __dadd_rn(psum, xbuf[t]);
 			const double bc = bck[k];
 			ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
-			sck[k] = __ddiv_rn(bc, psum);
+			const double sc = __ddiv_rn(bc, psum);
+			for (int q = 0; q < C; q++) cluster.map_shared_rank(sck, q)[k] = sc;
 		}
-		ll = block_sum_f64(ll, scratch);           // (its barriers also publish sck)
+		ll = block_sum_f64(ll, scratch);
 		if (tid < C) cluster.map_shared_rank(llp, tid)[(iter & 1) * MAX_CLUSTER + rank] = ll;
-		// (3) one thread per pair: the pair's contribution into the incidence slots of its two
-		//     haplotypes (slots of incompatible pairs were zeroed before the launch)
-		for (int t0 = t_lo + tid; t0 < t_hi; t0 += EM_THREADS * 8)
+		cluster.sync();        // scale factors and partial log-likelihoods of every CTA have landed
+		// (3) one thread per ELL slot of the groups dealt to this CTA: the contribution of the
+		//     pair recorded for the slot, r = x * (count / sum), rebuilt from shared memory (bit-
+		//     identical to pass 1's x) and written in slot order -- fully coalesced; empty slots
+		//     get 0.0 (s + 0.0 == s)
+		for (int gi = rank; gi < n_groups; gi += C)
 		{
-			int4 pr[8];
-#pragma unroll
-			for (int j = 0; j < 8; j++)
+			const int n_sl = 32 * glen[gi];
+			const int2 *src = sp + p.group_base[gi];
+			double *dst = rinc + p.group_base[gi];
+			for (int s0 = tid; s0 < n_sl; s0 += EM_THREADS * 4)
 			{
-				const int t = t0 + j * EM_THREADS;
-				pr[j] = (t < t_hi) ? __ldg(p.pairs4 + t) : make_int4(0, 0, 0, 0);
-			}
+				int2 rec[4];
 #pragma unroll
-			for (int j = 0; j < 8; j++)
-			{
-				const int t = t0 + j * EM_THREADS;
-				if (t < t_hi)
+				for (int q = 0; q < 4; q++)
 				{
-					const int u = pr[j].x & 0xffff, v = (int)((unsigned)pr[j].x >> 16);
-					const int g = gk[pr[j].y];
-					if (g == 3 || ((u & 1) + (v & 1)) == g)
+					const int sl = s0 + q * EM_THREADS;
+					rec[q] = (sl < n_sl) ? src[sl] : make_int2(0, -1);
+				}
+#pragma unroll
+				for (int q = 0; q < 4; q++)
+				{
+					const int sl = s0 + q * EM_THREADS;
+					if (sl < n_sl)
 					{
-						const double x = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v])
-						                          : __dmul_rn(fr[u], fr[v]);
-						const double r = __dmul_rn(x, sck[pr[j].y]);
-						rinc[pr[j].z] = r; rinc[pr[j].w] = r;
+						double r = 0.0;
+						if (rec[q].y >= 0)
+						{
+							const int u = rec[q].x & 0xffff, v = (int)((unsigned)rec[q].x >> 16);
+							const double x = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v])
+							                          : __dmul_rn(fr[u], fr[v]);
+							r = __dmul_rn(x, sck[rec[q].y]);
+						}
+						dst[sl] = r;
 					}
 				}
 			}
 		}
-		cluster.sync();        // every contribution of every CTA is in place (and fr is free to overwrite)
+		__syncthreads();
 		// ---- M step: one lane per haplotype, contributions in the reference's order. A warp
 		// takes the next-longest group of 32 chains dealt to this CTA and streams its ELL rows
-		// through a private shared-memory ring with cp.async (L2 -> shared, no L1: other CTAs of
-		// the cluster wrote them), RING_ROWS rows ahead of the fp64 add chain. ------------------
+		// through a private shared-memory ring with cp.async, RING_ROWS rows ahead of the fp64 add
+		// chain, so the chain runs at add latency instead of L2 latency. --------------------------
 		if ((tid >> 5) < p.m_warps)
 		{
-			const int lane = tid & 31;
 			const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(
 				rings + (size_t)(tid >> 5) * RING_ROWS * 32) + (uint32_t)lane * 16u;
 			constexpr int NB = RING_ROWS / 8;      // batches of 8 rows (4 row pairs) in flight
@@ -484,7 +632,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 				if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
 				gi = __shfl_sync(0xffffffffu, gi, 0) * C + rank;
 				if (gi >= n_groups) break;
-				const int nb = p.group_len[gi] >> 3;
+				const int nb = glen[gi] >> 3;
 				const char *src = (const char *)(rinc + p.group_base[gi]) + lane * 16;   // + 512 per row pair
 				for (int b = 0; b < NB - 1; b++)
 				{
@@ -523,11 +671,12 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 				{
 					const double f = __dmul_rn(acc, p.scale);
 					const int u = p.hap_sorted[r];
-					for (int q = 0; q < C; q++) cluster.map_shared_rank(fr, q)[u] = f;
+					const size_t o = (size_t)(fr_new - fr0) + u;
+					for (int q = 0; q < C; q++) cluster.map_shared_rank(fr0, q)[o] = f;
 				}
 			}
 		}
-		cluster.sync();        // new frequencies and all partial log-likelihoods have landed
+		cluster.sync();        // new frequencies have landed in every CTA
 		iters = iter + 1;
 		// ---- stopping rule (:1236-1250) with the guard band of em.h; every CTA evaluates the
 		// same numbers in the same order ---------------------------------------------------------
@@ -548,8 +697,9 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 	}
 	if (rank == 0)
 	{
+		const double *fin = fr0 + (size_t)(iters & 1) * n2;        // written by the last M step
 		double *out = p.out_freq + (size_t)c * n2;
-		for (int u = tid; u < n2; u += EM_THREADS) out[u] = fr[u];
+		for (int u = tid; u < n2; u += EM_THREADS) out[u] = fin[u];
 		if (tid == 0) { status[0] = result; status[1] = iters; }
 	}
 }
@@ -590,7 +740,7 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 	HB_CUDA(cudaMemcpyAsync(d_start_.get(), hs, b_st, cudaMemcpyHostToDevice, st));
 	h2d_bytes += b_hap + b_fr + b_st;
 
-	d_cnt_.ensure(n_entry + 1); d_off_.ensure(n_entry + 1); d_mind_.ensure(n_entry + 1);
+	d_cnt_.ensure(n_entry + 2); d_off_.ensure(n_entry + 1); d_mind_.ensure(n_entry + 1);
 	MatchArgs m;
 	memset(&m, 0, sizeof(m));
 	m.hap = d_hap_.get(); m.start = d_start_.get();
@@ -599,7 +749,8 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 	m.cnt = d_cnt_.get(); m.mind = d_mind_.get(); m.off = d_off_.get();
 	if (n_entry <= 0) throw std::runtime_error("prepare: no in-bag samples");
 	const int blocks = (n_entry + 127) / 128;
-	HB_CUDA(cudaMemsetAsync(d_cnt_.get() + n_entry, 0, sizeof(int), st));
+	HB_CUDA(cudaMemsetAsync(d_cnt_.get() + n_entry, 0, 2 * sizeof(int), st));
+	m.empty_flag = d_cnt_.get() + n_entry + 1;
 	haplomatch_kernel<0><<<blocks, 128, 0, st>>>(m);
 	HB_CUDA(cudaGetLastError());
 	size_t tmp_bytes = 0;
@@ -607,8 +758,10 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 	d_tmp_.ensure(tmp_bytes + 16);
 	HB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp_.get(), tmp_bytes, d_cnt_.get(), d_off_.get(), n_entry + 1, st));
 	HB_CUDA(cudaMemcpyAsync(h_total_.get(), d_off_.get() + n_entry, sizeof(int), cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 3, d_cnt_.get() + n_entry + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
 	HB_CUDA(cudaStreamSynchronize(st));
 	total_pairs_ = (size_t)h_total_.get()[0];
+	has_empty_entry_ = h_total_.get()[3] != 0;
 	d2h_bytes += sizeof(int);
 	launches += 2;
 	if (total_pairs_ == 0) return;
@@ -686,9 +839,15 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	for (int i = 0; i < m; i++) hc[i] = cand_snp[i];
 	d_cand_.ensure(m);
 	HB_CUDA(cudaMemcpyAsync(d_cand_.get(), hc, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, st));
+	const int n_groups = (n2_ + 31) / 32;
+	d_sp_.ensure(2 * (size_t)m * n_slots_ + 2);
+	HB_CUDA(cudaMemsetAsync(d_sp_.get(), 0xff, sizeof(int) * 2 * (size_t)m * n_slots_, st));   // entry = -1
 	d_rinc_.ensure((size_t)m * n_slots_ + 2);
-	HB_CUDA(cudaMemsetAsync(d_rinc_.get(), 0, sizeof(double) * (size_t)m * n_slots_, st));
+	d_cuv_.ensure((size_t)m * total_pairs_ + 1);
 	d_xbuf_.ensure((size_t)m * total_pairs_ + 2);
+	d_coff_.ensure((size_t)m * (n_entry_ + 1));
+	d_glen_.ensure((size_t)m * n_groups + 1);
+	HB_CUDA(cudaMemsetAsync(d_glen_.get(), 0, sizeof(int) * (size_t)m * n_groups, st));
 	d_freq_.ensure((size_t)m * n2_ + 2);
 	d_status_.ensure(4 * (size_t)m);
 	h_freq_.ensure((size_t)m * n2_ + 2);
@@ -698,15 +857,18 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	a.n_entry = n_entry_; a.n_cur = n_cur_; a.n_samp = n_samp;
 	a.ib = ib_; a.boot = boot_;
 	a.off = d_off_.get(); a.pairs4 = (const int4 *)d_pairs4_.get();
-	a.hap_sorted = d_hap_sorted_.get(); a.group_len = d_group_len_.get(); a.group_base = d_group_base_.get();
+	a.hap_sorted = d_hap_sorted_.get(); a.group_base = d_group_base_.get();
+	a.inc_off = d_inc_off_.get(); a.inc_val = d_val2_.get();
 	a.cur_freq = d_curfreq_.get();
 	a.n_slots = n_slots_;
-	a.xbuf = d_xbuf_.get(); a.total_pairs = (int)total_pairs_;
 	a.geno_t = geno_t; a.cand_snp = d_cand_.get();
-	a.rinc = d_rinc_.get(); a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
+	a.total_pairs = (int)total_pairs_;
+	a.sp = (int2 *)d_sp_.get(); a.rinc = d_rinc_.get(); a.cuv = d_cuv_.get(); a.xbuf = d_xbuf_.get();
+	a.coff = d_coff_.get(); a.glen = d_glen_.get();
+	a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
 	a.scale = 0.5 / n_samp;
 	a.em_reltol = std::sqrt(DBL_EPSILON);
-	const size_t smem_base = sizeof(double) * ((size_t)n2_ + 40 + 2 * MAX_CLUSTER + 2 * (size_t)n_entry_) +
+	const size_t smem_base = sizeof(double) * (2 * (size_t)n2_ + 40 + 3 * MAX_CLUSTER + 2 * (size_t)n_entry_) +
 		sizeof(int) * (size_t)n_entry_ + 16;
 	int m_warps = (int)((220 * 1024 - smem_base) / (sizeof(double) * RING_ROWS * 32));
 	if (m_warps > 8) m_warps = 8;
@@ -714,10 +876,11 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	a.m_warps = m_warps;
 	const size_t smem = smem_base + sizeof(double) * RING_ROWS * 32 * (size_t)m_warps;
 	// SMs per candidate: enough pairs per CTA to pay for the cluster barriers, and the whole
-	// round resident at once
+	// round on at most ~half of the SMs (the other lanes' scoring launches run beside it; the
+	// kernel is latency-bound, so SM-time per candidate is lowest for small clusters)
 	int cluster = 1;
 	while (cluster < MAX_CLUSTER && total_pairs_ / (2 * (size_t)cluster) >= 6000 &&
-		(size_t)m * 2 * cluster <= (size_t)current_device().sm_count) cluster *= 2;
+		(size_t)m * 2 * cluster <= (size_t)current_device().sm_count * 11 / 20) cluster *= 2;
 	if (const char *e = getenv("HIBAG_B200_EM_CLUSTER")) cluster = std::max(1, std::min(MAX_CLUSTER, atoi(e)));
 	HB_CUDA(cudaFuncSetAttribute(em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
 	HB_CUDA(cudaEventRecord(ev0_.e, st));
@@ -744,6 +907,21 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 	kernel_ms += ms;
 	launches++;
+	if (getenv("HIBAG_B200_EM_DEBUG"))
+	{
+		std::vector<int> gl((size_t)m * n_groups), co((size_t)m * (n_entry_ + 1));
+		HB_CUDA(cudaMemcpy(gl.data(), d_glen_.get(), sizeof(int) * gl.size(), cudaMemcpyDeviceToHost));
+		HB_CUDA(cudaMemcpy(co.data(), d_coff_.get(), sizeof(int) * co.size(), cudaMemcpyDeviceToHost));
+		long rows = 0; int gmax = 0; long compat = 0;
+		for (int i = 0; i < m; i++)
+		{
+			if (h_status_.get()[4 * i] == EM_INVALID) continue;
+			for (int g = 0; g < n_groups; g++) { rows += gl[(size_t)i * n_groups + g]; gmax = std::max(gmax, gl[(size_t)i * n_groups + g]); }
+			compat += co[(size_t)i * (n_entry_ + 1) + n_entry_];
+		}
+		fprintf(stderr, "em compaction: cluster %d, kernel %.3f ms, compat pairs/cand %.0f of %zu, ELL rows/cand %.0f, longest chain %d (uncompacted %d)\n",
+			cluster, ms, (double)compat / m, total_pairs_, (double)rows / m, gmax, max_chain_);
+	}
 	h2d_bytes += sizeof(int) * (size_t)m;
 	d2h_bytes += sizeof(double) * (size_t)m * n2_ + sizeof(int) * 4 * (size_t)m;
 }

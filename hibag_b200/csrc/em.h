@@ -35,7 +35,7 @@ public:
 	static bool supports(int n_cur, int n_entry)
 	{
 		return 2 * (size_t)n_cur <= 65535 &&
-			8 * (2 * (size_t)n_cur + 56 + 2 * (size_t)n_entry) + 4 * (size_t)n_entry + 16 + 16384 <= 220 * 1024;
+			8 * (4 * (size_t)n_cur + 64 + 2 * (size_t)n_entry) + 4 * (size_t)n_entry + 16 + 16384 <= 220 * 1024;
 	}
 
 	/// Pair matching for the in-bag entries on the current SNP set + incidence structure.
@@ -63,6 +63,9 @@ public:
 	size_t total_pairs() const { return total_pairs_; }
 	size_t ell_slots() const { return n_slots_; }
 	int max_chain() const { return max_chain_; }
+	/// an in-bag sample without any haplotype pair (one of its alleles lost all haplotypes): the
+	/// caller estimates such a round on the host, whose degenerate arithmetic is the reference's
+	bool has_empty_entry() const { return has_empty_entry_; }
 	double kernel_ms = 0;          // summed CUDA-event time of the EM launches
 	uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 
@@ -81,11 +84,13 @@ private:
 	DevBuf<int> d_pairs4_;            // int4 {u, v, slot_u, slot_v} per pair
 	size_t n_slots_ = 0;
 	int max_chain_ = 0;
+	bool has_empty_entry_ = false;
 	DevBuf<unsigned char> d_tmp_;     // cub temporary storage
 	PinBuf<int> h_total_;
 	DevBuf<int> d_cand_;
 	PinBuf<int> h_cand_;
-	DevBuf<double> d_rinc_, d_freq_, d_xbuf_;
+	DevBuf<double> d_freq_, d_xbuf_, d_rinc_;
+	DevBuf<int> d_sp_, d_cuv_, d_coff_, d_glen_;        // per-candidate compaction (em_kernel)
 	DevBuf<int> d_status_;
 	PinBuf<double> h_freq_;
 	PinBuf<int> h_status_;

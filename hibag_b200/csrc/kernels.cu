@@ -936,6 +936,12 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(int iters, uint32_t seed
 				d1 += lds_f64(lane_addr + ((x1 + u) & 63u) * 256u);
 				d2 += lds_f64(lane_addr + ((x2 + u) & 63u) * 256u);
 				d3 += lds_f64(lane_addr + ((x3 + u) & 63u) * 256u);
+			} else if (WHICH == 6)   // one dependent DADD chain per thread (latency)
+			{
+				d0 = __dadd_rn(d0, m0);
+			} else if (WHICH == 7)   // one dependent DMUL+DADD chain per thread (latency)
+			{
+				d0 = __dadd_rn(__dmul_rn(d0, m1), m0);
 			} else {                 // IADD3
 				x0 = x0 + y0 + y1; x1 = x1 + y1 + y2; x2 = x2 + y2 + y3; x3 = x3 + y3 + y0;
 				y0 = y0 + x1 + x2; y1 = y1 + x2 + x3; y2 = y2 + x3 + x0; y3 = y3 + x0 + x1;
@@ -952,9 +958,10 @@ double run_pipe_peak(int which, int sm_count, double *out_ms)
 	uint32_t *sink = nullptr;
 	CUDA_CHECK(cudaMalloc(&sink, 4));
 	const int iters = 4096;
-	const int grid = sm_count * 8, block = 256;
+	// 6, 7: dependent-chain latency -- one warp on one SM
+	const int grid = (which >= 6) ? 1 : sm_count * 8, block = (which >= 6) ? 32 : 256;
 	// lane-operations of the measured kind per thread per inner iteration (16x unrolled)
-	static const int ops_per_u[6] = { 8, 8, 8, 8, 4, 8 };
+	static const int ops_per_u[8] = { 8, 8, 8, 8, 4, 8, 1, 1 };
 	cudaEvent_t e0, e1;
 	CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
 	float best = 1e30f;
@@ -978,7 +985,7 @@ double run_pipe_peak(int which, int sm_count, double *out_ms)
 	}
 	CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
 	CUDA_CHECK(cudaFree(sink));
-	const int w = (which < 0 || which > 5) ? 5 : which;
+	const int w = (which < 0 || which > 7) ? 5 : which;
 	const double ops = (double)grid * block * (double)iters * 16.0 * ops_per_u[w];
 	if (out_ms) *out_ms = best;
 	return ops / (best * 1e-3);

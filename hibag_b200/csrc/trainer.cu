@@ -506,6 +506,13 @@ void Trainer::grow(Classifier &cl)
 				rem_->prepare(cur, d_s1_.get(), d_s2_.get(), n_samp_, d_a1_.get(), d_a2_.get(),
 					d_ib_.get(), (int)inbag_.size(), d_boot_.get(), main_st_.s);
 				host_rp_valid = false;
+				if (rem_->has_empty_entry())
+				{
+					// degenerate round (an in-bag sample without pairs): host arithmetic
+					rem_->fetch_pairs(rp, inbag_, boot_, main_st_.s);
+					host_rp_valid = true;
+					dev_em = false;
+				}
 			} else {
 				prepare_round(cur, geno_, a1_, a2_, boot_, inbag_, rp, pool_parallel_for, &pf);
 			}

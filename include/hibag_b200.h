@@ -242,8 +242,9 @@ int hibag_b200_host_build_tasks(const hibag_haplotype *haplo, int n_haplo, int n
 	int target_chunks, int32_t *out_cells, int32_t *out_chunks, int *n_chunks, uint64_t *pairs);
 
 /* ---- microbenchmarks of the pipes that bound this path ----------------- */
-/* which: 0 POPC.32, 1 LOP3, 2 DMUL+DADD, 3 DFMA, 4 LDS.64 (lane-private), 5 IADD3.
- * Returns lane-ops per second over the whole device in *out_ops_per_s. */
+/* which: 0 POPC.32, 1 LOP3, 2 DMUL+DADD, 3 DFMA, 4 LDS.64 (lane-private), 5 IADD3: lane-ops per
+ * second over the whole device in *out_ops_per_s. 6 DADD, 7 DMUL+DADD: ONE warp running one
+ * dependent chain per lane (32 * clock / *out_ops_per_s = dependent-issue latency in cycles). */
 int hibag_b200_pipe_peak(int which, double *out_ops_per_s, double *out_ms);
 
 #ifdef __cplusplus

@@ -241,6 +241,26 @@ def test_trainer_matches_reference_on_synthetic(gpu, ref):
     assert st["pair_evals"] == full.train_stats()["pair_evals"]
 
 
+def test_trainer_matches_reference_many_alleles(gpu):
+    """DRB1-like shape (many alleles, long haplotype lists, EM clusters of several CTAs):
+    bit-identical classifiers vs the reference's base target (fixture generated from the compiled
+    reference by tools/make_golden_synth.py)"""
+    from hibag_b200 import synth
+    gd = helpers.load_golden("synth_many_alleles_ref.npz")
+    coh = synth.make_cohort(int(gd["n_samp"]), int(gd["n_snp"]), int(gd["n_hla"]), seed=int(gd["cohort_seed"]))
+    n_cls = int(gd["n_cls"])
+    for kwargs in (dict(n_concurrent=2), dict(em_on_device=False, n_threads=8)):
+        m = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        m.set_training(coh.geno, coh.h1, coh.h2)
+        m.train(n_cls, gpu.default_mtry(coh.n_snp), prune=True, seed=int(gd["train_seed"]),
+                per_classifier_seed=True, **kwargs)
+        for k in range(n_cls):
+            want = dict(snpidx=gd["c%d_snpidx" % k], samp_num=gd["c%d_samp_num" % k], freq=gd["c%d_freq" % k],
+                        hla=gd["c%d_hla" % k], packed=gd["c%d_packed" % k], oob_acc=float(gd["c%d_oob_acc" % k]))
+            d = helpers.classifier_diff(m.classifier(k), want)
+            assert d == "", (kwargs, k, d)
+
+
 def _golden_model(gpu, ref, n_cls=100):
     geno, h1, h2, al, ml = helpers.hapmap_a_training()
     m = gpu.HLAModel(geno.shape[1], len(al), al)
