@@ -33,7 +33,7 @@ class TrainOpts(C.Structure):
                 ("n_threads", C.c_int), ("seed", C.c_int64), ("per_classifier_seed", C.c_int),
                 ("first_index", C.c_int), ("index_stride", C.c_int),
                 ("use_legacy_hooks", C.c_int), ("verbose", C.c_int), ("n_concurrent", C.c_int),
-                ("em_on_device", C.c_int)]
+                ("em_on_device", C.c_int), ("no_screening", C.c_int)]
 
 
 class TrainStats(C.Structure):
@@ -45,7 +45,8 @@ class TrainStats(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("cell_kernel_ms", C.c_double),
                 ("cell_kernel_launches", C.c_uint64), ("seconds_prepare", C.c_double),
                 ("seconds_phase_oob", C.c_double), ("seconds_phase_ib", C.c_double),
-                ("em_kernel_ms", C.c_double), ("n_em_host_fallback", C.c_uint64)]
+                ("em_kernel_ms", C.c_double), ("n_em_host_fallback", C.c_uint64),
+                ("pair_evals_nominal", C.c_uint64), ("n_screen_fallback", C.c_uint64)]
 
 
 class PredictOut(C.Structure):
@@ -255,10 +256,10 @@ class HLAModel:
 
     def train(self, nclassifier, mtry, prune=True, seed=100, n_threads=0, per_classifier_seed=False,
               first_index=0, index_stride=1, use_legacy_hooks=False, verbose=0, n_concurrent=1,
-              em_on_device=True):
+              em_on_device=True, screening=True):
         o = TrainOpts(nclassifier, mtry, int(prune), n_threads, seed, int(per_classifier_seed),
                       first_index, index_stride, int(use_legacy_hooks), verbose, int(n_concurrent),
-                      int(em_on_device))
+                      int(em_on_device), int(not screening))
         _chk(lib().hibag_b200_model_train(self._h, C.byref(o)))
 
     def train_stats(self):

@@ -15,7 +15,7 @@ struct CellTask
 	int b_start, b_n;    // haplotypes of allele b
 	int out_idx;         // H2 + H1*(2*n_hla-H1-1)/2
 	int diag;            // 1 when a == b (upper triangle of pairs, first term f*f)
-	int pad0, pad1;      // 32-byte records: two aligned vector loads in the kernel
+	int al_a, al_b;      // the two allele indices (32-byte records: two aligned vector loads)
 };
 
 /// A run of consecutive cells [cell_begin, cell_end) processed by one warp for one group of
@@ -122,6 +122,86 @@ void launch_normalize(double *P, size_t p_stride, int n_hla, int n_pos, double *
 
 /// transpose P[cell][pos] -> out[pos][cell]
 void launch_transpose(const double *P, size_t p_stride, int n_cells, int n_pos, double *out,
+	cudaStream_t st);
+
+
+// ---- exact screening of the training passes (screen.cu) --------------------------------------
+//
+// In training every sample's true HLA type is known, so the exact value x_ref of its true cell
+// is cheap to get first. A cell (a,b) whose value cannot exceed
+//     bound(a,b) = U_a * U_b * K,   U_a = sum_{i in a} f_i * T'[hom-SNP mismatches of h_i]
+// (the heterozygous SNPs can only add distance; T' = max(T, 1e-100), K covers 2x, the table's
+// rounding and the chains' rounding) is
+//   * out-of-bag (argmax): irrelevant when bound < x_ref  -- it cannot be the best guess;
+//   * in-bag (sequential sum): irrelevant when its bound is far below x_ref, which the
+//     reduction CERTIFIES: it adds the chain once with 0 and once with the bound for every
+//     skipped cell; fp64 addition is monotone, so equal results prove the full chain has that
+//     value. Samples that fail the certificate are rescored without screening.
+// Only the cells that survive are scored, by a gather kernel whose lanes are the samples that
+// need the cell. Every value that is produced is the reference's own chain, bit for bit.
+
+/// One haplotype list of a screened launch
+struct GatherList
+{
+	const void *hap;
+	const CellTask *cells;        // in decreasing-cost order (as in the blob)
+	const int8_t *cand_col;
+	double *P;                    // P[out_idx * p_stride + pos]
+	const int *count;             // [n_cells] by out_idx: positions that need the cell
+	const int *entries;           // positions, cell c at ent_off[c] .. + count[c]
+	const unsigned int *task_prefix;   // [n_cells + 1] over the blob's cell order, in 128-position tasks
+	int n_hap, cand_bit;
+};
+
+struct GatherBatch
+{
+	const double *table;
+	const uint32_t *s1, *s2;
+	const int *samp_list;
+	const int *ent_off;           // [n_cells] by out_idx (shared by the lists of a launch)
+	unsigned int *task_counters;  // [n_lists], zeroed before launch
+	size_t p_stride;
+	int n_dist, n_snp, geno_stride, n_pos;
+	int n_lists, max_hap, n_cells, pad;
+	GatherList lists[MAX_BATCH_LISTS];
+};
+
+/// the surviving cells of all lists in one launch. Returns POPC.32 per pair evaluation.
+int launch_cell_gather(const GatherBatch &b, int sm_count, cudaStream_t st);
+
+/// arguments shared by the screening kernels of one launch (list l uses slice l of every array)
+struct ScreenArgs
+{
+	const double *table_floor;    // T' on the device
+	const uint32_t *s1, *s2;
+	const int *samp_list;
+	const int *a1, *a2;           // true types by sample, a1 <= a2
+	int n_dist, n_snp, geno_stride, n_pos, n_hla, n_lists;
+	size_t p_stride;
+	double K;                     // bound factor
+	double tau;                   // need a cell when bound >= tau * x_ref
+	double *U;                    // [n_lists][n_hla][p_stride]
+	double *P;                    // [n_lists][n_cells][p_stride]
+	int *count;                   // [n_lists][n_cells]
+	int *entries;                 // [n_lists][n_cells][p_stride]
+	unsigned int *task_prefix;    // [n_lists][n_cells + 1]
+	unsigned long long *evals;    // [n_lists] pair evaluations the gather launch will execute
+};
+struct ScreenList { const void *hap; const CellTask *cells; const int8_t *cand_col; int n_hap, cand_bit; };
+struct ScreenLists { ScreenList l[MAX_BATCH_LISTS]; };
+
+/// U[l][a][pos]
+void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_t st);
+/// per list: task prefix over the blob's cell order from count (stride 0: one shared count array)
+/// and the pair evaluations those tasks hold (added to evals[l])
+void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
+	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, cudaStream_t st);
+/// per (list, pos): which cells are needed (appends to entries / count)
+void launch_screen_need(const ScreenArgs &a, cudaStream_t st);
+/// screened reductions (same outputs as launch_reduce_oob / launch_reduce_ib; an in-bag position
+/// whose sum could not be certified gets ratio -1)
+void launch_reduce_oob_screened(const ScreenArgs &a, int *out_count, cudaStream_t st);
+void launch_reduce_ib_screened(const ScreenArgs &a, double *out_ratio, size_t out_stride,
 	cudaStream_t st);
 
 // ---- prediction --------------------------------------------------------------------------

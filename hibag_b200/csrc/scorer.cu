@@ -2,6 +2,7 @@
 #include "scorer.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -68,6 +69,22 @@ const double *device_rare_freq_table()
 	HB_CUDA(cudaMalloc((void **)&d, bytes));
 	HB_CUDA(cudaMemcpy(d, host_rare_freq_table(), bytes, cudaMemcpyHostToDevice));
 	g_dev_table[di.device] = d;
+	return d;
+}
+
+static std::map<int, double *> g_dev_floor_table;
+
+const double *device_rare_freq_floor_table()
+{
+	const DeviceInfo &di = current_device();
+	std::lock_guard<std::mutex> lk(g_dev_mutex);
+	auto it = g_dev_floor_table.find(di.device);
+	if (it != g_dev_floor_table.end()) return it->second;
+	double *d = nullptr;
+	const size_t bytes = sizeof(double) * (2 * HIBAG_B200_MAX_SNP + 1);
+	HB_CUDA(cudaMalloc((void **)&d, bytes));
+	HB_CUDA(cudaMemcpy(d, host_rare_freq_floor_table(), bytes, cudaMemcpyHostToDevice));
+	g_dev_floor_table[di.device] = d;
 	return d;
 }
 
@@ -277,9 +294,11 @@ void BatchScorer::begin_round(int n_lists, int max_hap, int n_snp, int n_hla)
 	d_blobs_.ensure(cap_ * (size_t)n_lists);
 	blobs_.assign(n_lists, ListBlob());
 	cols_.assign(n_lists, nullptr);
-	counters_.ensure(n_lists);
+	counters_.ensure(2 * MAX_BATCH_LISTS);
 	d_counts_.ensure(n_lists);
 	h_counts_.ensure(n_lists);
+	d_evals_.ensure(n_lists);
+	h_evals_.ensure(n_lists);
 }
 
 void BatchScorer::upload(const std::vector<int> &which)
@@ -293,8 +312,44 @@ void BatchScorer::upload(const std::vector<int> &which)
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
 }
 
+void BatchScorer::set_sample_sets(const std::vector<int> &oob, const std::vector<int> &ib,
+	const std::vector<int> &a1, const std::vector<int> &a2, int n_hla)
+{
+	const int n_cells = n_hla * (n_hla + 1) / 2;
+	screen_ = false;
+	for (int kind = 0; kind < 2; kind++)
+	{
+		const std::vector<int> &s = kind ? ib : oob;
+		const size_t stride = (s.size() + 31) & ~(size_t)31;
+		if ((size_t)n_cells * stride > (size_t)0x7fffffff) return;    // positions are addressed with int
+		set_samples_[kind] = s;
+		std::vector<int> count(n_cells, 0), off(n_cells, 0), ent(s.size() + 1, 0), eoff(n_cells, 0);
+		std::vector<int> cell_of(s.size());
+		for (size_t p = 0; p < s.size(); p++)
+		{
+			const int t1 = a1[s[p]], t2 = a2[s[p]];
+			cell_of[p] = t2 + t1 * (2 * n_hla - t1 - 1) / 2;          // src/LibHLA.cpp:1712
+			count[cell_of[p]]++;
+		}
+		int run = 0;
+		for (int c = 0; c < n_cells; c++) { off[c] = run; run += count[c]; eoff[c] = (int)((size_t)c * stride); }
+		std::vector<int> cur(off);
+		for (size_t p = 0; p < s.size(); p++) ent[cur[cell_of[p]]++] = (int)p;
+		tc_count_[kind].ensure(n_cells); tc_off_[kind].ensure(n_cells);
+		tc_ent_[kind].ensure(ent.size()); ent_off_[kind].ensure(n_cells);
+		HB_CUDA(cudaMemcpyAsync(tc_count_[kind].get(), count.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
+		HB_CUDA(cudaMemcpyAsync(tc_off_[kind].get(), off.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
+		HB_CUDA(cudaMemcpyAsync(tc_ent_[kind].get(), ent.data(), sizeof(int) * ent.size(), cudaMemcpyHostToDevice, st_.s));
+		HB_CUDA(cudaMemcpyAsync(ent_off_[kind].get(), eoff.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
+		HB_CUDA(cudaStreamSynchronize(st_.s));       // the host vectors go out of scope
+		stats.h2d_bytes += sizeof(int) * (3 * (size_t)n_cells + ent.size());
+	}
+	device_rare_freq_floor_table();
+	screen_ = true;
+}
+
 void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<int> &which,
-	int first, int count, const int *pos_list, int n_pos)
+	int first, int count, const int *pos_list, int n_pos, double *P, size_t p_stride)
 {
 	const DeviceInfo &di = current_device();
 	CellBatch b;
@@ -303,7 +358,7 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 	b.s1 = g.s1; b.s2 = g.s2; b.geno_stride = g.stride;
 	b.samp_list = pos_list; b.n_pos = n_pos;
 	b.task_counters = counters_.get();
-	b.p_stride = p_stride_;
+	b.p_stride = p_stride;
 	b.n_snp = n_snp_;
 	b.n_lists = count;
 	int total_chunks = 0;
@@ -319,7 +374,7 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 		L.chunks = (const Chunk *)(d + lb.off_chunks);
 		L.cand_col = cols_[i];
 		L.cand_bit = cand_bit;
-		L.P = P_.get() + (size_t)(first + k) * n_cells_ * p_stride_;
+		L.P = P + (size_t)(first + k) * n_cells_ * p_stride;
 		L.n_hap = lb.n_hap; L.n_chunks = lb.n_chunks;
 		b.n_dist = lb.n_dist;
 		if (lb.n_hap > b.max_hap) b.max_hap = lb.n_hap;
@@ -345,20 +400,118 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 	stats.popc32 += pairs * (uint64_t)n_pos * (uint64_t)nw;
 }
 
+/// One sub-batch of a screened pass, all on the device's scoring stream: per-allele bounds,
+/// the true cells (gather launch A), the need lists, the surviving cells (gather launch B)
+/// and the screened reduction. kind: 0 out-of-bag, 1 in-bag.
+void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std::vector<int> &which,
+	int first, int count, const int *pos_list, int n_pos, int kind)
+{
+	const DeviceInfo &di = current_device();
+	const size_t n_cells = (size_t)n_cells_;
+	ScreenArgs a;
+	ScreenLists ls;
+	GatherBatch gb;
+	memset(&a, 0, sizeof(a)); memset(&ls, 0, sizeof(ls)); memset(&gb, 0, sizeof(gb));
+	a.table_floor = device_rare_freq_floor_table();
+	a.s1 = g.s1; a.s2 = g.s2; a.samp_list = pos_list; a.a1 = g.a1; a.a2 = g.a2;
+	a.n_snp = n_snp_; a.geno_stride = g.stride; a.n_pos = n_pos; a.n_hla = n_hla_; a.n_lists = count;
+	a.p_stride = p_stride_;
+	a.K = screen_bound_factor();
+	a.tau = kind ? 0x1p-63 : 1.0;
+	a.U = U_.get() + (size_t)first * n_hla_ * p_stride_;
+	a.P = P_.get() + (size_t)first * n_cells * p_stride_;
+	a.count = cnt_.get() + (size_t)first * n_cells;
+	a.entries = ent_.get() + (size_t)first * n_cells * p_stride_;
+	a.task_prefix = prefix_.get() + (size_t)first * (n_cells + 1);
+	a.evals = d_evals_.get() + first;
+	gb.table = device_rare_freq_table();
+	gb.s1 = g.s1; gb.s2 = g.s2; gb.samp_list = pos_list;
+	gb.p_stride = p_stride_; gb.n_snp = n_snp_; gb.geno_stride = g.stride; gb.n_pos = n_pos;
+	gb.n_lists = count; gb.n_cells = n_cells_;
+	uint64_t pairs = 0;
+	for (int k = 0; k < count; k++)
+	{
+		const int i = which[first + k];
+		const ListBlob &lb = blobs_[i];
+		const unsigned char *d = d_blobs_.get() + (size_t)i * cap_;
+		ScreenList &S = ls.l[k];
+		S.hap = d; S.cells = (const CellTask *)(d + lb.off_cells);
+		S.cand_col = cols_[i]; S.n_hap = lb.n_hap; S.cand_bit = cand_bit;
+		GatherList &L = gb.lists[k];
+		L.hap = d; L.cells = S.cells; L.cand_col = cols_[i];
+		L.P = a.P + (size_t)k * n_cells * p_stride_;
+		L.n_hap = lb.n_hap; L.cand_bit = cand_bit;
+		L.task_prefix = a.task_prefix + (size_t)k * (n_cells + 1);
+		// launch A: the true cells; one CSR over positions shared by all lists
+		L.count = tc_count_[kind].get();
+		L.entries = tc_ent_[kind].get();
+		a.n_dist = gb.n_dist = lb.n_dist;
+		if (lb.n_hap > gb.max_hap) gb.max_hap = lb.n_hap;
+		pairs += lb.pairs_per_sample;
+	}
+	ScoreQueue &q = ScoreQueue::get();
+	int nw;
+	{
+		std::lock_guard<std::mutex> lk(q.mu);
+		cudaStream_t s = q.st.s;
+		HB_CUDA(cudaStreamWaitEvent(s, ev_up_.e, 0));
+		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * 2 * MAX_BATCH_LISTS, s));
+		HB_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * (size_t)count * n_cells, s));
+		HB_CUDA(cudaEventRecord(ev0_.e, s));
+		launch_screen_bound(a, ls, s);
+		launch_screen_tasks(ls, count, n_cells_, tc_count_[kind].get(), 0, a.task_prefix, a.evals, s);
+		gb.ent_off = tc_off_[kind].get();
+		gb.task_counters = counters_.get();
+		nw = launch_cell_gather(gb, di.sm_count, s);
+		launch_screen_need(a, s);
+		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, s);
+		// launch B: the cells that survived the screen, per list
+		for (int k = 0; k < count; k++)
+		{
+			gb.lists[k].count = a.count + (size_t)k * n_cells;
+			gb.lists[k].entries = a.entries + (size_t)k * n_cells * p_stride_;
+		}
+		gb.ent_off = ent_off_[kind].get();
+		gb.task_counters = counters_.get() + MAX_BATCH_LISTS;
+		launch_cell_gather(gb, di.sm_count, s);
+		if (kind == 0)
+			launch_reduce_oob_screened(a, d_counts_.get() + first, s);
+		else
+			launch_reduce_ib_screened(a, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+		HB_CUDA(cudaEventRecord(ev1_.e, s));
+	}
+	HB_CUDA(cudaStreamWaitEvent(st_.s, ev1_.e, 0));
+	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	stats.launches += 7; stats.cell_launches += 2;
+	stats.pair_evals_nominal += pairs * (uint64_t)n_pos;
+	(void)nw;
+}
+
 void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<int> &which,
 	const int *pos_list, int n_pos, std::vector<int> &counts)
 {
 	const int n = (int)which.size();
 	counts.assign(n, 0);
 	if (n == 0 || n_pos <= 0) return;
+	const bool screen = screen_ && n_pos == (int)set_samples_[0].size();
 	p_stride_ = ((size_t)n_pos + 31) & ~(size_t)31;
 	P_.ensure((size_t)n * n_cells_ * p_stride_);
+	if (screen)
+	{
+		U_.ensure((size_t)n * n_hla_ * p_stride_);
+		cnt_.ensure((size_t)n * n_cells_);
+		ent_.ensure((size_t)n * n_cells_ * p_stride_);
+		prefix_.ensure((size_t)n * (n_cells_ + 1));
+		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)n, st_.s));
+	}
 	HB_CUDA(cudaMemsetAsync(d_counts_.get(), 0, sizeof(int) * (size_t)n, st_.s));
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	uint64_t before = stats.pair_evals;
 	for (int first = 0; first < n; first += MAX_BATCH_LISTS)
 	{
 		const int count = std::min(MAX_BATCH_LISTS, n - first);
-		run_cells(g, cand_bit, which, first, count, pos_list, n_pos);
+		if (screen) run_cells_screened(g, cand_bit, which, first, count, pos_list, n_pos, 0);
+		else run_cells(g, cand_bit, which, first, count, pos_list, n_pos, P_.get(), p_stride_);
 		float ms = 0;
 		if (first + count < n)        // counters are reused by the next sub-batch
 		{
@@ -367,8 +520,15 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 			stats.cell_ms += ms; stats.kernel_ms += ms;
 		}
 	}
-	launch_reduce_oob(P_.get(), p_stride_, n_hla_, pos_list, n_pos, g.a1, g.a2, d_counts_.get(),
-		st_.s, n, (size_t)n_cells_ * p_stride_);
+	if (!screen)
+	{
+		stats.pair_evals_nominal += stats.pair_evals - before;
+		launch_reduce_oob(P_.get(), p_stride_, n_hla_, pos_list, n_pos, g.a1, g.a2, d_counts_.get(),
+			st_.s, n, (size_t)n_cells_ * p_stride_);
+		stats.launches++;
+	} else
+		HB_CUDA(cudaMemcpyAsync(h_evals_.get(), d_evals_.get(), sizeof(unsigned long long) * (size_t)n,
+			cudaMemcpyDeviceToHost, st_.s));
 	HB_CUDA(cudaMemcpyAsync(h_counts_.get(), d_counts_.get(), sizeof(int) * (size_t)n,
 		cudaMemcpyDeviceToHost, st_.s));
 	HB_CUDA(cudaEventRecord(ev_done_.e, st_.s));
@@ -376,7 +536,17 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 	float ms = 0;
 	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 	stats.cell_ms += ms; stats.kernel_ms += ms;
-	stats.launches++; stats.d2h_bytes += sizeof(int) * (size_t)n;
+	stats.d2h_bytes += sizeof(int) * (size_t)n;
+	if (screen)
+	{
+		const int nw = geno_words(n_snp_);
+		for (int k = 0; k < n; k++)
+		{
+			stats.pair_evals += h_evals_.get()[k];
+			stats.popc32 += h_evals_.get()[k] * (uint64_t)nw;
+		}
+		stats.d2h_bytes += sizeof(unsigned long long) * (size_t)n;
+	}
 	for (int k = 0; k < n; k++) counts[k] = h_counts_.get()[k];
 }
 
@@ -385,16 +555,27 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 {
 	const int n = (int)which.size();
 	if (n == 0 || n_pos <= 0) return;
+	const bool screen = screen_ && n_pos == (int)set_samples_[1].size();
 	p_stride_ = ((size_t)n_pos + 31) & ~(size_t)31;
 	ratio_stride_ = p_stride_;
 	P_.ensure((size_t)n * n_cells_ * p_stride_);
 	d_ratio_.ensure((size_t)n * ratio_stride_);
 	h_ratio_.ensure((size_t)n * ratio_stride_);
+	if (screen)
+	{
+		U_.ensure((size_t)n * n_hla_ * p_stride_);
+		cnt_.ensure((size_t)n * n_cells_);
+		ent_.ensure((size_t)n * n_cells_ * p_stride_);
+		prefix_.ensure((size_t)n * (n_cells_ + 1));
+		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)n, st_.s));
+	}
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	uint64_t before = stats.pair_evals;
 	for (int first = 0; first < n; first += MAX_BATCH_LISTS)
 	{
 		const int count = std::min(MAX_BATCH_LISTS, n - first);
-		run_cells(g, cand_bit, which, first, count, pos_list, n_pos);
+		if (screen) run_cells_screened(g, cand_bit, which, first, count, pos_list, n_pos, 1);
+		else run_cells(g, cand_bit, which, first, count, pos_list, n_pos, P_.get(), p_stride_);
 		if (first + count < n)
 		{
 			float ms = 0;
@@ -403,8 +584,15 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 			stats.cell_ms += ms; stats.kernel_ms += ms;
 		}
 	}
-	launch_reduce_ib(P_.get(), p_stride_, n_hla_, pos_list, n_pos, g.a1, g.a2, d_ratio_.get(),
-		st_.s, n, (size_t)n_cells_ * p_stride_, ratio_stride_);
+	if (!screen)
+	{
+		stats.pair_evals_nominal += stats.pair_evals - before;
+		launch_reduce_ib(P_.get(), p_stride_, n_hla_, pos_list, n_pos, g.a1, g.a2, d_ratio_.get(),
+			st_.s, n, (size_t)n_cells_ * p_stride_, ratio_stride_);
+		stats.launches++;
+	} else
+		HB_CUDA(cudaMemcpyAsync(h_evals_.get(), d_evals_.get(), sizeof(unsigned long long) * (size_t)n,
+			cudaMemcpyDeviceToHost, st_.s));
 	HB_CUDA(cudaMemcpyAsync(h_ratio_.get(), d_ratio_.get(), sizeof(double) * (size_t)n * ratio_stride_,
 		cudaMemcpyDeviceToHost, st_.s));
 	HB_CUDA(cudaEventRecord(ev_done_.e, st_.s));
@@ -412,7 +600,78 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 	float ms = 0;
 	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 	stats.cell_ms += ms; stats.kernel_ms += ms;
-	stats.launches++; stats.d2h_bytes += sizeof(double) * (size_t)n * ratio_stride_;
+	stats.d2h_bytes += sizeof(double) * (size_t)n * ratio_stride_;
+	if (screen)
+	{
+		const int nw = geno_words(n_snp_);
+		for (int k = 0; k < n; k++)
+		{
+			stats.pair_evals += h_evals_.get()[k];
+			stats.popc32 += h_evals_.get()[k] * (uint64_t)nw;
+		}
+		stats.d2h_bytes += sizeof(unsigned long long) * (size_t)n;
+		rescore_uncertified(g, cand_bit, which);
+	}
+}
+
+/// In-bag positions whose screened sum could not be certified (ratio -1): score them against
+/// every cell with the plain kernel and patch their ratios.
+void BatchScorer::rescore_uncertified(const GenoView &g, int cand_bit, const std::vector<int> &which)
+{
+	const int n = (int)which.size();
+	const int n_pos = (int)set_samples_[1].size();
+	std::vector<int> lists_fb;               // positions k in `which`
+	std::vector<char> mark(n_pos, 0);
+	const bool force = getenv("HIBAG_B200_SCREEN_FORCE_FALLBACK") != nullptr;   // test hook
+	for (int k = 0; k < n; k++)
+	{
+		double *r = h_ratio_.get() + (size_t)k * ratio_stride_;
+		if (force) for (int p = k % 7; p < n_pos; p += 7) r[p] = -1.0;
+		bool any = false;
+		for (int p = 0; p < n_pos; p++)
+			if (r[p] == -1.0) { mark[p] = 1; any = true; }
+		if (any) lists_fb.push_back(k);
+	}
+	if (lists_fb.empty()) return;
+	std::vector<int> F, fb_samp;
+	for (int p = 0; p < n_pos; p++)
+		if (mark[p]) { F.push_back(p); fb_samp.push_back(set_samples_[1][p]); }
+	const int nf = (int)F.size(), nl = (int)lists_fb.size();
+	const size_t stride = ((size_t)nf + 31) & ~(size_t)31;
+	d_fb_samp_.ensure(nf);
+	P_fb_.ensure((size_t)nl * n_cells_ * stride);
+	d_ratio_fb_.ensure((size_t)nl * stride);
+	h_ratio_fb_.ensure((size_t)nl * stride);
+	HB_CUDA(cudaMemcpyAsync(d_fb_samp_.get(), fb_samp.data(), sizeof(int) * (size_t)nf,
+		cudaMemcpyHostToDevice, st_.s));
+	HB_CUDA(cudaStreamSynchronize(st_.s));
+	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	std::vector<int> which_fb(nl);
+	for (int j = 0; j < nl; j++) which_fb[j] = which[lists_fb[j]];
+	for (int first = 0; first < nl; first += MAX_BATCH_LISTS)
+	{
+		const int count = std::min(MAX_BATCH_LISTS, nl - first);
+		run_cells(g, cand_bit, which_fb, first, count, d_fb_samp_.get(), nf, P_fb_.get(), stride);
+		float ms = 0;
+		HB_CUDA(cudaEventSynchronize(ev1_.e));
+		HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+		stats.cell_ms += ms; stats.kernel_ms += ms;
+	}
+	launch_reduce_ib(P_fb_.get(), stride, n_hla_, d_fb_samp_.get(), nf, g.a1, g.a2, d_ratio_fb_.get(),
+		st_.s, nl, (size_t)n_cells_ * stride, stride);
+	HB_CUDA(cudaMemcpyAsync(h_ratio_fb_.get(), d_ratio_fb_.get(), sizeof(double) * (size_t)nl * stride,
+		cudaMemcpyDeviceToHost, st_.s));
+	HB_CUDA(cudaEventRecord(ev_done_.e, st_.s));
+	HB_CUDA(cudaEventSynchronize(ev_done_.e));
+	stats.launches++; stats.d2h_bytes += sizeof(double) * (size_t)nl * stride;
+	stats.h2d_bytes += sizeof(int) * (size_t)nf;
+	for (int j = 0; j < nl; j++)
+	{
+		double *r = h_ratio_.get() + (size_t)lists_fb[j] * ratio_stride_;
+		const double *fb = h_ratio_fb_.get() + (size_t)j * stride;
+		for (int i = 0; i < nf; i++)
+			if (r[F[i]] == -1.0) { r[F[i]] = fb[i]; stats.screen_fallback++; }
+	}
 }
 
 }  // namespace hb

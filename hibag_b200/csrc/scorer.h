@@ -14,17 +14,22 @@ namespace hb {
 
 /// device copy of EXP_LOG_MIN_RARE_FREQ for the current device (uploaded once per device)
 const double *device_rare_freq_table();
+/// device copy of the floored table T' = max(T, 1e-100) the screening bounds use
+const double *device_rare_freq_floor_table();
 
 /// counters shared by the training / prediction drivers
 struct ScoreStats
 {
 	uint64_t pair_evals = 0, popc32 = 0, launches = 0, cell_launches = 0;
+	uint64_t pair_evals_nominal = 0;     // what the reference evaluates for the same passes
+	uint64_t screen_fallback = 0;        // in-bag positions rescored without screening
 	uint64_t h2d_bytes = 0, d2h_bytes = 0;
 	double kernel_ms = 0, cell_ms = 0;
 	void add(const ScoreStats &o)
 	{
 		pair_evals += o.pair_evals; popc32 += o.popc32; launches += o.launches;
 		cell_launches += o.cell_launches; h2d_bytes += o.h2d_bytes; d2h_bytes += o.d2h_bytes;
+		pair_evals_nominal += o.pair_evals_nominal; screen_fallback += o.screen_fallback;
 		kernel_ms += o.kernel_ms; cell_ms += o.cell_ms;
 	}
 };
@@ -127,11 +132,35 @@ public:
 	void score_ib(const GenoView &g, int cand_bit, const std::vector<int> &which,
 		const int *pos_list, int n_pos);
 	const double *ratios(int k) const { return h_ratio_.get() + (size_t)k * ratio_stride_; }
+	/// Exact screening (kernels.h): the sample sets of the classifier being grown -- ascending
+	/// sample indices of the out-of-bag and in-bag samples (the same order as the device lists
+	/// passed to score_oob / score_ib) and every sample's true type (a1 <= a2). Turns screening
+	/// on for the following score_* calls.
+	void set_sample_sets(const std::vector<int> &oob, const std::vector<int> &ib,
+		const std::vector<int> &a1, const std::vector<int> &a2, int n_hla);
+	void disable_screening() { screen_ = false; }
 	ScoreStats stats;
 
 private:
 	void run_cells(const GenoView &g, int cand_bit, const std::vector<int> &which, int first,
-		int count, const int *pos_list, int n_pos);
+		int count, const int *pos_list, int n_pos, double *P, size_t p_stride);
+	void run_cells_screened(const GenoView &g, int cand_bit, const std::vector<int> &which,
+		int first, int count, const int *pos_list, int n_pos, int kind);
+	void rescore_uncertified(const GenoView &g, int cand_bit, const std::vector<int> &which);
+	// screening state
+	bool screen_ = false;
+	std::vector<int> set_samples_[2];            // host copy of the sample lists (0 oob, 1 in-bag)
+	DevBuf<int> tc_count_[2], tc_off_[2], tc_ent_[2];   // true-cell CSR over positions
+	DevBuf<int> ent_off_[2];                     // out_idx * p_stride of the set
+	DevBuf<double> U_;
+	DevBuf<int> cnt_, ent_;
+	DevBuf<unsigned int> prefix_;
+	DevBuf<unsigned long long> d_evals_;
+	PinBuf<unsigned long long> h_evals_;
+	DevBuf<int> d_fb_samp_;
+	DevBuf<double> P_fb_, d_ratio_fb_;
+	PinBuf<double> h_ratio_fb_;
+	std::vector<uint64_t> list_pairs_;           // pairs per sample of the lists of the pass
 	Stream st_;
 	Event ev_up_{false}, ev0_, ev1_;
 	Event ev_done_{false, true};

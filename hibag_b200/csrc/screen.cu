@@ -1,0 +1,594 @@
+// screen.cu -- exact screening of the training passes and the gather form of the pair-scoring
+// kernel (see the block comment in kernels.h).
+//
+// What is skipped is PROVEN irrelevant for the integer / fp64 outputs the reference computes
+// (out-of-bag best guess, src/LibHLA.cpp:1639-1704; in-bag P_true / sum, :1706-1767); what is
+// evaluated is the reference's own sequential chain -- identical code to cell_pass_kernel's
+// (kernels.cu), un-fused multiply then add in (i outer, j inner) order.
+
+#include "kernels.h"
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "devutil.cuh"
+
+namespace hb {
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+	throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + \
+		" at " __FILE__ ":" + std::to_string(__LINE__)); } while (0)
+
+static constexpr int GATHER_THREADS = 128;
+static constexpr int TASK_POS = 128;          // positions per gather task (4 per lane)
+static constexpr int NA_INT = INT32_MIN;
+
+/// genotype bit planes of one sample, candidate SNP patched in at bit cand_bit
+/// (CGenotypeList::AddSNP, src/LibHLA.cpp:609-622, 860-874); !ok -> everything missing
+template <int NW>
+__device__ __forceinline__ void load_geno(const uint32_t *__restrict__ s1,
+	const uint32_t *__restrict__ s2, int stride, int samp, bool ok,
+	const int8_t *__restrict__ cand_col, int cand_bit, uint32_t (&S1)[NW], uint32_t (&S2)[NW])
+{
+#pragma unroll
+	for (int w = 0; w < NW; w++)
+	{
+		S1[w] = ok ? __ldg(s1 + (size_t)w * stride + samp) : 0u;
+		S2[w] = ok ? __ldg(s2 + (size_t)w * stride + samp) : 0xffffffffu;
+	}
+	if (cand_col != nullptr && ok)
+	{
+		const int g = __ldg(cand_col + samp);
+		const int cw = cand_bit >> 5;
+		const uint32_t bit = 1u << (cand_bit & 31);
+#pragma unroll
+		for (int w = 0; w < NW; w++)
+		{
+			if (w == cw)
+			{
+				if (g == 1 || g == 2) S1[w] |= bit; else S1[w] &= ~bit;
+				if (g == 0 || g == 1) S2[w] &= ~bit; else S2[w] |= bit;
+			}
+		}
+	}
+}
+
+/// upper bound of a cell's chain value from the per-allele sums (identical in every kernel)
+__device__ __forceinline__ double screen_bound(double ua, double ub, double K)
+{
+	return __dmul_rn(__dmul_rn(ua, ub), K);
+}
+
+__device__ __forceinline__ int true_cell_index(int t1, int t2, int n_hla)
+{
+	return t2 + t1 * (2 * n_hla - t1 - 1) / 2;           // src/LibHLA.cpp:1712, t1 <= t2
+}
+
+// ---------------------------------------------------------------------------------------
+// U[l][a][pos] = sum_{i in allele a} f_i * T'[min(c_i, dmax)],  c_i = mismatches of h_i on the
+// sample's homozygous SNPs (the c_i of cell_pass_kernel's one-popcount distance)
+// ---------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(128)
+screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
+{
+	extern __shared__ int sh_al[];                        // start[n_hla], n[n_hla]
+	const int l = blockIdx.y;
+	const ScreenList &L = ls.l[l];
+	int *al_start = sh_al, *al_n = sh_al + a.n_hla;
+	const int n_cells = a.n_hla * (a.n_hla + 1) / 2;
+	for (int k = threadIdx.x; k < n_cells; k += blockDim.x)
+	{
+		const int4 ca = __ldg((const int4 *)(L.cells + k));
+		const int4 cb = __ldg((const int4 *)((const char *)(L.cells + k) + 16));
+		if (cb.y) { al_start[cb.z] = ca.x; al_n[cb.z] = ca.y; }
+	}
+	__syncthreads();
+
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool ok = pos < a.n_pos;
+	int samp = 0;
+	if (ok) samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+	uint32_t S1[NW], S2[NW], HOM[NW], G2[NW];
+	load_geno<NW>(a.s1, a.s2, a.geno_stride, samp, ok, L.cand_col, L.cand_bit, S1, S2);
+#pragma unroll
+	for (int w = 0; w < NW; w++) { HOM[w] = ~(S1[w] ^ S2[w]); G2[w] = S1[w] & S2[w]; }
+	const int dmax = a.n_dist - 1;
+	const char *hap_g = (const char *)L.hap;
+	double *U = a.U + (size_t)l * a.n_hla * a.p_stride;
+	for (int al = 0; al < a.n_hla; al++)
+	{
+		const int i0 = al_start[al], i1 = i0 + al_n[al];
+		double acc = 0.0;
+		for (int i = i0; i < i1; i++)
+		{
+			HapRec<NW, false> h;
+			h.load(0u, hap_g, i);
+			int c = 0;
+#pragma unroll
+			for (int w = 0; w < NW; w++) c += __popc((h.h[w] ^ G2[w]) & HOM[w]);
+			const double t = __ldg(a.table_floor + min(c, dmax));
+			acc = __dadd_rn(acc, __dmul_rn(h.f, t));
+		}
+		if (ok) U[(size_t)al * a.p_stride + pos] = acc;
+	}
+}
+
+void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	dim3 grid((a.n_pos + 127) / 128, a.n_lists);
+	const size_t smem = sizeof(int) * 2 * (size_t)a.n_hla;
+	switch (geno_words(a.n_snp))
+	{
+	case 1: screen_bound_kernel<1><<<grid, 128, smem, st>>>(a, ls); break;
+	case 2: screen_bound_kernel<2><<<grid, 128, smem, st>>>(a, ls); break;
+	default: screen_bound_kernel<4><<<grid, 128, smem, st>>>(a, ls); break;
+	}
+	CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// per list: exclusive prefix of ceil(count/128) over the blob's cell order
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
+	const int *__restrict__ count, size_t count_stride, unsigned int *task_prefix,
+	unsigned long long *evals)
+{
+	__shared__ unsigned int seg[256];
+	const int l = blockIdx.x, tid = threadIdx.x;
+	const CellTask *cells = ls.l[l].cells;
+	const int *cnt = count + (size_t)l * count_stride;
+	unsigned int *pre = task_prefix + (size_t)l * (n_cells + 1);
+	const int per = (n_cells + 255) / 256;
+	const int k0 = min(n_cells, tid * per), k1 = min(n_cells, k0 + per);
+	unsigned int s = 0;
+	unsigned long long ev = 0;
+	for (int k = k0; k < k1; k++)
+	{
+		const int4 ca = __ldg((const int4 *)(cells + k));
+		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
+		const int c = __ldg(cnt + cb.x);
+		s += (unsigned int)((c + TASK_POS - 1) / TASK_POS);
+		const unsigned long long pairs = cb.y ? (unsigned long long)ca.y * (ca.y + 1) / 2
+			: (unsigned long long)ca.y * (unsigned long long)ca.w;
+		ev += pairs * (unsigned long long)c;
+	}
+	seg[tid] = s;
+	__syncthreads();
+	if (tid == 0)
+	{
+		unsigned int run = 0;
+		for (int t = 0; t < 256; t++) { const unsigned int v = seg[t]; seg[t] = run; run += v; }
+		pre[n_cells] = run;
+	}
+	__syncthreads();
+	unsigned int run = seg[tid];
+	for (int k = k0; k < k1; k++)
+	{
+		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
+		const int c = __ldg(cnt + cb.x);
+		pre[k] = run;
+		run += (unsigned int)((c + TASK_POS - 1) / TASK_POS);
+	}
+	if (ev) atomicAdd(evals + l, ev);
+}
+
+void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
+	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, cudaStream_t st)
+{
+	if (n_lists <= 0) return;
+	screen_tasks_kernel<<<n_lists, 256, 0, st>>>(ls, n_cells, count, count_stride, task_prefix, evals);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// which cells does a position need? lanes = consecutive positions; warp-aggregated append
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+screen_need_kernel(const ScreenArgs a)
+{
+	const int l = blockIdx.y;
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool ok = pos < a.n_pos;
+	const int n = a.n_hla;
+	const int n_cells = n * (n + 1) / 2;
+	const double *U = a.U + (size_t)l * n * a.p_stride;
+	const double *P = a.P + (size_t)l * n_cells * a.p_stride;
+	int *cnt = a.count + (size_t)l * n_cells;
+	int *ent = a.entries + (size_t)l * n_cells * a.p_stride;
+	int true_idx = -1;
+	double thr = 0.0;
+	if (ok)
+	{
+		const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+		true_idx = true_cell_index(__ldg(a.a1 + samp), __ldg(a.a2 + samp), n);
+		thr = __dmul_rn(P[(size_t)true_idx * a.p_stride + pos], a.tau);
+	}
+	int idx = 0;
+	for (int al = 0; al < n; al++)
+	{
+		const double ua = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
+		for (int bl = al; bl < n; bl++, idx++)
+		{
+			const double ub = ok ? U[(size_t)bl * a.p_stride + pos] : 0.0;
+			const double bd = screen_bound(ua, ub, a.K);
+			const bool need = ok && idx != true_idx && bd >= thr && bd > 0.0;
+			const unsigned mask = __ballot_sync(0xffffffffu, need);
+			if (mask)
+			{
+				const int leader = __ffs(mask) - 1;
+				int base = 0;
+				if (lane == leader) base = atomicAdd(cnt + idx, __popc(mask));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if (need)
+					ent[(size_t)idx * a.p_stride + base + __popc(mask & ((1u << lane) - 1u))] = pos;
+			}
+		}
+	}
+}
+
+void launch_screen_need(const ScreenArgs &a, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	dim3 grid((a.n_pos + 127) / 128, a.n_lists);
+	screen_need_kernel<<<grid, 128, 0, st>>>(a);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// screened reductions
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
+{
+	const int l = blockIdx.y;
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n = a.n_hla;
+	const int n_cells = n * (n + 1) / 2;
+	int cnt = 0;
+	if (pos < a.n_pos)
+	{
+		const double *U = a.U + (size_t)l * n * a.p_stride + pos;
+		const double *P = a.P + (size_t)l * n_cells * a.p_stride + pos;
+		const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+		int t1 = __ldg(a.a1 + samp), t2 = __ldg(a.a2 + samp);
+		const int true_idx = true_cell_index(t1, t2, n);
+		const double thr = __dmul_rn(P[(size_t)true_idx * a.p_stride], a.tau);
+		// strict '<' scan in cell order over the cells that were scored; a skipped cell is
+		// strictly below the true cell's value and can never be the first maximum
+		double best = 0.0;
+		int p1 = NA_INT, p2 = NA_INT;
+		int idx = 0;
+		for (int al = 0; al < n; al++)
+		{
+			const double ua = U[(size_t)al * a.p_stride];
+			for (int bl = al; bl < n; bl++, idx++)
+			{
+				const double bd = screen_bound(ua, U[(size_t)bl * a.p_stride], a.K);
+				if (idx == true_idx || (bd >= thr && bd > 0.0))
+				{
+					const double v = P[(size_t)idx * a.p_stride];
+					if (best < v) { best = v; p1 = al; p2 = bl; }
+				}
+			}
+		}
+		// CHLATypeList::Compare (src/LibHLA.cpp:912-924)
+		if (p1 == t1) { cnt = 1; t1 = -1; }
+		else if (p1 == t2) { cnt = 1; t2 = -1; }
+		if (p2 == t1 || p2 == t2) cnt++;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out_count + l, cnt);
+}
+
+void launch_reduce_oob_screened(const ScreenArgs &a, int *out_count, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	dim3 grid((a.n_pos + 63) / 64, a.n_lists);
+	reduce_oob_screened_kernel<<<grid, 64, 0, st>>>(a, out_count);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(64)
+reduce_ib_screened_kernel(const ScreenArgs a, double *out_ratio, size_t out_stride)
+{
+	const int l = blockIdx.y;
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos >= a.n_pos) return;
+	const int n = a.n_hla;
+	const int n_cells = n * (n + 1) / 2;
+	const double *U = a.U + (size_t)l * n * a.p_stride + pos;
+	const double *P = a.P + (size_t)l * n_cells * a.p_stride + pos;
+	const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+	const int true_idx = true_cell_index(__ldg(a.a1 + samp), __ldg(a.a2 + samp), n);
+	const double x_true = P[(size_t)true_idx * a.p_stride];
+	const double thr = __dmul_rn(x_true, a.tau);
+	// the sequential sum in cell order, once with 0 and once with the bound for every skipped
+	// cell: addition is monotone, so lo <= (the full chain) <= hi, and lo == hi certifies it
+	double lo = 0.0, hi = 0.0;
+	int idx = 0;
+	for (int al = 0; al < n; al++)
+	{
+		const double ua = U[(size_t)al * a.p_stride];
+		for (int bl = al; bl < n; bl++, idx++)
+		{
+			const double bd = screen_bound(ua, U[(size_t)bl * a.p_stride], a.K);
+			if (idx == true_idx || (bd >= thr && bd > 0.0))
+			{
+				const double v = P[(size_t)idx * a.p_stride];
+				lo = __dadd_rn(lo, v);
+				hi = __dadd_rn(hi, v);
+			} else
+				hi = __dadd_rn(hi, bd);
+		}
+	}
+	out_ratio[(size_t)l * out_stride + pos] = (lo == hi) ? __ddiv_rn(x_true, lo) : -1.0;
+}
+
+void launch_reduce_ib_screened(const ScreenArgs &a, double *out_ratio, size_t out_stride,
+	cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	dim3 grid((a.n_pos + 63) / 64, a.n_lists);
+	reduce_ib_screened_kernel<<<grid, 64, 0, st>>>(a, out_ratio, out_stride);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// the gather form of the pair-scoring kernel
+// ---------------------------------------------------------------------------------------
+
+/// the reference's chain of one cell for R samples per lane (same instruction sequence as the
+/// body of cell_pass_kernel, kernels.cu)
+template <int NW, int R, bool CLAMP, bool SMEM>
+__device__ __forceinline__ void cell_chain(uint32_t hap_base, const char *hap_g,
+	uint32_t tbl_lane, int dmax, int a_start, int a_n, int b_start, int b_n, bool diag,
+	const uint32_t (*S1)[NW], const uint32_t (*S2)[NW], double *sum)
+{
+	uint32_t V[R][NW];
+#pragma unroll
+	for (int r = 0; r < R; r++)
+	{
+		sum[r] = 0.0;
+#pragma unroll
+		for (int w = 0; w < NW; w++) V[r][w] = S1[r][w] | ~S2[r][w];
+	}
+	for (int ii = 0; ii < a_n; ii++)
+	{
+		HapRec<NW, SMEM> hi;
+		hi.load(hap_base, hap_g, a_start + ii);
+		uint32_t K[R][NW];
+		uint32_t tb[R];
+		int ci[R];
+#pragma unroll
+		for (int r = 0; r < R; r++)
+		{
+			int c0 = 0;
+#pragma unroll
+			for (int w = 0; w < NW; w++)
+			{
+				K[r][w] = S1[r][w] & (S2[r][w] | ~hi.h[w]);
+				c0 += __popc((hi.h[w] ^ (S1[r][w] & S2[r][w])) & ~(S1[r][w] ^ S2[r][w]));
+			}
+			ci[r] = c0;
+			tb[r] = tbl_lane + (uint32_t)c0 * 256u;
+		}
+		int j0 = 0;
+		if (diag)
+		{
+			const double p2 = __dmul_rn(hi.f, hi.f);          // src/LibHLA.cpp:1658-1659
+#pragma unroll
+			for (int r = 0; r < R; r++)
+			{
+				int pc = 0;
+#pragma unroll
+				for (int w = 0; w < NW; w++) pc += __popc((hi.h[w] ^ K[r][w]) & V[r][w]);
+				double t;
+				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
+				else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
+				sum[r] = __dadd_rn(sum[r], __dmul_rn(p2, t));
+			}
+			j0 = ii + 1;
+		}
+		const double ff = __dmul_rn(2.0, hi.f);               // exact
+#pragma unroll 2
+		for (int j = j0; j < b_n; j++)
+		{
+			HapRec<NW, SMEM> hj;
+			hj.load(hap_base, hap_g, b_start + j);
+			const double pf = __dmul_rn(ff, hj.f);
+#pragma unroll
+			for (int r = 0; r < R; r++)
+			{
+				int pc = 0;
+#pragma unroll
+				for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
+				double t;
+				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
+				else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
+				sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
+			}
+		}
+	}
+}
+
+template <int NW, bool CLAMP, bool SMEM>
+__global__ void __launch_bounds__(GATHER_THREADS)
+cell_gather_kernel(const __grid_constant__ GatherBatch p)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// [0,16): mbarrier | [16,24): flags | 128: table n_dist x 32 lanes x 8 B | task prefix | records
+	const uint32_t smem_base = smem_u32(smem_raw);
+	const uint32_t bar = smem_base;
+	volatile int *sh_flag = (volatile int *)(smem_raw + 16);
+	const uint32_t tbl_base = smem_base + 128;
+	const uint32_t pre_off = 128u + (uint32_t)p.n_dist * 256u;
+	const uint32_t pre_bytes = (((uint32_t)p.n_cells + 1u) * 4u + 15u) & ~15u;
+	unsigned int *sh_pre = (unsigned int *)(smem_raw + pre_off);
+	const uint32_t hap_base = smem_base + pre_off + pre_bytes;
+	constexpr int REC = (NW <= 2) ? 16 : 32;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+
+	if (SMEM && tid == 0)
+	{
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	{
+		double *tbl = (double *)(smem_raw + 128);
+		const int n = p.n_dist * 32;
+		for (int k = tid; k < n; k += GATHER_THREADS)
+			tbl[k] = __ldg(p.table + (k >> 5));
+	}
+	__syncthreads();
+
+	const uint32_t tbl_lane = tbl_base + lane * 8;
+	const int dmax = p.n_dist - 1;
+	uint32_t phase = 0;
+
+	for (int k = 0; k < p.n_lists; k++)
+	{
+		int l = (int)(blockIdx.x % (unsigned)p.n_lists) + k;
+		if (l >= p.n_lists) l -= p.n_lists;
+		const GatherList &L = p.lists[l];
+		const unsigned n_tasks = __ldg(L.task_prefix + p.n_cells);
+		unsigned int *counter = p.task_counters + l;
+
+		if (tid == 0) sh_flag[k & 1] = (*(volatile unsigned int *)counter < n_tasks) ? 1 : 0;
+		__syncthreads();
+		if (!sh_flag[k & 1]) continue;
+
+		if (SMEM && tid == 0)
+		{
+			const uint32_t total = (uint32_t)L.n_hap * REC;
+			mbar_expect_tx(bar, total);
+			const char *src = (const char *)L.hap;
+			uint32_t off = 0;
+			while (off < total)
+			{
+				uint32_t nb = total - off;
+				if (nb > 65536u) nb = 65536u;
+				tma_bulk_g2s(hap_base + off, src + off, nb, bar);
+				off += nb;
+			}
+		}
+		for (int q = tid; q <= p.n_cells; q += GATHER_THREADS) sh_pre[q] = __ldg(L.task_prefix + q);
+		__syncthreads();
+		if (SMEM)
+		{
+			mbar_wait(bar, phase);
+			phase ^= 1u;
+		}
+
+		const char *hap_g = (const char *)L.hap;
+		double *Pl = L.P;
+
+		unsigned task = 0;
+		if (lane == 0) task = atomicAdd(counter, 1u);
+		task = __shfl_sync(0xffffffffu, task, 0);
+
+		while (task < n_tasks)
+		{
+			unsigned next_task = 0;
+			if (lane == 0) next_task = atomicAdd(counter, 1u);
+
+			// largest q with prefix[q] <= task (cells without positions have empty ranges)
+			int lo = 0, hi = p.n_cells;
+			while (hi - lo > 1)
+			{
+				const int mid = (lo + hi) >> 1;
+				if (sh_pre[mid] <= task) lo = mid; else hi = mid;
+			}
+			const int blk = (int)(task - sh_pre[lo]);
+			const int4 ca = __ldg((const int4 *)(L.cells + lo));
+			const int2 cb = __ldg((const int2 *)((const char *)(L.cells + lo) + 16));
+			const int rem = __ldg(L.count + cb.x) - blk * TASK_POS;
+			const int nr = min(4, (rem + 31) >> 5);
+			const int *ent = L.entries + (size_t)__ldg(p.ent_off + cb.x) + (size_t)blk * TASK_POS;
+
+			uint32_t S1[4][NW], S2[4][NW];
+			int pos[4];
+			double sum[4];
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+			{
+				const int e = r * 32 + lane;
+				const bool ok = e < rem;
+				pos[r] = ok ? __ldg(ent + e) : -1;
+				int samp = 0;
+				if (ok) samp = p.samp_list ? __ldg(p.samp_list + pos[r]) : pos[r];
+				load_geno<NW>(p.s1, p.s2, p.geno_stride, samp, ok, L.cand_col, L.cand_bit, S1[r], S2[r]);
+			}
+			const bool diag = cb.y != 0;
+			switch (nr)
+			{
+			case 1: cell_chain<NW, 1, CLAMP, SMEM>(hap_base, hap_g, tbl_lane, dmax, ca.x, ca.y, ca.z, ca.w, diag, S1, S2, sum); break;
+			case 2: cell_chain<NW, 2, CLAMP, SMEM>(hap_base, hap_g, tbl_lane, dmax, ca.x, ca.y, ca.z, ca.w, diag, S1, S2, sum); break;
+			case 3: cell_chain<NW, 3, CLAMP, SMEM>(hap_base, hap_g, tbl_lane, dmax, ca.x, ca.y, ca.z, ca.w, diag, S1, S2, sum); break;
+			default: cell_chain<NW, 4, CLAMP, SMEM>(hap_base, hap_g, tbl_lane, dmax, ca.x, ca.y, ca.z, ca.w, diag, S1, S2, sum); break;
+			}
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+				if (r < nr && pos[r] >= 0)
+					Pl[(size_t)cb.x * p.p_stride + pos[r]] = sum[r];
+
+			task = __shfl_sync(0xffffffffu, next_task, 0);
+		}
+		// every warp is done with this list's records / prefix before the next list overwrites them
+		__syncthreads();
+	}
+}
+
+template <int NW, bool CLAMP>
+static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream_t st)
+{
+	const size_t rec = (NW <= 2) ? 16 : 32;
+	const size_t fixed = 128 + (size_t)p.n_dist * 256 + ((((size_t)p.n_cells + 1) * 4 + 15) & ~(size_t)15);
+	const size_t with_hap = fixed + (size_t)p.max_hap * rec;
+	const size_t smem_limit = 227 * 1024;
+	if (fixed > smem_limit) throw std::runtime_error("launch_cell_gather: too many cells for shared memory");
+	const bool in_smem = with_hap <= smem_limit;
+	const size_t smem = in_smem ? with_hap : fixed;
+	int cta_per_sm = (int)((228 * 1024) / (smem + 1024));
+	if (cta_per_sm > 8) cta_per_sm = 8;
+	if (cta_per_sm < 1) cta_per_sm = 1;
+	long long grid = (long long)sm_count * cta_per_sm;
+	if (grid < p.n_lists) grid = p.n_lists;
+	if (in_smem)
+	{
+		auto k = cell_gather_kernel<NW, CLAMP, true>;
+		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+		k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(p);
+	} else {
+		auto k = cell_gather_kernel<NW, CLAMP, false>;
+		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+		k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(p);
+	}
+	CUDA_CHECK(cudaGetLastError());
+}
+
+int launch_cell_gather(const GatherBatch &p, int sm_count, cudaStream_t st)
+{
+	if (p.n_lists < 1 || p.n_lists > MAX_BATCH_LISTS)
+		throw std::runtime_error("launch_cell_gather: invalid number of lists");
+	const int nw = geno_words(p.n_snp);
+	const bool clamp = (2 * p.n_snp) > (p.n_dist - 1);
+#define HB_GCASE(NW_) \
+	if (nw == NW_) { \
+		if (clamp) launch_gather_variant<NW_, true>(p, sm_count, st); \
+		else launch_gather_variant<NW_, false>(p, sm_count, st); \
+		return NW_; }
+	HB_GCASE(1) HB_GCASE(2) HB_GCASE(4)
+#undef HB_GCASE
+	throw std::runtime_error("launch_cell_gather: unsupported configuration");
+}
+
+}  // namespace hb

@@ -5,12 +5,16 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace hb {
 
 static double g_table[2 * HIBAG_B200_MAX_SNP + 1];
 static int g_first_zero = 0;
 static std::once_flag g_table_once;
+
+static double g_floor_table[2 * HIBAG_B200_MAX_SNP + 1];
+static double g_bound_factor = 0;
 
 static void init_table()
 {
@@ -26,6 +30,30 @@ static void init_table()
 	int z = n + 1;
 	while (z > 0 && g_table[z - 1] == 0) z--;
 	g_first_zero = z;
+	// screening: floored table and bound factor
+	for (int d = 0; d <= n; d++) g_floor_table[d] = (g_table[d] > 1e-100) ? g_table[d] : 1e-100;
+	std::vector<double> suffix_max(n + 2, 0.0);
+	for (int d = n; d >= 0; d--) suffix_max[d] = std::max(g_table[d], suffix_max[d + 1]);
+	double kappa = 1.0;
+	for (int p = 0; p <= n; p++)
+		for (int q = 0; p + q <= n; q++)
+		{
+			const double r = suffix_max[p + q] / (g_floor_table[p] * g_floor_table[q]);
+			if (r > kappa) kappa = r;
+		}
+	g_bound_factor = 2.0 * kappa * (1.0 + 1e-12) * (1.0 + 1e-8);
+}
+
+const double *host_rare_freq_floor_table()
+{
+	std::call_once(g_table_once, init_table);
+	return g_floor_table;
+}
+
+double screen_bound_factor()
+{
+	std::call_once(g_table_once, init_table);
+	return g_bound_factor;
 }
 
 const double *host_rare_freq_table()
@@ -116,7 +144,7 @@ ListBlob build_list_blob(const hibag_haplotype *haplo, int n_hap, int n_hla, int
 				t.a_start = start[a]; t.a_n = na;
 				t.b_start = start[c]; t.b_n = nb;
 				t.out_idx = idx; t.diag = (a == c) ? 1 : 0;
-				t.pad0 = t.pad1 = 0;
+				t.al_a = a; t.al_b = c;
 				const uint64_t pairs = (a == c) ? (uint64_t)na * (na + 1) / 2 : (uint64_t)na * nb;
 				total += pairs;
 				order[idx] = std::make_pair(pairs + 2 * (uint64_t)na + 4, idx);

@@ -17,6 +17,14 @@ int rare_freq_first_zero();
 /// number of table rows the kernel needs for n_snp SNPs
 int table_rows_for(int n_snp);
 
+/// Screening (kernels.h): T' = max(T, 1e-100), and the factor K of the cell bound
+/// U_a * U_b * K: 2 (the c_ij of off-diagonal pairs) x kappa x (1 + 1e-8), with
+/// kappa = max_{p,q} max_{d >= p+q} T[d] / (T'[p] T'[q]) taken over the host table itself, so
+/// that T[d(g,i,j)] <= kappa T'[c_i] T'[c_j] whenever d >= c_i + c_j; 1e-8 covers the rounding
+/// of the chains (< 4e7 terms) and of the bound's own arithmetic.
+const double *host_rare_freq_floor_table();
+double screen_bound_factor();
+
 /// A haplotype list laid out for one H2D copy: [records | cells | chunks]
 struct ListBlob
 {

@@ -387,6 +387,7 @@ void Trainer::run(const std::vector<int> &indices)
 		now.launches -= plugin_before.launches; now.cell_launches -= plugin_before.cell_launches;
 		now.h2d_bytes -= plugin_before.h2d_bytes; now.d2h_bytes -= plugin_before.d2h_bytes;
 		now.kernel_ms -= plugin_before.kernel_ms; now.cell_ms -= plugin_before.cell_ms;
+		now.pair_evals_nominal = now.pair_evals; now.screen_fallback = 0;
 		stats_.add(now);
 	}
 	hibag_b200_train_stats &ts = ts_;
@@ -395,6 +396,8 @@ void Trainer::run(const std::vector<int> &indices)
 	for (double v : wait_seconds_) ts.seconds_gpu_wait += v;
 	ts.gpu_kernel_ms += stats_.kernel_ms;
 	ts.pair_evals += stats_.pair_evals;
+	ts.pair_evals_nominal += stats_.pair_evals_nominal;
+	ts.n_screen_fallback += stats_.screen_fallback;
 	ts.popc32_issued += stats_.popc32;
 	ts.kernel_launches += stats_.launches;
 	ts.cell_kernel_ms += stats_.cell_ms;
@@ -432,6 +435,8 @@ void Trainer::grow(Classifier &cl)
 			cudaMemcpyHostToDevice, main_st_.s));
 		stats_.h2d_bytes += 2 * sizeof(int) * (size_t)n_samp_;
 		upload_base_geno();
+		if (o_.no_screening) scorer_->disable_screening();
+		else scorer_->set_sample_sets(oob_, inbag_, a1_, a2_, n_hla_);
 	}
 
 	// ---- _InitHaplotype (:1880-1911): one SNP-less haplotype per allele present in the bag ---
@@ -784,6 +789,7 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 	if (!g || g->legacy != (opts.use_legacy_hooks != 0) || g->req_threads != opts.n_threads ||
 		g->req_concurrent != opts.n_concurrent || g->mtry != mtry || (int)g->lanes.size() < n_lanes ||
 		g->dev_em != (opts.em_on_device != 0))
+		// (no_screening is read per classifier: Trainer::configure)
 	{
 		m.tsession.reset();
 		g = new LaneGroup();
@@ -877,6 +883,7 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 		ts.seconds_prepare += a.seconds_prepare; ts.seconds_phase_oob += a.seconds_phase_oob;
 		ts.seconds_phase_ib += a.seconds_phase_ib;
 		ts.em_kernel_ms += a.em_kernel_ms; ts.n_em_host_fallback += a.n_em_host_fallback;
+		ts.pair_evals_nominal += a.pair_evals_nominal; ts.n_screen_fallback += a.n_screen_fallback;
 		m.train_trace.insert(m.train_trace.end(), t.trace_.begin(), t.trace_.end());
 		t.built_.clear();
 	}

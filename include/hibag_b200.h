@@ -146,6 +146,10 @@ typedef struct hibag_b200_train_opts {
 	int      em_on_device;      /* 1: haplotype-pair matching and the candidates' EM run on the
 	                               GPU (bit-identical results); 0: on the
 	                               host thread pool. Ignored with use_legacy_hooks */
+	int      no_screening;      /* 0 (default): the out-of-bag / in-bag passes score only the allele-pair
+	                               cells that can matter (exact screening, DESIGN.md 4.5: skipped cells
+	                               are proven irrelevant, results stay bit-identical); 1: every cell.
+	                               Ignored with use_legacy_hooks (always every cell) */
 } hibag_b200_train_opts;
 
 /* reference CAttrBag_Model::BuildClassifiers, src/LibHLA.cpp:2268-2305 */
@@ -169,6 +173,10 @@ typedef struct hibag_b200_train_stats {
 	double   seconds_phase_ib;    /* wall: in-bag scoring of the candidates that need it */
 	double   em_kernel_ms;        /* summed CUDA-event durations of the device EM launches */
 	uint64_t n_em_host_fallback;  /* candidates re-estimated on the host (undecidable stop test) */
+	uint64_t pair_evals_nominal;  /* pair evaluations the reference performs for the same passes
+	                                 (pair_evals = those the GPU executed after screening) */
+	uint64_t n_screen_fallback;   /* in-bag (sample, candidate) sums the screen could not certify,
+	                                 rescored against every cell */
 } hibag_b200_train_stats;
 int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_stats *out);
 

@@ -241,6 +241,35 @@ def test_trainer_matches_reference_on_synthetic(gpu, ref):
     assert st["pair_evals"] == full.train_stats()["pair_evals"]
 
 
+def test_exact_screening_changes_nothing_but_the_work(gpu, monkeypatch):
+    """exact screening of the training passes: with it and without it the same
+    classifiers and the same search trace; it skips pair evaluations; samples whose in-bag sum the
+    screen cannot certify take the rescoring path (forced here) with the same result"""
+    from hibag_b200 import synth
+    coh = synth.make_cohort(700, 140, 25, seed=5)
+    mtry = gpu.default_mtry(coh.n_snp)
+
+    def run(**kw):
+        m = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        m.set_training(coh.geno, coh.h1, coh.h2)
+        m.train(3, mtry, prune=True, seed=77, per_classifier_seed=True, n_threads=6, **kw)
+        return m
+
+    plain, scr = run(screening=False), run(screening=True)
+    for k in range(3):
+        assert helpers.classifier_diff(scr.classifier(k), plain.classifier(k)) == "", k
+    assert np.array_equal(scr.train_trace(), plain.train_trace())
+    sp, ss = plain.train_stats(), scr.train_stats()
+    assert sp["pair_evals"] == sp["pair_evals_nominal"] == ss["pair_evals_nominal"]
+    assert 0 < ss["pair_evals"] < sp["pair_evals"]
+    assert sp["n_screen_fallback"] == 0
+    monkeypatch.setenv("HIBAG_B200_SCREEN_FORCE_FALLBACK", "1")
+    forced = run(screening=True, n_concurrent=2)
+    for k in range(3):
+        assert helpers.classifier_diff(forced.classifier(k), plain.classifier(k)) == "", k
+    assert forced.train_stats()["n_screen_fallback"] > 0
+
+
 def test_trainer_matches_reference_many_alleles(gpu):
     """DRB1-like shape (many alleles, long haplotype lists, EM clusters of several CTAs):
     bit-identical classifiers vs the reference's base target (fixture generated from the compiled
