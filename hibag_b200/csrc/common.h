@@ -92,7 +92,18 @@ private:
 struct Stream
 {
 	cudaStream_t s = nullptr;
-	Stream() { HB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+	/// high_priority: the stream's kernels are dispatched before pending work of default-priority
+	/// streams (short scoring launches ahead of the long, SM-filling EM launches)
+	explicit Stream(bool high_priority = false)
+	{
+		if (high_priority)
+		{
+			int lo = 0, hi = 0;
+			HB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+			HB_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+		} else
+			HB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	}
 	~Stream() { if (s) cudaStreamDestroy(s); }
 	Stream(const Stream &) = delete;
 	Stream &operator=(const Stream &) = delete;

@@ -19,7 +19,7 @@ namespace hb {
 
 namespace {
 
-constexpr int EM_THREADS = 1024;
+constexpr int EM_THREADS_MAX = 1024;
 constexpr int EM_MAX_ITER = 500;                 // src/LibHLA.cpp:98
 constexpr double EM_INIT_VAL_FRAC = 0.001;       // :100
 // Half-width of the band around the stopping tolerance inside which the device does not decide,
@@ -324,6 +324,7 @@ __device__ __forceinline__ double block_sum_f64(double v, double *scratch)
 /// contributions are then produced IN SLOT ORDER -- r = (c * f_u * f_v) * (count / sum) rebuilt from
 /// shared memory, bit-identical to the E step's value -- so the writes are coalesced, and the M
 /// step walks chains a half to a third as long.
+template <int EM_THREADS>
 __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 {
 	cg::cluster_group cluster = cg::this_cluster();
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		__syncthreads();
 		if (tid < 32)
 		{
-			int w = wsum[tid];
+			int w = (tid < (EM_THREADS >> 5)) ? wsum[tid] : 0;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1)
 			{
@@ -871,7 +872,14 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	const size_t smem_base = sizeof(double) * (2 * (size_t)n2_ + 40 + 3 * MAX_CLUSTER + 2 * (size_t)n_entry_) +
 		sizeof(int) * (size_t)n_entry_ + 16;
 	int m_warps = (int)((220 * 1024 - smem_base) / (sizeof(double) * RING_ROWS * 32));
-	if (m_warps > 8) m_warps = 8;
+	// Threads per CTA and M-step rings. 512 threads (half the register file) and 4 rings would let
+	// pair-scoring CTAs of other lanes share an EM CTA's SM, but measured on config 2 the longer
+	// iterations cost more than the sharing gains (12 lanes: 384 vs 474 classifiers/min), so the
+	// default stays at the lowest-latency shape.
+	int em_threads = 1024, max_rings = 8;
+	if (const char *e = getenv("HIBAG_B200_EM_THREADS")) em_threads = (atoi(e) >= 1024) ? 1024 : 512;
+	if (const char *e = getenv("HIBAG_B200_EM_RINGS")) max_rings = std::max(1, std::min(8, atoi(e)));
+	if (m_warps > max_rings) m_warps = max_rings;
 	if (m_warps < 1) throw std::runtime_error("run_em: list too large for the device EM");
 	a.m_warps = m_warps;
 	const size_t smem = smem_base + sizeof(double) * RING_ROWS * 32 * (size_t)m_warps;
@@ -882,18 +890,19 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	while (cluster < MAX_CLUSTER && total_pairs_ / (2 * (size_t)cluster) >= 6000 &&
 		(size_t)m * 2 * cluster <= (size_t)current_device().sm_count * 11 / 20) cluster *= 2;
 	if (const char *e = getenv("HIBAG_B200_EM_CLUSTER")) cluster = std::max(1, std::min(MAX_CLUSTER, atoi(e)));
-	HB_CUDA(cudaFuncSetAttribute(em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+	auto kern = (em_threads == 1024) ? em_kernel<1024> : em_kernel<512>;
+	HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
 	HB_CUDA(cudaEventRecord(ev0_.e, st));
 	{
 		cudaLaunchConfig_t cfg;
 		memset(&cfg, 0, sizeof(cfg));
-		cfg.gridDim = dim3((unsigned)(m * cluster)); cfg.blockDim = dim3(EM_THREADS);
+		cfg.gridDim = dim3((unsigned)(m * cluster)); cfg.blockDim = dim3((unsigned)em_threads);
 		cfg.dynamicSmemBytes = smem; cfg.stream = st;
 		cudaLaunchAttribute attr[1];
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 		cfg.attrs = attr; cfg.numAttrs = 1;
-		HB_CUDA(cudaLaunchKernelEx(&cfg, em_kernel, a));
+		HB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
 	}
 	HB_CUDA(cudaGetLastError());
 	HB_CUDA(cudaEventRecord(ev1_.e, st));

@@ -127,8 +127,10 @@ void launch_transpose(const double *P, size_t p_stride, int n_cells, int n_pos, 
 
 // ---- exact screening of the training passes (screen.cu) --------------------------------------
 //
-// In training every sample's true HLA type is known, so the exact value x_ref of its true cell
-// is cheap to get first. A cell (a,b) whose value cannot exceed
+// In training every sample's true HLA type is known. One term of the true cell's chain -- the
+// best haplotype of one true allele with its best partner in the other -- evaluated exactly as
+// the chain evaluates it, is a lower bound x_ref of the true cell's value (a sum of non-negative
+// terms is at least each term), hence of the best cell's. A cell (a,b) whose value cannot exceed
 //     bound(a,b) = U_a * U_b * K,   U_a = sum_{i in a} f_i * T'[hom-SNP mismatches of h_i]
 // (the heterozygous SNPs can only add distance; T' = max(T, 1e-100), K covers 2x, the table's
 // rounding and the chains' rounding) is
@@ -137,8 +139,9 @@ void launch_transpose(const double *P, size_t p_stride, int n_cells, int n_pos, 
 //     reduction CERTIFIES: it adds the chain once with 0 and once with the bound for every
 //     skipped cell; fp64 addition is monotone, so equal results prove the full chain has that
 //     value. Samples that fail the certificate are rescored without screening.
-// Only the cells that survive are scored, by a gather kernel whose lanes are the samples that
-// need the cell. Every value that is produced is the reference's own chain, bit for bit.
+// Only the cells that survive (and always the true cell) are scored, by a gather kernel whose
+// lanes are the samples that need the cell. Every value that is produced is the reference's own
+// chain, bit for bit.
 
 /// One haplotype list of a screened launch
 struct GatherList
@@ -149,7 +152,7 @@ struct GatherList
 	double *P;                    // P[out_idx * p_stride + pos]
 	const int *count;             // [n_cells] by out_idx: positions that need the cell
 	const int *entries;           // positions, cell c at ent_off[c] .. + count[c]
-	const unsigned int *task_prefix;   // [n_cells + 1] over the blob's cell order, in 128-position tasks
+	const unsigned int *task_prefix;   // [n_cells + 2]: prefix over the blob's cell order, n_tasks, log2(positions per task)
 	int n_hap, cand_bit;
 };
 
@@ -167,12 +170,14 @@ struct GatherBatch
 };
 
 /// the surviving cells of all lists in one launch. Returns POPC.32 per pair evaluation.
-int launch_cell_gather(const GatherBatch &b, int sm_count, cudaStream_t st);
+/// max_ctas > 0 caps the persistent grid (small passes leave room for other lanes' launches).
+int launch_cell_gather(const GatherBatch &b, int sm_count, cudaStream_t st, long long max_ctas = 0);
 
 /// arguments shared by the screening kernels of one launch (list l uses slice l of every array)
 struct ScreenArgs
 {
 	const double *table_floor;    // T' on the device
+	const double *table;          // T on the device (rescue path of the in-bag reduction)
 	const uint32_t *s1, *s2;
 	const int *samp_list;
 	const int *a1, *a2;           // true types by sample, a1 <= a2
@@ -181,28 +186,37 @@ struct ScreenArgs
 	double K;                     // bound factor
 	double tau;                   // need a cell when bound >= tau * x_ref
 	double *U;                    // [n_lists][n_hla][p_stride]
+	double *xref;                 // [n_lists][p_stride] lower bound of the true cell's value
 	double *P;                    // [n_lists][n_cells][p_stride]
 	int *count;                   // [n_lists][n_cells]
 	int *entries;                 // [n_lists][n_cells][p_stride]
-	unsigned int *task_prefix;    // [n_lists][n_cells + 1]
+	unsigned int *task_prefix;    // [n_lists][n_cells + 2]
 	unsigned long long *evals;    // [n_lists] pair evaluations the gather launch will execute
+	unsigned long long *rescued;  // [1] in-bag positions the reduction rescued
+	int *al_tab;                  // [n_lists][n_hla][2] first haplotype and count per allele
+	int force_rescue;             // test hook: > 0 rescues every force_rescue-th position
+	int device_rescue;            // 1: uncertified sums are rescued inside the reduction; 0: reported
+	                              // as ratio -1 and rescored by the caller with the plain kernel
 };
 struct ScreenList { const void *hap; const CellTask *cells; const int8_t *cand_col; int n_hap, cand_bit; };
 struct ScreenLists { ScreenList l[MAX_BATCH_LISTS]; };
 
-/// U[l][a][pos]
+/// U[l][a][pos] and xref[l][pos]
 void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_t st);
 /// per list: task prefix over the blob's cell order from count (stride 0: one shared count array)
 /// and the pair evaluations those tasks hold (added to evals[l])
 void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
-	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, cudaStream_t st);
+	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, int target_tasks,
+	cudaStream_t st);
 /// per (list, pos): which cells are needed (appends to entries / count)
 void launch_screen_need(const ScreenArgs &a, cudaStream_t st);
-/// screened reductions (same outputs as launch_reduce_oob / launch_reduce_ib; an in-bag position
-/// whose sum could not be certified gets ratio -1)
+/// screened reductions (same outputs as launch_reduce_oob / launch_reduce_ib). An in-bag position
+/// whose sum is not certified is rescued inside the reduction: the lanes of its warp score its
+/// skipped cells one by one, then the plain sequential sum is taken. (ratio -1 = not certified
+/// is still understood by the caller, which rescores such positions with the plain kernel.)
 void launch_reduce_oob_screened(const ScreenArgs &a, int *out_count, cudaStream_t st);
-void launch_reduce_ib_screened(const ScreenArgs &a, double *out_ratio, size_t out_stride,
-	cudaStream_t st);
+void launch_reduce_ib_screened(const ScreenArgs &a, const ScreenLists &ls, double *out_ratio,
+	size_t out_stride, cudaStream_t st);
 
 // ---- prediction --------------------------------------------------------------------------
 

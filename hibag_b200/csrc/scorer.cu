@@ -2,6 +2,8 @@
 #include "scorer.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -270,20 +272,32 @@ void EvalSlot::sync()
 static std::mutex g_queue_mutex;
 static std::map<int, ScoreQueue *> g_queues;
 
-ScoreQueue &ScoreQueue::get()
+ScoreQueue &ScoreQueue::get(int id)
 {
 	const DeviceInfo &di = current_device();
 	std::lock_guard<std::mutex> lk(g_queue_mutex);
-	auto it = g_queues.find(di.device);
+	const int key = di.device * 64 + (id & 63);
+	auto it = g_queues.find(key);
 	if (it != g_queues.end()) return *it->second;
-	ScoreQueue *q = new ScoreQueue();       // lives for the process (one stream per device)
-	g_queues[di.device] = q;
+	const char *pe = getenv("HIBAG_B200_SCORE_PRIO");
+	ScoreQueue *q = new ScoreQueue(pe == nullptr || atoi(pe) != 0);       // lives for the process
+	g_queues[key] = q;
 	return *q;
 }
+
+static std::atomic<int> g_next_scorer{0};
 
 BatchScorer::BatchScorer()
 {
 	current_device();
+	// screened passes are chains of small, latency-bound launches that do not fill the GPU:
+	// the lanes' passes are spread over a few streams so that they overlap
+	int k = 3;
+	if (const char *e = getenv("HIBAG_B200_SCORE_QUEUES")) k = std::max(1, std::min(16, atoi(e)));
+	queue_id_ = g_next_scorer.fetch_add(1) % k;
+	int lg = 70;
+	if (const char *e = getenv("HIBAG_B200_SCREEN_TAU_LOG2")) lg = std::max(54, std::min(200, atoi(e)));
+	screen_tau_ = std::ldexp(1.0, -lg);
 }
 
 void BatchScorer::begin_round(int n_lists, int max_hap, int n_snp, int n_hla)
@@ -297,8 +311,9 @@ void BatchScorer::begin_round(int n_lists, int max_hap, int n_snp, int n_hla)
 	counters_.ensure(2 * MAX_BATCH_LISTS);
 	d_counts_.ensure(n_lists);
 	h_counts_.ensure(n_lists);
-	d_evals_.ensure(n_lists);
-	h_evals_.ensure(n_lists);
+	d_evals_.ensure(n_lists + 1);
+	h_evals_.ensure(n_lists + 1);
+	al_tab_.ensure(2 * (size_t)n_lists * n_hla);
 }
 
 void BatchScorer::upload(const std::vector<int> &which)
@@ -315,6 +330,7 @@ void BatchScorer::upload(const std::vector<int> &which)
 void BatchScorer::set_sample_sets(const std::vector<int> &oob, const std::vector<int> &ib,
 	const std::vector<int> &a1, const std::vector<int> &a2, int n_hla)
 {
+	(void)a1; (void)a2;
 	const int n_cells = n_hla * (n_hla + 1) / 2;
 	screen_ = false;
 	for (int kind = 0; kind < 2; kind++)
@@ -323,33 +339,20 @@ void BatchScorer::set_sample_sets(const std::vector<int> &oob, const std::vector
 		const size_t stride = (s.size() + 31) & ~(size_t)31;
 		if ((size_t)n_cells * stride > (size_t)0x7fffffff) return;    // positions are addressed with int
 		set_samples_[kind] = s;
-		std::vector<int> count(n_cells, 0), off(n_cells, 0), ent(s.size() + 1, 0), eoff(n_cells, 0);
-		std::vector<int> cell_of(s.size());
-		for (size_t p = 0; p < s.size(); p++)
-		{
-			const int t1 = a1[s[p]], t2 = a2[s[p]];
-			cell_of[p] = t2 + t1 * (2 * n_hla - t1 - 1) / 2;          // src/LibHLA.cpp:1712
-			count[cell_of[p]]++;
-		}
-		int run = 0;
-		for (int c = 0; c < n_cells; c++) { off[c] = run; run += count[c]; eoff[c] = (int)((size_t)c * stride); }
-		std::vector<int> cur(off);
-		for (size_t p = 0; p < s.size(); p++) ent[cur[cell_of[p]]++] = (int)p;
-		tc_count_[kind].ensure(n_cells); tc_off_[kind].ensure(n_cells);
-		tc_ent_[kind].ensure(ent.size()); ent_off_[kind].ensure(n_cells);
-		HB_CUDA(cudaMemcpyAsync(tc_count_[kind].get(), count.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
-		HB_CUDA(cudaMemcpyAsync(tc_off_[kind].get(), off.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
-		HB_CUDA(cudaMemcpyAsync(tc_ent_[kind].get(), ent.data(), sizeof(int) * ent.size(), cudaMemcpyHostToDevice, st_.s));
+		std::vector<int> eoff(n_cells, 0);
+		for (int c = 0; c < n_cells; c++) eoff[c] = (int)((size_t)c * stride);
+		ent_off_[kind].ensure(n_cells);
 		HB_CUDA(cudaMemcpyAsync(ent_off_[kind].get(), eoff.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
-		HB_CUDA(cudaStreamSynchronize(st_.s));       // the host vectors go out of scope
-		stats.h2d_bytes += sizeof(int) * (3 * (size_t)n_cells + ent.size());
+		HB_CUDA(cudaStreamSynchronize(st_.s));       // the host vector goes out of scope
+		stats.h2d_bytes += sizeof(int) * (size_t)n_cells;
+		evals_per_list_[kind] = 0;
 	}
 	device_rare_freq_floor_table();
 	screen_ = true;
 }
 
 void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<int> &which,
-	int first, int count, const int *pos_list, int n_pos, double *P, size_t p_stride)
+	int first, int count, const int *pos_list, int n_pos, double *P, size_t p_stride, int queue)
 {
 	const DeviceInfo &di = current_device();
 	CellBatch b;
@@ -382,7 +385,7 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 		pairs += lb.pairs_per_sample;
 	}
 	const int R = choose_samples_per_lane(n_pos, total_chunks, n_snp_, di.sm_count);
-	ScoreQueue &q = ScoreQueue::get();
+	ScoreQueue &q = ScoreQueue::get(queue);
 	int nw;
 	{
 		std::lock_guard<std::mutex> lk(q.mu);
@@ -400,9 +403,9 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 	stats.popc32 += pairs * (uint64_t)n_pos * (uint64_t)nw;
 }
 
-/// One sub-batch of a screened pass, all on the device's scoring stream: per-allele bounds,
-/// the true cells (gather launch A), the need lists, the surviving cells (gather launch B)
-/// and the screened reduction. kind: 0 out-of-bag, 1 in-bag.
+/// One sub-batch of a screened pass, all on one of the device's scoring streams: per-allele
+/// bounds and x_ref, the need lists, their tasks, the surviving cells (gather launch) and the
+/// screened reduction. kind: 0 out-of-bag, 1 in-bag.
 void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std::vector<int> &which,
 	int first, int count, const int *pos_list, int n_pos, int kind)
 {
@@ -413,21 +416,29 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	GatherBatch gb;
 	memset(&a, 0, sizeof(a)); memset(&ls, 0, sizeof(ls)); memset(&gb, 0, sizeof(gb));
 	a.table_floor = device_rare_freq_floor_table();
+	a.table = device_rare_freq_table();
 	a.s1 = g.s1; a.s2 = g.s2; a.samp_list = pos_list; a.a1 = g.a1; a.a2 = g.a2;
 	a.n_snp = n_snp_; a.geno_stride = g.stride; a.n_pos = n_pos; a.n_hla = n_hla_; a.n_lists = count;
 	a.p_stride = p_stride_;
 	a.K = screen_bound_factor();
-	a.tau = kind ? 0x1p-63 : 1.0;
+	a.tau = kind ? screen_tau_ : 1.0;
 	a.U = U_.get() + (size_t)first * n_hla_ * p_stride_;
+	a.xref = xref_.get() + (size_t)first * p_stride_;
 	a.P = P_.get() + (size_t)first * n_cells * p_stride_;
 	a.count = cnt_.get() + (size_t)first * n_cells;
 	a.entries = ent_.get() + (size_t)first * n_cells * p_stride_;
-	a.task_prefix = prefix_.get() + (size_t)first * (n_cells + 1);
+	a.task_prefix = prefix_.get() + (size_t)first * (n_cells + 2);
 	a.evals = d_evals_.get() + first;
-	gb.table = device_rare_freq_table();
+	a.rescued = d_evals_.get() + which.size();
+	a.al_tab = al_tab_.get() + 2 * (size_t)first * n_hla_;
+	if (const char *e = getenv("HIBAG_B200_SCREEN_FORCE_RESCUE")) a.force_rescue = std::max(0, atoi(e));
+	if (const char *e = getenv("HIBAG_B200_SCREEN_DEVICE_RESCUE")) a.device_rescue = atoi(e) != 0;
+	gb.table = a.table;
 	gb.s1 = g.s1; gb.s2 = g.s2; gb.samp_list = pos_list;
 	gb.p_stride = p_stride_; gb.n_snp = n_snp_; gb.geno_stride = g.stride; gb.n_pos = n_pos;
 	gb.n_lists = count; gb.n_cells = n_cells_;
+	gb.ent_off = ent_off_[kind].get();
+	gb.task_counters = counters_.get();
 	uint64_t pairs = 0;
 	for (int k = 0; k < count; k++)
 	{
@@ -441,48 +452,46 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		L.hap = d; L.cells = S.cells; L.cand_col = cols_[i];
 		L.P = a.P + (size_t)k * n_cells * p_stride_;
 		L.n_hap = lb.n_hap; L.cand_bit = cand_bit;
-		L.task_prefix = a.task_prefix + (size_t)k * (n_cells + 1);
-		// launch A: the true cells; one CSR over positions shared by all lists
-		L.count = tc_count_[kind].get();
-		L.entries = tc_ent_[kind].get();
+		L.task_prefix = a.task_prefix + (size_t)k * (n_cells + 2);
+		L.count = a.count + (size_t)k * n_cells;
+		L.entries = a.entries + (size_t)k * n_cells * p_stride_;
 		a.n_dist = gb.n_dist = lb.n_dist;
 		if (lb.n_hap > gb.max_hap) gb.max_hap = lb.n_hap;
 		pairs += lb.pairs_per_sample;
 	}
-	ScoreQueue &q = ScoreQueue::get();
+	// tasks per list that give every warp slot of the GPU a couple of tasks
+	const int target_tasks = (di.sm_count * 48 + count - 1) / count;
+	// persistent CTAs of the gather launch: sized from what the previous pass of this kind
+	// executed per list (the lists of consecutive rounds are alike), so that a small pass does not
+	// occupy every SM and the passes of other lanes (other streams) run beside it
+	long long max_ctas = 0;
+	if (evals_per_list_[kind] > 0)
+	{
+		max_ctas = (long long)(evals_per_list_[kind] * 1.5 * count / 4e5) + di.sm_count / 2;
+		if (max_ctas < di.sm_count) max_ctas = di.sm_count;
+	}
+	ScoreQueue &q = ScoreQueue::get(queue_id_);
 	int nw;
 	{
 		std::lock_guard<std::mutex> lk(q.mu);
 		cudaStream_t s = q.st.s;
 		HB_CUDA(cudaStreamWaitEvent(s, ev_up_.e, 0));
-		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * 2 * MAX_BATCH_LISTS, s));
+		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * MAX_BATCH_LISTS, s));
 		HB_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * (size_t)count * n_cells, s));
 		HB_CUDA(cudaEventRecord(ev0_.e, s));
 		launch_screen_bound(a, ls, s);
-		launch_screen_tasks(ls, count, n_cells_, tc_count_[kind].get(), 0, a.task_prefix, a.evals, s);
-		gb.ent_off = tc_off_[kind].get();
-		gb.task_counters = counters_.get();
-		nw = launch_cell_gather(gb, di.sm_count, s);
 		launch_screen_need(a, s);
-		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, s);
-		// launch B: the cells that survived the screen, per list
-		for (int k = 0; k < count; k++)
-		{
-			gb.lists[k].count = a.count + (size_t)k * n_cells;
-			gb.lists[k].entries = a.entries + (size_t)k * n_cells * p_stride_;
-		}
-		gb.ent_off = ent_off_[kind].get();
-		gb.task_counters = counters_.get() + MAX_BATCH_LISTS;
-		launch_cell_gather(gb, di.sm_count, s);
+		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks, s);
+		nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
 		if (kind == 0)
 			launch_reduce_oob_screened(a, d_counts_.get() + first, s);
 		else
-			launch_reduce_ib_screened(a, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+			launch_reduce_ib_screened(a, ls, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
 		HB_CUDA(cudaEventRecord(ev1_.e, s));
 	}
 	HB_CUDA(cudaStreamWaitEvent(st_.s, ev1_.e, 0));
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
-	stats.launches += 7; stats.cell_launches += 2;
+	stats.launches += 5; stats.cell_launches += 1;
 	stats.pair_evals_nominal += pairs * (uint64_t)n_pos;
 	(void)nw;
 }
@@ -499,10 +508,11 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 	if (screen)
 	{
 		U_.ensure((size_t)n * n_hla_ * p_stride_);
+		xref_.ensure((size_t)n * p_stride_);
 		cnt_.ensure((size_t)n * n_cells_);
 		ent_.ensure((size_t)n * n_cells_ * p_stride_);
-		prefix_.ensure((size_t)n * (n_cells_ + 1));
-		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)n, st_.s));
+		prefix_.ensure((size_t)n * (n_cells_ + 2));
+		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)(n + 1), st_.s));
 	}
 	HB_CUDA(cudaMemsetAsync(d_counts_.get(), 0, sizeof(int) * (size_t)n, st_.s));
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
@@ -527,7 +537,7 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 			st_.s, n, (size_t)n_cells_ * p_stride_);
 		stats.launches++;
 	} else
-		HB_CUDA(cudaMemcpyAsync(h_evals_.get(), d_evals_.get(), sizeof(unsigned long long) * (size_t)n,
+		HB_CUDA(cudaMemcpyAsync(h_evals_.get(), d_evals_.get(), sizeof(unsigned long long) * (size_t)(n + 1),
 			cudaMemcpyDeviceToHost, st_.s));
 	HB_CUDA(cudaMemcpyAsync(h_counts_.get(), d_counts_.get(), sizeof(int) * (size_t)n,
 		cudaMemcpyDeviceToHost, st_.s));
@@ -540,11 +550,11 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 	if (screen)
 	{
 		const int nw = geno_words(n_snp_);
-		for (int k = 0; k < n; k++)
-		{
-			stats.pair_evals += h_evals_.get()[k];
-			stats.popc32 += h_evals_.get()[k] * (uint64_t)nw;
-		}
+		uint64_t tot = 0;
+		for (int k = 0; k < n; k++) tot += h_evals_.get()[k];
+		stats.pair_evals += tot;
+		stats.popc32 += tot * (uint64_t)nw;
+		evals_per_list_[0] = (double)tot / n;
 		stats.d2h_bytes += sizeof(unsigned long long) * (size_t)n;
 	}
 	for (int k = 0; k < n; k++) counts[k] = h_counts_.get()[k];
@@ -564,10 +574,11 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 	if (screen)
 	{
 		U_.ensure((size_t)n * n_hla_ * p_stride_);
+		xref_.ensure((size_t)n * p_stride_);
 		cnt_.ensure((size_t)n * n_cells_);
 		ent_.ensure((size_t)n * n_cells_ * p_stride_);
-		prefix_.ensure((size_t)n * (n_cells_ + 1));
-		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)n, st_.s));
+		prefix_.ensure((size_t)n * (n_cells_ + 2));
+		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)(n + 1), st_.s));
 	}
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
 	uint64_t before = stats.pair_evals;
@@ -591,7 +602,7 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 			st_.s, n, (size_t)n_cells_ * p_stride_, ratio_stride_);
 		stats.launches++;
 	} else
-		HB_CUDA(cudaMemcpyAsync(h_evals_.get(), d_evals_.get(), sizeof(unsigned long long) * (size_t)n,
+		HB_CUDA(cudaMemcpyAsync(h_evals_.get(), d_evals_.get(), sizeof(unsigned long long) * (size_t)(n + 1),
 			cudaMemcpyDeviceToHost, st_.s));
 	HB_CUDA(cudaMemcpyAsync(h_ratio_.get(), d_ratio_.get(), sizeof(double) * (size_t)n * ratio_stride_,
 		cudaMemcpyDeviceToHost, st_.s));
@@ -604,12 +615,13 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 	if (screen)
 	{
 		const int nw = geno_words(n_snp_);
-		for (int k = 0; k < n; k++)
-		{
-			stats.pair_evals += h_evals_.get()[k];
-			stats.popc32 += h_evals_.get()[k] * (uint64_t)nw;
-		}
-		stats.d2h_bytes += sizeof(unsigned long long) * (size_t)n;
+		uint64_t tot = 0;
+		for (int k = 0; k < n; k++) tot += h_evals_.get()[k];
+		stats.pair_evals += tot;
+		stats.popc32 += tot * (uint64_t)nw;
+		evals_per_list_[1] = (double)tot / n;
+		stats.screen_fallback += h_evals_.get()[n];
+		stats.d2h_bytes += sizeof(unsigned long long) * (size_t)(n + 1);
 		rescore_uncertified(g, cand_bit, which);
 	}
 }
@@ -651,7 +663,7 @@ void BatchScorer::rescore_uncertified(const GenoView &g, int cand_bit, const std
 	for (int first = 0; first < nl; first += MAX_BATCH_LISTS)
 	{
 		const int count = std::min(MAX_BATCH_LISTS, nl - first);
-		run_cells(g, cand_bit, which_fb, first, count, d_fb_samp_.get(), nf, P_fb_.get(), stride);
+		run_cells(g, cand_bit, which_fb, first, count, d_fb_samp_.get(), nf, P_fb_.get(), stride, queue_id_);
 		float ms = 0;
 		HB_CUDA(cudaEventSynchronize(ev1_.e));
 		HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));

@@ -100,15 +100,17 @@ private:
 	PinBuf<double> h_ratio_;
 };
 
-/// The one stream per device on which every batched pair-scoring launch of the training path
-/// is enqueued, from however many classifiers are being grown concurrently: launches run one
-/// after the other (each fills the GPU), so the CUDA events around a launch time that launch
-/// alone.
+/// Streams of the current device on which the batched pair-scoring launches of the training
+/// path are enqueued, from however many classifiers are being grown concurrently. Queue 0
+/// takes every unscreened launch: those fill the GPU, run one after the other, and the CUDA
+/// events around a launch time that launch alone. Screened passes (chains of small launches)
+/// are spread over a few queues so that the lanes' passes overlap.
 struct ScoreQueue
 {
 	std::mutex mu;
 	Stream st;
-	static ScoreQueue &get();            // of the current device
+	explicit ScoreQueue(bool high_priority) : st(high_priority) {}
+	static ScoreQueue &get(int id);      // of the current device
 };
 
 /// Scores the candidate haplotype lists of one selection round in ONE launch per pass
@@ -143,17 +145,19 @@ public:
 
 private:
 	void run_cells(const GenoView &g, int cand_bit, const std::vector<int> &which, int first,
-		int count, const int *pos_list, int n_pos, double *P, size_t p_stride);
+		int count, const int *pos_list, int n_pos, double *P, size_t p_stride, int queue = 0);
 	void run_cells_screened(const GenoView &g, int cand_bit, const std::vector<int> &which,
 		int first, int count, const int *pos_list, int n_pos, int kind);
 	void rescore_uncertified(const GenoView &g, int cand_bit, const std::vector<int> &which);
 	// screening state
 	bool screen_ = false;
+	int queue_id_ = 0;
+	double screen_tau_ = 0x1p-70;                // in-bag: a cell is scored when bound >= tau * x_true
 	std::vector<int> set_samples_[2];            // host copy of the sample lists (0 oob, 1 in-bag)
-	DevBuf<int> tc_count_[2], tc_off_[2], tc_ent_[2];   // true-cell CSR over positions
 	DevBuf<int> ent_off_[2];                     // out_idx * p_stride of the set
-	DevBuf<double> U_;
-	DevBuf<int> cnt_, ent_;
+	DevBuf<double> U_, xref_;
+	double evals_per_list_[2] = { 0, 0 };        // executed by the previous pass of the kind
+	DevBuf<int> cnt_, ent_, al_tab_;
 	DevBuf<unsigned int> prefix_;
 	DevBuf<unsigned long long> d_evals_;
 	PinBuf<unsigned long long> h_evals_;

@@ -22,7 +22,6 @@ namespace hb {
 		" at " __FILE__ ":" + std::to_string(__LINE__)); } while (0)
 
 static constexpr int GATHER_THREADS = 128;
-static constexpr int TASK_POS = 128;          // positions per gather task (4 per lane)
 static constexpr int NA_INT = INT32_MIN;
 
 /// genotype bit planes of one sample, candidate SNP patched in at bit cand_bit
@@ -61,6 +60,11 @@ __device__ __forceinline__ double screen_bound(double ua, double ub, double K)
 	return __dmul_rn(__dmul_rn(ua, ub), K);
 }
 
+__device__ __forceinline__ int geno_words_dev(int n_snp)
+{
+	return (n_snp <= 32) ? 1 : ((n_snp <= 64) ? 2 : 4);
+}
+
 __device__ __forceinline__ int true_cell_index(int t1, int t2, int n_hla)
 {
 	return t2 + t1 * (2 * n_hla - t1 - 1) / 2;           // src/LibHLA.cpp:1712, t1 <= t2
@@ -83,21 +87,39 @@ screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 	{
 		const int4 ca = __ldg((const int4 *)(L.cells + k));
 		const int4 cb = __ldg((const int4 *)((const char *)(L.cells + k) + 16));
-		if (cb.y) { al_start[cb.z] = ca.x; al_n[cb.z] = ca.y; }
+		if (cb.y)
+		{
+			al_start[cb.z] = ca.x; al_n[cb.z] = ca.y;
+			if (blockIdx.x == 0)     // kept for the in-bag reduction's rescue path
+			{
+				a.al_tab[((size_t)l * a.n_hla + cb.z) * 2] = ca.x;
+				a.al_tab[((size_t)l * a.n_hla + cb.z) * 2 + 1] = ca.y;
+			}
+		}
 	}
 	__syncthreads();
 
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool ok = pos < a.n_pos;
-	int samp = 0;
-	if (ok) samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
-	uint32_t S1[NW], S2[NW], HOM[NW], G2[NW];
+	int samp = 0, t1 = -1, t2 = -1;
+	if (ok)
+	{
+		samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+		t1 = __ldg(a.a1 + samp); t2 = __ldg(a.a2 + samp);
+	}
+	uint32_t S1[NW], S2[NW], HOM[NW], G2[NW], V[NW];
 	load_geno<NW>(a.s1, a.s2, a.geno_stride, samp, ok, L.cand_col, L.cand_bit, S1, S2);
 #pragma unroll
-	for (int w = 0; w < NW; w++) { HOM[w] = ~(S1[w] ^ S2[w]); G2[w] = S1[w] & S2[w]; }
+	for (int w = 0; w < NW; w++)
+	{
+		HOM[w] = ~(S1[w] ^ S2[w]); G2[w] = S1[w] & S2[w]; V[w] = S1[w] | ~S2[w];
+	}
 	const int dmax = a.n_dist - 1;
 	const char *hap_g = (const char *)L.hap;
 	double *U = a.U + (size_t)l * a.n_hla * a.p_stride;
+	// the haplotype of each true allele with the largest f * T'[c] (first one on ties)
+	int best1 = -1, best2 = -1;
+	double bu1 = -1.0, bu2 = -1.0;
 	for (int al = 0; al < a.n_hla; al++)
 	{
 		const int i0 = al_start[al], i1 = i0 + al_n[al];
@@ -110,10 +132,71 @@ screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 #pragma unroll
 			for (int w = 0; w < NW; w++) c += __popc((h.h[w] ^ G2[w]) & HOM[w]);
 			const double t = __ldg(a.table_floor + min(c, dmax));
-			acc = __dadd_rn(acc, __dmul_rn(h.f, t));
+			const double u = __dmul_rn(h.f, t);
+			acc = __dadd_rn(acc, u);
+			if (al == t1 && u > bu1) { bu1 = u; best1 = i; }
+			if (al == t2 && u > bu2) { bu2 = u; best2 = i; }
 		}
 		if (ok) U[(size_t)al * a.p_stride + pos] = acc;
 	}
+	// ---- x_ref: ONE term of the true cell's chain, evaluated exactly as the chain does (kernels.cu)
+	// -- a sum of non-negative terms is at least each term, so x_ref <= the true cell's value <= the
+	// best cell's. The pair: the best haplotype of one allele with its best partner in the other,
+	// tried from both sides.
+	double xref = 0.0;
+	if (ok && best1 >= 0 && best2 >= 0)
+	{
+		const bool diag = (t1 == t2);
+		{
+			HapRec<NW, false> hi;
+			hi.load(0u, hap_g, best1);
+			uint32_t K[NW];
+			int ci = 0;
+#pragma unroll
+			for (int w = 0; w < NW; w++)
+			{
+				K[w] = S1[w] & (S2[w] | ~hi.h[w]);
+				ci += __popc((hi.h[w] ^ G2[w]) & HOM[w]);
+			}
+			const double ff = __dmul_rn(2.0, hi.f);
+			const int j0 = al_start[t2], j1 = j0 + al_n[t2];
+			for (int j = diag ? best1 : j0; j < j1; j++)
+			{
+				HapRec<NW, false> hj;
+				hj.load(0u, hap_g, j);
+				int pc = 0;
+#pragma unroll
+				for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[w]) & V[w]);
+				const double t = __ldg(a.table + min(ci + pc, dmax));
+				const double v = (diag && j == best1) ? __dmul_rn(__dmul_rn(hi.f, hi.f), t)
+					: __dmul_rn(__dmul_rn(ff, hj.f), t);
+				if (v > xref) xref = v;
+			}
+		}
+		{
+			HapRec<NW, false> hj;
+			hj.load(0u, hap_g, best2);
+			const int i0 = al_start[t1], i1 = i0 + al_n[t1];
+			for (int i = i0; i < (diag ? best2 + 1 : i1); i++)
+			{
+				HapRec<NW, false> hi;
+				hi.load(0u, hap_g, i);
+				int ci = 0, pc = 0;
+#pragma unroll
+				for (int w = 0; w < NW; w++)
+				{
+					const uint32_t K = S1[w] & (S2[w] | ~hi.h[w]);
+					ci += __popc((hi.h[w] ^ G2[w]) & HOM[w]);
+					pc += __popc((hj.h[w] ^ K) & V[w]);
+				}
+				const double t = __ldg(a.table + min(ci + pc, dmax));
+				const double v = (diag && i == best2) ? __dmul_rn(__dmul_rn(hi.f, hi.f), t)
+					: __dmul_rn(__dmul_rn(__dmul_rn(2.0, hi.f), hj.f), t);
+				if (v > xref) xref = v;
+			}
+		}
+	}
+	if (ok) a.xref[(size_t)l * a.p_stride + pos] = xref;
 }
 
 void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_t st)
@@ -131,32 +214,55 @@ void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_
 }
 
 // ---------------------------------------------------------------------------------------
-// per list: exclusive prefix of ceil(count/128) over the blob's cell order
+// per list: how many positions one gather task takes (32, 64 or 128 -- small when the launch
+// would otherwise have too few tasks to fill the GPU) and the exclusive prefix of
+// ceil(count / that) over the blob's cell order.  task_prefix[l]: [n_cells] prefix,
+// [n_cells] = number of tasks, [n_cells + 1] = log2(positions per task)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 	const int *__restrict__ count, size_t count_stride, unsigned int *task_prefix,
-	unsigned long long *evals)
+	unsigned long long *evals, int target_tasks)
 {
 	__shared__ unsigned int seg[256];
+	__shared__ unsigned int sh_shift;
 	const int l = blockIdx.x, tid = threadIdx.x;
 	const CellTask *cells = ls.l[l].cells;
 	const int *cnt = count + (size_t)l * count_stride;
-	unsigned int *pre = task_prefix + (size_t)l * (n_cells + 1);
+	unsigned int *pre = task_prefix + (size_t)l * (n_cells + 2);
 	const int per = (n_cells + 255) / 256;
 	const int k0 = min(n_cells, tid * per), k1 = min(n_cells, k0 + per);
-	unsigned int s = 0;
+	unsigned int tot = 0;
 	unsigned long long ev = 0;
 	for (int k = k0; k < k1; k++)
 	{
 		const int4 ca = __ldg((const int4 *)(cells + k));
 		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
 		const int c = __ldg(cnt + cb.x);
-		s += (unsigned int)((c + TASK_POS - 1) / TASK_POS);
+		tot += (unsigned int)c;
 		const unsigned long long pairs = cb.y ? (unsigned long long)ca.y * (ca.y + 1) / 2
 			: (unsigned long long)ca.y * (unsigned long long)ca.w;
 		ev += pairs * (unsigned long long)c;
 	}
+	seg[tid] = tot;
+	__syncthreads();
+	if (tid == 0)
+	{
+		unsigned int e = 0;
+		for (int t = 0; t < 256; t++) e += seg[t];
+		unsigned int sh = 7;
+		while (sh > 5 && (e >> sh) < (unsigned int)target_tasks) sh--;
+		sh_shift = sh;
+	}
+	__syncthreads();
+	const unsigned int sh = sh_shift, rnd = (1u << sh) - 1u;
+	unsigned int s = 0;
+	for (int k = k0; k < k1; k++)
+	{
+		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
+		s += ((unsigned int)__ldg(cnt + cb.x) + rnd) >> sh;
+	}
+	__syncthreads();
 	seg[tid] = s;
 	__syncthreads();
 	if (tid == 0)
@@ -164,71 +270,94 @@ screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 		unsigned int run = 0;
 		for (int t = 0; t < 256; t++) { const unsigned int v = seg[t]; seg[t] = run; run += v; }
 		pre[n_cells] = run;
+		pre[n_cells + 1] = sh;
 	}
 	__syncthreads();
 	unsigned int run = seg[tid];
 	for (int k = k0; k < k1; k++)
 	{
 		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
-		const int c = __ldg(cnt + cb.x);
 		pre[k] = run;
-		run += (unsigned int)((c + TASK_POS - 1) / TASK_POS);
+		run += ((unsigned int)__ldg(cnt + cb.x) + rnd) >> sh;
 	}
 	if (ev) atomicAdd(evals + l, ev);
 }
 
 void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
-	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, cudaStream_t st)
+	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, int target_tasks,
+	cudaStream_t st)
 {
 	if (n_lists <= 0) return;
-	screen_tasks_kernel<<<n_lists, 256, 0, st>>>(ls, n_cells, count, count_stride, task_prefix, evals);
+	screen_tasks_kernel<<<n_lists, 256, 0, st>>>(ls, n_cells, count, count_stride, task_prefix, evals,
+		target_tasks);
 	CUDA_CHECK(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------
 // which cells does a position need? lanes = consecutive positions; warp-aggregated append
 // ---------------------------------------------------------------------------------------
+static constexpr int NEED_TILE = 1024;       // cells per pass over the shared-memory masks
+
 __global__ void __launch_bounds__(128)
 screen_need_kernel(const ScreenArgs a)
 {
+	// per warp: the ballot of every cell of the tile, then the base offsets the appends start at.
+	// The atomics of a tile are issued one per lane, all in flight together, instead of one
+	// round trip to L2 per cell.
+	__shared__ unsigned int sh_mask[4][NEED_TILE];
+	__shared__ int sh_base[4][NEED_TILE];
 	const int l = blockIdx.y;
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const bool ok = pos < a.n_pos;
 	const int n = a.n_hla;
 	const int n_cells = n * (n + 1) / 2;
 	const double *U = a.U + (size_t)l * n * a.p_stride;
-	const double *P = a.P + (size_t)l * n_cells * a.p_stride;
 	int *cnt = a.count + (size_t)l * n_cells;
 	int *ent = a.entries + (size_t)l * n_cells * a.p_stride;
+	unsigned int *wm = sh_mask[wid];
+	int *wb = sh_base[wid];
 	int true_idx = -1;
 	double thr = 0.0;
 	if (ok)
 	{
 		const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
 		true_idx = true_cell_index(__ldg(a.a1 + samp), __ldg(a.a2 + samp), n);
-		thr = __dmul_rn(P[(size_t)true_idx * a.p_stride + pos], a.tau);
+		thr = __dmul_rn(a.xref[(size_t)l * a.p_stride + pos], a.tau);
 	}
-	int idx = 0;
-	for (int al = 0; al < n; al++)
+	int al = 0, bl = 0;
+	double ua = ok ? U[pos] : 0.0;
+	for (int t0 = 0; t0 < n_cells; t0 += NEED_TILE)
 	{
-		const double ua = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
-		for (int bl = al; bl < n; bl++, idx++)
+		const int nt = min(NEED_TILE, n_cells - t0);
+		for (int q = 0; q < nt; q++)
 		{
 			const double ub = ok ? U[(size_t)bl * a.p_stride + pos] : 0.0;
 			const double bd = screen_bound(ua, ub, a.K);
-			const bool need = ok && idx != true_idx && bd >= thr && bd > 0.0;
+			const bool need = ok && ((t0 + q) == true_idx || (bd >= thr && bd > 0.0));
 			const unsigned mask = __ballot_sync(0xffffffffu, need);
-			if (mask)
+			if (lane == 0) wm[q] = mask;
+			if (++bl == n)
 			{
-				const int leader = __ffs(mask) - 1;
-				int base = 0;
-				if (lane == leader) base = atomicAdd(cnt + idx, __popc(mask));
-				base = __shfl_sync(0xffffffffu, base, leader);
-				if (need)
-					ent[(size_t)idx * a.p_stride + base + __popc(mask & ((1u << lane) - 1u))] = pos;
+				al++; bl = al;
+				ua = (ok && al < n) ? U[(size_t)al * a.p_stride + pos] : 0.0;
 			}
 		}
+		__syncwarp();
+		for (int q = lane; q < nt; q += 32)
+		{
+			const unsigned m = wm[q];
+			if (m) wb[q] = atomicAdd(cnt + t0 + q, __popc(m));
+		}
+		__syncwarp();
+		const unsigned lt = (1u << lane) - 1u;
+		for (int q = 0; q < nt; q++)
+		{
+			const unsigned m = wm[q];
+			if ((m >> lane) & 1u)
+				ent[(size_t)(t0 + q) * a.p_stride + wb[q] + __popc(m & lt)] = pos;
+		}
+		__syncwarp();
 	}
 }
 
@@ -258,24 +387,34 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 		const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
 		int t1 = __ldg(a.a1 + samp), t2 = __ldg(a.a2 + samp);
 		const int true_idx = true_cell_index(t1, t2, n);
-		const double thr = __dmul_rn(P[(size_t)true_idx * a.p_stride], a.tau);
+		const double thr = __dmul_rn(a.xref[(size_t)l * a.p_stride + pos], a.tau);
 		// strict '<' scan in cell order over the cells that were scored; a skipped cell is
-		// strictly below the true cell's value and can never be the first maximum
+		// strictly below x_ref <= the true cell's value and can never be the first maximum
 		double best = 0.0;
 		int p1 = NA_INT, p2 = NA_INT;
 		int idx = 0;
 		for (int al = 0; al < n; al++)
 		{
 			const double ua = U[(size_t)al * a.p_stride];
-			for (int bl = al; bl < n; bl++, idx++)
+			for (int bl = al; bl < n; bl += 8, idx += 8)       // 8 cells per step: the loads overlap
 			{
-				const double bd = screen_bound(ua, U[(size_t)bl * a.p_stride], a.K);
-				if (idx == true_idx || (bd >= thr && bd > 0.0))
+				const int nb = min(8, n - bl);
+				double v[8];
+				bool nd[8];
+#pragma unroll
+				for (int q = 0; q < 8; q++)
 				{
-					const double v = P[(size_t)idx * a.p_stride];
-					if (best < v) { best = v; p1 = al; p2 = bl; }
+					const double ub = (q < nb) ? U[(size_t)(bl + q) * a.p_stride] : 0.0;
+					const double bd = screen_bound(ua, ub, a.K);
+					nd[q] = (q < nb) && ((idx + q) == true_idx || (bd >= thr && bd > 0.0));
 				}
+#pragma unroll
+				for (int q = 0; q < 8; q++) v[q] = nd[q] ? P[(size_t)(idx + q) * a.p_stride] : 0.0;
+#pragma unroll
+				for (int q = 0; q < 8; q++)
+					if (nd[q] && best < v[q]) { best = v[q]; p1 = al; p2 = bl + q; }
 			}
+			idx -= (8 - ((n - al) & 7)) & 7;                    // undo the overshoot of the last step
 		}
 		// CHLATypeList::Compare (src/LibHLA.cpp:912-924)
 		if (p1 == t1) { cnt = 1; t1 = -1; }
@@ -295,48 +434,174 @@ void launch_reduce_oob_screened(const ScreenArgs &a, int *out_count, cudaStream_
 	CUDA_CHECK(cudaGetLastError());
 }
 
+/// The reference's chain of one cell for one sample by ONE lane, everything read from global
+/// memory: the rescue path of the in-bag reduction (rare, so simple beats fast). Same operations
+/// in the same order as cell_chain below.
+__device__ double rescue_chain(const char *__restrict__ hap, int nw, const double *__restrict__ table,
+	int dmax, int a_start, int a_n, int b_start, int b_n, bool diag, const uint32_t (&S1)[4],
+	const uint32_t (&S2)[4])
+{
+	const int rec = (nw <= 2) ? 16 : 32;
+	double sum = 0.0;
+	for (int ii = 0; ii < a_n; ii++)
+	{
+		const uint32_t *ri = (const uint32_t *)(hap + (size_t)(a_start + ii) * rec);
+		uint32_t hi[4], K[4];
+		int ci = 0;
+		for (int w = 0; w < 4; w++)
+		{
+			hi[w] = (w < nw) ? __ldg(ri + w) : 0u;
+			K[w] = S1[w] & (S2[w] | ~hi[w]);
+			ci += __popc((hi[w] ^ (S1[w] & S2[w])) & ~(S1[w] ^ S2[w]));
+		}
+		const double fi = __ldg((const double *)((const char *)ri + ((nw <= 2) ? 8 : 16)));
+		int j0 = 0;
+		if (diag)
+		{
+			int pc = 0;
+			for (int w = 0; w < 4; w++) pc += __popc((hi[w] ^ K[w]) & (S1[w] | ~S2[w]));
+			sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(fi, fi), __ldg(table + min(ci + pc, dmax))));
+			j0 = ii + 1;
+		}
+		const double ff = __dmul_rn(2.0, fi);
+		for (int j = j0; j < b_n; j++)
+		{
+			const uint32_t *rj = (const uint32_t *)(hap + (size_t)(b_start + j) * rec);
+			int pc = 0;
+			for (int w = 0; w < 4; w++)
+			{
+				const uint32_t hj = (w < nw) ? __ldg(rj + w) : 0u;
+				pc += __popc((hj ^ K[w]) & (S1[w] | ~S2[w]));
+			}
+			const double fj = __ldg((const double *)((const char *)rj + ((nw <= 2) ? 8 : 16)));
+			sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ff, fj), __ldg(table + min(ci + pc, dmax))));
+		}
+	}
+	return sum;
+}
+
 __global__ void __launch_bounds__(64)
-reduce_ib_screened_kernel(const ScreenArgs a, double *out_ratio, size_t out_stride)
+reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls,
+	double *out_ratio, size_t out_stride)
 {
 	const int l = blockIdx.y;
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-	if (pos >= a.n_pos) return;
+	const int lane = threadIdx.x & 31;
+	const bool ok = pos < a.n_pos;
 	const int n = a.n_hla;
 	const int n_cells = n * (n + 1) / 2;
-	const double *U = a.U + (size_t)l * n * a.p_stride + pos;
-	const double *P = a.P + (size_t)l * n_cells * a.p_stride + pos;
-	const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
-	const int true_idx = true_cell_index(__ldg(a.a1 + samp), __ldg(a.a2 + samp), n);
-	const double x_true = P[(size_t)true_idx * a.p_stride];
-	const double thr = __dmul_rn(x_true, a.tau);
-	// the sequential sum in cell order, once with 0 and once with the bound for every skipped
-	// cell: addition is monotone, so lo <= (the full chain) <= hi, and lo == hi certifies it
-	double lo = 0.0, hi = 0.0;
-	int idx = 0;
-	for (int al = 0; al < n; al++)
+	const double *U = a.U + (size_t)l * n * a.p_stride;
+	double *P = a.P + (size_t)l * n_cells * a.p_stride;
+	int samp = 0, true_idx = 0;
+	double x_true = 0.0, thr = 0.0, lo = 0.0, hi = 0.0;
+	if (ok)
 	{
-		const double ua = U[(size_t)al * a.p_stride];
-		for (int bl = al; bl < n; bl++, idx++)
+		samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+		true_idx = true_cell_index(__ldg(a.a1 + samp), __ldg(a.a2 + samp), n);
+		x_true = P[(size_t)true_idx * a.p_stride + pos];
+		thr = __dmul_rn(a.xref[(size_t)l * a.p_stride + pos], a.tau);
+		// the sequential sum in cell order, once with 0 and once with the bound for every skipped
+		// cell: addition is monotone, so lo <= (the full chain) <= hi, and lo == hi certifies it
+		const double *Up = U + pos;
+		const double *Pp = P + pos;
+		int idx = 0;
+		for (int al = 0; al < n; al++)
 		{
-			const double bd = screen_bound(ua, U[(size_t)bl * a.p_stride], a.K);
-			if (idx == true_idx || (bd >= thr && bd > 0.0))
+			const double ua = Up[(size_t)al * a.p_stride];
+			for (int bl = al; bl < n; bl += 8, idx += 8)           // 8 cells per step: the loads overlap
 			{
-				const double v = P[(size_t)idx * a.p_stride];
-				lo = __dadd_rn(lo, v);
-				hi = __dadd_rn(hi, v);
-			} else
-				hi = __dadd_rn(hi, bd);
+				const int nb = min(8, n - bl);
+				double v[8], bd[8];
+				bool nd[8];
+#pragma unroll
+				for (int q = 0; q < 8; q++)
+				{
+					const double ub = (q < nb) ? Up[(size_t)(bl + q) * a.p_stride] : 0.0;
+					bd[q] = screen_bound(ua, ub, a.K);
+					nd[q] = (q < nb) && ((idx + q) == true_idx || (bd[q] >= thr && bd[q] > 0.0));
+				}
+#pragma unroll
+				for (int q = 0; q < 8; q++) v[q] = nd[q] ? Pp[(size_t)(idx + q) * a.p_stride] : 0.0;
+#pragma unroll
+				for (int q = 0; q < 8; q++)
+				{
+					if (nd[q])
+					{
+						lo = __dadd_rn(lo, v[q]);
+						hi = __dadd_rn(hi, v[q]);
+					} else if (q < nb)
+						hi = __dadd_rn(hi, bd[q]);
+				}
+			}
+			idx -= (8 - ((n - al) & 7)) & 7;                        // undo the overshoot of the last step
 		}
 	}
-	out_ratio[(size_t)l * out_stride + pos] = (lo == hi) ? __ddiv_rn(x_true, lo) : -1.0;
+	// ---- rescue: a position whose sum is not certified gets its skipped cells scored here, the
+	// 32 lanes of its warp taking the cells in turn, and then the plain sequential sum -----------
+	bool failed = ok && !(lo == hi);
+	if (a.force_rescue && ok && ((pos + l) % a.force_rescue) == 0) failed = true;       // test hook
+	if (failed && !a.device_rescue && !a.force_rescue) { lo = 0.0; hi = 1.0; }             // -> ratio -1: the caller rescores
+	unsigned fm = __ballot_sync(0xffffffffu, failed && (a.device_rescue || a.force_rescue));
+	if (fm)
+	{
+		const ScreenList &L = ls.l[l];
+		const int nw = geno_words_dev(a.n_snp);
+		const int dmax = a.n_dist - 1;
+		const int *al_tab = a.al_tab + (size_t)l * n * 2;
+		while (fm)
+		{
+			const int src = __ffs(fm) - 1;
+			fm &= fm - 1;
+			const int fpos = __shfl_sync(0xffffffffu, pos, src);
+			const int fsamp = __shfl_sync(0xffffffffu, samp, src);
+			const int ftrue = __shfl_sync(0xffffffffu, true_idx, src);
+			const double fthr = __shfl_sync(0xffffffffu, thr, src);
+			uint32_t S1[4], S2[4];
+			load_geno<4>(a.s1, a.s2, a.geno_stride, fsamp, true, L.cand_col, L.cand_bit, S1, S2);
+			for (int w = nw; w < 4; w++) { S1[w] = 0u; S2[w] = 0xffffffffu; }
+			int row = 0, row0 = 0;                               // row `row` starts at cell row0
+			for (int idx = lane; idx < n_cells; idx += 32)
+			{
+				while (idx >= row0 + (n - row)) { row0 += n - row; row++; }
+				const int al = row, bl = row + (idx - row0);
+				const double bd = screen_bound(U[(size_t)al * a.p_stride + fpos],
+					U[(size_t)bl * a.p_stride + fpos], a.K);
+				if (idx == ftrue || (bd >= fthr && bd > 0.0)) continue;      // already scored
+				double x = 0.0;
+				if (bd > 0.0)
+					x = rescue_chain((const char *)L.hap, nw, a.table, dmax, al_tab[2 * al], al_tab[2 * al + 1],
+						al_tab[2 * bl], al_tab[2 * bl + 1], al == bl, S1, S2);
+				P[(size_t)idx * a.p_stride + fpos] = x;
+			}
+			__syncwarp();
+			if (lane == src)
+			{
+				double s = 0.0;
+				int idx = 0;
+				for (; idx + 8 <= n_cells; idx += 8)
+				{
+					double v[8];
+#pragma unroll
+					for (int q = 0; q < 8; q++) v[q] = P[(size_t)(idx + q) * a.p_stride + pos];
+#pragma unroll
+					for (int q = 0; q < 8; q++) s = __dadd_rn(s, v[q]);
+				}
+				for (; idx < n_cells; idx++) s = __dadd_rn(s, P[(size_t)idx * a.p_stride + pos]);
+				lo = hi = s;
+				atomicAdd(a.rescued, 1ull);
+			}
+			__syncwarp();
+		}
+	}
+	if (ok) out_ratio[(size_t)l * out_stride + pos] = (lo == hi) ? __ddiv_rn(x_true, lo) : -1.0;
 }
 
-void launch_reduce_ib_screened(const ScreenArgs &a, double *out_ratio, size_t out_stride,
-	cudaStream_t st)
+void launch_reduce_ib_screened(const ScreenArgs &a, const ScreenLists &ls, double *out_ratio,
+	size_t out_stride, cudaStream_t st)
 {
 	if (a.n_pos <= 0 || a.n_lists <= 0) return;
 	dim3 grid((a.n_pos + 63) / 64, a.n_lists);
-	reduce_ib_screened_kernel<<<grid, 64, 0, st>>>(a, out_ratio, out_stride);
+	reduce_ib_screened_kernel<<<grid, 64, 0, st>>>(a, ls, out_ratio, out_stride);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -429,7 +694,7 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 	volatile int *sh_flag = (volatile int *)(smem_raw + 16);
 	const uint32_t tbl_base = smem_base + 128;
 	const uint32_t pre_off = 128u + (uint32_t)p.n_dist * 256u;
-	const uint32_t pre_bytes = (((uint32_t)p.n_cells + 1u) * 4u + 15u) & ~15u;
+	const uint32_t pre_bytes = (((uint32_t)p.n_cells + 2u) * 4u + 15u) & ~15u;
 	unsigned int *sh_pre = (unsigned int *)(smem_raw + pre_off);
 	const uint32_t hap_base = smem_base + pre_off + pre_bytes;
 	constexpr int REC = (NW <= 2) ? 16 : 32;
@@ -480,7 +745,7 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 				off += nb;
 			}
 		}
-		for (int q = tid; q <= p.n_cells; q += GATHER_THREADS) sh_pre[q] = __ldg(L.task_prefix + q);
+		for (int q = tid; q < p.n_cells + 2; q += GATHER_THREADS) sh_pre[q] = __ldg(L.task_prefix + q);
 		__syncthreads();
 		if (SMEM)
 		{
@@ -490,6 +755,8 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 
 		const char *hap_g = (const char *)L.hap;
 		double *Pl = L.P;
+		const int task_shift = (int)sh_pre[p.n_cells + 1];       // log2(positions per task)
+		const int task_pos = 1 << task_shift;
 
 		unsigned task = 0;
 		if (lane == 0) task = atomicAdd(counter, 1u);
@@ -510,9 +777,9 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 			const int blk = (int)(task - sh_pre[lo]);
 			const int4 ca = __ldg((const int4 *)(L.cells + lo));
 			const int2 cb = __ldg((const int2 *)((const char *)(L.cells + lo) + 16));
-			const int rem = __ldg(L.count + cb.x) - blk * TASK_POS;
-			const int nr = min(4, (rem + 31) >> 5);
-			const int *ent = L.entries + (size_t)__ldg(p.ent_off + cb.x) + (size_t)blk * TASK_POS;
+			const int rem = min(task_pos, __ldg(L.count + cb.x) - (blk << task_shift));
+			const int nr = (rem + 31) >> 5;
+			const int *ent = L.entries + (size_t)__ldg(p.ent_off + cb.x) + ((size_t)blk << task_shift);
 
 			uint32_t S1[4][NW], S2[4][NW];
 			int pos[4];
@@ -548,10 +815,10 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 }
 
 template <int NW, bool CLAMP>
-static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream_t st)
+static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream_t st, long long max_ctas)
 {
 	const size_t rec = (NW <= 2) ? 16 : 32;
-	const size_t fixed = 128 + (size_t)p.n_dist * 256 + ((((size_t)p.n_cells + 1) * 4 + 15) & ~(size_t)15);
+	const size_t fixed = 128 + (size_t)p.n_dist * 256 + ((((size_t)p.n_cells + 2) * 4 + 15) & ~(size_t)15);
 	const size_t with_hap = fixed + (size_t)p.max_hap * rec;
 	const size_t smem_limit = 227 * 1024;
 	if (fixed > smem_limit) throw std::runtime_error("launch_cell_gather: too many cells for shared memory");
@@ -561,6 +828,7 @@ static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream
 	if (cta_per_sm > 8) cta_per_sm = 8;
 	if (cta_per_sm < 1) cta_per_sm = 1;
 	long long grid = (long long)sm_count * cta_per_sm;
+	if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
 	if (grid < p.n_lists) grid = p.n_lists;
 	if (in_smem)
 	{
@@ -575,7 +843,7 @@ static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream
 	CUDA_CHECK(cudaGetLastError());
 }
 
-int launch_cell_gather(const GatherBatch &p, int sm_count, cudaStream_t st)
+int launch_cell_gather(const GatherBatch &p, int sm_count, cudaStream_t st, long long max_ctas)
 {
 	if (p.n_lists < 1 || p.n_lists > MAX_BATCH_LISTS)
 		throw std::runtime_error("launch_cell_gather: invalid number of lists");
@@ -583,8 +851,8 @@ int launch_cell_gather(const GatherBatch &p, int sm_count, cudaStream_t st)
 	const bool clamp = (2 * p.n_snp) > (p.n_dist - 1);
 #define HB_GCASE(NW_) \
 	if (nw == NW_) { \
-		if (clamp) launch_gather_variant<NW_, true>(p, sm_count, st); \
-		else launch_gather_variant<NW_, false>(p, sm_count, st); \
+		if (clamp) launch_gather_variant<NW_, true>(p, sm_count, st, max_ctas); \
+		else launch_gather_variant<NW_, false>(p, sm_count, st, max_ctas); \
 		return NW_; }
 	HB_GCASE(1) HB_GCASE(2) HB_GCASE(4)
 #undef HB_GCASE
