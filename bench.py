@@ -40,7 +40,7 @@ if ROOT not in sys.path:
 N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
-LANES = 6            # classifiers in flight per GPU (one step = LANES classifiers per GPU)
+LANES = 12           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
 WORKLOAD_JSON = os.path.join(ROOT, "profiles", "c2_workload.json")
@@ -249,9 +249,9 @@ def workload_config(n_gpus):
                         "(per-classifier seed %d + index)" % (LANES, TRAIN_SEED),
             "n_samp": N_SAMP, "n_snp": N_SNP, "mtry": MTRY, "parallelism": "classifier-sharded x%d" % n_gpus,
             "lanes": LANES,
-            "l2": "inputs larger than L2: every pair-scoring launch writes a fresh 280-480 MB cell matrix "
-                  "(23 candidate lists x 820 cells x 1,840-3,160 samples x 8 B) and its operands are rebuilt "
-                  "per selection round, so nothing is reused from L2 between timed launches"}
+            "l2": "inputs larger than L2: the 12 lanes' cell matrices, need lists and bound tables (each lane "
+                  "~0.5 GB per selection round: 23 candidate lists x 595 cells x 1,840-3,160 samples) are "
+                  "rebuilt every round, so nothing is reused from L2 between timed steps"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -359,33 +359,70 @@ def run_b200_arm(args):
                             "TGenotype[5000] + haplotype list from host memory per candidate SNP, scalar "
                             "results back per hook call, strictly sequential as the reference host calls them"}
 
-    # ---- roofline of the dominant kernel (pair scoring), training region ---------------------------
+    # ---- roofline of the pair-scoring kernel, training region -----------------------------------------
     peaks = json.load(open(PEAKS_JSON)) if os.path.exists(PEAKS_JSON) else None
     popc_peak = (peaks or {}).get("popc32_per_s", 148 * 16 * 1.965e9)
     peak_src = "measured (profiles/pipe_peaks.json, POPC.32 microbenchmark on this pool's B200)" if peaks \
         else "nominal 148 SM x 16 POPC/clk x 1.965 GHz (no measured file)"
-    n_l = max(d["cell_kernel_launches"], 1)
-    avg_ms = d["cell_kernel_ms"] / n_l
-    pair_rate = d["pair_evals"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
-    issued_rate = d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
+    screened = d["gather_kernel_launches"] > 0
+    k_ms = d["gather_kernel_ms"] if screened else d["cell_kernel_ms"]
+    n_l = max(d["gather_kernel_launches"] if screened else d["cell_kernel_launches"], 1)
+    avg_ms = k_ms / n_l
+    pair_rate = d["pair_evals"] / max(k_ms * 1e-3, 1e-12)
+    issued_rate = d["popc32_issued"] / max(k_ms * 1e-3, 1e-12)
+    eff_rate = d["pair_evals_nominal"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)
     roofline = {
-        "bound": "popc", "kernel": "cell_pass_kernel",
+        "bound": "popc", "kernel": "cell_gather_kernel" if screened else "cell_pass_kernel",
         "achieved": issued_rate / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s",
         "frac": issued_rate / popc_peak,
         "achieved_reference_formulation": pair_rate * 4 / 1e9,
         "frac_reference_formulation": pair_rate * 4 / popc_peak,
-        "pair_evals_per_s": pair_rate, "avg_launch_ms": avg_ms, "launches": int(d["cell_kernel_launches"]),
+        "pair_evals_per_s": pair_rate, "avg_launch_ms": avg_ms, "launches": int(n_l),
         "pair_evals_per_launch": d["pair_evals"] / n_l,
-        "note": "achieved = POPC.32 the kernel issues (1 per pair evaluation per 32 SNPs: the one-popcount "
-                "distance) / summed launch durations; POPC (XU pipe) and the lane-private LDS.64 table lookup "
-                "co-bind at the same 16 /clk/SM, so frac is also the fraction of the shared-memory-pipe bound. "
-                "*_reference_formulation counts the 4 POPC.32 per pair evaluation of the reference's hamm_d "
-                "(SURVEY.md 8d) and can exceed 1. One launch scores all candidate lists of a selection round; "
-                "launches of all lanes are serialised on one stream, so a launch's CUDA events time it alone "
-                "(EM clusters of other lanes may hold some of the SMs meanwhile).",
+        "screening": {
+            "pair_evals_executed": int(d["pair_evals"]), "pair_evals_reference": int(d["pair_evals_nominal"]),
+            "executed_fraction": d["pair_evals"] / max(d["pair_evals_nominal"], 1),
+            "uncertified_sums_rescored": int(d["n_screen_fallback"]),
+            "scoring_pass_ms": d["cell_kernel_ms"],
+            "effective_pair_evals_per_s": eff_rate,
+            "effective_frac_reference_formulation": eff_rate * 4 / popc_peak,
+            "note": "exact screening (DESIGN.md 4.5): cells proven irrelevant for the reference's outputs are "
+                    "not scored; 'effective' = the pair evaluations the reference performs for the same "
+                    "passes / the summed durations of the whole screened passes (bounds, need lists, gather "
+                    "launch, reduction)"},
+        "note": "achieved = POPC.32 the pair-scoring kernel issues (1 per executed pair evaluation per 32 "
+                "SNPs: the one-popcount distance) / its summed launch durations (CUDA events around the "
+                "kernel on its stream). POPC (XU pipe) and the lane-private LDS.64 table lookup co-bind at the "
+                "same 16 /clk/SM. *_reference_formulation counts the 4 POPC.32 per pair evaluation of the "
+                "reference's hamm_d (SURVEY.md 8d). The lanes' passes run on three streams and share the SMs "
+                "with each other and with other lanes' EM clusters, so a launch's duration is an upper bound "
+                "of the time it would take alone: frac is conservative. The gather form is ragged (a warp's "
+                "lanes are the samples that need the cell) and latency-bound on the small passes; the plain "
+                "kernel's fraction (every cell, full warps) is under roofline_unscreened and predict.roofline.",
         "peak_source": peak_src, "traffic": None,
         "fp64_frac": pair_rate * 3 / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9),
+        "em_kernel_ms": d["em_kernel_ms"],
     }
+    # one step with screening off: the plain pair-scoring kernel alone on its stream
+    roofline_plain = None
+    if screened and not args.no_unscreened:
+        m2 = api.HLAModel(N_SNP, coh.n_hla)
+        m2.set_training(geno, coh.h1, coh.h2)
+        n_plain = min(lanes, 6)
+        m2.train(n_plain, MTRY, prune=True, seed=TRAIN_SEED, per_classifier_seed=True, first_index=rank * n_plain,
+                 n_threads=n_threads, n_concurrent=n_plain, em_on_device=dev_em, screening=False)
+        torch.cuda.synchronize()
+        sp = m2.train_stats()
+        r_issued = sp["popc32_issued"] / max(sp["cell_kernel_ms"] * 1e-3, 1e-12)
+        roofline_plain = {"kernel": "cell_pass_kernel", "classifiers": n_plain, "achieved": r_issued / 1e9,
+                          "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": r_issued / popc_peak,
+                          "pair_evals_per_s": sp["pair_evals"] / max(sp["cell_kernel_ms"] * 1e-3, 1e-12),
+                          "launches": int(sp["cell_kernel_launches"]),
+                          "avg_launch_ms": sp["cell_kernel_ms"] / max(sp["cell_kernel_launches"], 1),
+                          "classifiers_per_min": 60.0 * n_plain / max(sp["seconds_total"], 1e-9),
+                          "note": "screening off: every cell of every candidate scored by cell_pass_kernel, "
+                                  "launches serialised on one stream"}
+        del m2
 
     # ---- secondary metric: prediction (configs[2]) ---------------------------------------------------
     predict = None
@@ -413,14 +450,16 @@ def run_b200_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
             "e2e": e2e, "e2e_legacy_hooks": e2e_hooks, "gpu_launches": int(d["kernel_launches"]),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "predict": predict,
+            "clocks": clocks, "roofline": roofline, "roofline_unscreened": roofline_plain,
+            "cpu_baseline": cpu, "predict": predict,
             "train_detail": {
                 "host_threads": n_threads, "lanes": lanes, "em_on_device": dev_em,
                 "em_kernel_ms": d["em_kernel_ms"], "em_host_fallbacks": int(d["n_em_host_fallback"]),
                 "seconds_em_sum": d["seconds_em"],
                 "seconds_prepare": d["seconds_prepare"], "seconds_candidates": d["seconds_phase_oob"],
                 "seconds_gpu_wait_sum": d["seconds_gpu_wait"], "gpu_kernel_span_ms": d["gpu_kernel_ms"],
-                "pair_evals": int(d["pair_evals"]), "oob_evals": int(d["n_oob_evals"]),
+                "pair_evals": int(d["pair_evals"]), "pair_evals_reference": int(d["pair_evals_nominal"]),
+                "oob_evals": int(d["n_oob_evals"]),
                 "ib_evals": int(d["n_ib_evals"]), "em_runs": int(d["n_em"]),
                 "h2d_bytes_per_step": int(d["h2d_bytes"] / args.steps),
                 "d2h_bytes_per_step": int(d["d2h_bytes"] / args.steps), "wall_s": wall,
@@ -514,6 +553,7 @@ def main():
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-unscreened", action="store_true", help="skip the extra step with screening off")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--cpu-procs", type=int, default=0)
     args = ap.parse_args()

@@ -46,7 +46,8 @@ class TrainStats(C.Structure):
                 ("cell_kernel_launches", C.c_uint64), ("seconds_prepare", C.c_double),
                 ("seconds_phase_oob", C.c_double), ("seconds_phase_ib", C.c_double),
                 ("em_kernel_ms", C.c_double), ("n_em_host_fallback", C.c_uint64),
-                ("pair_evals_nominal", C.c_uint64), ("n_screen_fallback", C.c_uint64)]
+                ("pair_evals_nominal", C.c_uint64), ("n_screen_fallback", C.c_uint64),
+                ("gather_kernel_ms", C.c_double), ("gather_kernel_launches", C.c_uint64)]
 
 
 class PredictOut(C.Structure):
@@ -393,7 +394,8 @@ def default_mtry(n_snp, mtry="sqrt"):
 
 def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=True, seed=100,
                    nthread=0, per_classifier_seed=False, use_legacy_hooks=False, verbose=False,
-                   hla_allele=None, first_index=0, index_stride=1, n_concurrent=1, em_on_device=True):
+                   hla_allele=None, first_index=0, index_stride=1, n_concurrent=1, em_on_device=True,
+                   screening=True):
     """Train a model. hla = (h1, h2) integer allele indices (or labels with hla_allele given),
     snp = int matrix [n_samp, n_snp] with 0/1/2 and anything else missing.
     Mirrors reference hlaAttrBagging (R/HIBAG.R:48-275): monomorphic SNPs are removed when mono_rm,
@@ -419,7 +421,7 @@ def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=T
     model.train(nclassifier, default_mtry(g.shape[1], mtry), prune=prune, seed=seed, n_threads=nthread,
                 per_classifier_seed=per_classifier_seed, first_index=first_index,
                 index_stride=index_stride, use_legacy_hooks=use_legacy_hooks, verbose=int(verbose),
-                n_concurrent=n_concurrent, em_on_device=em_on_device)
+                n_concurrent=n_concurrent, em_on_device=em_on_device, screening=screening)
     return model
 
 

@@ -482,7 +482,9 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
 		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks, s);
+		HB_CUDA(cudaEventRecord(ev_g0_.e, s));
 		nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
+		HB_CUDA(cudaEventRecord(ev_g1_.e, s));
 		if (kind == 0)
 			launch_reduce_oob_screened(a, d_counts_.get() + first, s);
 		else
@@ -494,6 +496,13 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	stats.launches += 5; stats.cell_launches += 1;
 	stats.pair_evals_nominal += pairs * (uint64_t)n_pos;
 	(void)nw;
+}
+
+void BatchScorer::add_gather_time()
+{
+	float ms = 0;
+	HB_CUDA(cudaEventElapsedTime(&ms, ev_g0_.e, ev_g1_.e));
+	stats.gather_ms += ms; stats.gather_launches++;
 }
 
 void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<int> &which,
@@ -528,6 +537,7 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 			HB_CUDA(cudaEventSynchronize(ev1_.e));
 			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 			stats.cell_ms += ms; stats.kernel_ms += ms;
+			if (screen) add_gather_time();
 		}
 	}
 	if (!screen)
@@ -549,6 +559,7 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 	stats.d2h_bytes += sizeof(int) * (size_t)n;
 	if (screen)
 	{
+		add_gather_time();
 		const int nw = geno_words(n_snp_);
 		uint64_t tot = 0;
 		for (int k = 0; k < n; k++) tot += h_evals_.get()[k];
@@ -593,6 +604,7 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 			HB_CUDA(cudaEventSynchronize(ev1_.e));
 			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 			stats.cell_ms += ms; stats.kernel_ms += ms;
+			if (screen) add_gather_time();
 		}
 	}
 	if (!screen)
@@ -614,6 +626,7 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 	stats.d2h_bytes += sizeof(double) * (size_t)n * ratio_stride_;
 	if (screen)
 	{
+		add_gather_time();
 		const int nw = geno_words(n_snp_);
 		uint64_t tot = 0;
 		for (int k = 0; k < n; k++) tot += h_evals_.get()[k];

@@ -25,12 +25,15 @@ struct ScoreStats
 	uint64_t screen_fallback = 0;        // in-bag positions rescored without screening
 	uint64_t h2d_bytes = 0, d2h_bytes = 0;
 	double kernel_ms = 0, cell_ms = 0;
+	double gather_ms = 0;                // summed CUDA-event durations of cell_gather_kernel alone
+	uint64_t gather_launches = 0;
 	void add(const ScoreStats &o)
 	{
 		pair_evals += o.pair_evals; popc32 += o.popc32; launches += o.launches;
 		cell_launches += o.cell_launches; h2d_bytes += o.h2d_bytes; d2h_bytes += o.d2h_bytes;
 		pair_evals_nominal += o.pair_evals_nominal; screen_fallback += o.screen_fallback;
 		kernel_ms += o.kernel_ms; cell_ms += o.cell_ms;
+		gather_ms += o.gather_ms; gather_launches += o.gather_launches;
 	}
 };
 
@@ -166,7 +169,8 @@ private:
 	PinBuf<double> h_ratio_fb_;
 	std::vector<uint64_t> list_pairs_;           // pairs per sample of the lists of the pass
 	Stream st_;
-	Event ev_up_{false}, ev0_, ev1_;
+	Event ev_up_{false}, ev0_, ev1_, ev_g0_, ev_g1_;
+	void add_gather_time();
 	Event ev_done_{false, true};
 	size_t cap_ = 0;
 	int n_snp_ = 0, n_hla_ = 0, n_cells_ = 0;

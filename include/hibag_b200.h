@@ -177,6 +177,10 @@ typedef struct hibag_b200_train_stats {
 	                                 (pair_evals = those the GPU executed after screening) */
 	uint64_t n_screen_fallback;   /* in-bag (sample, candidate) sums the screen could not certify,
 	                                 rescored against every cell */
+	double   gather_kernel_ms;    /* summed CUDA-event durations of cell_gather_kernel alone (the
+	                                 screened passes; cell_kernel_ms spans a whole pass, bounds to
+	                                 reduction) */
+	uint64_t gather_kernel_launches;
 } hibag_b200_train_stats;
 int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_stats *out);
 
