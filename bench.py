@@ -36,11 +36,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# before any CUDA context exists (torch creates it): see hibag_b200/api.py lib()
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
-LANES = 12           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
+LANES = 24           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
 WORKLOAD_JSON = os.path.join(ROOT, "profiles", "c2_workload.json")
@@ -221,7 +223,7 @@ def run_reference_arm(args):
         "unit": "classifiers/min", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 60000.0 / value * procs if value > 0 else None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, args.lanes or default_lanes(args.gpus)),
         "cpu_baseline": {"value": value, "unit": "classifiers/min", "cores": procs, "kind": "reference",
                          "target": info,
                          "sample": "per step: %d worker processes x one classifier each for %.0f s of the "
@@ -243,13 +245,20 @@ def emit(text):
     out.flush()
 
 
-def workload_config(n_gpus):
+def default_lanes(world):
+    """classifiers in flight per GPU: enough to cover the per-round latency chain of a lane (EM
+    launch, two scoring passes, host decisions); bounded by the host cores a rank can count on"""
+    cores = max(1, (os.cpu_count() or 1) // max(world, 1))
+    return max(4, min(LANES, 2 * cores))
+
+
+def workload_config(n_gpus, lanes):
     return {"workload": "synthetic HLA-A training: 5000 samples x 500 SNPs, 34 alleles (40 drawn), "
                         "cohort seed 1, mtry 23, prune, %d classifiers per GPU per step, all in flight "
-                        "(per-classifier seed %d + index)" % (LANES, TRAIN_SEED),
+                        "(per-classifier seed %d + index)" % (lanes, TRAIN_SEED),
             "n_samp": N_SAMP, "n_snp": N_SNP, "mtry": MTRY, "parallelism": "classifier-sharded x%d" % n_gpus,
-            "lanes": LANES,
-            "l2": "inputs larger than L2: the 12 lanes' cell matrices, need lists and bound tables (each lane "
+            "lanes": lanes,
+            "l2": "inputs larger than L2: the lanes' cell matrices, need lists and bound tables (each lane "
                   "~0.5 GB per selection round: 23 candidate lists x 595 cells x 1,840-3,160 samples) are "
                   "rebuilt every round, so nothing is reused from L2 between timed steps"}
 
@@ -269,6 +278,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     info = api.device_info()
     lanes = args.lanes
+    if not lanes:
+        lanes = default_lanes(world)
     n_threads = args.threads
     if not n_threads:
         n_threads = max(2 * lanes, ((os.cpu_count() or 1) // max(world, 1)) * 3 // 2)
@@ -448,7 +459,7 @@ def run_b200_arm(args):
             "unit": "classifiers/min", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, lanes),
             "e2e": e2e, "e2e_legacy_hooks": e2e_hooks, "gpu_launches": int(d["kernel_launches"]),
             "clocks": clocks, "roofline": roofline, "roofline_unscreened": roofline_plain,
             "cpu_baseline": cpu, "predict": predict,
@@ -547,7 +558,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default cores/ranks)")
-    ap.add_argument("--lanes", type=int, default=LANES, help="classifiers in flight per GPU")
+    ap.add_argument("--lanes", type=int, default=0, help="classifiers in flight per GPU (0: %d, fewer on "
+                    "boxes with few host cores per GPU)" % LANES)
     ap.add_argument("--host-em", action="store_true", help="candidate EM on the host thread pool")
     ap.add_argument("--predict-samples", type=int, default=N_PREDICT)
     ap.add_argument("--no-predict", action="store_true")

@@ -87,6 +87,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    # Training keeps many classifiers in flight, each with its own streams; with the default of 8
+    # hardware connections unrelated streams share a queue and wait for each other's kernels
+    # (read by the driver when the CUDA context is created; harmless if that has happened)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("hibag_b200: %s is missing -- build it with __graft_entry__.build(); "
                            "there is no CPU fallback" % LIB_PATH)

@@ -260,7 +260,6 @@ struct EmArgs
 	double em_reltol;                 // sqrt(DBL_EPSILON)
 };
 
-constexpr int RING_ROWS = 64;      // ELL rows (256 B each) a warp keeps in flight in the M step
 constexpr int MAX_CLUSTER = 8;
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void *src)
@@ -324,7 +323,8 @@ __device__ __forceinline__ double block_sum_f64(double v, double *scratch)
 /// contributions are then produced IN SLOT ORDER -- r = (c * f_u * f_v) * (count / sum) rebuilt from
 /// shared memory, bit-identical to the E step's value -- so the writes are coalesced, and the M
 /// step walks chains a half to a third as long.
-template <int EM_THREADS>
+/// EM_THREADS threads per CTA; RING_ROWS = ELL rows (256 B each) an M-step warp keeps in flight
+template <int EM_THREADS, int RING_ROWS>
 __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 {
 	cg::cluster_group cluster = cg::this_cluster();
@@ -337,10 +337,10 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 	double *scratch = fr0 + 2 * (size_t)n2;    // [40]
 	double *llp = scratch + 40;                // [2][MAX_CLUSTER] partial log-likelihoods
 	int *tot = (int *)(llp + 2 * MAX_CLUSTER); // [MAX_CLUSTER] compatible pairs per CTA (8 doubles reserved)
-	double *bck = llp + 3 * MAX_CLUSTER;       // [n_entry] bootstrap count of the entry
-	double *sck = bck + p.n_entry;             // [n_entry] count / sum of the entry's GenoFreq (all entries)
-	double *rings = sck + p.n_entry;           // [m_warps][RING_ROWS][32] M-step rings
-	int *gk = (int *)(rings + (size_t)p.m_warps * RING_ROWS * 32);   // [n_entry] candidate genotype, 3 = missing
+	double *sck = llp + 3 * MAX_CLUSTER;       // [n_entry] count / sum of the entry's GenoFreq (all entries)
+	double *rings = sck + ((p.n_entry + 1) & ~1);   // [m_warps][RING_ROWS][32] M-step rings (16-byte aligned)
+	// [n_entry] bootstrap count of the entry << 2 | candidate genotype (3 = missing)
+	int *eg = (int *)(rings + (size_t)p.m_warps * RING_ROWS * 32);
 	__shared__ int sh_i[4];
 
 	const int c = blockIdx.x / C;
@@ -362,8 +362,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 			const int s = p.ib[k];
 			const int g = col[s];
 			const int b = p.boot[s];
-			bck[k] = (double)b;
-			gk[k] = (0 <= g && g <= 2) ? g : 3;
+			eg[k] = (b << 2) | ((0 <= g && g <= 2) ? g : 3);
 			if (0 <= g && g <= 2) { ac += g * b; vc += 2 * b; }
 		}
 		if (tid < 4) sh_i[tid] = 0;
@@ -423,7 +422,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		{
 			const int4 pr = __ldg(p.pairs4 + t);
 			const int u = pr.x & 0xffff, v = (int)((unsigned)pr.x >> 16);
-			const int g = gk[pr.y];
+			const int g = eg[pr.y] & 3;
 			cnt += (g == 3 || ((u & 1) + (v & 1)) == g) ? 1 : 0;
 		}
 		// block exclusive scan of cnt (warp shuffles + one pass over the 32 warp totals)
@@ -462,7 +461,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		{
 			const int4 pr = __ldg(p.pairs4 + t);
 			const int u = pr.x & 0xffff, v = (int)((unsigned)pr.x >> 16);
-			const int g = gk[pr.y];
+			const int g = eg[pr.y] & 3;
 			if (t == p.off[pr.y]) coff[pr.y] = j;          // first pair of its entry
 			if (g == 3 || ((u & 1) + (v & 1)) == g) cuv[j++] = pr.x;
 		}
@@ -506,7 +505,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 					if (e[w] >= 0)
 					{
 						const int uu = pr[w].x & 0xffff, vv = (int)((unsigned)pr[w].x >> 16);
-						const int g = gk[pr[w].y];
+						const int g = eg[pr[w].y] & 3;
 						ok = (g == 3 || ((uu & 1) + (vv & 1)) == g);
 					}
 					const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -572,7 +571,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 				for (int q = 0; q < 8; q++) psum = __dadd_rn(psum, x[q]);
 			}
 			for (; t < e; t++) psum = __dadd_rn(psum, xbuf[t]);
-			const double bc = bck[k];
+			const double bc = (double)(eg[k] >> 2);
 			ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
 			const double sc = __ddiv_rn(bc, psum);
 			for (int q = 0; q < C; q++) cluster.map_shared_rank(sck, q)[k] = sc;
@@ -869,28 +868,34 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
 	a.scale = 0.5 / n_samp;
 	a.em_reltol = std::sqrt(DBL_EPSILON);
-	const size_t smem_base = sizeof(double) * (2 * (size_t)n2_ + 40 + 3 * MAX_CLUSTER + 2 * (size_t)n_entry_) +
+	const size_t smem_base = sizeof(double) * (2 * (size_t)n2_ + 40 + 3 * MAX_CLUSTER + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
 		sizeof(int) * (size_t)n_entry_ + 16;
-	int m_warps = (int)((220 * 1024 - smem_base) / (sizeof(double) * RING_ROWS * 32));
-	// Threads per CTA and M-step rings. 512 threads (half the register file) and 4 rings would let
-	// pair-scoring CTAs of other lanes share an EM CTA's SM, but measured on config 2 the longer
-	// iterations cost more than the sharing gains (12 lanes: 384 vs 474 classifiers/min), so the
-	// default stays at the lowest-latency shape.
-	int em_threads = 1024, max_rings = 8;
-	if (const char *e = getenv("HIBAG_B200_EM_THREADS")) em_threads = (atoi(e) >= 1024) ? 1024 : 512;
+	// "dense" shape: 512 threads, 32-row rings and at most half of an SM's shared memory, so that two
+	// EM CTAs (of any lanes) share an SM -- the kernel is latency-bound (~20 % issue utilisation alone)
+	bool dense = n_dense_lanes_ > 1;
+	if (const char *e = getenv("HIBAG_B200_EM_DENSE")) dense = atoi(e) != 0;
+	size_t budget = dense ? (size_t)112 * 1024 : (size_t)220 * 1024;
+	if (dense && smem_base + sizeof(double) * 32 * 32 > budget) { dense = false; budget = (size_t)220 * 1024; }
+	const size_t ring_b = sizeof(double) * 32 * (size_t)(dense ? 32 : 64);
+	int m_warps = (smem_base < budget) ? (int)((budget - smem_base) / ring_b) : 0;
+	int em_threads = dense ? 512 : 1024, max_rings = 8;
 	if (const char *e = getenv("HIBAG_B200_EM_RINGS")) max_rings = std::max(1, std::min(8, atoi(e)));
 	if (m_warps > max_rings) m_warps = max_rings;
 	if (m_warps < 1) throw std::runtime_error("run_em: list too large for the device EM");
 	a.m_warps = m_warps;
-	const size_t smem = smem_base + sizeof(double) * RING_ROWS * 32 * (size_t)m_warps;
+	const size_t smem = smem_base + ring_b * (size_t)m_warps;
 	// SMs per candidate: enough pairs per CTA to pay for the cluster barriers, and the whole
 	// round on at most ~half of the SMs (the other lanes' scoring launches run beside it; the
 	// kernel is latency-bound, so SM-time per candidate is lowest for small clusters)
 	int cluster = 1;
 	while (cluster < MAX_CLUSTER && total_pairs_ / (2 * (size_t)cluster) >= 6000 &&
 		(size_t)m * 2 * cluster <= (size_t)current_device().sm_count * 11 / 20) cluster *= 2;
+	// many classifiers in flight: the GPU is shared by dozens of EM launches and the SM-time per
+	// candidate is what counts -- one CTA per candidate (measured, config 2, 24 lanes: 783 vs 678
+	// classifiers/min for clusters of 2)
+	if (dense && n_dense_lanes_ >= 8) cluster = 1;
 	if (const char *e = getenv("HIBAG_B200_EM_CLUSTER")) cluster = std::max(1, std::min(MAX_CLUSTER, atoi(e)));
-	auto kern = (em_threads == 1024) ? em_kernel<1024> : em_kernel<512>;
+	auto kern = dense ? em_kernel<512, 32> : em_kernel<1024, 64>;
 	HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
 	HB_CUDA(cudaEventRecord(ev0_.e, st));
 	{

@@ -35,7 +35,7 @@ public:
 	static bool supports(int n_cur, int n_entry)
 	{
 		return 2 * (size_t)n_cur <= 65535 &&
-			8 * (4 * (size_t)n_cur + 64 + 2 * (size_t)n_entry) + 4 * (size_t)n_entry + 16 + 16384 <= 220 * 1024;
+			8 * (4 * (size_t)n_cur + 64 + (size_t)n_entry) + 4 * (size_t)n_entry + 16 + 16384 <= 220 * 1024;
 	}
 
 	/// Pair matching for the in-bag entries on the current SNP set + incidence structure.
@@ -59,6 +59,8 @@ public:
 	void fetch_pairs(RoundPairs &out, const std::vector<int> &inbag, const std::vector<int> &boot,
 		cudaStream_t st);
 
+	/// lanes sharing the GPU (> 1 selects the dense EM shape, see run_em)
+	void set_lanes(int n) { n_dense_lanes_ = n; }
 	int n_entry() const { return n_entry_; }
 	size_t total_pairs() const { return total_pairs_; }
 	size_t ell_slots() const { return n_slots_; }
@@ -70,7 +72,7 @@ public:
 	uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 
 private:
-	int n_entry_ = 0, n_cur_ = 0, n2_ = 0, n_snp_ = 0;
+	int n_entry_ = 0, n_cur_ = 0, n2_ = 0, n_snp_ = 0, n_dense_lanes_ = 1;
 	size_t total_pairs_ = 0;
 	const int *ib_ = nullptr, *boot_ = nullptr;
 	PinBuf<unsigned char> h_stage_;

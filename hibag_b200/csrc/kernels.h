@@ -207,7 +207,7 @@ void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_
 /// and the pair evaluations those tasks hold (added to evals[l])
 void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
 	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, int target_tasks,
-	cudaStream_t st);
+	int warp_slots, cudaStream_t st);
 /// per (list, pos): which cells are needed (appends to entries / count)
 void launch_screen_need(const ScreenArgs &a, cudaStream_t st);
 /// screened reductions (same outputs as launch_reduce_oob / launch_reduce_ib). An in-bag position

@@ -292,7 +292,7 @@ BatchScorer::BatchScorer()
 	current_device();
 	// screened passes are chains of small, latency-bound launches that do not fill the GPU:
 	// the lanes' passes are spread over a few streams so that they overlap
-	int k = 3;
+	int k = 6;
 	if (const char *e = getenv("HIBAG_B200_SCORE_QUEUES")) k = std::max(1, std::min(16, atoi(e)));
 	queue_id_ = g_next_scorer.fetch_add(1) % k;
 	int lg = 70;
@@ -481,7 +481,8 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		HB_CUDA(cudaEventRecord(ev0_.e, s));
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
-		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks, s);
+		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks,
+			di.sm_count * 32, s);
 		HB_CUDA(cudaEventRecord(ev_g0_.e, s));
 		nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
 		HB_CUDA(cudaEventRecord(ev_g1_.e, s));

@@ -217,15 +217,18 @@ void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_
 // per list: how many positions one gather task takes (32, 64 or 128 -- small when the launch
 // would otherwise have too few tasks to fill the GPU) and the exclusive prefix of
 // ceil(count / that) over the blob's cell order.  task_prefix[l]: [n_cells] prefix,
-// [n_cells] = number of tasks, [n_cells + 1] = log2(positions per task)
+// (bits 30-31 of an entry: log2(positions per task of that cell) - 5; fewer for the largest cells),
+// [n_cells] = number of tasks
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 	const int *__restrict__ count, size_t count_stride, unsigned int *task_prefix,
-	unsigned long long *evals, int target_tasks)
+	unsigned long long *evals, int target_tasks, int n_lists, int warp_slots)
 {
 	__shared__ unsigned int seg[256];
+	__shared__ unsigned long long seg_ev[256];
 	__shared__ unsigned int sh_shift;
+	__shared__ unsigned long long sh_limit;
 	const int l = blockIdx.x, tid = threadIdx.x;
 	const CellTask *cells = ls.l[l].cells;
 	const int *cnt = count + (size_t)l * count_stride;
@@ -244,23 +247,36 @@ screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 			: (unsigned long long)ca.y * (unsigned long long)ca.w;
 		ev += pairs * (unsigned long long)c;
 	}
-	seg[tid] = tot;
+	seg[tid] = tot; seg_ev[tid] = ev;
 	__syncthreads();
 	if (tid == 0)
 	{
 		unsigned int e = 0;
-		for (int t = 0; t < 256; t++) e += seg[t];
+		unsigned long long w = 0;
+		for (int t = 0; t < 256; t++) { e += seg[t]; w += seg_ev[t]; }
+		// few positions in the whole list: small tasks, so that the launch still has enough of them
 		unsigned int sh = 7;
 		while (sh > 5 && (e >> sh) < (unsigned int)target_tasks) sh--;
 		sh_shift = sh;
+		// no task above ~0.4 of a warp slot's share of the launch (the lists of a launch are alike):
+		// the chains of the largest cells would otherwise be the tail of the launch
+		unsigned long long lim = w * (unsigned long long)n_lists * 2ull / (5ull * (unsigned long long)warp_slots);
+		if (lim < 32768ull) lim = 32768ull;
+		sh_limit = lim;
 	}
 	__syncthreads();
-	const unsigned int sh = sh_shift, rnd = (1u << sh) - 1u;
+	const unsigned int gsh = sh_shift;
+	const unsigned long long lim = sh_limit;
 	unsigned int s = 0;
 	for (int k = k0; k < k1; k++)
 	{
+		const int4 ca = __ldg((const int4 *)(cells + k));
 		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
-		s += ((unsigned int)__ldg(cnt + cb.x) + rnd) >> sh;
+		const unsigned long long pairs = cb.y ? (unsigned long long)ca.y * (ca.y + 1) / 2
+			: (unsigned long long)ca.y * (unsigned long long)ca.w;
+		unsigned int sh = gsh;
+		while (sh > 5 && (pairs << sh) > lim) sh--;
+		s += ((unsigned int)__ldg(cnt + cb.x) + ((1u << sh) - 1u)) >> sh;
 	}
 	__syncthreads();
 	seg[tid] = s;
@@ -270,26 +286,31 @@ screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 		unsigned int run = 0;
 		for (int t = 0; t < 256; t++) { const unsigned int v = seg[t]; seg[t] = run; run += v; }
 		pre[n_cells] = run;
-		pre[n_cells + 1] = sh;
+		pre[n_cells + 1] = gsh;
 	}
 	__syncthreads();
 	unsigned int run = seg[tid];
 	for (int k = k0; k < k1; k++)
 	{
+		const int4 ca = __ldg((const int4 *)(cells + k));
 		const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
-		pre[k] = run;
-		run += ((unsigned int)__ldg(cnt + cb.x) + rnd) >> sh;
+		const unsigned long long pairs = cb.y ? (unsigned long long)ca.y * (ca.y + 1) / 2
+			: (unsigned long long)ca.y * (unsigned long long)ca.w;
+		unsigned int sh = gsh;
+		while (sh > 5 && (pairs << sh) > lim) sh--;
+		pre[k] = run | ((sh - 5u) << 30);            // bits 30-31: log2(positions per task) - 5
+		run += ((unsigned int)__ldg(cnt + cb.x) + ((1u << sh) - 1u)) >> sh;
 	}
 	if (ev) atomicAdd(evals + l, ev);
 }
 
 void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
 	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, int target_tasks,
-	cudaStream_t st)
+	int warp_slots, cudaStream_t st)
 {
 	if (n_lists <= 0) return;
 	screen_tasks_kernel<<<n_lists, 256, 0, st>>>(ls, n_cells, count, count_stride, task_prefix, evals,
-		target_tasks);
+		target_tasks, n_lists, warp_slots);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -755,8 +776,6 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 
 		const char *hap_g = (const char *)L.hap;
 		double *Pl = L.P;
-		const int task_shift = (int)sh_pre[p.n_cells + 1];       // log2(positions per task)
-		const int task_pos = 1 << task_shift;
 
 		unsigned task = 0;
 		if (lane == 0) task = atomicAdd(counter, 1u);
@@ -772,9 +791,12 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 			while (hi - lo > 1)
 			{
 				const int mid = (lo + hi) >> 1;
-				if (sh_pre[mid] <= task) lo = mid; else hi = mid;
+				if ((sh_pre[mid] & 0x3fffffffu) <= task) lo = mid; else hi = mid;
 			}
-			const int blk = (int)(task - sh_pre[lo]);
+			const unsigned int pk = sh_pre[lo];
+			const int blk = (int)(task - (pk & 0x3fffffffu));
+			const int task_shift = 5 + (int)(pk >> 30);              // log2(positions per task of this cell)
+			const int task_pos = 1 << task_shift;
 			const int4 ca = __ldg((const int4 *)(L.cells + lo));
 			const int2 cb = __ldg((const int2 *)((const char *)(L.cells + lo) + 16));
 			const int rem = min(task_pos, __ldg(L.count + cb.x) - (blk << task_shift));

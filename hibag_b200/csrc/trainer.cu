@@ -161,7 +161,7 @@ struct Candidate
 class Trainer : public TrainSession
 {
 public:
-	Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads);
+	Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads, int n_lanes);
 	~Trainer() override;
 	/// grow the classifiers with the given global indices into built_ / ts_ / trace_
 	void run(const std::vector<int> &indices);
@@ -212,7 +212,7 @@ private:
 	ScoreStats stats_;
 };
 
-Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads)
+Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads, int n_lanes)
 	: m_(m), o_(o)
 {
 	dev_ = &current_device();
@@ -253,6 +253,7 @@ Trainer::Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool
 		scorer_.reset(new BatchScorer());
 		d_boot_.ensure(n_samp_);
 		rem_.reset(new RoundEM());
+		rem_->set_lanes(n_lanes);
 	}
 }
 
@@ -819,7 +820,7 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 			nt = std::max(1, (nt + n_lanes - 1) / n_lanes);
 		}
 		for (int l = 0; l < n_lanes; l++)
-			g->lanes.emplace_back(new Trainer(m, opts, nt));
+			g->lanes.emplace_back(new Trainer(m, opts, nt, n_lanes));
 	}
 	(void)di;
 
