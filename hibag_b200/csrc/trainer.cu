@@ -163,8 +163,10 @@ class Trainer : public TrainSession
 public:
 	Trainer(hibag_b200_model &m, const hibag_b200_train_opts &o, int n_pool_threads, int n_lanes);
 	~Trainer() override;
-	/// grow the classifiers with the given global indices into built_ / ts_ / trace_
-	void run(const std::vector<int> &indices);
+	/// grow classifiers into built_ / ts_ / trace_: next() hands out global classifier indices
+	/// (< 0: none left); the lanes of a model share one dispenser, so a lane that finishes a
+	/// classifier early takes the next one
+	void run(const std::function<int()> &next);
 	/// can this session (threads, scoring mode) serve a call with these options?
 	void configure(const hibag_b200_train_opts &o)
 	{
@@ -325,7 +327,7 @@ double Trainer::ib_loss(const double *ratio) const
 	return loglik * -2;
 }
 
-void Trainer::run(const std::vector<int> &indices)
+void Trainer::run(const std::function<int()> &next)
 {
 	const double t0 = now_s();
 	// the session outlives a call: start this call's counters from zero
@@ -339,9 +341,10 @@ void Trainer::run(const std::vector<int> &indices)
 	std::fill(em_seconds_.begin(), em_seconds_.end(), 0.0);
 	std::fill(wait_seconds_.begin(), wait_seconds_.end(), 0.0);
 	if (!o_.per_classifier_seed) rng_.set_seed((uint32_t)o_.seed);
-	for (size_t c = 0; c < indices.size(); c++)
+	for (;;)
 	{
-		const int global_k = indices[c];
+		const int global_k = next();
+		if (global_k < 0) break;
 		if (o_.per_classifier_seed) rng_.set_seed((uint32_t)(o_.seed + global_k));
 		// bootstrap; redraw the whole sample when nobody is left out of the bag (:2229-2240)
 		boot_.assign(n_samp_, 0);
@@ -825,9 +828,11 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 	(void)di;
 
 	const int stride = opts.index_stride > 0 ? opts.index_stride : 1;
-	std::vector<std::vector<int> > idx(n_lanes);
-	for (int c = 0; c < opts.nclassifier; c++)
-		idx[c % n_lanes].push_back(opts.first_index + c * stride);
+	std::atomic<int> next_c{0};
+	const std::function<int()> dispenser = [&]() {
+		const int c = next_c.fetch_add(1);
+		return (c < opts.nclassifier) ? opts.first_index + c * stride : -1;
+	};
 
 	const double t0 = now_s();
 	std::vector<std::string> errors(n_lanes);
@@ -836,7 +841,7 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 		{
 			cudaSetDevice(di.device);
 			g->lanes[l]->configure(opts);
-			g->lanes[l]->run(idx[l]);
+			g->lanes[l]->run(dispenser);
 		} catch (std::exception &e)
 		{
 			errors[l] = e.what();
