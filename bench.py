@@ -311,6 +311,8 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import resource
+    ru0 = resource.getrusage(resource.RUSAGE_SELF)
     e0.record()
     t0 = time.time()
     for s in range(args.steps):
@@ -318,6 +320,8 @@ def run_b200_arm(args):
     e1.record()
     sync_all()
     wall = time.time() - t0
+    ru1 = resource.getrusage(resource.RUSAGE_SELF)
+    host_cpu_s = (ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)
     ms = hd.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop() if rank == 0 else None
     st1 = model.train_stats()
@@ -465,6 +469,8 @@ def run_b200_arm(args):
             "cpu_baseline": cpu, "predict": predict,
             "train_detail": {
                 "host_threads": n_threads, "lanes": lanes, "em_on_device": dev_em,
+                "host_cores": os.cpu_count(), "host_cpu_seconds": host_cpu_s,
+                "host_cores_busy": host_cpu_s / max(wall, 1e-9),
                 "em_kernel_ms": d["em_kernel_ms"], "em_host_fallbacks": int(d["n_em_host_fallback"]),
                 "seconds_em_sum": d["seconds_em"],
                 "seconds_prepare": d["seconds_prepare"], "seconds_candidates": d["seconds_phase_oob"],

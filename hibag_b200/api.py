@@ -75,7 +75,7 @@ EXPORTS = [
     "hibag_b200_model_predict_device", "hibag_b200_model_predict_stats",
     "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
     "hibag_b200_model_snp_weights", "hibag_b200_pipe_peak",
-    "hibag_b200_host_unif_rand", "hibag_b200_host_build_tasks",
+    "hibag_b200_host_unif_rand", "hibag_b200_host_build_tasks", "hibag_b200_host_screen_constants",
     "hibag_b200_get_procs_ex", "hibag_b200_haplomatch", "hibag_b200_free",
 ]
 
@@ -206,6 +206,13 @@ def host_build_tasks(haplo, n_hla, n_snp, target_chunks=512):
     _chk(lib().hibag_b200_host_build_tasks(_p(haplo), len(haplo), n_hla, n_snp, target_chunks, _p(cells),
                                            _p(chunks), C.byref(n), C.byref(pairs)))
     return cells, chunks[:n.value], pairs.value
+
+
+def host_screen_constants():
+    """(T[257], T'[257], K) of the exact screening"""
+    t = np.zeros(257); f = np.zeros(257); k = C.c_double()
+    _chk(lib().hibag_b200_host_screen_constants(_p(t), _p(f), C.byref(k)))
+    return t, f, k.value
 
 
 # ---- kernel-level batched scoring -----------------------------------------------------------

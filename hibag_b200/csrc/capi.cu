@@ -324,6 +324,17 @@ int hibag_b200_host_unif_rand(uint32_t seed, int n, double *out)
 	});
 }
 
+int hibag_b200_host_screen_constants(double *table, double *floor_table, double *bound_factor)
+{
+	return guarded([&]() {
+		require(table != nullptr && floor_table != nullptr && bound_factor != nullptr, "invalid argument");
+		const size_t n = 2 * HIBAG_B200_MAX_SNP + 1;
+		memcpy(table, hb::host_rare_freq_table(), sizeof(double) * n);
+		memcpy(floor_table, hb::host_rare_freq_floor_table(), sizeof(double) * n);
+		*bound_factor = hb::screen_bound_factor();
+	});
+}
+
 int hibag_b200_host_build_tasks(const hibag_haplotype *haplo, int n_haplo, int n_hla, int n_snp,
 	int target_chunks, int32_t *out_cells, int32_t *out_chunks, int *n_chunks, uint64_t *pairs)
 {

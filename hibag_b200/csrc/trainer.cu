@@ -369,7 +369,11 @@ void Trainer::run(const std::function<int()> &next)
 			fprintf(stderr, "=== building individual classifier %d, out-of-bag (%d/%.1f%%) ===\n",
 				global_k + 1, n_samp_ - n_unique, 100.0 * (n_samp_ - n_unique) / n_samp_);
 		}
+		const double t_grow = now_s();
 		grow(cl);
+		if (getenv("HIBAG_B200_TIMING"))
+			fprintf(stderr, "classifier %d: start %.3f s, %.3f s, %d SNPs\n", global_k, t_grow - t0, now_s() - t_grow,
+				(int)cl.snpidx.size());
 		if (o_.verbose)
 		{
 			fprintf(stderr, "[%d] oob acc: %0.2f%%, # of SNPs: %d, # of haplo: %d\n", global_k + 1,

@@ -248,10 +248,14 @@ int hibag_b200_model_snp_weights(const hibag_b200_model *m, int32_t *out_weight)
 /* R's Mersenne-Twister after set.seed(seed): n draws of unif_rand() */
 int hibag_b200_host_unif_rand(uint32_t seed, int n, double *out);
 /* the work list the scoring kernel receives for a haplotype list: out_cells int32[n_cells][8]
- * = {a_start,a_n,b_start,b_n,out_idx,diag,0,0} in launch order, out_chunks int32[<=n_cells][2]
+ * = {a_start,a_n,b_start,b_n,out_idx,diag,allele a,allele b} in launch order, out_chunks int32[<=n_cells][2]
  * = {cell_begin,cell_end}; *pairs = haplotype pairs scored per sample */
 int hibag_b200_host_build_tasks(const hibag_haplotype *haplo, int n_haplo, int n_hla, int n_snp,
 	int target_chunks, int32_t *out_cells, int32_t *out_chunks, int *n_chunks, uint64_t *pairs);
+/* constants of the exact screening of the training passes: table[257] =
+ * EXP_LOG_MIN_RARE_FREQ as the host computed it (src/LibHLA.cpp:166-183), floor_table[257] =
+ * max(table, 1e-100), *bound_factor = K of bound(a,b) = U_a * U_b * K */
+int hibag_b200_host_screen_constants(double *table, double *floor_table, double *bound_factor);
 
 /* ---- microbenchmarks of the pipes that bound this path ----------------- */
 /* which: 0 POPC.32, 1 LOP3, 2 DMUL+DADD, 3 DFMA, 4 LDS.64 (lane-private), 5 IADD3: lane-ops per

@@ -10,11 +10,18 @@ n_cls = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 coh = synth.make_cohort(n_samp, n_snp, n_hla, seed=2)
 g = np.ascontiguousarray(coh.geno, dtype=np.int8)
 mtry = api.default_mtry(n_snp)
+lanes = int(sys.argv[5]) if len(sys.argv) > 5 else min(n_cls, 3)
+screening = (sys.argv[6] != "0") if len(sys.argv) > 6 else True
 m = api.HLAModel(n_snp, coh.n_hla); m.set_training(g, coh.h1, coh.h2)
 t0 = time.time()
-m.train(n_cls, mtry, seed=7, per_classifier_seed=True, n_concurrent=min(n_cls, 3))
+m.train(n_cls, mtry, seed=7, per_classifier_seed=True, n_concurrent=lanes, screening=screening)
 dt = time.time() - t0
 st = m.train_stats()
+print("screening %s lanes %d: executed %.3e of %.3e pair evaluations (%.1f %%), uncertified %d" % (
+    screening, lanes, st["pair_evals"], st["pair_evals_nominal"], 100.0 * st["pair_evals"] / max(1, st["pair_evals_nominal"]),
+    st["n_screen_fallback"]))
+import hashlib
+print("model digest", hashlib.sha1(b"".join(m.classifier(k)["freq"].tobytes() + m.classifier(k)["packed"].tobytes() for k in range(n_cls))).hexdigest())
 print("alleles %d, mtry %d: %d classifiers in %.1f s (%.2f /min); %s" % (coh.n_hla, mtry, n_cls, dt, 60 * n_cls / dt,
       [(len(m.classifier(k)["snpidx"]), len(m.classifier(k)["freq"]), round(m.classifier(k)["oob_acc"], 4)) for k in range(n_cls)]))
 print("pair evals %.3e, cell kernel %.0f ms -> %.3e /s; em kernel %.0f ms, host fallbacks %d, em runs %d" % (
