@@ -76,6 +76,7 @@ EXPORTS = [
     "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
     "hibag_b200_model_snp_weights", "hibag_b200_pipe_peak",
     "hibag_b200_host_unif_rand", "hibag_b200_host_build_tasks", "hibag_b200_host_screen_constants",
+    "hibag_b200_bed_decode", "hibag_b200_bed_decode_device",
     "hibag_b200_get_procs_ex", "hibag_b200_haplomatch", "hibag_b200_free",
 ]
 
@@ -135,6 +136,10 @@ def lib():
     L.hibag_b200_host_unif_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
     L.hibag_b200_host_build_tasks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    L.hibag_b200_bed_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.hibag_b200_bed_decode_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_void_p]
     L.hibag_b200_pipe_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -434,6 +439,68 @@ def hlaAttrBagging(hla, snp, nclassifier=100, mtry="sqrt", prune=True, mono_rm=T
                 index_stride=index_stride, use_legacy_hooks=use_legacy_hooks, verbose=int(verbose),
                 n_concurrent=n_concurrent, em_on_device=em_on_device, screening=screening)
     return model
+
+
+def bed_decode(bed_bytes, n_samp, n_snp, snp_flag=None, return_ms=False):
+    """PLINK .bed bytes (whole file, prefix included) -> int8 [n_samp][n_kept] on the GPU
+    (reference HIBAG_ConvBED, src/HIBAG.cpp:1094-1191; missing = -1)"""
+    raw = np.frombuffer(bed_bytes, dtype=np.uint8) if not isinstance(bed_bytes, np.ndarray) else \
+        np.ascontiguousarray(bed_bytes, dtype=np.uint8)
+    flag = None if snp_flag is None else np.ascontiguousarray(snp_flag, dtype=np.int32)
+    n_save, ms = C.c_int(), C.c_double()
+    _chk(lib().hibag_b200_bed_decode(_p(raw), raw.size, n_samp, n_snp, _p(flag), None, C.byref(n_save), None))
+    out = np.zeros((n_samp, n_save.value), dtype=np.int8)
+    if n_save.value > 0:
+        _chk(lib().hibag_b200_bed_decode(_p(raw), raw.size, n_samp, n_snp, _p(flag), _p(out), C.byref(n_save),
+                                         C.byref(ms)))
+    return (out, ms.value) if return_ms else out
+
+
+def bed_decode_device(payload_ptr, mode, n_samp, n_snp, sel_ptr, n_save, out_ptr, stream=0):
+    """device-resident BED decoding: payload / selection / output are device pointers"""
+    _chk(lib().hibag_b200_bed_decode_device(C.c_void_p(payload_ptr), mode, n_samp, n_snp,
+                                            C.c_void_p(sel_ptr) if sel_ptr else None, n_save,
+                                            C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def hlaBED2Geno(bed_fn, fam_fn, bim_fn, import_chr="", region=None, snp_flag=None):
+    """Import a PLINK binary file set (reference hlaBED2Geno, R/DataUtilities.R:703-780): sample ids
+    from the .fam (InvID, or FamilyID-InvID when not unique), SNP ids / positions / alleles from the
+    .bim, genotypes decoded on the GPU. SNP selection: import_chr = "" keeps every SNP, a
+    chromosome name or list keeps those with a positive position (R/DataUtilities.R:688-697);
+    region = (chr, start, end) keeps a position window (the reference's "xMHC" preset needs its
+    per-assembly gene table, which is R-side data: pass the window instead); snp_flag overrides.
+    Returns a dict shaped like hlaSNPGenoClass with genotype as int8 [n_samp][n_snp] (sample-major,
+    what hlaAttrBagging / hlaPredict take here)."""
+    fam = [ln.split() for ln in open(fam_fn) if ln.strip()]
+    bim = [ln.split() for ln in open(bim_fn) if ln.strip()]
+    inv = [f[1] for f in fam]
+    if len(set(inv)) == len(inv):
+        sample_id = inv
+    else:
+        sample_id = ["%s-%s" % (f[0], f[1]) for f in fam]
+        if len(set(sample_id)) != len(sample_id):
+            raise ValueError("IDs in PLINK bed are not unique!")
+    snp_id = [b[1] for b in bim]
+    if len(set(snp_id)) != len(snp_id):
+        raise ValueError("The SNP IDs in the PLINK binary file should be unique!")
+    chrom = np.array([b[0] for b in bim])
+    pos = np.array([int(b[3]) if b[3].lstrip("-").isdigit() else 0 for b in bim], dtype=np.int64)
+    if snp_flag is not None:
+        flag = np.asarray(snp_flag, dtype=bool)
+    elif region is not None:
+        flag = (chrom == str(region[0])) & (pos >= region[1]) & (pos <= region[2])
+    elif import_chr == "" or import_chr is None:
+        flag = np.ones(len(bim), dtype=bool)
+    else:
+        want = [str(c) for c in (import_chr if isinstance(import_chr, (list, tuple)) else [import_chr])]
+        flag = np.isin(chrom, want) & (pos > 0)
+    if not flag.any():
+        raise ValueError("There is no SNP imported.")
+    g = bed_decode(np.fromfile(bed_fn, dtype=np.uint8), len(fam), len(bim), flag.astype(np.int32))
+    keep = np.nonzero(flag)[0]
+    return dict(genotype=g, sample_id=sample_id, snp_id=[snp_id[i] for i in keep], snp_position=pos[keep],
+                snp_allele=["%s/%s" % (bim[i][4], bim[i][5]) for i in keep])
 
 
 def hlaPredict(model, snp, type="response+prob"):

@@ -324,6 +324,58 @@ int hibag_b200_host_unif_rand(uint32_t seed, int n, double *out)
 	});
 }
 
+int hibag_b200_bed_decode(const uint8_t *bed_file, size_t n_bytes, int n_samp, int n_snp,
+	const int32_t *snp_flag, int8_t *out, int *n_save, double *kernel_ms)
+{
+	return guarded([&]() {
+		require(bed_file != nullptr && n_samp > 0 && n_snp > 0, "invalid argument");
+		if (n_bytes < 3 || bed_file[0] != 0x6C || bed_file[1] != 0x1B)
+			throw std::runtime_error("Invalid prefix in the PLINK BED file.");
+		const int mode = bed_file[2];
+		const size_t bps = (mode == 0) ? ((size_t)n_snp + 3) / 4 : ((size_t)n_samp + 3) / 4;
+		const size_t payload = bps * (size_t)(mode == 0 ? n_samp : n_snp);
+		require(n_bytes >= 3 + payload, "the PLINK BED file is shorter than n_samp x n_snp genotypes");
+		std::vector<int32_t> sel;
+		for (int s = 0; s < n_snp; s++)
+			if (snp_flag == nullptr || snp_flag[s]) sel.push_back(s);
+		if (n_save) *n_save = (int)sel.size();
+		if (out == nullptr || sel.empty()) return;
+		hb::current_device();
+		hb::Stream st;
+		hb::DevBuf<uint8_t> d_in;
+		hb::DevBuf<int32_t> d_sel;
+		hb::DevBuf<int8_t> d_out;
+		const size_t n_out = (size_t)n_samp * sel.size();
+		d_in.ensure(payload); d_sel.ensure(sel.size()); d_out.ensure(n_out);
+		HB_CUDA(cudaMemcpyAsync(d_in.get(), bed_file + 3, payload, cudaMemcpyHostToDevice, st.s));
+		HB_CUDA(cudaMemcpyAsync(d_sel.get(), sel.data(), sizeof(int32_t) * sel.size(), cudaMemcpyHostToDevice, st.s));
+		hb::Event e0, e1;
+		HB_CUDA(cudaEventRecord(e0.e, st.s));
+		hb::launch_bed_decode(d_in.get(), mode, n_samp, n_snp, snp_flag ? d_sel.get() : nullptr,
+			(int)sel.size(), d_out.get(), st.s);
+		HB_CUDA(cudaEventRecord(e1.e, st.s));
+		HB_CUDA(cudaMemcpyAsync(out, d_out.get(), n_out, cudaMemcpyDeviceToHost, st.s));
+		HB_CUDA(cudaStreamSynchronize(st.s));
+		if (kernel_ms)
+		{
+			float ms = 0;
+			HB_CUDA(cudaEventElapsedTime(&ms, e0.e, e1.e));
+			*kernel_ms = ms;
+		}
+	});
+}
+
+int hibag_b200_bed_decode_device(const uint8_t *payload_dev, int mode, int n_samp, int n_snp,
+	const int32_t *sel_dev, int n_save, int8_t *out_dev, void *cuda_stream)
+{
+	return guarded([&]() {
+		require(payload_dev != nullptr && out_dev != nullptr && n_samp > 0 && n_snp > 0 && n_save > 0 &&
+			(sel_dev != nullptr || n_save == n_snp), "invalid argument");
+		hb::current_device();
+		hb::launch_bed_decode(payload_dev, mode, n_samp, n_snp, sel_dev, n_save, out_dev, (cudaStream_t)cuda_stream);
+	});
+}
+
 int hibag_b200_host_screen_constants(double *table, double *floor_table, double *bound_factor)
 {
 	return guarded([&]() {

@@ -248,6 +248,13 @@ void launch_finalize_from_partial(const double *partial, int n_hla, int n_samp, 
 	int *h2, double *max_prob, double *matching, double *dosage, double *post_prob,
 	cudaStream_t st);
 
+// ---- PLINK BED decoding (bed.cu) ----------------------------------------------------------------
+/// payload = the file's bytes after the 3-byte prefix (device); mode 0 individual-major, else
+/// SNP-major; sel = indices of the SNPs to keep (device, ascending; null = all n_snp, n_save =
+/// n_snp); out = int8 [n_samp][n_save] (device), 0/1/2 and -1 for missing
+void launch_bed_decode(const uint8_t *payload, int mode, int n_samp, int n_snp, const int32_t *sel,
+	int n_save, int8_t *out, cudaStream_t st);
+
 // ---- microbenchmarks ---------------------------------------------------------------------
 double run_pipe_peak(int which, int sm_count, double *out_ms);
 

@@ -244,6 +244,21 @@ int hibag_b200_predict_finalize_device(int n_hla, int n_samp, const double *acc_
 /* number of classifiers using each SNP (reference _GetSNPWeights, src/LibHLA.cpp:2484) */
 int hibag_b200_model_snp_weights(const hibag_b200_model *m, int32_t *out_weight);
 
+/* ---- PLINK BED import ------------------------------------------------------ */
+/* reference HIBAG_ConvBED, src/HIBAG.cpp:1094-1191 (+ HIBAG_BEDFlag :1062-1083): decode the
+ * 2-bit packed genotypes of a .bed file on the GPU. bed_file = the whole file (host, n_bytes,
+ * 3-byte prefix included; both the SNP-major and the individual-major mode); snp_flag[n_snp] != 0
+ * keeps a SNP (NULL: all); out = int8 [n_samp][n_save] sample-major, 0/1/2 = count of the .bim's
+ * first allele as the reference reports it, -1 = missing (the reference's NA); *n_save = SNPs kept.
+ * out may be NULL to query *n_save. Errors as the reference's: "Invalid prefix in the PLINK BED
+ * file." */
+int hibag_b200_bed_decode(const uint8_t *bed_file, size_t n_bytes, int n_samp, int n_snp,
+	const int32_t *snp_flag, int8_t *out, int *n_save, double *kernel_ms);
+/* device-resident variant: payload_dev = the bytes after the prefix, sel_dev = ascending indices of
+ * the SNPs to keep (NULL: all), out_dev = int8 [n_samp][n_save]; enqueued on cuda_stream */
+int hibag_b200_bed_decode_device(const uint8_t *payload_dev, int mode, int n_samp, int n_snp,
+	const int32_t *sel_dev, int n_save, int8_t *out_dev, void *cuda_stream);
+
 /* ---- host-only pieces exposed for the CPU test-suite (no GPU needed) ------------------------- */
 /* R's Mersenne-Twister after set.seed(seed): n draws of unif_rand() */
 int hibag_b200_host_unif_rand(uint32_t seed, int n, double *out);

@@ -328,3 +328,56 @@ long hibag_oracle_haplomatch_records(const oracle_haplo_t *haplo, const int64_t 
 	free(st);
 	return n;
 }
+
+
+/* PLINK BED -> genotype matrix: reference HIBAG_ConvBED, src/HIBAG.cpp:1094-1191 (prefix check
+ * :1113-1117, pack geometry :1120-1137, code table {2, NA, 1, 0} :1141, unpack :1153-1169,
+ * individual-major store :1172-1180, SNP-major store :1181-1192). `file` is the whole file
+ * including the 3-byte prefix; out is int32 [n_samp][n_save] (the reference's INTEGER matrix
+ * [n_save x n_samp], column-major) with NA = INT32_MIN. Returns 0, -1 for an invalid prefix, -2 when
+ * the file is too short. */
+int hibag_oracle_bed_decode(const uint8_t *file, long n_bytes, int n_samp, int n_snp,
+	const int32_t *snp_flag, int n_save, int32_t *out)
+{
+	static const int32_t cvt[4] = { 2, INT32_MIN, 1, 0 };
+	if (n_bytes < 3 || file[0] != 0x6C || file[1] != 0x1B) return -1;
+	const int mode = file[2];
+	int n_re, n_numpack, n_pack, n_num;
+	if (mode == 0) { n_re = n_snp % 4; n_numpack = n_snp / 4; n_num = n_samp; }
+	else { n_re = n_samp % 4; n_numpack = n_samp / 4; n_num = n_snp; }
+	n_pack = (n_re > 0) ? (n_numpack + 1) : n_numpack;
+	if (n_bytes < 3 + (long)n_pack * n_num) return -2;
+	int32_t *dst = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n_numpack + 1) * 4);
+	int i_snp = 0;
+	const uint8_t *src = file + 3;
+	for (int i = 0; i < n_num; i++, src += n_pack)
+	{
+		int32_t *p = dst;
+		for (int k = 0; k < n_numpack; k++)
+		{
+			unsigned char g = src[k];
+			*p++ = cvt[g & 0x03]; g >>= 2;
+			*p++ = cvt[g & 0x03]; g >>= 2;
+			*p++ = cvt[g & 0x03]; g >>= 2;
+			*p++ = cvt[g & 0x03];
+		}
+		if (n_re > 0)
+		{
+			unsigned char g = src[n_numpack];
+			for (int k = 0; k < n_re; k++) { *p++ = cvt[g & 0x03]; g >>= 2; }
+		}
+		if (mode == 0)
+		{
+			int32_t *pi = out + (size_t)i * n_save;
+			for (int j = 0; j < n_snp; j++)
+				if (snp_flag == NULL || snp_flag[j]) *pi++ = dst[j];
+		} else if (snp_flag == NULL || snp_flag[i])
+		{
+			int32_t *pi = out + i_snp;
+			i_snp++;
+			for (int j = 0; j < n_samp; j++) { *pi = dst[j]; pi += n_save; }
+		}
+	}
+	free(dst);
+	return 0;
+}

@@ -83,6 +83,10 @@ void hibag_oracle_classifier_weights(int n_classifier, const int *n_snp,
 long hibag_oracle_haplomatch_records(const oracle_haplo_t *haplo, const int64_t *n_haplo,
 	int n_hla, int n_snp, const oracle_geno_t *geno, int n_samp, uint32_t *out, long max_records);
 
+/* PLINK BED decoding, src/HIBAG.cpp:1094-1191 (see the .c file) */
+int hibag_oracle_bed_decode(const uint8_t *file, long n_bytes, int n_samp, int n_snp,
+	const int32_t *snp_flag, int n_save, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -281,6 +281,21 @@ class OracleLib:
         self.lib.hibag_oracle_table(_p(t))
         return t
 
+    def bed_decode(self, bed_bytes, n_samp, n_snp, snp_flag=None):
+        """reference HIBAG_ConvBED restated: int32 [n_samp][n_kept], NA = INT32_MIN"""
+        raw = np.ascontiguousarray(np.frombuffer(bed_bytes, dtype=np.uint8) if not isinstance(bed_bytes, np.ndarray)
+                                   else bed_bytes, dtype=np.uint8)
+        flag = None if snp_flag is None else np.ascontiguousarray(snp_flag, dtype=np.int32)
+        n_save = n_snp if flag is None else int((flag != 0).sum())
+        out = np.zeros((n_samp, max(n_save, 1)), dtype=np.int32)
+        L = self.lib
+        L.hibag_oracle_bed_decode.restype = C.c_int
+        L.hibag_oracle_bed_decode.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        rc = L.hibag_oracle_bed_decode(_p(raw), raw.size, n_samp, n_snp, _p(flag), n_save, _p(out))
+        if rc != 0:
+            raise RuntimeError("Invalid prefix in the PLINK BED file." if rc == -1 else "BED file too short")
+        return out[:, :n_save]
+
     def haplomatch_records(self, haplo, len_per_hla, n_snp, geno):
         """records a build_haplomatch plugin returns: uint32 [n][2] = (in-bag index, (i2<<16)|i1)"""
         L = self.lib

@@ -396,3 +396,41 @@ def test_round_trip_properties_at_scale(gpu):
     part = m.predict(new.geno[12345:23456])
     for key in ("h1", "h2", "prob", "matching", "dosage", "postprob"):
         assert np.array_equal(part[key], got[key][12345:23456], equal_nan=True), key
+
+
+# ---- PLINK BED import --------------------------------------------------------
+
+def test_bed_decode_matches_oracle(gpu, orc, tmp_path):
+    """bed_snp_major_kernel / bed_ind_major_kernel through the C ABI vs the restated HIBAG_ConvBED:
+    both file modes, ragged sizes, SNP selection, the reference's example file set, the file-level
+    mirror of hlaBED2Geno, and the reference's error for a bad prefix"""
+    rng = np.random.default_rng(12)
+    na = np.iinfo(np.int32).min
+    for mode in (0, 1):
+        for n_samp, n_snp in ((1, 1), (5, 7), (127, 129), (128, 128), (1000, 517), (3001, 260)):
+            rows, per = (n_samp, n_snp) if mode == 0 else (n_snp, n_samp)
+            pay = rng.integers(0, 256, size=rows * ((per + 3) // 4), dtype=np.uint8)
+            raw = np.concatenate([np.array([0x6C, 0x1B, mode], dtype=np.uint8), pay])
+            for flag in (None, (rng.random(n_snp) < 0.5).astype(np.int32)):
+                if flag is not None:
+                    flag[n_snp // 2] = 1
+                want = orc.bed_decode(raw, n_samp, n_snp, flag)
+                got = gpu.bed_decode(raw, n_samp, n_snp, flag)
+                assert got.dtype == np.int8 and got.shape == want.shape
+                assert np.array_equal(got, np.where(want == na, -1, want)), (mode, n_samp, n_snp)
+    pk = helpers.load_golden("hapmap_ceu_plink.npz")
+    hm = helpers.load_golden("hapmap_ceu.npz")
+    # write the file set and import it the way a user would
+    (tmp_path / "x.bed").write_bytes(pk["bed"].tobytes())
+    (tmp_path / "x.fam").write_text("".join("%s\t%s\t0\t0\t0\t-9\n" % (f, i) for f, i in zip(pk["fam_family"], pk["fam_id"])))
+    (tmp_path / "x.bim").write_text("".join("%s\t%s\t0\t%d\t%s\t%s\n" % r for r in zip(
+        pk["bim_chr"], pk["bim_snp"], pk["bim_pos"], pk["bim_a1"], pk["bim_a2"])))
+    lo, hi = int(hm["snp_position"].min()), int(hm["snp_position"].max())
+    geno = gpu.hlaBED2Geno(str(tmp_path / "x.bed"), str(tmp_path / "x.fam"), str(tmp_path / "x.bim"),
+                           region=("6", lo, hi))
+    si = [geno["sample_id"].index(s) for s in hm["sample_id"]]
+    sj = [geno["snp_id"].index(s) for s in hm["snp_id"]]
+    want = hm["genotype"].astype(np.int16)
+    assert np.array_equal(geno["genotype"][np.ix_(si, sj)], np.where((want < 0) | (want > 2), -1, want))
+    with pytest.raises(RuntimeError, match="Invalid prefix in the PLINK BED file"):
+        gpu.bed_decode(np.array([1, 2, 3, 4, 5], dtype=np.uint8), 2, 2)

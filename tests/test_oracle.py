@@ -127,3 +127,56 @@ def test_haplomatch_records_follow_reference_pair_matcher(ref, orc):
                 want.append((k, (i2 << 16) | i1))
             k += 1
         assert [tuple(r) for r in rec.tolist()] == want
+
+
+# ---- PLINK BED import -----------------------------------------------------
+
+def _np_bed_decode(raw, n_samp, n_snp):
+    """independent numpy decoding of a .bed byte string -> int8 [n_samp][n_snp], missing -1"""
+    cvt = np.array([2, -1, 1, 0], dtype=np.int8)
+    mode = raw[2]
+    rows, per = (n_samp, n_snp) if mode == 0 else (n_snp, n_samp)
+    pay = raw[3:3 + rows * ((per + 3) // 4)].reshape(rows, -1)
+    g = np.zeros((rows, pay.shape[1] * 4), dtype=np.int8)
+    for k in range(4):
+        g[:, k::4] = cvt[(pay >> (2 * k)) & 3]
+    g = g[:, :per]
+    return g if mode == 0 else np.ascontiguousarray(g.T)
+
+
+def test_bed_decode_reproduces_reference_dataset(orc):
+    """the reference's example PLINK files decode to the reference's own HapMap_CEU_Geno dataset
+    (60 shared samples x 1,564 shared SNPs): the pin of the BED decoder"""
+    pk = helpers.load_golden("hapmap_ceu_plink.npz")
+    hm = helpers.load_golden("hapmap_ceu.npz")
+    n_samp, n_snp = len(pk["fam_id"]), len(pk["bim_snp"])
+    full = orc.bed_decode(pk["bed"], n_samp, n_snp)
+    assert full.shape == (n_samp, n_snp) and pk["bed"][2] == 0          # an individual-major file
+    g = np.where(full == np.iinfo(np.int32).min, -1, full).astype(np.int8)
+    assert np.array_equal(g, _np_bed_decode(pk["bed"], n_samp, n_snp))
+    si = [list(pk["fam_id"]).index(s) for s in hm["sample_id"]]
+    snp_ix = {s: i for i, s in enumerate(pk["bim_snp"])}
+    sj = [snp_ix[s] for s in hm["snp_id"]]
+    want = hm["genotype"].astype(np.int16)
+    want = np.where((want < 0) | (want > 2), -1, want)
+    assert np.array_equal(g[np.ix_(si, sj)], want)
+    assert np.array_equal(pk["bim_pos"][sj], hm["snp_position"])
+    # SNP selection keeps the flagged columns in file order
+    flag = np.zeros(n_snp, dtype=np.int32); flag[sj] = 1
+    sel = orc.bed_decode(pk["bed"], n_samp, n_snp, flag)
+    assert np.array_equal(sel, full[:, np.nonzero(flag)[0]])
+
+
+def test_bed_decode_both_modes_and_ragged_sizes(orc):
+    rng = np.random.default_rng(11)
+    for mode in (0, 1):
+        for n_samp, n_snp in ((1, 1), (5, 7), (64, 33), (131, 258)):
+            rows, per = (n_samp, n_snp) if mode == 0 else (n_snp, n_samp)
+            pay = rng.integers(0, 256, size=rows * ((per + 3) // 4), dtype=np.uint8)
+            raw = np.concatenate([np.array([0x6C, 0x1B, mode], dtype=np.uint8), pay])
+            flag = (rng.random(n_snp) < 0.6).astype(np.int32); flag[0] = 1
+            got = orc.bed_decode(raw, n_samp, n_snp, flag)
+            want = _np_bed_decode(raw, n_samp, n_snp)[:, np.nonzero(flag)[0]]
+            assert np.array_equal(np.where(got == np.iinfo(np.int32).min, -1, got), want), (mode, n_samp, n_snp)
+    with pytest.raises(RuntimeError, match="Invalid prefix"):
+        orc.bed_decode(np.array([1, 2, 3, 4], dtype=np.uint8), 2, 2)
