@@ -42,6 +42,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
+NCU_GATHER_DRAM_BYTES_PER_IB_LAUNCH = 141967872 + 124222208   # profiles/r01_gather_r2_ncu_raw.csv
 LANES = 24           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
@@ -414,10 +415,46 @@ def run_b200_arm(args):
                 "of the time it would take alone: frac is conservative. The gather form is ragged (a warp's "
                 "lanes are the samples that need the cell) and latency-bound on the small passes; the plain "
                 "kernel's fraction (every cell, full warps) is under roofline_unscreened and predict.roofline.",
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one in-bag launch (ncu --set full,
+        # profiles/r01_gather_r2_ncu_raw.csv): the surviving entries of the cell matrix written once and
+        # the need lists read once; the path is not HBM-bound
+        "traffic": NCU_GATHER_DRAM_BYTES_PER_IB_LAUNCH,
+        "traffic_note": "bytes per in-bag launch of selection round ~30 of one classifier (1.44 ms, 142 MB "
+                        "read + 124 MB written), from the ncu capture in profiles/; the launches of a step differ in size",
         "fp64_frac": pair_rate * 3 / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9),
         "em_kernel_ms": d["em_kernel_ms"],
     }
+    if screened and d["gather_ib_launches"] > 0:
+        ib_rate = d["gather_ib_popc32"] / max(d["gather_ib_kernel_ms"] * 1e-3, 1e-12)
+        roofline["in_bag_launches"] = {
+            "launches": int(d["gather_ib_launches"]), "avg_launch_ms": d["gather_ib_kernel_ms"] / d["gather_ib_launches"],
+            "achieved": ib_rate / 1e9, "frac": ib_rate / popc_peak,
+            "share_of_gather_ms": d["gather_ib_kernel_ms"] / max(d["gather_kernel_ms"], 1e-12),
+            "note": "the in-bag launches alone (86 of 595 cells per sample survive: full warps); the out-of-bag "
+                    "launches (2.5 cells per sample) are latency-bound"}
+    # the same kernel timed ALONE: one lane, its launches serialised, nothing else on the GPU
+    if screened and not args.no_unscreened:
+        m3 = api.HLAModel(N_SNP, coh.n_hla)
+        m3.set_training(geno, coh.h1, coh.h2)
+        n_alone = 2
+        m3.train(n_alone, MTRY, prune=True, seed=TRAIN_SEED, per_classifier_seed=True, first_index=rank * n_alone,
+                 n_threads=n_threads, n_concurrent=1, em_on_device=dev_em)
+        torch.cuda.synchronize()
+        sa = m3.train_stats()
+        a_all = sa["popc32_issued"] / max(sa["gather_kernel_ms"] * 1e-3, 1e-12)
+        a_ib = sa["gather_ib_popc32"] / max(sa["gather_ib_kernel_ms"] * 1e-3, 1e-12)
+        roofline["alone"] = {
+            "classifiers": n_alone, "lanes": 1,
+            "launches": int(sa["gather_kernel_launches"]), "avg_launch_ms": sa["gather_kernel_ms"] / max(sa["gather_kernel_launches"], 1),
+            "achieved": a_all / 1e9, "frac": a_all / popc_peak,
+            "in_bag_launches": int(sa["gather_ib_launches"]),
+            "in_bag_avg_launch_ms": sa["gather_ib_kernel_ms"] / max(sa["gather_ib_launches"], 1),
+            "in_bag_achieved": a_ib / 1e9, "in_bag_frac": a_ib / popc_peak,
+            "note": "same kernel, same workload, ONE classifier in flight: every gather launch has the GPU to "
+                    "itself, so launch duration = kernel time (the burst figure). In the timed region 24 lanes "
+                    "overlap their launches on six streams and share the SMs with the EM CTAs of other lanes."}
+        del m3
     # one step with screening off: the plain pair-scoring kernel alone on its stream
     roofline_plain = None
     if screened and not args.no_unscreened:

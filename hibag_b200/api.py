@@ -47,7 +47,9 @@ class TrainStats(C.Structure):
                 ("seconds_phase_oob", C.c_double), ("seconds_phase_ib", C.c_double),
                 ("em_kernel_ms", C.c_double), ("n_em_host_fallback", C.c_uint64),
                 ("pair_evals_nominal", C.c_uint64), ("n_screen_fallback", C.c_uint64),
-                ("gather_kernel_ms", C.c_double), ("gather_kernel_launches", C.c_uint64)]
+                ("gather_kernel_ms", C.c_double), ("gather_kernel_launches", C.c_uint64),
+                ("gather_ib_kernel_ms", C.c_double), ("gather_ib_launches", C.c_uint64),
+                ("gather_ib_popc32", C.c_uint64)]
 
 
 class PredictOut(C.Structure):

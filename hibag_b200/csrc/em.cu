@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "kernels.h"
 
@@ -248,7 +249,7 @@ struct EmArgs
 	int total_pairs;
 	int m_warps;                      // warps that run the M step, each with a RING_ROWS-row ring
 	// per-candidate scratch
-	int2 *sp;                         // [m][n_slots] slot -> {u | v << 16, entry}; entry < 0: empty
+	int *pmap;                        // [m][4 * total_pairs] pair -> compact index | entry | two ELL slots of a compatible pair
 	double *rinc;                     // [m][n_slots] contributions in ELL slot order
 	int *cuv;                         // [m][total_pairs] u | v << 16 of the compatible pairs
 	double *xbuf;                     // [m][total_pairs] GenoFreq of the compatible pairs
@@ -258,6 +259,7 @@ struct EmArgs
 	int *out_status;                  // [m][4] = status, iterations, 0, 0
 	double scale;                     // 0.5 / n_samp
 	double em_reltol;                 // sqrt(DBL_EPSILON)
+	unsigned long long *prof;         // [m][8] clock64 ticks per phase (HIBAG_B200_EM_PROF), or null
 };
 
 constexpr int MAX_CLUSTER = 8;
@@ -313,19 +315,23 @@ __device__ __forceinline__ double block_sum_f64(double v, double *scratch)
 /// are split evenly over the CTAs for the E step; the groups of haplotype chains are dealt
 /// round-robin for the M step. Every CTA keeps the full frequency vector (double-buffered) and
 /// the per-entry scale factors in shared memory; new frequencies, scale factors and partial
-/// log-likelihoods are written into all CTAs through distributed shared memory, so two cluster
-/// barriers per iteration are the only synchronisation.
+/// log-likelihoods are written into all CTAs through distributed shared memory.
 ///
 /// Only the pairs compatible with the candidate's genotype take part in EM (:1157-1180, about a
 /// third of all pairs). Once per candidate the kernel (A) compacts them in pair order and (B)
 /// assigns every compatible contribution its ELL slot counted among the compatible contributions
-/// of its haplotype only, recording slot -> (pair haplotypes, entry). Per iteration the
-/// contributions are then produced IN SLOT ORDER -- r = (c * f_u * f_v) * (count / sum) rebuilt from
-/// shared memory, bit-identical to the E step's value -- so the writes are coalesced, and the M
-/// step walks chains a half to a third as long.
+/// of its haplotype only, recording per compatible pair the slots of its two contributions.
+/// Per iteration: (1) pair pass, coalesced: GenoFreq x of every compatible pair; (2) entry pass:
+/// the sum of an entry's x in list order, its log-likelihood term and scale factor count / sum;
+/// (3) contribution pass, coalesced over the pairs: r = x * (count / sum) stored into the two ELL
+/// slots of the pair (the slots nothing is stored into hold 0.0 from the start: s + 0.0 == s);
+/// (4) M step: every lane adds its own chain in the reference's order.
+/// (Round 1 history, measured with the phase clocks below at config 2, 24 lanes: a pass over the
+/// ELL slots that rebuilt r per slot from shared memory cost 150 k cycles per iteration -- 48 warp
+/// instructions per 32 slots of which 60 % are padding -- against 72 k for the pair-order pass.)
 /// EM_THREADS threads per CTA; RING_ROWS = ELL rows (256 B each) an M-step warp keeps in flight
 template <int EM_THREADS, int RING_ROWS>
-__global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
+__global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_kernel(const EmArgs p)
 {
 	cg::cluster_group cluster = cg::this_cluster();
 	const int C = (int)cluster.num_blocks();
@@ -346,8 +352,18 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 	const int c = blockIdx.x / C;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
+	const int warp = tid >> 5;
+	// phase clocks of thread 0 (it leaves every phase through the phase's barrier)
+	const bool prof = (p.prof != nullptr) && tid == 0 && rank == 0;
+	__shared__ long long sh_pt[6];             // [0..4] ticks per phase, [5] last clock
+	if (prof) { for (int q = 0; q < 5; q++) sh_pt[q] = 0; sh_pt[5] = clock64(); }
+#define EM_TICK(i_) do { if (prof) { const long long n_ = clock64(); sh_pt[i_] += n_ - sh_pt[5]; sh_pt[5] = n_; } } while (0)
 	const int8_t *col = p.geno_t + (size_t)p.cand_snp[c] * p.n_samp;
-	int2 *sp = p.sp + (size_t)c * p.n_slots;
+	// per-candidate scratch: per original pair its index among the compatible pairs; per compatible
+	// pair its entry and the ELL slots of its two contributions
+	int *jmap = p.pmap + (size_t)c * 4 * p.total_pairs;
+	int *ce = jmap + p.total_pairs;
+	int2 *cslot = (int2 *)(ce + p.total_pairs);
 	double *rinc = p.rinc + (size_t)c * p.n_slots;
 	int *cuv = p.cuv + (size_t)c * p.total_pairs;
 	double *xbuf = p.xbuf + (size_t)c * p.total_pairs;
@@ -418,12 +434,18 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		const int chunk = (n_slice + EM_THREADS - 1) / EM_THREADS;
 		const int tb = min(t_hi, t_lo + tid * chunk), te = min(t_hi, tb + chunk);
 		int cnt = 0;
-		for (int t = tb; t < te; t++)
+		for (int t = tb; t < te; t += 4)           // four pair records in flight per thread
 		{
-			const int4 pr = __ldg(p.pairs4 + t);
-			const int u = pr.x & 0xffff, v = (int)((unsigned)pr.x >> 16);
-			const int g = eg[pr.y] & 3;
-			cnt += (g == 3 || ((u & 1) + (v & 1)) == g) ? 1 : 0;
+			int4 pr[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) pr[q] = (t + q < te) ? __ldg(p.pairs4 + t + q) : make_int4(0, 0, 0, 0);
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const int u = pr[q].x & 0xffff, v = (int)((unsigned)pr[q].x >> 16);
+				const int g = eg[pr[q].y] & 3;
+				cnt += (t + q < te && (g == 3 || ((u & 1) + (v & 1)) == g)) ? 1 : 0;
+			}
 		}
 		// block exclusive scan of cnt (warp shuffles + one pass over the 32 warp totals)
 		int incl = cnt;
@@ -435,7 +457,7 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		}
 		int *wsum = (int *)scratch;             // [32] ints (scratch is 40 doubles)
 		__syncthreads();
-		if (lane == 31) wsum[tid >> 5] = incl;
+		if (lane == 31) wsum[warp] = incl;
 		__syncthreads();
 		if (tid < 32)
 		{
@@ -450,24 +472,37 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		}
 		__syncthreads();
 		const int cta_total = wsum[31];
-		const int start = incl - cnt + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0);
+		const int start = incl - cnt + (warp ? wsum[warp - 1] : 0);
 		if (tid < C) cluster.map_shared_rank(tot, tid)[rank] = cta_total;
 		cluster.sync();
 		int base = 0;
 		for (int q = 0; q < rank; q++) base += tot[q];
 		jb_lo = base; jb_hi = base + cta_total;
 		int j = base + start;
-		for (int t = tb; t < te; t++)
+		for (int t = tb; t < te; t += 4)
 		{
-			const int4 pr = __ldg(p.pairs4 + t);
-			const int u = pr.x & 0xffff, v = (int)((unsigned)pr.x >> 16);
-			const int g = eg[pr.y] & 3;
-			if (t == p.off[pr.y]) coff[pr.y] = j;          // first pair of its entry
-			if (g == 3 || ((u & 1) + (v & 1)) == g) cuv[j++] = pr.x;
+			int4 pr[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) pr[q] = (t + q < te) ? __ldg(p.pairs4 + t + q) : make_int4(0, 0, 0, 0);
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				if (t + q < te)
+				{
+					const int u = pr[q].x & 0xffff, v = (int)((unsigned)pr[q].x >> 16);
+					const int g = eg[pr[q].y] & 3;
+					if (t + q == p.off[pr[q].y]) coff[pr[q].y] = j;      // first pair of its entry
+					if (g == 3 || ((u & 1) + (v & 1)) == g)
+					{
+						jmap[t + q] = j; ce[j] = pr[q].y;
+						cuv[j++] = pr[q].x;
+					}
+				}
+			}
 		}
 		if (rank == C - 1 && tid == 0) coff[p.n_entry] = jb_hi;
 		if (tid == 0) sh_i[3] = 0;
-		__syncthreads();
+		cluster.sync();                            // (B) reads the jmap entries of every CTA's pairs
 	}
 	// ---- (B) ELL slots of the compatible contributions: a warp takes one haplotype of the groups
 	// dealt to this CTA at a time and walks its incidence list 128 contributions per step ---------
@@ -512,7 +547,8 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 					if (ok)
 					{
 						const int rk = n + __popc(m & ((1u << lane) - 1u));
-						sp[gbase + 64 * (rk >> 1) + 2 * l + (rk & 1)] = make_int2(pr[w].x, pr[w].y);
+						const int slot = gbase + 64 * (rk >> 1) + 2 * l + (rk & 1);
+						((int *)cslot)[2 * jmap[e[w] >> 1] + (e[w] & 1)] = slot;
 					}
 					n += __popc(m);
 				}
@@ -521,6 +557,61 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		}
 	}
 	cluster.sync();        // compact lists, entry ranges, slots and group lengths of every CTA are in place
+	const int n_lg = (n_groups > rank) ? (n_groups - rank + C - 1) / C : 0;   // groups dealt to this CTA
+
+	/// M step of one group of 32 chains by one warp: every lane adds its own chain in the
+	/// reference's order, streaming the ELL rows through the warp's shared-memory ring with
+	/// cp.async, RING_ROWS rows ahead of the fp64 add chain, so that the chain runs at add latency
+	/// (16.9 cycles) instead of L2 latency
+	auto chain_group = [&](int gi, double *fr_new)
+	{
+		const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(
+			rings + (size_t)warp * RING_ROWS * 32) + (uint32_t)lane * 16u;
+		constexpr int NB = RING_ROWS / 8;      // batches of 8 rows (4 row pairs) in flight
+		const int nb = glen[gi] >> 3;
+		const char *src = (const char *)(rinc + p.group_base[gi]) + lane * 16;   // + 512 per row pair
+		for (int b = 0; b < NB - 1; b++)
+		{
+			if (b < nb)
+			{
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					cp_async16_cg(ring_s + (uint32_t)(b * 4 + k) * 512u, src + (size_t)(b * 4 + k) * 512);
+			}
+			cp_async_commit();
+		}
+		double acc = 0;
+		int rb = 0;                         // b mod NB
+		for (int b = 0; b < nb; b++)
+		{
+			const int bn = b + NB - 1;
+			if (bn < nb)
+			{
+				const int rbn = (rb + NB - 1) & (NB - 1);
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					cp_async16_cg(ring_s + (uint32_t)(rbn * 4 + k) * 512u, src + (size_t)(bn * 4 + k) * 512);
+			}
+			cp_async_commit();
+			cp_async_wait<NB - 1>();
+			double2 r[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) r[k] = lds_f64x2(ring_s + (uint32_t)(rb * 4 + k) * 512u);
+#pragma unroll
+			for (int k = 0; k < 4; k++) { acc = __dadd_rn(acc, r[k].x); acc = __dadd_rn(acc, r[k].y); }
+			rb = (rb + 1) & (NB - 1);
+		}
+		cp_async_wait<0>();
+		const int r = 32 * gi + lane;
+		if (r < n2)
+		{
+			const double f = __dmul_rn(acc, p.scale);
+			const int u = p.hap_sorted[r];
+			const size_t o = (size_t)(fr_new - fr0) + u;
+			for (int q = 0; q < C; q++) cluster.map_shared_rank(fr0, q)[o] = f;
+		}
+	};
+	EM_TICK(0);
 
 	double conv_tol = 0, loglik = -1e+30;
 	int result = EM_OK, iters = 0;
@@ -554,129 +645,85 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		}
 		if (tid == 0) sh_i[2] = 0;                 // group counter of the M step
 		__syncthreads();
+		EM_TICK(1);
 		// (2) one thread per in-bag entry: sum of its pairs in list order, log-likelihood term,
-		//     scale factor count / sum into every CTA of the cluster
+		//     scale factor count / sum into every CTA of the cluster. An entry has ~6 compatible
+		//     pairs: eight predicated loads in flight (one round trip to L2 for most entries), the
+		//     next entry's range prefetched.
 		double ll = 0;
-		for (int k = k_lo + tid; k < k_hi; k += EM_THREADS)
 		{
-			const int b = coff[k], e = coff[k + 1];
-			double psum = 0;
-			int t = b;
-			for (; t + 8 <= e; t += 8)
+			int k = k_lo + tid;
+			int b = 0, e = 0;
+			if (k < k_hi) { b = coff[k]; e = coff[k + 1]; }
+			while (k < k_hi)
 			{
-				double x[8];
+				const int kn = k + EM_THREADS;
+				int bn = 0, en = 0;
+				if (kn < k_hi) { bn = coff[kn]; en = coff[kn + 1]; }
+				double psum = 0;
+				for (int t = b; t < e; t += 8)
+				{
+					double x[8];
 #pragma unroll
-				for (int q = 0; q < 8; q++) x[q] = xbuf[t + q];
+					for (int q = 0; q < 8; q++) x[q] = (t + q < e) ? xbuf[t + q] : 0.0;
 #pragma unroll
-				for (int q = 0; q < 8; q++) psum = __dadd_rn(psum, x[q]);
+					for (int q = 0; q < 8; q++) if (t + q < e) psum = __dadd_rn(psum, x[q]);
+				}
+				const double bc = (double)(eg[k] >> 2);
+				ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
+				const double sc = __ddiv_rn(bc, psum);
+				for (int q = 0; q < C; q++) cluster.map_shared_rank(sck, q)[k] = sc;
+				k = kn; b = bn; e = en;
 			}
-			for (; t < e; t++) psum = __dadd_rn(psum, xbuf[t]);
-			const double bc = (double)(eg[k] >> 2);
-			ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
-			const double sc = __ddiv_rn(bc, psum);
-			for (int q = 0; q < C; q++) cluster.map_shared_rank(sck, q)[k] = sc;
 		}
 		ll = block_sum_f64(ll, scratch);
 		if (tid < C) cluster.map_shared_rank(llp, tid)[(iter & 1) * MAX_CLUSTER + rank] = ll;
 		cluster.sync();        // scale factors and partial log-likelihoods of every CTA have landed
-		// (3) one thread per ELL slot of the groups dealt to this CTA: the contribution of the
-		//     pair recorded for the slot, r = x * (count / sum), rebuilt from shared memory (bit-
-		//     identical to pass 1's x) and written in slot order -- fully coalesced; empty slots
-		//     get 0.0 (s + 0.0 == s)
-		for (int gi = rank; gi < n_groups; gi += C)
+		EM_TICK(2);
+		// (3) one thread per compatible pair, coalesced: its contribution r = x * (count / sum) goes
+		//     to the ELL slots of both of its haplotypes
+		for (int j0 = jb_lo + tid; j0 < jb_hi; j0 += EM_THREADS * 4)
 		{
-			const int n_sl = 32 * glen[gi];
-			const int2 *src = sp + p.group_base[gi];
-			double *dst = rinc + p.group_base[gi];
-			for (int s0 = tid; s0 < n_sl; s0 += EM_THREADS * 4)
+			double x[4];
+			int en[4];
+			int2 sl[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++)
 			{
-				int2 rec[4];
+				const int j = j0 + q * EM_THREADS;
+				const bool ok = j < jb_hi;
+				x[q] = ok ? xbuf[j] : 0.0;
+				en[q] = ok ? ce[j] : 0;
+				sl[q] = ok ? cslot[j] : make_int2(-1, -1);
+			}
 #pragma unroll
-				for (int q = 0; q < 4; q++)
+			for (int q = 0; q < 4; q++)
+			{
+				if (sl[q].x >= 0)
 				{
-					const int sl = s0 + q * EM_THREADS;
-					rec[q] = (sl < n_sl) ? src[sl] : make_int2(0, -1);
-				}
-#pragma unroll
-				for (int q = 0; q < 4; q++)
-				{
-					const int sl = s0 + q * EM_THREADS;
-					if (sl < n_sl)
-					{
-						double r = 0.0;
-						if (rec[q].y >= 0)
-						{
-							const int u = rec[q].x & 0xffff, v = (int)((unsigned)rec[q].x >> 16);
-							const double x = (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v])
-							                          : __dmul_rn(fr[u], fr[v]);
-							r = __dmul_rn(x, sck[rec[q].y]);
-						}
-						dst[sl] = r;
-					}
+					const double r = __dmul_rn(x[q], sck[en[q]]);
+					rinc[sl[q].x] = r;
+					rinc[sl[q].y] = r;
 				}
 			}
 		}
-		__syncthreads();
-		// ---- M step: one lane per haplotype, contributions in the reference's order. A warp
-		// takes the next-longest group of 32 chains dealt to this CTA and streams its ELL rows
-		// through a private shared-memory ring with cp.async, RING_ROWS rows ahead of the fp64 add
-		// chain, so the chain runs at add latency instead of L2 latency. --------------------------
-		if ((tid >> 5) < p.m_warps)
+		if (C > 1) cluster.sync(); else __syncthreads();   // the chains read every CTA's contributions
+		EM_TICK(3);
+		// ---- M step: a warp that owns a ring takes the next-longest group of 32 chains dealt to
+		// this CTA -----------------------------------------------------------------------------
+		if (warp < p.m_warps)
 		{
-			const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(
-				rings + (size_t)(tid >> 5) * RING_ROWS * 32) + (uint32_t)lane * 16u;
-			constexpr int NB = RING_ROWS / 8;      // batches of 8 rows (4 row pairs) in flight
 			for (;;)
 			{
-				int gi = 0;
-				if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
-				gi = __shfl_sync(0xffffffffu, gi, 0) * C + rank;
-				if (gi >= n_groups) break;
-				const int nb = glen[gi] >> 3;
-				const char *src = (const char *)(rinc + p.group_base[gi]) + lane * 16;   // + 512 per row pair
-				for (int b = 0; b < NB - 1; b++)
-				{
-					if (b < nb)
-					{
-#pragma unroll
-						for (int k = 0; k < 4; k++)
-							cp_async16_cg(ring_s + (uint32_t)(b * 4 + k) * 512u, src + (size_t)(b * 4 + k) * 512);
-					}
-					cp_async_commit();
-				}
-				double acc = 0;
-				int rb = 0;                         // b mod NB
-				for (int b = 0; b < nb; b++)
-				{
-					const int bn = b + NB - 1;
-					if (bn < nb)
-					{
-						const int rbn = (rb + NB - 1) & (NB - 1);
-#pragma unroll
-						for (int k = 0; k < 4; k++)
-							cp_async16_cg(ring_s + (uint32_t)(rbn * 4 + k) * 512u, src + (size_t)(bn * 4 + k) * 512);
-					}
-					cp_async_commit();
-					cp_async_wait<NB - 1>();
-					double2 r[4];
-#pragma unroll
-					for (int k = 0; k < 4; k++) r[k] = lds_f64x2(ring_s + (uint32_t)(rb * 4 + k) * 512u);
-#pragma unroll
-					for (int k = 0; k < 4; k++) { acc = __dadd_rn(acc, r[k].x); acc = __dadd_rn(acc, r[k].y); }
-					rb = (rb + 1) & (NB - 1);
-				}
-				cp_async_wait<0>();
-				const int r = 32 * gi + lane;
-				if (r < n2)
-				{
-					const double f = __dmul_rn(acc, p.scale);
-					const int u = p.hap_sorted[r];
-					const size_t o = (size_t)(fr_new - fr0) + u;
-					for (int q = 0; q < C; q++) cluster.map_shared_rank(fr0, q)[o] = f;
-				}
+				int i = 0;
+				if (lane == 0) i = atomicAdd(&sh_i[2], 1);
+				i = __shfl_sync(0xffffffffu, i, 0);
+				if (i >= n_lg) break;
+				chain_group(rank + C * i, fr_new);
 			}
 		}
 		cluster.sync();        // new frequencies have landed in every CTA
+		EM_TICK(4);
 		iters = iter + 1;
 		// ---- stopping rule (:1236-1250) with the guard band of em.h; every CTA evaluates the
 		// same numbers in the same order ---------------------------------------------------------
@@ -702,11 +749,42 @@ __global__ void __launch_bounds__(EM_THREADS) em_kernel(const EmArgs p)
 		for (int u = tid; u < n2; u += EM_THREADS) out[u] = fin[u];
 		if (tid == 0) { status[0] = result; status[1] = iters; }
 	}
+	if (prof)
+	{
+		for (int q = 0; q < 5; q++) p.prof[8 * c + q] = (unsigned long long)sh_pt[q];
+		p.prof[8 * c + 5] = (unsigned long long)iters;
+		p.prof[8 * c + 6] = (unsigned long long)(jb_hi - jb_lo);
+	}
+#undef EM_TICK
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// HIBAG_B200_EM_PROF=1: per-phase clock64 totals of the EM kernel over the process, printed at exit
+namespace {
+struct EmProf
+{
+	std::mutex mu;
+	unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned long long cands = 0, launches = 0, slots = 0, pairs = 0;
+	bool registered = false;
+	static void dump();
+} g_em_prof;
+void EmProf::dump()
+{
+	EmProf &g = g_em_prof;
+	if (!g.cands) return;
+	const double it = (double)g.t[5];
+	fprintf(stderr, "em prof: %llu launches, %llu candidates, %.0f iterations (mean %.1f), compat pairs/cand %.0f, "
+		"all pairs/cand %.0f, ELL slots/cand %.0f | kcycles per candidate: setup %.1f | per iteration: "
+		"pairs %.2f entries %.2f slots %.2f chains %.2f (sum %.2f)\n",
+		g.launches, g.cands, it, it / g.cands, (double)g.t[6] / g.cands, (double)g.pairs / g.cands,
+		(double)g.slots / g.cands, g.t[0] * 1e-3 / g.cands, g.t[1] * 1e-3 / it, g.t[2] * 1e-3 / it,
+		g.t[3] * 1e-3 / it, g.t[4] * 1e-3 / it, (g.t[1] + g.t[2] + g.t[3] + g.t[4]) * 1e-3 / it);
+}
+}  // namespace
+
 RoundEM::RoundEM() { current_device(); h_total_.ensure(4); }
 RoundEM::~RoundEM() {}
 
@@ -840,9 +918,10 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	d_cand_.ensure(m);
 	HB_CUDA(cudaMemcpyAsync(d_cand_.get(), hc, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, st));
 	const int n_groups = (n2_ + 31) / 32;
-	d_sp_.ensure(2 * (size_t)m * n_slots_ + 2);
-	HB_CUDA(cudaMemsetAsync(d_sp_.get(), 0xff, sizeof(int) * 2 * (size_t)m * n_slots_, st));   // entry = -1
+	d_pmap_.ensure(4 * (size_t)m * total_pairs_ + 4);
 	d_rinc_.ensure((size_t)m * n_slots_ + 2);
+	// slots without a compatible contribution stay 0.0
+	HB_CUDA(cudaMemsetAsync(d_rinc_.get(), 0, sizeof(double) * (size_t)m * n_slots_, st));
 	d_cuv_.ensure((size_t)m * total_pairs_ + 1);
 	d_xbuf_.ensure((size_t)m * total_pairs_ + 2);
 	d_coff_.ensure((size_t)m * (n_entry_ + 1));
@@ -863,11 +942,18 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	a.n_slots = n_slots_;
 	a.geno_t = geno_t; a.cand_snp = d_cand_.get();
 	a.total_pairs = (int)total_pairs_;
-	a.sp = (int2 *)d_sp_.get(); a.rinc = d_rinc_.get(); a.cuv = d_cuv_.get(); a.xbuf = d_xbuf_.get();
+	a.pmap = d_pmap_.get(); a.rinc = d_rinc_.get(); a.cuv = d_cuv_.get(); a.xbuf = d_xbuf_.get();
 	a.coff = d_coff_.get(); a.glen = d_glen_.get();
 	a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
 	a.scale = 0.5 / n_samp;
 	a.em_reltol = std::sqrt(DBL_EPSILON);
+	static const bool want_prof = getenv("HIBAG_B200_EM_PROF") != nullptr;
+	if (want_prof)
+	{
+		d_prof_.ensure(8 * (size_t)m);
+		HB_CUDA(cudaMemsetAsync(d_prof_.get(), 0, sizeof(unsigned long long) * 8 * (size_t)m, st));
+		a.prof = d_prof_.get();
+	}
 	const size_t smem_base = sizeof(double) * (2 * (size_t)n2_ + 40 + 3 * MAX_CLUSTER + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
 		sizeof(int) * (size_t)n_entry_ + 16;
 	// "dense" shape: 512 threads, 32-row rings and at most half of an SM's shared memory, so that two
@@ -876,7 +962,11 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	if (const char *e = getenv("HIBAG_B200_EM_DENSE")) dense = atoi(e) != 0;
 	size_t budget = dense ? (size_t)112 * 1024 : (size_t)220 * 1024;
 	if (dense && smem_base + sizeof(double) * 32 * 32 > budget) { dense = false; budget = (size_t)220 * 1024; }
-	const size_t ring_b = sizeof(double) * 32 * (size_t)(dense ? 32 : 64);
+	int ring_rows = dense ? 32 : 64;
+	if (const char *e = getenv("HIBAG_B200_EM_RING_ROWS")) ring_rows = (atoi(e) >= 64) ? 64 : 32;
+	if (dense && smem_base + sizeof(double) * 32 * (size_t)ring_rows > budget) ring_rows = 32;
+	if (!dense) ring_rows = 64;
+	const size_t ring_b = sizeof(double) * 32 * (size_t)ring_rows;
 	int m_warps = (smem_base < budget) ? (int)((budget - smem_base) / ring_b) : 0;
 	int em_threads = dense ? 512 : 1024, max_rings = 8;
 	if (const char *e = getenv("HIBAG_B200_EM_RINGS")) max_rings = std::max(1, std::min(8, atoi(e)));
@@ -895,7 +985,7 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	// classifiers/min for clusters of 2)
 	if (dense && n_dense_lanes_ >= 8) cluster = 1;
 	if (const char *e = getenv("HIBAG_B200_EM_CLUSTER")) cluster = std::max(1, std::min(MAX_CLUSTER, atoi(e)));
-	auto kern = dense ? em_kernel<512, 32> : em_kernel<1024, 64>;
+	auto kern = dense ? (ring_rows == 64 ? em_kernel<512, 64> : em_kernel<512, 32>) : em_kernel<1024, 64>;
 	HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
 	HB_CUDA(cudaEventRecord(ev0_.e, st));
 	{
@@ -921,6 +1011,20 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 	kernel_ms += ms;
 	launches++;
+	if (want_prof)
+	{
+		std::vector<unsigned long long> hp(8 * (size_t)m);
+		HB_CUDA(cudaMemcpy(hp.data(), d_prof_.get(), sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
+		std::lock_guard<std::mutex> lk(g_em_prof.mu);
+		for (int i = 0; i < m; i++)
+		{
+			if (h_status_.get()[4 * i] == EM_INVALID) continue;
+			for (int q = 0; q < 7; q++) g_em_prof.t[q] += hp[8 * (size_t)i + q];
+			g_em_prof.cands++; g_em_prof.slots += n_slots_; g_em_prof.pairs += total_pairs_;
+		}
+		g_em_prof.launches++;
+		if (!g_em_prof.registered) { g_em_prof.registered = true; atexit(EmProf::dump); }
+	}
 	if (getenv("HIBAG_B200_EM_DEBUG"))
 	{
 		std::vector<int> gl((size_t)m * n_groups), co((size_t)m * (n_entry_ + 1));

@@ -92,8 +92,9 @@ private:
 	DevBuf<int> d_cand_;
 	PinBuf<int> h_cand_;
 	DevBuf<double> d_freq_, d_xbuf_, d_rinc_;
-	DevBuf<int> d_sp_, d_cuv_, d_coff_, d_glen_;        // per-candidate compaction (em_kernel)
+	DevBuf<int> d_pmap_, d_cuv_, d_coff_, d_glen_;      // per-candidate compaction (em_kernel)
 	DevBuf<int> d_status_;
+	DevBuf<unsigned long long> d_prof_;   // HIBAG_B200_EM_PROF
 	PinBuf<double> h_freq_;
 	PinBuf<int> h_status_;
 	Event ev0_, ev1_;

@@ -499,11 +499,12 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	(void)nw;
 }
 
-void BatchScorer::add_gather_time()
+void BatchScorer::add_gather_time(bool in_bag)
 {
 	float ms = 0;
 	HB_CUDA(cudaEventElapsedTime(&ms, ev_g0_.e, ev_g1_.e));
 	stats.gather_ms += ms; stats.gather_launches++;
+	if (in_bag) { stats.gather_ib_ms += ms; stats.gather_ib_launches++; }
 }
 
 void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<int> &which,
@@ -538,7 +539,7 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 			HB_CUDA(cudaEventSynchronize(ev1_.e));
 			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 			stats.cell_ms += ms; stats.kernel_ms += ms;
-			if (screen) add_gather_time();
+			if (screen) add_gather_time(false);
 		}
 	}
 	if (!screen)
@@ -560,7 +561,7 @@ void BatchScorer::score_oob(const GenoView &g, int cand_bit, const std::vector<i
 	stats.d2h_bytes += sizeof(int) * (size_t)n;
 	if (screen)
 	{
-		add_gather_time();
+		add_gather_time(false);
 		const int nw = geno_words(n_snp_);
 		uint64_t tot = 0;
 		for (int k = 0; k < n; k++) tot += h_evals_.get()[k];
@@ -605,7 +606,7 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 			HB_CUDA(cudaEventSynchronize(ev1_.e));
 			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 			stats.cell_ms += ms; stats.kernel_ms += ms;
-			if (screen) add_gather_time();
+			if (screen) add_gather_time(true);
 		}
 	}
 	if (!screen)
@@ -627,12 +628,13 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 	stats.d2h_bytes += sizeof(double) * (size_t)n * ratio_stride_;
 	if (screen)
 	{
-		add_gather_time();
+		add_gather_time(true);
 		const int nw = geno_words(n_snp_);
 		uint64_t tot = 0;
 		for (int k = 0; k < n; k++) tot += h_evals_.get()[k];
 		stats.pair_evals += tot;
 		stats.popc32 += tot * (uint64_t)nw;
+		stats.gather_ib_popc32 += tot * (uint64_t)nw;
 		evals_per_list_[1] = (double)tot / n;
 		stats.screen_fallback += h_evals_.get()[n];
 		stats.d2h_bytes += sizeof(unsigned long long) * (size_t)(n + 1);

@@ -27,6 +27,8 @@ struct ScoreStats
 	double kernel_ms = 0, cell_ms = 0;
 	double gather_ms = 0;                // summed CUDA-event durations of cell_gather_kernel alone
 	uint64_t gather_launches = 0;
+	double gather_ib_ms = 0;             // ... of the in-bag launches only
+	uint64_t gather_ib_launches = 0, gather_ib_popc32 = 0;
 	void add(const ScoreStats &o)
 	{
 		pair_evals += o.pair_evals; popc32 += o.popc32; launches += o.launches;
@@ -34,6 +36,8 @@ struct ScoreStats
 		pair_evals_nominal += o.pair_evals_nominal; screen_fallback += o.screen_fallback;
 		kernel_ms += o.kernel_ms; cell_ms += o.cell_ms;
 		gather_ms += o.gather_ms; gather_launches += o.gather_launches;
+		gather_ib_ms += o.gather_ib_ms; gather_ib_launches += o.gather_ib_launches;
+		gather_ib_popc32 += o.gather_ib_popc32;
 	}
 };
 
@@ -170,7 +174,7 @@ private:
 	std::vector<uint64_t> list_pairs_;           // pairs per sample of the lists of the pass
 	Stream st_;
 	Event ev_up_{false}, ev0_, ev1_, ev_g0_, ev_g1_;
-	void add_gather_time();
+	void add_gather_time(bool in_bag);
 	Event ev_done_{false, true};
 	size_t cap_ = 0;
 	int n_snp_ = 0, n_hla_ = 0, n_cells_ = 0;

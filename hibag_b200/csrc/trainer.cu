@@ -408,6 +408,9 @@ void Trainer::run(const std::function<int()> &next)
 	ts.n_screen_fallback += stats_.screen_fallback;
 	ts.gather_kernel_ms += stats_.gather_ms;
 	ts.gather_kernel_launches += stats_.gather_launches;
+	ts.gather_ib_kernel_ms += stats_.gather_ib_ms;
+	ts.gather_ib_launches += stats_.gather_ib_launches;
+	ts.gather_ib_popc32 += stats_.gather_ib_popc32;
 	ts.popc32_issued += stats_.popc32;
 	ts.kernel_launches += stats_.launches;
 	ts.cell_kernel_ms += stats_.cell_ms;
@@ -897,6 +900,8 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 		ts.em_kernel_ms += a.em_kernel_ms; ts.n_em_host_fallback += a.n_em_host_fallback;
 		ts.pair_evals_nominal += a.pair_evals_nominal; ts.n_screen_fallback += a.n_screen_fallback;
 		ts.gather_kernel_ms += a.gather_kernel_ms; ts.gather_kernel_launches += a.gather_kernel_launches;
+		ts.gather_ib_kernel_ms += a.gather_ib_kernel_ms; ts.gather_ib_launches += a.gather_ib_launches;
+		ts.gather_ib_popc32 += a.gather_ib_popc32;
 		m.train_trace.insert(m.train_trace.end(), t.trace_.begin(), t.trace_.end());
 		t.built_.clear();
 	}

@@ -181,6 +181,10 @@ typedef struct hibag_b200_train_stats {
 	                                 screened passes; cell_kernel_ms spans a whole pass, bounds to
 	                                 reduction) */
 	uint64_t gather_kernel_launches;
+	double   gather_ib_kernel_ms; /* the in-bag launches of cell_gather_kernel alone (the out-of-bag
+	                                 launches score ~2.5 cells per sample and are latency-bound) */
+	uint64_t gather_ib_launches;
+	uint64_t gather_ib_popc32;    /* POPC.32 issued by the in-bag launches */
 } hibag_b200_train_stats;
 int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_stats *out);
 
