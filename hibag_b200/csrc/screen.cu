@@ -630,6 +630,15 @@ void launch_reduce_ib_screened(const ScreenArgs &a, const ScreenLists &ls, doubl
 // the gather form of the pair-scoring kernel
 // ---------------------------------------------------------------------------------------
 
+/// shared address of T[c_i + pc][lane] from the row address of T[c_i][lane]: one IMAD. (Written as
+/// plain C the compiler re-associates it into (c_i + pc) * 256 + base: an extra IADD per pair.)
+__device__ __forceinline__ uint32_t table_row(uint32_t row_ci, int pc)
+{
+	uint32_t a;
+	asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(a) : "r"((uint32_t)pc), "r"(row_ci));
+	return a;
+}
+
 /// the reference's chain of one cell for R samples per lane (same instruction sequence as the
 /// body of cell_pass_kernel, kernels.cu)
 template <int NW, int R, bool CLAMP, bool SMEM>
@@ -637,6 +646,10 @@ __device__ __forceinline__ void cell_chain(uint32_t hap_base, const char *hap_g,
 	uint32_t tbl_lane, int dmax, int a_start, int a_n, int b_start, int b_n, bool diag,
 	const uint32_t (*S1)[NW], const uint32_t (*S2)[NW], double *sum)
 {
+	// warp-uniform by construction (the task is broadcast from lane 0); the shuffles let the compiler
+	// keep the loop bounds and the record addresses in uniform registers, as in cell_pass_kernel
+	a_start = __shfl_sync(0xffffffffu, a_start, 0); a_n = __shfl_sync(0xffffffffu, a_n, 0);
+	b_start = __shfl_sync(0xffffffffu, b_start, 0); b_n = __shfl_sync(0xffffffffu, b_n, 0);
 	uint32_t V[R][NW];
 #pragma unroll
 	for (int r = 0; r < R; r++)
@@ -677,7 +690,7 @@ __device__ __forceinline__ void cell_chain(uint32_t hap_base, const char *hap_g,
 				for (int w = 0; w < NW; w++) pc += __popc((hi.h[w] ^ K[r][w]) & V[r][w]);
 				double t;
 				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
-				else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
+				else t = lds_f64(table_row(tb[r], pc));
 				sum[r] = __dadd_rn(sum[r], __dmul_rn(p2, t));
 			}
 			j0 = ii + 1;
@@ -697,7 +710,7 @@ __device__ __forceinline__ void cell_chain(uint32_t hap_base, const char *hap_g,
 				for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
 				double t;
 				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
-				else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
+				else t = lds_f64(table_row(tb[r], pc));
 				sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
 			}
 		}
