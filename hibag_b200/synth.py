@@ -72,3 +72,24 @@ def draw_more(cohort, n_samp, seed=2, noise=0.01, missing=0.01):
                          n_samp, noise, missing)
     return Cohort(geno, h1, h2, cohort.n_hla, cohort._founders, cohort._founder_allele,
                   cohort._allele_freq)
+
+
+def make_thermo_cohort(n_samp, n_hla, seed=1, noise=0.0, missing=0.005):
+    """Cohort whose classifiers need MANY SNPs (test shape, not a BASELINE config): allele a carries
+    1 at the SNPs below a ("thermometer code", SNP order shuffled), so every SNP separates exactly
+    one more pair of neighbouring alleles and the search keeps accepting SNPs up to n_hla - 1 of
+    them; `noise` flips alleles per sample and grows the haplotype lists. Returns (geno int8
+    [n_samp, n_hla - 1], h1, h2)."""
+    rng = np.random.default_rng(seed)
+    n_snp = n_hla - 1
+    code = np.zeros((n_hla, n_snp), dtype=bool)
+    for a in range(n_hla):
+        code[a, :a] = True
+    code = code[:, rng.permutation(n_snp)]
+    a1 = rng.integers(0, n_hla, n_samp)
+    a2 = rng.integers(0, n_hla, n_samp)
+    x = code[a1] ^ (rng.random((n_samp, n_snp)) < noise)
+    y = code[a2] ^ (rng.random((n_samp, n_snp)) < noise)
+    geno = x.astype(np.int8) + y.astype(np.int8)
+    geno[rng.random((n_samp, n_snp)) < missing] = -1
+    return geno, a1.astype(np.int32), a2.astype(np.int32)

@@ -294,6 +294,30 @@ def test_trainer_matches_reference_many_alleles(gpu):
             assert d == "", (kwargs, k, d)
 
 
+def test_trainer_matches_reference_many_snps(gpu):
+    """Classifiers of 37 and 67 SNPs (two- and four-word packed genotypes; the BASELINE-shaped cohorts
+    stop at 20-27 SNPs): bit-identical to the reference's base target with the screened passes and the
+    device EM, and with every cell scored and the host EM (fixture generated from the compiled reference
+    by tools/make_golden_thermo.py)"""
+    from hibag_b200 import synth
+    gd = helpers.load_golden("synth_thermo_ref.npz")
+    for i in range(int(gd["n_specs"])):
+        geno, h1, h2 = synth.make_thermo_cohort(int(gd["s%d_n_samp" % i]), int(gd["s%d_n_hla" % i]),
+                                                seed=int(gd["s%d_cohort_seed" % i]), noise=float(gd["s%d_noise" % i]))
+        want = dict(snpidx=gd["s%d_snpidx" % i], samp_num=gd["s%d_samp_num" % i], freq=gd["s%d_freq" % i],
+                    hla=gd["s%d_hla" % i], packed=gd["s%d_packed" % i], oob_acc=float(gd["s%d_oob_acc" % i]))
+        assert len(want["snpidx"]) > (32, 64)[i]
+        for kwargs in (dict(n_concurrent=1), dict(em_on_device=False, n_threads=8, screening=False)):
+            m = gpu.HLAModel(geno.shape[1], int(gd["s%d_n_hla" % i]))
+            m.set_training(geno, h1, h2)
+            m.train(1, geno.shape[1], prune=True, seed=int(gd["s%d_train_seed" % i]), per_classifier_seed=True, **kwargs)
+            d = helpers.classifier_diff(m.classifier(0), want)
+            assert d == "", (i, kwargs, d)
+            if "screening" not in kwargs:
+                st = m.train_stats()
+                assert st["pair_evals"] < st["pair_evals_nominal"]          # the screen was on
+
+
 def _golden_model(gpu, ref, n_cls=100):
     geno, h1, h2, al, ml = helpers.hapmap_a_training()
     m = gpu.HLAModel(geno.shape[1], len(al), al)
