@@ -528,6 +528,7 @@ def run_b200_arm(args):
             "device": info,
         }
         emit(json.dumps(line))
+    hd.shutdown()
 
 
 def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):

@@ -89,3 +89,10 @@ def allreduce_partial(acc):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     return acc
+
+
+def shutdown():
+    """Tear the process group down (no-op on a single rank)."""
+    import torch.distributed as td
+    if td.is_available() and td.is_initialized():
+        td.destroy_process_group()
