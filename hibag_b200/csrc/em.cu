@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 	const int n_groups = (n2 + 31) >> 5;
 	int *coff = p.coff + (size_t)c * (p.n_entry + 1);
 	int *glen = p.glen + (size_t)c * n_groups;
-	cluster.sync();                             // all CTAs are running: remote shared memory is live
+	// one CTA per candidate (the dense shape with many lanes): a CTA barrier and plain shared-memory
+	// stores do what the cluster barrier and the DSMEM stores do for C > 1
+	auto csync = [&]() { if (C > 1) cluster.sync(); else __syncthreads(); };
+	csync();                                    // all CTAs are running: remote shared memory is live
 
 	// ---- (A) compact list of the compatible pairs of this CTA's slice, in pair order ------------
 	int jb_lo, jb_hi;
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 		const int cta_total = wsum[31];
 		const int start = incl - cnt + (warp ? wsum[warp - 1] : 0);
 		if (tid < C) cluster.map_shared_rank(tot, tid)[rank] = cta_total;
-		cluster.sync();
+		csync();
 		int base = 0;
 		for (int q = 0; q < rank; q++) base += tot[q];
 		jb_lo = base; jb_hi = base + cta_total;
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 		}
 		if (rank == C - 1 && tid == 0) coff[p.n_entry] = jb_hi;
 		if (tid == 0) sh_i[3] = 0;
-		cluster.sync();                            // (B) reads the jmap entries of every CTA's pairs
+		csync();                                   // (B) reads the jmap entries of every CTA's pairs
 	}
 	// ---- (B) ELL slots of the compatible contributions: a warp takes one haplotype of the groups
 	// dealt to this CTA at a time and walks its incidence list 128 contributions per step ---------
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 			if (lane == 0 && n > 0) atomicMax(&glen[gi], (n + 7) & ~7);
 		}
 	}
-	cluster.sync();        // compact lists, entry ranges, slots and group lengths of every CTA are in place
+	csync();               // compact lists, entry ranges, slots and group lengths of every CTA are in place
 	const int n_lg = (n_groups > rank) ? (n_groups - rank + C - 1) / C : 0;   // groups dealt to this CTA
 
 	/// M step of one group of 32 chains by one warp: every lane adds its own chain in the
@@ -608,7 +611,8 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 			const double f = __dmul_rn(acc, p.scale);
 			const int u = p.hap_sorted[r];
 			const size_t o = (size_t)(fr_new - fr0) + u;
-			for (int q = 0; q < C; q++) cluster.map_shared_rank(fr0, q)[o] = f;
+			if (C == 1) fr0[o] = f;
+			else for (int q = 0; q < C; q++) cluster.map_shared_rank(fr0, q)[o] = f;
 		}
 	};
 	EM_TICK(0);
@@ -672,13 +676,14 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 				const double bc = (double)(eg[k] >> 2);
 				ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
 				const double sc = __ddiv_rn(bc, psum);
-				for (int q = 0; q < C; q++) cluster.map_shared_rank(sck, q)[k] = sc;
+				if (C == 1) sck[k] = sc;
+				else for (int q = 0; q < C; q++) cluster.map_shared_rank(sck, q)[k] = sc;
 				k = kn; b = bn; e = en;
 			}
 		}
 		ll = block_sum_f64(ll, scratch);
 		if (tid < C) cluster.map_shared_rank(llp, tid)[(iter & 1) * MAX_CLUSTER + rank] = ll;
-		cluster.sync();        // scale factors and partial log-likelihoods of every CTA have landed
+		csync();               // scale factors and partial log-likelihoods of every CTA have landed
 		EM_TICK(2);
 		// (3) one thread per compatible pair, coalesced: its contribution r = x * (count / sum) goes
 		//     to the ELL slots of both of its haplotypes
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 				}
 			}
 		}
-		if (C > 1) cluster.sync(); else __syncthreads();   // the chains read every CTA's contributions
+		csync();               // the chains read every CTA's contributions
 		EM_TICK(3);
 		// ---- M step: a warp that owns a ring takes the next-longest group of 32 chains dealt to
 		// this CTA -----------------------------------------------------------------------------
@@ -722,7 +727,7 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 				chain_group(rank + C * i, fr_new);
 			}
 		}
-		cluster.sync();        // new frequencies have landed in every CTA
+		csync();               // new frequencies have landed in every CTA
 		EM_TICK(4);
 		iters = iter + 1;
 		// ---- stopping rule (:1236-1250) with the guard band of em.h; every CTA evaluates the

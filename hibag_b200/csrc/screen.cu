@@ -124,6 +124,7 @@ screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 	{
 		const int i0 = al_start[al], i1 = i0 + al_n[al];
 		double acc = 0.0;
+#pragma unroll 4
 		for (int i = i0; i < i1; i++)
 		{
 			HapRec<NW, false> h;
@@ -346,24 +347,10 @@ screen_need_kernel(const ScreenArgs a)
 		true_idx = true_cell_index(__ldg(a.a1 + samp), __ldg(a.a2 + samp), n);
 		thr = __dmul_rn(a.xref[(size_t)l * a.p_stride + pos], a.tau);
 	}
-	int al = 0, bl = 0;
-	double ua = ok ? U[pos] : 0.0;
-	for (int t0 = 0; t0 < n_cells; t0 += NEED_TILE)
+	// a tile of cell masks is flushed: one atomic per cell per LANE reserves the slots of the warp's
+	// positions, then the lanes append their positions
+	auto flush = [&](int t0, int nt)
 	{
-		const int nt = min(NEED_TILE, n_cells - t0);
-		for (int q = 0; q < nt; q++)
-		{
-			const double ub = ok ? U[(size_t)bl * a.p_stride + pos] : 0.0;
-			const double bd = screen_bound(ua, ub, a.K);
-			const bool need = ok && ((t0 + q) == true_idx || (bd >= thr && bd > 0.0));
-			const unsigned mask = __ballot_sync(0xffffffffu, need);
-			if (lane == 0) wm[q] = mask;
-			if (++bl == n)
-			{
-				al++; bl = al;
-				ua = (ok && al < n) ? U[(size_t)al * a.p_stride + pos] : 0.0;
-			}
-		}
 		__syncwarp();
 		for (int q = lane; q < nt; q += 32)
 		{
@@ -379,7 +366,35 @@ screen_need_kernel(const ScreenArgs a)
 				ent[(size_t)(t0 + q) * a.p_stride + wb[q] + __popc(m & lt)] = pos;
 		}
 		__syncwarp();
+	};
+	// cells in the blob's order (row al, columns bl >= al), eight per step so that the loads of the
+	// per-allele sums overlap (one dependent L2 round trip per cell otherwise)
+	int idx = 0, t0 = 0;
+	for (int al = 0; al < n; al++)
+	{
+		const double ua = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
+		for (int bl = al; bl < n; bl += 8)
+		{
+			const int nb = min(8, n - bl);
+			if (idx - t0 + nb > NEED_TILE) { flush(t0, idx - t0); t0 = idx; }
+			double ub[8];
+#pragma unroll
+			for (int q = 0; q < 8; q++) ub[q] = (ok && q < nb) ? U[(size_t)(bl + q) * a.p_stride + pos] : 0.0;
+#pragma unroll
+			for (int q = 0; q < 8; q++)
+			{
+				if (q < nb)                        // warp-uniform
+				{
+					const double bd = screen_bound(ua, ub[q], a.K);
+					const bool need = ok && ((idx + q) == true_idx || (bd >= thr && bd > 0.0));
+					const unsigned mask = __ballot_sync(0xffffffffu, need);
+					if (lane == 0) wm[idx + q - t0] = mask;
+				}
+			}
+			idx += nb;
+		}
 	}
+	if (idx > t0) flush(t0, idx - t0);
 }
 
 void launch_screen_need(const ScreenArgs &a, cudaStream_t st)
