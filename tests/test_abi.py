@@ -113,3 +113,27 @@ def test_default_mtry_rule():
     assert api.default_mtry(266) == 17 and api.default_mtry(500) == 23      # ceil(sqrt(n))
     assert api.default_mtry(100, "all") == 100 and api.default_mtry(100, "one") == 1
     assert api.default_mtry(100, 0.25) == 25 and api.default_mtry(10, 50) == 10
+
+
+def test_ctypes_mirrors_have_the_header_struct_sizes(built, tmp_path):
+    """hibag_b200/api.py mirrors the structs of include/hibag_b200.h by hand: compile the header as C
+    and compare sizeof (a missing field would let the library write past the Python object)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from hibag_b200 import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "hibag_b200.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(hibag_haplotype), sizeof(hibag_genotype), sizeof(hibag_gpu_ext_proc), '
+                   'sizeof(hibag_b200_train_opts), sizeof(hibag_b200_train_stats), sizeof(hibag_b200_predict_out), '
+                   'sizeof(hibag_b200_predict_stats)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes[0] == api.HAPLO_DT.itemsize and sizes[1] == api.GENO_DT.itemsize
+    assert sizes[2] == 10 * C.sizeof(C.c_void_p)
+    assert sizes[3] == C.sizeof(api.TrainOpts)
+    assert sizes[4] == C.sizeof(api.TrainStats)
+    assert sizes[5] == C.sizeof(api.PredictOut)
+    assert sizes[6] == C.sizeof(api.PredictStats)
