@@ -146,3 +146,58 @@ def test_certificate_is_monotone_sandwich():
             lo += 0.0 if skip[c] else x[c]
             hi += b[c] if skip[c] else x[c]
         assert lo <= full <= hi
+
+
+def _class_bounds(haplo, n_hla, n_snp, g, T, Tf, K3, k):
+    """The class-split bound of DESIGN.md 9 (not built on the device yet): per-allele sums split by
+    the haplotypes' alleles at the sample's first k heterozygous SNPs; a pair of classes (s, t) agrees
+    on k_eff - popc(s ^ t) of them, and every agreement on a heterozygous SNP is one more mismatch."""
+    H = _decode(haplo, n_snp)
+    f = haplo["freq"]
+    hom0, hom2 = g == 0, g == 2
+    het = np.nonzero(g == 1)[0][:k]
+    k_eff = len(het)
+    c = (H[:, hom0] == 1).sum(1) + (H[:, hom2] == 0).sum(1)
+    u = f * Tf[c]
+    cls = (H[:, het].astype(np.int64) << np.arange(k_eff)).sum(1) if k_eff else np.zeros(len(f), dtype=np.int64)
+    Uc = np.zeros((n_hla, 1 << k))
+    np.add.at(Uc, (haplo["hla"], cls), u)
+    M = np.array([[Tf[max(k_eff - bin(a ^ b).count("1"), 0)] for b in range(1 << k)] for a in range(1 << k)])
+    B = (Uc @ M @ Uc.T) * K3
+    iu = np.triu_indices(n_hla)
+    return B[iu]
+
+
+@pytest.mark.parametrize("n_snp", [5, 23, 40, 70])
+def test_class_split_bound_is_a_bound_and_tighter(consts, orc, n_snp):
+    """groundwork for the next screening level: the class-split bound holds
+    against every cell value of the oracle's chain, never exceeds the product bound by more than its
+    rounding slack, and keeps fewer cells at the in-bag threshold"""
+    T, Tf, K = consts
+    # T[d] <= kappa3 * T'[p] * T'[q] * T'[m] for p + q + m <= d, m <= 3 -- taken over the host table itself
+    suffix = np.maximum.accumulate(T[::-1])[::-1]
+    kappa3 = 1.0
+    for m in range(4):
+        p, q = np.meshgrid(np.arange(257), np.arange(257), indexing="ij")
+        ok = p + q + m <= 256
+        r = suffix[np.minimum(p + q + m, 256)][ok] / (Tf[p[ok]] * Tf[q[ok]] * Tf[m])
+        kappa3 = max(kappa3, float(r.max()))
+    assert kappa3 < 1 + 1e-6
+    K3 = 2.0 * kappa3 * (1 + 1e-8)
+    rng = np.random.default_rng(300 + n_snp)
+    haplo, n_hla, n_snp = helpers.random_haplo_list(rng, n_hla=9, n_snp=n_snp, max_per_allele=7)
+    geno = helpers.random_genotypes(rng, 100, n_snp, n_hla, haplo=haplo)
+    G = _genotype_rows(geno, n_snp)
+    p2, s2 = orc.post_prob2(haplo, n_hla, n_snp, geno)
+    pp = p2 * s2[:, None]
+    kept = {0: 0, 1: 0, 2: 0, 3: 0}
+    for s in range(len(geno)):
+        t1, t2 = sorted((int(geno["a1"][s]), int(geno["a2"][s])))
+        b0, xref = _bounds_and_xref(haplo, n_hla, n_snp, G[s], t1, t2, T, Tf, K)
+        kept[0] += int(((b0 >= xref * 2.0 ** -70) & (b0 > 0)).sum())
+        for k in (1, 2, 3):
+            bk = _class_bounds(haplo, n_hla, n_snp, G[s], T, Tf, K3, k)
+            assert np.all(pp[s] <= bk * (1 + 1e-12)), "a cell value exceeds its class-split bound"
+            assert np.all(bk <= b0 * (1 + 1e-6))
+            kept[k] += int(((bk >= xref * 2.0 ** -70) & (bk > 0)).sum())
+    assert kept[3] <= kept[2] <= kept[1] <= kept[0]
