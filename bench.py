@@ -410,9 +410,11 @@ def run_b200_arm(args):
                 "SNPs: the one-popcount distance) / its summed launch durations (CUDA events around the "
                 "kernel on its stream). POPC (XU pipe) and the lane-private LDS.64 table lookup co-bind at the "
                 "same 16 /clk/SM. *_reference_formulation counts the 4 POPC.32 per pair evaluation of the "
-                "reference's hamm_d (SURVEY.md 8d). The lanes' passes run on three streams and share the SMs "
-                "with each other and with other lanes' EM clusters, so a launch's duration is an upper bound "
-                "of the time it would take alone: frac is conservative. The gather form is ragged (a warp's "
+                "reference's hamm_d (SURVEY.md 8d). The lanes' passes run on six streams and share the SMs "
+                "with each other and with other lanes' EM CTAs (two of them take an SM's whole register file), so a "
+                "launch's CUDA-event duration is an upper bound of its kernel time: frac is conservative -- "
+                "'alone' holds the same launches with one classifier in flight (every launch alone on the GPU), "
+                "'in_bag_launches' the launches that carry the work. The gather form is ragged (a warp's "
                 "lanes are the samples that need the cell) and latency-bound on the small passes; the plain "
                 "kernel's fraction (every cell, full warps) is under roofline_unscreened and predict.roofline.",
         "peak_source": peak_src,
