@@ -25,6 +25,7 @@ import json
 import math
 import multiprocessing as mp
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -42,12 +43,37 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
-NCU_GATHER_DRAM_BYTES_PER_IB_LAUNCH = 141967872 + 124222208   # profiles/r01_gather_r2_ncu_raw.csv
+GATHER_NCU_CSV = ("r02_gather_ncu_raw.csv", "r01_gather_final_ncu_raw.csv")   # newest capture first
 LANES = 24           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
 WORKLOAD_JSON = os.path.join(ROOT, "profiles", "c2_workload.json")
 PEAKS_JSON = os.path.join(ROOT, "profiles", "pipe_peaks.json")
+
+
+def gather_traffic_from_ncu():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the largest cell_gather_kernel launch in the
+    committed `ncu --set full` capture (profiles/*.csv, --page raw --csv): bytes per launch"""
+    import csv
+    for name in GATHER_NCU_CSV:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        try:
+            kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        best = None
+        for r in rows[2:]:
+            if len(r) > wr and "cell_gather_kernel" in r[kn]:
+                b = float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
+                best = b if best is None or b > best else best
+        if best is not None:
+            return int(best), "profiles/" + name
+    return None, None
 
 
 def make_cohort():
@@ -119,24 +145,37 @@ def load_workload():
 
 
 def _ref_train_worker(args):
-    """One host process: the reference's BuildClassifiers (target 'max') on classifier `k` of the
-    workload until `budget` seconds have passed (checked at accepted SNPs); returns (k, accepted
-    SNPs, seconds, finished)."""
-    k, budget = args
+    """One host process: the reference's BuildClassifiers on classifier `k` of the workload until
+    `budget` seconds have passed (checked at accepted SNPs), verbose.detail on so that the accepted
+    SNPs (src/LibHLA.cpp:2104-2111) can be compared with the B200 model's; returns (k, number of
+    accepted SNPs, seconds, finished, cpu info, accepted SNP indices)."""
+    k, budget, target = args
     from oracle import refpy
     ref = refpy.RefLib()
-    info = ref.set_target("max")
+    info = ref.set_target(target)
     ref.set_gpu_procs(None)
     coh = make_cohort()
     m = ref.new_model()
     m.init_training(coh.geno, coh.h1, coh.h2, coh.n_hla)
+    fd, log = tempfile.mkstemp(suffix=".log")      # the reference prints through Rprintf -> fd 2
+    saved = os.dup(2)
+    os.dup2(fd, 2)
     ref.set_interrupt(seconds=budget)
     t0 = time.time()
-    rc = m.build(1, MTRY, prune=True, reseed_base=TRAIN_SEED, first_index=k, allow_interrupt=True)
-    dt = time.time() - t0
-    accepted = int(ref.lib.ref_interrupt_checks())
+    try:
+        rc = m.build(1, MTRY, prune=True, verbose=2, reseed_base=TRAIN_SEED, first_index=k, allow_interrupt=True)
+    finally:
+        dt = time.time() - t0
+        os.dup2(saved, 2)
+        os.close(fd); os.close(saved)
+    snps = []
+    for ln in open(log).read().splitlines():
+        mt = re.match(r"^\s*(\d+), SNP: (\d+), loss:", ln)
+        if mt:
+            snps.append(int(mt.group(2)) - 1)
+    os.unlink(log)
     ref.set_interrupt(0.0, -1)
-    return k, accepted, dt, rc == 0, info
+    return k, len(snps), dt, rc == 0, info, snps
 
 
 def _ref_predict_worker(args):
@@ -164,48 +203,78 @@ def _ref_predict_worker(args):
     return done, time.time() - t0
 
 
-def reference_train_rate(step, procs, budget, wl):
-    """classifiers/min of the reference CPU path with `procs` worker processes"""
+def reference_train_rate(step, procs, budget, wl, target="max", parity_worker=False):
+    """classifiers/min of the reference CPU path with `procs` worker processes; with
+    parity_worker one more process runs classifier 0 under target avx2 (== base, the parity
+    oracle) for the prefix check only"""
     n_tr = len(wl["classifiers"]) if wl else 0
     ks = [(step * procs + p) % max(n_tr, 1) for p in range(procs)]
-    with mp.get_context("spawn").Pool(procs) as pool:
-        res = pool.map(_ref_train_worker, [(k, budget) for k in ks])
+    jobs = [(k, budget, target) for k in ks] + ([(0, budget, "avx2")] if parity_worker else [])
+    with mp.get_context("spawn").Pool(len(jobs)) as pool:
+        res = pool.map(_ref_train_worker, jobs)
     rate, detail = 0.0, []
-    for k, accepted, dt, finished, info in res:
+    for k, accepted, dt, finished, info, snps in res[:procs]:
         if finished or not wl:
             est = dt
         else:
             tr = wl["classifiers"][k]
             cum = {a: p for a, p in tr["accepted_pairs"]}
-            part = cum.get(accepted) or cum.get(max(x for x in cum if x <= accepted), None)
+            part = cum.get(accepted) or cum.get(max([x for x in cum if x <= accepted] or [0]), None)
             est = dt * tr["total_pairs"] / part if part else float("nan")
-        rate += 60.0 / est
+        if est == est and est > 0:
+            rate += 60.0 / est
         detail.append(dict(classifier=k, accepted_snps=accepted, seconds=round(dt, 2),
-                           est_seconds_per_classifier=round(est, 1)))
-    return rate, detail, res[0][4]
+                           est_seconds_per_classifier=round(est, 1), snps=snps))
+    extra = [dict(classifier=r[0], snps=r[5], target="avx2") for r in res[procs:]]
+    return rate, detail, res[0][4], extra
 
 
-def cpu_baseline(procs, budget, wl, with_predict=True):
-    rate, detail, info = reference_train_rate(0, procs, budget, wl)
+def load_calibration():
+    """profiles/ref_full_classifier.json: one classifier of the workload timed to completion with
+    the reference (target max) in the build container vs the extrapolation of its 15 s prefix"""
+    path = os.path.join(ROOT, "profiles", "ref_full_classifier.json")
+    if os.path.exists(path):
+        c = json.load(open(path))
+        return "full classifier %.0f s vs extrapolated %.0f s (x%.2f), %s" % (
+            c["full_seconds"], c["extrapolated_seconds"], c["full_seconds"] / c["extrapolated_seconds"], c.get("where", ""))
+    return None
+
+
+def cpu_baseline(procs, budget, wl, with_predict=True, snp_lookup=None):
+    """the reference's CPU path on this box's host cores (bounded sample). snp_lookup(k) -> the B200
+    model's accepted SNPs of classifier k: the prefix the reference reached must equal them."""
+    rate, detail, info, extra = reference_train_rate(0, procs, budget, wl, parity_worker=snp_lookup is not None)
     out = {"value": rate, "unit": "classifiers/min", "cores": procs, "kind": "reference",
            "target": info,
-           "sample": "reference BuildClassifiers, kernel target max, %d worker processes x one classifier "
-                     "each for %.0f s (until the next accepted SNP), extrapolated by pair evaluations "
-                     "done / pair evaluations of the whole classifier (profiles/c2_workload.json)"
-                     % (procs, budget),
-           "per_process": detail[:4]}
+           "sample": "%d procs x 1 classifier x %.0f s of reference BuildClassifiers (target max), extrapolated by "
+                     "pair evaluations (profiles/c2_workload.json)" % (procs, budget),
+           "calibration": load_calibration(),
+           "per_process": [{k: v for k, v in dd.items() if k != "snps"} for dd in detail[:4]]}
+    if snp_lookup is not None:
+        ok, n_cmp, ok_max = True, 0, True
+        for dd in extra:                    # target avx2 == base: the parity oracle
+            mine = list(snp_lookup(dd["classifier"]))
+            ok = ok and len(dd["snps"]) > 0 and mine[:len(dd["snps"])] == dd["snps"]
+            n_cmp += len(dd["snps"])
+        for dd in detail:                   # target max (AVX-512 sums are reassociated: informative only)
+            mine = list(snp_lookup(dd["classifier"]))
+            ok_max = ok_max and mine[:len(dd["snps"])] == dd["snps"]
+        out["parity_prefix_ok"] = bool(ok)
+        out["parity_prefix_snps"] = n_cmp
+        out["parity_prefix_ok_target_max"] = bool(ok_max)
+        out["parity_prefix_snps_target_max"] = sum(len(dd["snps"]) for dd in detail)
     if with_predict and os.path.exists(os.path.join(ROOT, "tests", "golden", "c2_model.npz")):
         with mp.get_context("spawn").Pool(procs) as pool:
             res = pool.map(_ref_predict_worker, [(p, budget / 2) for p in range(procs)])
-        out["predict_value"] = sum(d / t for d, t in res)
+        out["predict_value"] = sum(dn / t for dn, t in res)
         out["predict_unit"] = "samples/s"
         out["predict_sample"] = "%d samples over %d processes, 100-classifier model" % (
-            sum(d for d, _ in res), procs)
+            sum(dn for dn, _ in res), procs)
     return out
 
 
 def run_reference_arm(args):
-    rank, local_rank, world = int(os.environ.get("RANK", 0)), 0, int(os.environ.get("WORLD_SIZE", 1))
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
     wl = load_workload()
@@ -213,28 +282,129 @@ def run_reference_arm(args):
     rates, detail, info = [], None, ""
     t0 = time.time()
     for s in range(args.warmup):
-        reference_train_rate(s, procs, min(args.cpu_seconds, 5.0), wl)
+        reference_train_rate(s, procs, min(args.cpu_seconds, 3.0), wl)
     tw = time.time()
     for s in range(args.steps):
-        r, detail, info = reference_train_rate(args.warmup + s, procs, args.cpu_seconds, wl)
+        r, detail, info, _ = reference_train_rate(args.warmup + s, procs, args.cpu_seconds, wl)
         rates.append(r)
+    timed = time.time() - tw
     value = float(np.mean(rates))
-    line = {
+    full = {
         "impl": "reference", "metric": "classifiers/min trained (HLA-A 5k x 500 SNP)", "value": value,
         "unit": "classifiers/min", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 60000.0 / value * procs if value > 0 else None, "higher_is_better": True,
+        # the arm's real wall clock per step (a step = one bounded sample on every host core)
+        "ms_per_step": 1e3 * timed / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, args.lanes or default_lanes(args.gpus)),
         "cpu_baseline": {"value": value, "unit": "classifiers/min", "cores": procs, "kind": "reference",
                          "target": info,
-                         "sample": "per step: %d worker processes x one classifier each for %.0f s of the "
-                                   "reference BuildClassifiers (target max), extrapolated by pair "
-                                   "evaluations" % (procs, args.cpu_seconds),
-                         "per_process": (detail or [])[:4]},
+                         "sample": "per step: %d procs x 1 classifier x %.0f s of reference BuildClassifiers (target "
+                                   "max), extrapolated by pair evaluations" % (procs, args.cpu_seconds),
+                         "calibration": load_calibration(),
+                         "extrapolated_seconds_per_classifier": 60.0 * procs / value if value > 0 else None,
+                         "per_process": [{k: v for k, v in dd.items() if k != "snps"} for dd in (detail or [])[:4]]},
         "e2e": {"value": value, "unit": "classifiers/min", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": round(time.time() - t0, 1), "timed_wall_s": round(time.time() - tw, 1),
+        "wall_s": round(time.time() - t0, 1), "timed_wall_s": round(timed, 1),
     }
+    side = write_detail(full, args.gpus)
+    line = compact_line(full)
+    line["detail_file"] = side
     emit(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# the stdout line: bounded (< 4 KB), flat scalars under the contract's keys; everything else goes
+# to gpurun_out/bench_detail_n<N>.json and stderr
+# ---------------------------------------------------------------------------------------------
+LINE_LIMIT = 4096
+
+
+def _short(v, n=120):
+    if isinstance(v, str):
+        return v if len(v) <= n else v[:n - 3] + "..."
+    if isinstance(v, float):
+        return float("%.6g" % v)
+    return v
+
+
+def _flat(dst, src, keys, prefix=""):
+    for k in keys:
+        if src and src.get(k) is not None and not isinstance(src.get(k), (dict, list)):
+            dst[prefix + k] = _short(src[k])
+
+
+def compact_line(detail):
+    """The contract's keys with flat scalar members only; never longer than LINE_LIMIT bytes
+    (tests/test_bench_contract.py)."""
+    line = {k: _short(detail.get(k)) for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                                               "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                                               "gpu_launches")}
+    if detail.get("impl"):
+        line["impl"] = detail["impl"]
+    cfg = detail.get("config") or {}
+    line["config"] = {k: _short(v) for k, v in cfg.items() if not isinstance(v, (dict, list))}
+    if detail.get("clocks"):
+        c = detail["clocks"]
+        line["clocks"] = {k: c.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w_max") if k in c}
+    e = {}
+    _flat(e, detail.get("e2e"), ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "api"))
+    hooks, pred = detail.get("e2e_legacy_hooks"), detail.get("predict")
+    if hooks:
+        e["legacy_hooks_value"] = _short(hooks.get("value"))
+    if pred:
+        e["predict_value"] = _short(pred.get("value"))
+        e["predict_e2e_value"] = _short((pred.get("e2e") or {}).get("value"))
+        e["predict_unit"] = pred.get("unit")
+        for k in ("sharded_by_classifier_value", "allreduce_ms", "allreduce_bytes"):
+            if pred.get(k) is not None:
+                e["predict_" + k] = _short(pred[k])
+    line["e2e"] = e or None
+    r = {}
+    rf = detail.get("roofline")
+    _flat(r, rf, ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic", "avg_launch_ms", "launches",
+                  "pair_evals_per_s", "frac_reference_formulation", "fp64_frac", "peak_source", "timing"))
+    if rf:
+        _flat(r, rf.get("in_bag_launches"), ("frac", "avg_launch_ms"), "in_bag_")
+        _flat(r, rf.get("out_of_bag_launches"), ("frac", "avg_launch_ms"), "out_of_bag_")
+        _flat(r, rf.get("alone"), ("frac", "in_bag_frac"), "alone_")
+        _flat(r, rf.get("screening"), ("executed_fraction", "effective_frac_reference_formulation"), "screen_")
+        _flat(r, rf.get("em"), ("frac", "achieved", "peak", "unit", "sm_time_share"), "em_")
+        _flat(r, rf.get("sm_time"), ("scoring_share", "em_share", "other_share", "busy"), "sm_time_")
+    if detail.get("roofline_unscreened"):
+        r["unscreened_frac"] = _short(detail["roofline_unscreened"].get("frac"))
+    if pred and pred.get("roofline"):
+        r["predict_frac"] = _short(pred["roofline"].get("frac"))
+    line["roofline"] = r or None
+    c = {}
+    cb = detail.get("cpu_baseline")
+    _flat(c, cb, ("value", "unit", "cores", "kind", "target", "sample", "predict_value", "predict_unit",
+                  "parity_prefix_ok", "parity_prefix_snps", "calibration"))
+    line["cpu_baseline"] = c or None
+    # hard bound: drop the longest strings first, then optional members
+    def size():
+        return len(json.dumps(line))
+    for key, sub in (("cpu_baseline", "sample"), ("roofline", "peak_source"), ("config", "l2"), ("e2e", "api"),
+                     ("roofline", "timing"), ("config", "workload")):
+        if size() <= LINE_LIMIT:
+            break
+        if line.get(key) and sub in line[key]:
+            line[key][sub] = _short(line[key][sub], 48)
+    assert size() <= LINE_LIMIT, size()
+    return line
+
+
+def write_detail(detail, world):
+    """full record -> gpurun_out/bench_detail_n<N>.json (+ stderr); returns the relative path"""
+    rel = os.path.join("gpurun_out", "bench_detail_%sn%d.json" % ("ref_" if detail.get("impl") else "", world))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, rel), "w") as f:
+            json.dump(detail, f, indent=1)
+    except OSError:
+        rel = None
+    sys.stderr.write("bench detail: " + json.dumps(detail) + "\n")
+    sys.stderr.flush()
+    return rel
 
 
 _REAL_STDOUT = None
@@ -248,20 +418,25 @@ def emit(text):
 
 def default_lanes(world):
     """classifiers in flight per GPU: enough to cover the per-round latency chain of a lane (EM
-    launch, two scoring passes, host decisions); bounded by the host cores a rank can count on"""
+    launch, two scoring passes, host decisions). The SAME at every N (weak scaling of one per-GPU
+    configuration): the lanes block on CUDA events, so they do not need a host core each."""
+    return LANES
+
+
+def default_threads(world, lanes):
+    """host threads per rank handed to the trainer (split over the lanes' pools): two per lane when
+    the rank can count on that many cores, one per lane otherwise"""
     cores = max(1, (os.cpu_count() or 1) // max(world, 1))
-    return max(4, min(LANES, 2 * cores))
+    return 2 * lanes if cores >= 12 else lanes
 
 
 def workload_config(n_gpus, lanes):
-    return {"workload": "synthetic HLA-A training: 5000 samples x 500 SNPs, 34 alleles (40 drawn), "
-                        "cohort seed 1, mtry 23, prune, %d classifiers per GPU per step, all in flight "
-                        "(per-classifier seed %d + index)" % (lanes, TRAIN_SEED),
-            "n_samp": N_SAMP, "n_snp": N_SNP, "mtry": MTRY, "parallelism": "classifier-sharded x%d" % n_gpus,
-            "lanes": lanes,
-            "l2": "inputs larger than L2: the lanes' cell matrices, need lists and bound tables (each lane "
-                  "~0.5 GB per selection round: 23 candidate lists x 595 cells x 1,840-3,160 samples) are "
-                  "rebuilt every round, so nothing is reused from L2 between timed steps"}
+    return {"workload": "configs[1]: synthetic HLA-A training 5000 samples x 500 SNPs, 34 alleles, mtry 23, prune; "
+                        "step = %d classifiers/GPU" % lanes,
+            "n_samp": N_SAMP, "n_snp": N_SNP, "n_hla": 34, "mtry": MTRY, "cohort_seed": COHORT_SEED,
+            "train_seed": TRAIN_SEED, "parallelism": "classifier-sharded x%d" % n_gpus,
+            "lanes": lanes, "classifiers_per_step": lanes * n_gpus,
+            "l2": "inputs > L2: each lane rebuilds ~0.5 GB of cell matrix, need lists, bounds per selection round"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -281,9 +456,7 @@ def run_b200_arm(args):
     lanes = args.lanes
     if not lanes:
         lanes = default_lanes(world)
-    n_threads = args.threads
-    if not n_threads:
-        n_threads = max(2 * lanes, ((os.cpu_count() or 1) // max(world, 1)) * 3 // 2)
+    n_threads = args.threads or default_threads(world, lanes)
 
     coh = make_cohort()
     geno = np.ascontiguousarray(coh.geno, dtype=np.int8)
@@ -421,9 +594,10 @@ def run_b200_arm(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of one in-bag launch (ncu --set full,
         # profiles/r01_gather_r2_ncu_raw.csv): the surviving entries of the cell matrix written once and
         # the need lists read once; the path is not HBM-bound
-        "traffic": NCU_GATHER_DRAM_BYTES_PER_IB_LAUNCH,
-        "traffic_note": "bytes per in-bag launch of selection round ~30 of one classifier (1.44 ms, 142 MB "
-                        "read + 124 MB written), from the ncu capture in profiles/; the launches of a step differ in size",
+        "traffic": gather_traffic_from_ncu()[0],
+        "traffic_note": "dram bytes read + written by the largest in-bag gather launch of the ncu --set full capture "
+                        "%s (a late selection round of one classifier); the launches of a step differ in "
+                        "size" % gather_traffic_from_ncu()[1],
         "fp64_frac": pair_rate * 3 / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9),
         "em_kernel_ms": d["em_kernel_ms"],
     }
@@ -496,13 +670,20 @@ def run_b200_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_baseline(args.cpu_procs or os.cpu_count() or 1, args.cpu_seconds, load_workload())
+            # classifiers 0..lanes-1 were built by warm-up step 0 (rank 0): the reference's accepted-SNP
+            # prefixes of the same classifiers must equal them
+            def snp_lookup(k):
+                return [int(x) for x in model.classifier(k)["snpidx"]] if k < model.num_classifiers() and args.warmup > 0 else []
+            cpu = cpu_baseline(args.cpu_procs or os.cpu_count() or 1, args.cpu_seconds, load_workload(),
+                               snp_lookup=snp_lookup if args.warmup > 0 else None)
         except Exception as ex:        # the checker library may be absent on some boxes
             cpu = {"value": None, "unit": "classifiers/min", "cores": 0, "kind": "reference",
                    "sample": "unavailable: %s" % ex}
 
     if rank == 0:
-        line = {
+        n_snps = [len(model.classifier(k)["snpidx"]) for k in range(model.num_classifiers())]
+        n_haps = [len(model.classifier(k)["freq"]) for k in range(model.num_classifiers())]
+        detail = {
             "metric": "classifiers/min trained (HLA-A 5k x 500 SNP)", "value": value,
             "unit": "classifiers/min", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -524,11 +705,15 @@ def run_b200_arm(args):
                 "ib_evals": int(d["n_ib_evals"]), "em_runs": int(d["n_em"]),
                 "h2d_bytes_per_step": int(d["h2d_bytes"] / args.steps),
                 "d2h_bytes_per_step": int(d["d2h_bytes"] / args.steps), "wall_s": wall,
-                "classifiers": [dict(zip(("n_snp", "n_haplo"), (len(model.classifier(k)["snpidx"]),
-                                                                 len(model.classifier(k)["freq"]))))
-                                for k in range(model.num_classifiers())]},
+                "classifiers": {"count": len(n_snps), "n_snp_mean": float(np.mean(n_snps)), "n_snp_min": int(min(n_snps)),
+                                "n_snp_max": int(max(n_snps)), "n_haplo_mean": float(np.mean(n_haps)),
+                                "n_haplo_min": int(min(n_haps)), "n_haplo_max": int(max(n_haps))}},
             "device": info,
         }
+        # the full record goes to a side file (and stderr); stdout carries ONE bounded line
+        side = write_detail(detail, world)
+        line = compact_line(detail)
+        line["detail_file"] = side
         emit(json.dumps(line))
     hd.shutdown()
 
