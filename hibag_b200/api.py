@@ -73,6 +73,7 @@ EXPORTS = [
     "hibag_b200_model_train", "hibag_b200_model_train_stats", "hibag_b200_model_train_trace",
     "hibag_b200_model_num_classifiers", "hibag_b200_model_clear",
     "hibag_b200_model_classifier_info", "hibag_b200_model_classifier_get",
+    "hibag_b200_model_classifier_samp_num_len",
     "hibag_b200_model_add_classifier", "hibag_b200_model_predict",
     "hibag_b200_model_predict_device", "hibag_b200_model_predict_stats",
     "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
@@ -309,11 +310,12 @@ class HLAModel:
         ns, nh, acc = C.c_int(), C.c_int(), C.c_double()
         _chk(lib().hibag_b200_model_classifier_info(self._h, k, C.byref(ns), C.byref(nh), C.byref(acc)))
         snpidx = np.zeros(ns.value, dtype=np.int32)
-        samp = np.zeros(max(self.n_samp, 1), dtype=np.int32)
+        n_sn = lib().hibag_b200_model_classifier_samp_num_len(self._h, k)
+        samp = np.zeros(max(n_sn, 1), dtype=np.int32)
         freq = np.zeros(nh.value); hla = np.zeros(nh.value, dtype=np.int32)
         packed = np.zeros((nh.value, 2), dtype=np.uint64)
         _chk(lib().hibag_b200_model_classifier_get(self._h, k, _p(snpidx), _p(samp), _p(freq), _p(hla), _p(packed)))
-        return dict(snpidx=snpidx, samp_num=samp[:self.n_samp], freq=freq, hla=hla, packed=packed,
+        return dict(snpidx=snpidx, samp_num=samp[:max(n_sn, 0)], freq=freq, hla=hla, packed=packed,
                     oob_acc=acc.value)
 
     def add_classifier(self, snpidx, freq, hla, packed, samp_num=None, oob_acc=0.0):
@@ -358,8 +360,12 @@ class HLAModel:
             self._h, C.c_void_p(geno_ptr), n_samp, C.c_void_p(snp_weight_ptr) if snp_weight_ptr else None,
             C.c_void_p(acc_ptr), C.c_void_p(stream) if stream else None, int(sync)))
 
-    # reference hlaModelToObj / hlaModelFromObj (R/HIBAG.R:1041-1178): the interchange format
+    # reference hlaModelToObj / hlaModelFromObj (R/HIBAG.R:1041-1178): the interchange format of
+    # trained models (C side: HIBAG_GetClassifierList / HIBAG_NewClassifierHaplo, src/HIBAG.cpp:817-958)
     def to_obj(self):
+        """The "hlaAttrBagObj" list as a dict: n_samp, n_snp, hla_allele, snp_id, classifiers =
+        [{samp_num, snpidx (1-based), haplos {freq, hla (labels), haplo ("0101.." strings)},
+        outofbag_acc}]."""
         cls = []
         for k in range(self.num_classifiers()):
             c = self.classifier(k)
@@ -367,19 +373,137 @@ class HLAModel:
                             haplos=dict(freq=c["freq"], hla=[self.hla_allele[i] for i in c["hla"]],
                                         haplo=[_bits(p, len(c["snpidx"])) for p in c["packed"]]),
                             outofbag_acc=c["oob_acc"]))
-        return dict(n_samp=self.n_samp, n_snp=self.n_snp, hla_allele=self.hla_allele,
+        return dict(n_samp=self.n_samp, n_snp=self.n_snp, hla_allele=list(self.hla_allele),
                     snp_id=self.snp_id, classifiers=cls)
 
     @staticmethod
     def from_obj(obj):
         m = HLAModel(obj["n_snp"], len(obj["hla_allele"]), obj["hla_allele"], obj.get("snp_id"))
-        m.n_samp = int(obj.get("n_samp", 0))
+        m.n_samp = int(obj.get("n_samp") or 0)
+        alleles = [str(a) for a in obj["hla_allele"]]
         for c in obj["classifiers"]:
-            hla = [obj["hla_allele"].index(x) for x in c["haplos"]["hla"]]
-            packed = np.array([_unbits(s) for s in c["haplos"]["haplo"]], dtype=np.uint64).reshape(-1, 2)
-            m.add_classifier(np.asarray(c["snpidx"]) - 1, c["haplos"]["freq"], hla, packed,
-                             samp_num=c.get("samp_num"), oob_acc=float(c.get("outofbag_acc", 0)))
+            hla = [alleles.index(str(x)) for x in c["haplos"]["hla"]]
+            strs = list(c["haplos"]["haplo"])
+            n_snp_c = len(np.atleast_1d(c["snpidx"]))
+            if any(len(st) != n_snp_c for st in strs):
+                raise ValueError("from_obj: haplotype string length differs from the number of SNPs")
+            packed = np.array([_unbits(st) for st in strs], dtype=np.uint64).reshape(-1, 2)
+            sn = c.get("samp_num")
+            if sn is not None and len(sn) == 0:
+                sn = None
+            if sn is not None and m.n_samp and len(sn) != m.n_samp:
+                raise ValueError("from_obj: samp_num has %d entries, the model %d samples" % (len(sn), m.n_samp))
+            m.add_classifier(np.atleast_1d(np.asarray(c["snpidx"])) - 1, c["haplos"]["freq"], hla, packed,
+                             samp_num=sn, oob_acc=float(c.get("outofbag_acc", 0)))
         return m
+
+    # ---- on-disk forms ------------------------------------------------------------------------
+    def save(self, path):
+        """Write the model: *.json = the hlaAttrBagObj dict as JSON (frequencies as C99 hex floats, so
+        the round trip is bit-exact); anything else = NumPy .npz (flat arrays with offsets)."""
+        obj = self.to_obj()
+        if str(path).endswith(".json"):
+            import json
+            js = dict(format="hibag_b200.hlaAttrBagObj/1", n_samp=int(obj["n_samp"]), n_snp=int(obj["n_snp"]),
+                      hla_allele=[str(a) for a in obj["hla_allele"]],
+                      snp_id=None if obj["snp_id"] is None else [str(x) for x in obj["snp_id"]],
+                      classifiers=[dict(samp_num=[int(x) for x in c["samp_num"]],
+                                        snpidx=[int(x) for x in c["snpidx"]],
+                                        haplos=dict(freq=[float(x).hex() for x in c["haplos"]["freq"]],
+                                                    hla=[str(x) for x in c["haplos"]["hla"]],
+                                                    haplo=list(c["haplos"]["haplo"])),
+                                        outofbag_acc=float(c["outofbag_acc"]).hex()) for c in obj["classifiers"]])
+            with open(path, "w") as f:
+                json.dump(js, f)
+            return
+        cls = [self.classifier(k) for k in range(self.num_classifiers())]
+        cat = lambda key, dt: np.concatenate([np.asarray(c[key], dtype=dt).reshape(-1) for c in cls]) \
+            if cls else np.zeros(0, dtype=dt)
+        np.savez_compressed(
+            path, format=np.array("hibag_b200.model/1"), n_snp=np.int64(self.n_snp), n_samp=np.int64(self.n_samp),
+            hla_allele=np.array([str(a) for a in self.hla_allele]),
+            snp_id=np.array([] if self.snp_id is None else [str(x) for x in self.snp_id]),
+            snp_off=np.cumsum([0] + [len(c["snpidx"]) for c in cls]), snpidx=cat("snpidx", np.int32),
+            hap_off=np.cumsum([0] + [len(c["freq"]) for c in cls]), freq=cat("freq", np.float64),
+            hla=cat("hla", np.int32), packed=cat("packed", np.uint64).reshape(-1, 2),
+            samp_off=np.cumsum([0] + [len(c["samp_num"]) for c in cls]), samp_num=cat("samp_num", np.int32),
+            oob_acc=np.array([c["oob_acc"] for c in cls], dtype=np.float64))
+
+    @staticmethod
+    def load(path):
+        """Read a model written by save() (.json / .npz) or an R workspace (.RData/.rdata/.rda/.rds-less
+        RDX2 stream) holding one hlaAttrBagObj -- see hlaModelFromRData for workspaces with several."""
+        p = str(path)
+        if p.endswith(".json"):
+            import json
+            js = json.load(open(p))
+            for c in js["classifiers"]:
+                c["haplos"]["freq"] = [float.fromhex(x) for x in c["haplos"]["freq"]]
+                c["outofbag_acc"] = float.fromhex(c["outofbag_acc"])
+            return HLAModel.from_obj(js)
+        if p.lower().endswith((".rdata", ".rda")):
+            return hlaModelFromRData(p)
+        z = np.load(p, allow_pickle=False)
+        alleles = [str(a) for a in z["hla_allele"]]
+        m = HLAModel(int(z["n_snp"]), len(alleles), alleles, [str(x) for x in z["snp_id"]] or None)
+        m.n_samp = int(z["n_samp"])
+        for k in range(len(z["oob_acc"])):
+            a, b = z["snp_off"][k:k + 2]; q, r = z["hap_off"][k:k + 2]; u, v = z["samp_off"][k:k + 2]
+            m.add_classifier(z["snpidx"][a:b], z["freq"][q:r], z["hla"][q:r], z["packed"][q:r],
+                             samp_num=z["samp_num"][u:v] if v > u else None, oob_acc=float(z["oob_acc"][k]))
+        return m
+
+
+def _find_model_objs(obj, path=()):
+    """(path, RObj) of every hlaAttrBagObj-shaped list inside a loaded R workspace"""
+    from . import rdx2
+    out = []
+    if isinstance(obj, rdx2.RObj) and isinstance(obj.value, list) and obj.names():
+        names = obj.names()
+        if "classifiers" in names and "hla.allele" in names and "n.snp" in names:
+            return [(path, obj)]
+        for nm, v in zip(names, obj.value):
+            out += _find_model_objs(v, path + (nm,))
+    return out
+
+
+def hlaModelFromRData(path, name=None):
+    """Load a pre-fit model from an R workspace without R (reference: load() + hlaModelFromObj,
+    R/HIBAG.R:1135-1178; e.g. inst/extdata/ModelList.RData holds `modellist$A`). `name` selects
+    the object ("modellist/A" or just "A") when the file holds several."""
+    from . import rdx2
+    ws = rdx2.load(path)
+    found = []
+    for top, val in ws.items():
+        found += _find_model_objs(val, (top,))
+    if name is not None:
+        found = [f for f in found if "/".join(f[0]) == name or f[0][-1] == name]
+    if len(found) != 1:
+        raise ValueError("hlaModelFromRData: %d model objects match in %s (%s)" % (
+            len(found), path, ", ".join("/".join(f[0]) for f in found)))
+    A = found[0][1]
+    vec = lambda o: list(o.value) if isinstance(o.value, list) else o.value
+    cls = []
+    for c in A["classifiers"].value:
+        h = c["haplos"]
+        cls.append(dict(samp_num=np.asarray(c["samp.num"].value, dtype=np.int32),
+                        snpidx=np.asarray(c["snpidx"].value, dtype=np.int32),
+                        haplos=dict(freq=np.asarray(h["freq"].value, dtype=np.float64), hla=vec(h["hla"]),
+                                    haplo=vec(h["haplo"])),
+                        outofbag_acc=float(c["outofbag.acc"].value[0])))
+    obj = dict(n_samp=int(A["n.samp"].value[0]), n_snp=int(A["n.snp"].value[0]),
+               hla_allele=[str(a) for a in A["hla.allele"].value], snp_id=[str(x) for x in vec(A["snp.id"])],
+               classifiers=cls)
+    m = HLAModel.from_obj(obj)
+    names = A.names()
+    m.sample_id = vec(A["sample.id"]) if "sample.id" in names else None
+    m.snp_position = np.asarray(A["snp.position"].value) if "snp.position" in names else None
+    m.hla_locus = A["hla.locus"].value[0] if "hla.locus" in names else None
+    return m
+
+
+hlaModelToObj = HLAModel.to_obj
+hlaModelFromObj = HLAModel.from_obj
 
 
 def _bits(p, n):

@@ -197,6 +197,12 @@ int hibag_b200_model_classifier_info(const hibag_b200_model *m, int k, int *n_sn
 	});
 }
 
+int hibag_b200_model_classifier_samp_num_len(const hibag_b200_model *m, int k)
+{
+	if (!m || k < 0 || k >= (int)m->cls.size()) return -1;
+	return (int)m->cls[k].samp_num.size();
+}
+
 int hibag_b200_model_classifier_get(const hibag_b200_model *m, int k, int32_t *snpidx,
 	int32_t *samp_num, double *freq, int32_t *hla, uint64_t *packed)
 {

@@ -978,7 +978,11 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	if (m_warps > max_rings) m_warps = max_rings;
 	if (m_warps < 1) throw std::runtime_error("run_em: list too large for the device EM");
 	a.m_warps = m_warps;
-	const size_t smem = smem_base + ring_b * (size_t)m_warps;
+	size_t smem = smem_base + ring_b * (size_t)m_warps;
+	// HIBAG_B200_EM_SMEM_KB: pad the request so that fewer EM CTAs fit an SM (116: one per SM) and the
+	// scoring CTAs of other lanes always find room beside them
+	static const int pad_kb = []() { const char *e = getenv("HIBAG_B200_EM_SMEM_KB"); return e ? atoi(e) : 0; }();
+	if (pad_kb > 0 && smem < (size_t)pad_kb * 1024) smem = std::min((size_t)pad_kb * 1024, (size_t)220 * 1024);
 	// SMs per candidate: enough pairs per CTA to pay for the cluster barriers, and the whole
 	// round on at most ~half of the SMs (the other lanes' scoring launches run beside it; the
 	// kernel is latency-bound, so SM-time per candidate is lowest for small clusters)

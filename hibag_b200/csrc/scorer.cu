@@ -470,8 +470,49 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		max_ctas = (long long)(evals_per_list_[kind] * 1.5 * count / 4e5) + di.sm_count / 2;
 		if (max_ctas < di.sm_count) max_ctas = di.sm_count;
 	}
-	ScoreQueue &q = ScoreQueue::get(queue_id_);
 	int nw;
+	static const int excl = []() { const char *e = getenv("HIBAG_B200_GATHER_EXCL"); return e ? atoi(e) : 0; }();
+	if (excl)
+	{
+		// the small kernels of the pass run on this lane's own stream; only the gather launch goes
+		// to the device's ONE exclusive scoring stream, so that gather launches of different lanes
+		// never overlap each other: each has the GPU's scoring resources to itself and the CUDA
+		// events around it time it alone
+		cudaStream_t s = st_.s;
+		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * MAX_BATCH_LISTS, s));
+		HB_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * (size_t)count * n_cells, s));
+		HB_CUDA(cudaEventRecord(ev0_.e, s));
+		launch_screen_bound(a, ls, s);
+		launch_screen_need(a, s);
+		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks,
+			di.sm_count * 32, s);
+		HB_CUDA(cudaEventRecord(ev_up_.e, s));
+		// HIBAG_B200_GATHER_OOB: 0 out-of-bag launches share the exclusive stream, 1 their own exclusive
+		// stream (they are latency-bound and small: they run beside the in-bag launches), 2 the lane's
+		// own stream (also concurrent with each other)
+		static const int oob_mode = []() { const char *e = getenv("HIBAG_B200_GATHER_OOB"); return e ? atoi(e) : 0; }();
+		if (kind == 0 && oob_mode == 2)
+		{
+			HB_CUDA(cudaEventRecord(ev_g0_.e, s));
+			nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
+			HB_CUDA(cudaEventRecord(ev_g1_.e, s));
+		} else {
+			ScoreQueue &q = ScoreQueue::get((kind == 0 && oob_mode == 1) ? 62 : 63);
+			std::lock_guard<std::mutex> lk(q.mu);
+			HB_CUDA(cudaStreamWaitEvent(q.st.s, ev_up_.e, 0));
+			HB_CUDA(cudaEventRecord(ev_g0_.e, q.st.s));
+			nw = launch_cell_gather(gb, di.sm_count, q.st.s, (excl > 1 || kind == 0) ? max_ctas : 0);
+			HB_CUDA(cudaEventRecord(ev_g1_.e, q.st.s));
+			HB_CUDA(cudaStreamWaitEvent(s, ev_g1_.e, 0));
+		}
+		if (kind == 0)
+			launch_reduce_oob_screened(a, d_counts_.get() + first, s);
+		else
+			launch_reduce_ib_screened(a, ls, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+		HB_CUDA(cudaEventRecord(ev1_.e, s));
+		HB_CUDA(cudaEventRecord(ev_up_.e, s));
+	} else {
+	ScoreQueue &q = ScoreQueue::get(queue_id_);
 	{
 		std::lock_guard<std::mutex> lk(q.mu);
 		cudaStream_t s = q.st.s;
@@ -494,6 +535,7 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	}
 	HB_CUDA(cudaStreamWaitEvent(st_.s, ev1_.e, 0));
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
+	}
 	stats.launches += 5; stats.cell_launches += 1;
 	stats.pair_evals_nominal += pairs * (uint64_t)n_pos;
 	(void)nw;

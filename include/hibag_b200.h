@@ -198,8 +198,11 @@ int hibag_b200_model_num_classifiers(const hibag_b200_model *m);
 int hibag_b200_model_clear(hibag_b200_model *m);
 int hibag_b200_model_classifier_info(const hibag_b200_model *m, int k, int *n_snp,
 	int *n_haplo, double *oob_acc);
-/* snpidx[n_snp] 0-based, samp_num[n_samp] (may be NULL), freq[n_haplo], hla[n_haplo],
- * packed[n_haplo][2] with bits >= n_snp cleared */
+/* number of bootstrap counts classifier k carries (the n_samp it was trained on or loaded with;
+ * 0 when none), i.e. the ints hibag_b200_model_classifier_get writes into samp_num; < 0: error */
+int hibag_b200_model_classifier_samp_num_len(const hibag_b200_model *m, int k);
+/* snpidx[n_snp] 0-based, samp_num[hibag_b200_model_classifier_samp_num_len()] (may be NULL),
+ * freq[n_haplo], hla[n_haplo], packed[n_haplo][2] with bits >= n_snp cleared */
 int hibag_b200_model_classifier_get(const hibag_b200_model *m, int k, int32_t *snpidx,
 	int32_t *samp_num, double *freq, int32_t *hla, uint64_t *packed);
 /* reference HIBAG_NewClassifierHaplo / CAttrBag_Classifier::Assign, src/LibHLA.cpp:2142 */
