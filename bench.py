@@ -203,40 +203,69 @@ def _ref_predict_worker(args):
     return done, time.time() - t0
 
 
+TIME_PROFILE_JSON = os.path.join(ROOT, "profiles", "ref_time_profile.json")
+
+
+def load_time_profile():
+    if os.path.exists(TIME_PROFILE_JSON):
+        return json.load(open(TIME_PROFILE_JSON))
+    return None
+
+
 def reference_train_rate(step, procs, budget, wl, target="max", parity_worker=False):
-    """classifiers/min of the reference CPU path with `procs` worker processes; with
-    parity_worker one more process runs classifier 0 under target avx2 (== base, the parity
-    oracle) for the prefix check only"""
+    """classifiers/min of the reference CPU path with `procs` worker processes, each growing one
+    classifier of the workload for `budget` seconds (until the next accepted SNP). The prefix is
+    extrapolated to the whole classifier with the reference's own TIME PROFILE of that classifier
+    (profiles/ref_time_profile.json: seconds at every accepted SNP and to completion, measured once
+    with the same binary and target): est = t_box(n) * T_full / T(n). Round 1 extrapolated by pair
+    evaluations, which overestimates the classifier 2.4x (early rounds run short lists at a far
+    lower pair rate; profiles/ref_full_classifier.json) -- kept only as the fallback for classifiers
+    without a profile. With parity_worker one more process runs classifier 0 under target avx2
+    (== base, the parity oracle) for the prefix check only."""
+    prof = (load_time_profile() or {}).get("classifiers", {}) if target == "max" else {}
+    cal = sorted(int(k) for k in prof)
     n_tr = len(wl["classifiers"]) if wl else 0
-    ks = [(step * procs + p) % max(n_tr, 1) for p in range(procs)]
+    if cal:
+        ks = [cal[(step * procs + p) % len(cal)] for p in range(procs)]
+    else:
+        ks = [(step * procs + p) % max(n_tr, 1) for p in range(procs)]
     jobs = [(k, budget, target) for k in ks] + ([(0, budget, "avx2")] if parity_worker else [])
     with mp.get_context("spawn").Pool(len(jobs)) as pool:
         res = pool.map(_ref_train_worker, jobs)
     rate, detail = 0.0, []
     for k, accepted, dt, finished, info, snps in res[:procs]:
-        if finished or not wl:
+        how = "finished"
+        if finished:
             est = dt
-        else:
+        elif str(k) in prof and 0 < accepted <= len(prof[str(k)]["seconds_at_accepted_snp"]):
+            pk = prof[str(k)]
+            est = dt * pk["full_seconds"] / pk["seconds_at_accepted_snp"][accepted - 1]
+            how = "time profile"
+        elif wl and k < n_tr:
             tr = wl["classifiers"][k]
             cum = {a: p for a, p in tr["accepted_pairs"]}
             part = cum.get(accepted) or cum.get(max([x for x in cum if x <= accepted] or [0]), None)
             est = dt * tr["total_pairs"] / part if part else float("nan")
+            how = "pair evaluations (overestimates)"
+        else:
+            est = float("nan")
         if est == est and est > 0:
             rate += 60.0 / est
         detail.append(dict(classifier=k, accepted_snps=accepted, seconds=round(dt, 2),
-                           est_seconds_per_classifier=round(est, 1), snps=snps))
+                           est_seconds_per_classifier=round(est, 1), extrapolated_by=how, snps=snps))
     extra = [dict(classifier=r[0], snps=r[5], target="avx2") for r in res[procs:]]
     return rate, detail, res[0][4], extra
 
 
 def load_calibration():
-    """profiles/ref_full_classifier.json: one classifier of the workload timed to completion with
-    the reference (target max) in the build container vs the extrapolation of its 15 s prefix"""
-    path = os.path.join(ROOT, "profiles", "ref_full_classifier.json")
-    if os.path.exists(path):
-        c = json.load(open(path))
-        return "full classifier %.0f s vs extrapolated %.0f s (x%.2f), %s" % (
-            c["full_seconds"], c["extrapolated_seconds"], c["full_seconds"] / c["extrapolated_seconds"], c.get("where", ""))
+    """one line on how the bounded prefix is extrapolated and how well that works"""
+    tp = load_time_profile()
+    if tp:
+        cl = tp["classifiers"]
+        return "time profile of classifiers %s run to completion (%s s); cross-profile error of a 15 s prefix %s" % (
+            ",".join(sorted(cl)), "/".join("%.0f" % cl[k]["full_seconds"] for k in sorted(cl)),
+            "/".join("%+.0f%%" % (100.0 * (cl[k]["cross_profile_estimate_from_15s_prefix"] / cl[k]["full_seconds"] - 1))
+                     for k in sorted(cl)))
     return None
 
 
@@ -246,8 +275,8 @@ def cpu_baseline(procs, budget, wl, with_predict=True, snp_lookup=None):
     rate, detail, info, extra = reference_train_rate(0, procs, budget, wl, parity_worker=snp_lookup is not None)
     out = {"value": rate, "unit": "classifiers/min", "cores": procs, "kind": "reference",
            "target": info,
-           "sample": "%d procs x 1 classifier x %.0f s of reference BuildClassifiers (target max), extrapolated by "
-                     "pair evaluations (profiles/c2_workload.json)" % (procs, budget),
+           "sample": "%d procs x 1 classifier x %.0f s of reference BuildClassifiers (target max), extrapolated with the "
+                     "classifier's measured time profile (profiles/ref_time_profile.json)" % (procs, budget),
            "calibration": load_calibration(),
            "per_process": [{k: v for k, v in dd.items() if k != "snps"} for dd in detail[:4]]}
     if snp_lookup is not None:
@@ -299,7 +328,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "classifiers/min", "cores": procs, "kind": "reference",
                          "target": info,
                          "sample": "per step: %d procs x 1 classifier x %.0f s of reference BuildClassifiers (target "
-                                   "max), extrapolated by pair evaluations" % (procs, args.cpu_seconds),
+                                   "max), extrapolated with its time profile" % (procs, args.cpu_seconds),
                          "calibration": load_calibration(),
                          "extrapolated_seconds_per_classifier": 60.0 * procs / value if value > 0 else None,
                          "per_process": [{k: v for k, v in dd.items() if k != "snps"} for dd in (detail or [])[:4]]},
@@ -728,7 +757,8 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
     n_total = args.predict_samples
     b, e = hd.shard_range(n_total, rank, world)
     n = e - b
-    host = np.ascontiguousarray(synth.draw_more(coh, n_total, seed=99).geno[b:e], dtype=np.int8)
+    all_host = np.ascontiguousarray(synth.draw_more(coh, n_total, seed=99).geno, dtype=np.int8)
+    host = np.ascontiguousarray(all_host[b:e])
     pinned = torch.from_numpy(host).pin_memory()
     g = pinned.to(dev, non_blocking=False)
     nc = big.n_cells
@@ -778,6 +808,31 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
                      "cell_kernel_share_of_step": d["cell_kernel_ms"] / max(d["gpu_kernel_ms"], 1e-9)},
         "gpu_launches": int(d["kernel_launches"]),
     }
+    if world > 1:
+        # the other multi-GPU mode (SURVEY.md 8e, config 5's shape of work): classifiers sharded, every
+        # rank scores ALL samples with its share of the classifiers, one NCCL all-reduce of the
+        # [tile, n_cells + 3] fp64 partial posterior sums per tile of 65,536 samples, then finalise
+        sub = hd.sub_model(big, rank, world)
+        wts = torch.from_numpy(big.snp_weights()).to(dev)
+        g_all = torch.from_numpy(all_host).to(dev)
+        hd.predict_classifier_sharded(sub, wts, coh.n_hla, g_all[:4096])          # warm-up (buffers, NCCL)
+        torch.cuda.synchronize(); hd.barrier()
+        tm = {}
+        e0.record()
+        res_cs = hd.predict_classifier_sharded(sub, wts, coh.n_hla, g_all, timing=tm)
+        e1.record()
+        torch.cuda.synchronize(); hd.barrier()
+        ms3 = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+        same_cs = bool(torch.equal(res_cs["h1"][b:e], h1) and torch.equal(res_cs["h2"][b:e], h2))
+        rel = float(((res_cs["postprob"][b:e] - pp).abs() / pp.abs().clamp_min(1e-300)).max().item()) if n > 0 else 0.0
+        out.update({"sharded_by_classifier_value": n_total / (ms3 * 1e-3), "sharded_by_classifier_ms": ms3,
+                    "allreduce_ms": tm["allreduce_ms"], "allreduce_bytes": int(tm["allreduce_bytes"]),
+                    "allreduce_gbs": tm["allreduce_bytes"] / max(tm["allreduce_ms"] * 1e-3, 1e-12) / 1e9,
+                    "sharded_by_classifier_calls_equal": same_cs, "sharded_by_classifier_max_rel_err": rel,
+                    "sharded_by_classifier_note": "%d classifiers per rank x all %d samples; one NCCL all-reduce (fp64 sum) of "
+                                                  "[65536, %d] per tile; calls equal / posteriors vs the sample-sharded "
+                                                  "(sequential classifier order) result on this rank's slice" % (
+                                                      sub.num_classifiers(), n_total, nc + 3)})
     return out
 
 
@@ -849,7 +904,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-unscreened", action="store_true", help="skip the extra step with screening off")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-procs", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":

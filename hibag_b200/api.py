@@ -73,7 +73,7 @@ EXPORTS = [
     "hibag_b200_model_train", "hibag_b200_model_train_stats", "hibag_b200_model_train_trace",
     "hibag_b200_model_num_classifiers", "hibag_b200_model_clear",
     "hibag_b200_model_classifier_info", "hibag_b200_model_classifier_get",
-    "hibag_b200_model_classifier_samp_num_len",
+    "hibag_b200_model_classifier_samp_num_len", "hibag_b200_trim_cache",
     "hibag_b200_model_add_classifier", "hibag_b200_model_predict",
     "hibag_b200_model_predict_device", "hibag_b200_model_predict_stats",
     "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
@@ -163,6 +163,12 @@ def device_count():
 
 def set_device(i):
     _chk(lib().hibag_b200_set_device(i))
+
+
+def trim_cache():
+    """release the library's cached device / pinned blocks; returns the bytes given back"""
+    lib().hibag_b200_trim_cache.restype = C.c_size_t
+    return int(lib().hibag_b200_trim_cache())
 
 
 def device_info():

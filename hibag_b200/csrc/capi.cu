@@ -180,6 +180,7 @@ int hibag_b200_model_clear(hibag_b200_model *m)
 	return guarded([&]() {
 		require(m != nullptr, "null argument");
 		m->cls.clear(); m->pcache.reset(); m->train_trace.clear();
+		m->rng_seeded = false;
 		memset(&m->train_stats, 0, sizeof(m->train_stats));
 		memset(&m->predict_stats, 0, sizeof(m->predict_stats));
 	});
@@ -195,6 +196,11 @@ int hibag_b200_model_classifier_info(const hibag_b200_model *m, int k, int *n_sn
 		if (n_haplo) *n_haplo = (int)c.haplo.h.size();
 		if (oob_acc) *oob_acc = c.oob_acc;
 	});
+}
+
+size_t hibag_b200_trim_cache(void)
+{
+	try { return hb::pool_trim(); } catch (...) { return 0; }
 }
 
 int hibag_b200_model_classifier_samp_num_len(const hibag_b200_model *m, int k)

@@ -33,6 +33,8 @@ void select_device(int device);
 /// sessions and predict calls come and go, so released blocks are kept and handed out again.
 void *pool_alloc(bool pinned, size_t bytes, size_t *got_bytes);
 void pool_free(bool pinned, void *p, size_t bytes);
+/// give every cached block back to the driver (returns the bytes released)
+size_t pool_trim();
 
 /// growable device buffer (contents are NOT preserved on growth)
 template <typename T>
@@ -47,6 +49,9 @@ public:
 	{
 		if (n > cap_)
 		{
+			// the old block goes back to the process-wide cache, where any other thread may take it at
+			// once: nothing enqueued earlier (on any stream, e.g. an async predict call) may still use it
+			if (p_) cudaDeviceSynchronize();
 			release();
 			const size_t want = n + n / 4 + 64;
 			p_ = (T *)pool_alloc(false, want * sizeof(T), &bytes_);

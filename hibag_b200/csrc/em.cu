@@ -24,11 +24,14 @@ constexpr int EM_THREADS_MAX = 1024;
 constexpr int EM_MAX_ITER = 500;                 // src/LibHLA.cpp:98
 constexpr double EM_INIT_VAL_FRAC = 0.001;       // :100
 // Half-width of the band around the stopping tolerance inside which the device does not decide,
-// relative to |LL|: device log and glibc log are both within 1 ulp (2.2e-16 per term) and the
-// host's sequential sum of n same-sign terms carries at most n*u/2 relative error (u = 1.1e-16),
-// the device's tree sum far less; the difference of two such sums at most twice that. The band is
-// twice the bound. It is ~1e-4 of the tolerance sqrt(eps)*|LL| at n = 5000.
-__host__ __device__ inline double em_guard_rel(int n_entry) { return 2.0 * (n_entry * 1.2e-16 + 1e-15); }
+// relative to |LL|. LL = sum of n same-sign terms bc*log(psum). With u = 2^-53 = 1.11e-16: every
+// term carries <= 1 ulp of log (2u; glibc and the device log alike) plus u of the product, the
+// host's sequential sum at most (n-1)*u relative (the standard worst case), the device's tree sum
+// at most (log2 n + 1)*u; the test compares |LL - LL_old|, two such sums on either side, so host
+// and device differ by at most 2*((n + 2) + (log2 n + 4))*u*|LL| <= 2*(n + 24)*u*|LL| for
+// n < 2^17. The band is 1.5 times that bound (the former 2*(1.2e-16*n + 1e-15) cleared
+// the worst case by 9 % only). At n = 3,160 it is 1.1e-12, i.e. 7e-5 of the tolerance sqrt(eps).
+__host__ __device__ inline double em_guard_rel(int n_entry) { return 3.0 * ((n_entry + 24) * 1.12e-16); }
 
 // ---------------------------------------------------------------------------------------------
 // haplotype-pair matching

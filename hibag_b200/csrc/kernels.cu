@@ -360,6 +360,30 @@ void launch_unpack_genotypes(const void *geno_aos, int n, uint32_t *s1, uint32_t
 	CUDA_CHECK(cudaGetLastError());
 }
 
+/// one SNP column of the bit planes rewritten from 2-bit genotype codes (legacy hook path: between
+/// two build_set_haplo_geno calls only the candidate SNP's column of TGenotype[] changes)
+__global__ void patch_column_kernel(const int8_t *__restrict__ code, int n, uint32_t *s1,
+	uint32_t *s2, int stride, int word, uint32_t bit)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int c = code[i];              // bit 0 = PackedSNP1 bit, bit 1 = PackedSNP2 bit
+	uint32_t a = s1[(size_t)word * stride + i], b = s2[(size_t)word * stride + i];
+	a = (c & 1) ? (a | bit) : (a & ~bit);
+	b = (c & 2) ? (b | bit) : (b & ~bit);
+	s1[(size_t)word * stride + i] = a;
+	s2[(size_t)word * stride + i] = b;
+}
+
+void launch_patch_column(const int8_t *code, int n, uint32_t *s1, uint32_t *s2, int stride,
+	int snp_bit, cudaStream_t st)
+{
+	if (n <= 0) return;
+	patch_column_kernel<<<(n + 255) / 256, 256, 0, st>>>(code, n, s1, s2, stride, snp_bit >> 5,
+		1u << (snp_bit & 31));
+	CUDA_CHECK(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------------------
 // reductions over the cell vector of one sample (all sequential in cell order)
 // ---------------------------------------------------------------------------------------

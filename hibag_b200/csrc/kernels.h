@@ -96,6 +96,9 @@ int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cuda
 int launch_cell_batch(const CellBatch &b, int samples_per_lane, int sm_count, cudaStream_t st);
 
 /// AoS TGenotype[n] (48 B) -> SoA words + true alleles + bootstrap counts
+/// rewrite SNP column snp_bit (0..127) of the SoA planes from codes (bit0 -> s1, bit1 -> s2)
+void launch_patch_column(const int8_t *code, int n, uint32_t *s1, uint32_t *s2, int stride,
+	int snp_bit, cudaStream_t st);
 void launch_unpack_genotypes(const void *geno_aos, int n, uint32_t *s1, uint32_t *s2,
 	int stride, int *a1, int *a2, int *boot, cudaStream_t st);
 

@@ -42,6 +42,11 @@ struct hibag_b200_model
 	std::vector<int64_t> train_trace;   // rows of 4, see hibag_b200_model_train_trace
 	std::shared_ptr<hb::PredictCache> pcache;
 	std::shared_ptr<hb::TrainSession> tsession;
+	// single-stream seeding (per_classifier_seed = 0): the RNG state is the MODEL's, seeded once per
+	// seed value and continued by later train calls, as R's set.seed + repeated hlaAttrBagging do
+	hb::RRng rng;
+	bool rng_seeded = false;
+	int64_t rng_seed = 0;
 	hibag_b200_model();
 };
 

@@ -26,8 +26,12 @@ struct BuildState
 {
 	int n_hla = 0, n_samp = 0, n_snp = 0;
 	GenoSet geno;
-	PinBuf<unsigned char> h_aos;
+	PinBuf<unsigned char> h_aos;      // pinned SHADOW of the TGenotype[] the device planes were built from
 	DevBuf<unsigned char> d_aos;
+	bool shadow_valid = false;
+	PinBuf<int8_t> h_code;            // [4][n_samp] column codes of up to four changed SNP columns
+	DevBuf<int8_t> d_code;
+	uint64_t n_full_uploads = 0, n_column_uploads = 0, n_unchanged = 0;
 	std::vector<int> boot;            // bootstrap multiplicities currently on the device
 	std::vector<int> oob, ib;         // ascending sample indices (src/LibHLA.cpp:1858-1874)
 	DevBuf<int> d_oob, d_ib;
@@ -76,6 +80,8 @@ static void hook_build_init(int n_hla, int n_sample)
 	g_build->geno.ensure(n_sample);
 	g_build->h_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
 	g_build->d_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
+	g_build->h_code.ensure(4 * (size_t)n_sample);
+	g_build->d_code.ensure(4 * (size_t)n_sample);
 }
 
 static void hook_build_done()
@@ -108,15 +114,69 @@ static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo
 	}
 	b->n_snp = n_snp;
 	const size_t bytes = sizeof(hibag_genotype) * (size_t)b->n_samp;
-	// the previous evaluation has been synchronised (acc_* return values), so the pinned
-	// staging buffers are free to overwrite
-	memcpy(b->h_aos.get(), geno, bytes);
-	HB_CUDA(cudaMemcpyAsync(b->d_aos.get(), b->h_aos.get(), bytes, cudaMemcpyHostToDevice,
-		b->slot.stream()));
-	b->slot.stats.h2d_bytes += bytes;
-	launch_unpack_genotypes(b->d_aos.get(), b->n_samp, b->geno.s1.get(), b->geno.s2.get(),
-		b->n_samp, b->geno.a1.get(), b->geno.a2.get(), b->geno.boot.get(), b->slot.stream());
-	b->slot.stats.launches++;
+	// The reference hands over the whole TGenotype[nSample] with every candidate SNP (240 KB at
+	// 5,000 samples), but between two calls it has only rewritten the candidate's bit column
+	// (CGenotypeList::AddSNP / ReduceSNP, src/LibHLA.cpp:860-881) -- or two columns after an accepted
+	// SNP. The previous evaluation has been synchronised (acc_* return values), so the pinned shadow
+	// is free: diff against it, and when the change is confined to <= 4 bit columns upload those
+	// columns as 2-bit codes (n bytes each) and patch the device planes; otherwise upload everything.
+	hibag_genotype *shadow = (hibag_genotype *)b->h_aos.get();
+	uint64_t d1[2] = { 0, 0 }, d2[2] = { 0, 0 };
+	bool other = !b->shadow_valid;
+	if (!other)
+	{
+		for (int i = 0; i < b->n_samp; i++)
+		{
+			const hibag_genotype &x = geno[i], &y = shadow[i];
+			d1[0] |= (uint64_t)(x.snp1[0] ^ y.snp1[0]); d1[1] |= (uint64_t)(x.snp1[1] ^ y.snp1[1]);
+			d2[0] |= (uint64_t)(x.snp2[0] ^ y.snp2[0]); d2[1] |= (uint64_t)(x.snp2[1] ^ y.snp2[1]);
+			other |= (x.bootstrap_count != y.bootstrap_count) | (x.allele1 != y.allele1) | (x.allele2 != y.allele2);
+		}
+	}
+	const uint64_t u[2] = { d1[0] | d2[0], d1[1] | d2[1] };
+	const int n_changed = __builtin_popcountll(u[0]) + __builtin_popcountll(u[1]);
+	if (other || n_changed > 4)
+	{
+		memcpy(shadow, geno, bytes);
+		HB_CUDA(cudaMemcpyAsync(b->d_aos.get(), b->h_aos.get(), bytes, cudaMemcpyHostToDevice,
+			b->slot.stream()));
+		b->slot.stats.h2d_bytes += bytes;
+		launch_unpack_genotypes(b->d_aos.get(), b->n_samp, b->geno.s1.get(), b->geno.s2.get(),
+			b->n_samp, b->geno.a1.get(), b->geno.a2.get(), b->geno.boot.get(), b->slot.stream());
+		b->slot.stats.launches++;
+		b->shadow_valid = true;
+		b->n_full_uploads++;
+	} else if (n_changed > 0)
+	{
+		int k = 0;
+		for (int w = 0; w < 2; w++)
+			for (uint64_t m = u[w]; m; m &= m - 1, k++)
+			{
+				const int bit = __builtin_ctzll(m);
+				const uint64_t one = (uint64_t)1 << bit;
+				int8_t *code = b->h_code.get() + (size_t)k * b->n_samp;
+				for (int i = 0; i < b->n_samp; i++)
+				{
+					const uint64_t a = (uint64_t)geno[i].snp1[w] & one, c = (uint64_t)geno[i].snp2[w] & one;
+					code[i] = (int8_t)((a ? 1 : 0) | (c ? 2 : 0));
+					shadow[i].snp1[w] = (int64_t)(((uint64_t)shadow[i].snp1[w] & ~one) | a);
+					shadow[i].snp2[w] = (int64_t)(((uint64_t)shadow[i].snp2[w] & ~one) | c);
+				}
+			}
+		HB_CUDA(cudaMemcpyAsync(b->d_code.get(), b->h_code.get(), (size_t)k * b->n_samp,
+			cudaMemcpyHostToDevice, b->slot.stream()));
+		b->slot.stats.h2d_bytes += (size_t)k * b->n_samp;
+		k = 0;
+		for (int w = 0; w < 2; w++)
+			for (uint64_t m = u[w]; m; m &= m - 1, k++)
+			{
+				launch_patch_column(b->d_code.get() + (size_t)k * b->n_samp, b->n_samp, b->geno.s1.get(),
+					b->geno.s2.get(), b->n_samp, 64 * w + __builtin_ctzll(m), b->slot.stream());
+				b->slot.stats.launches++;
+			}
+		b->n_column_uploads++;
+	} else
+		b->n_unchanged++;
 	b->slot.stage_list(haplo, n_haplo, b->n_hla, n_snp);
 	b->have_list_staged = true;
 }

@@ -116,7 +116,7 @@ struct BlockPool
 };
 BlockPool g_pool[2];                                 // [0] device (per current device), [1] pinned
 std::map<void *, int> g_block_device;                // device blocks: which device owns them
-const size_t POOL_LIMIT[2] = { (size_t)96 << 30, (size_t)8 << 30 };   // of 180 GB HBM / host RAM
+const size_t POOL_LIMIT[2] = { (size_t)48 << 30, (size_t)8 << 30 };   // of 180 GB HBM / host RAM
 }
 
 void *pool_alloc(bool pinned, size_t bytes, size_t *got_bytes)
@@ -153,7 +153,11 @@ void *pool_alloc(bool pinned, size_t bytes, size_t *got_bytes)
 		std::vector<void *> drop;
 		{
 			std::lock_guard<std::mutex> lk(bp.mu);
-			for (auto &kv : bp.free_blocks) drop.push_back(kv.second);
+			for (auto &kv : bp.free_blocks)
+			{
+				drop.push_back(kv.second);
+				if (!pinned) g_block_device.erase(kv.second);
+			}
 			bp.free_blocks.clear();
 			bp.cached_bytes = 0;
 		}
@@ -188,6 +192,31 @@ void pool_free(bool pinned, void *p, size_t bytes)
 		if (!pinned) g_block_device.erase(p);
 	}
 	if (pinned) cudaFreeHost(p); else cudaFree(p);
+}
+
+size_t pool_trim()
+{
+	size_t freed = 0;
+	cudaDeviceSynchronize();
+	for (int k = 0; k < 2; k++)
+	{
+		BlockPool &bp = g_pool[k];
+		std::vector<void *> drop;
+		{
+			std::lock_guard<std::mutex> lk(bp.mu);
+			for (auto &kv : bp.free_blocks)
+			{
+				drop.push_back(kv.second);
+				if (k == 0) g_block_device.erase(kv.second);
+			}
+			freed += bp.cached_bytes;
+			bp.free_blocks.clear();
+			bp.cached_bytes = 0;
+		}
+		for (void *q : drop) { if (k) cudaFreeHost(q); else cudaFree(q); }
+	}
+	cudaGetLastError();
+	return freed;
 }
 
 // ---- EvalSlot ---------------------------------------------------------------------------------

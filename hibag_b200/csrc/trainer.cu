@@ -340,7 +340,19 @@ void Trainer::run(const std::function<int()> &next)
 	const ScoreStats plugin_before = procs_ ? plugin_build_stats() : ScoreStats();
 	std::fill(em_seconds_.begin(), em_seconds_.end(), 0.0);
 	std::fill(wait_seconds_.begin(), wait_seconds_.end(), 0.0);
-	if (!o_.per_classifier_seed) rng_.set_seed((uint32_t)o_.seed);
+	if (!o_.per_classifier_seed)
+	{
+		// reference: the user seeds R's generator once and every BuildClassifiers call continues the
+		// stream (src/LibHLA.cpp:120-126). Here: seeded when the model sees this seed value for the
+		// first time; a later call with the same seed continues where the last one stopped.
+		if (!m_.rng_seeded || m_.rng_seed != (int64_t)o_.seed)
+		{
+			m_.rng.set_seed((uint32_t)o_.seed);
+			m_.rng_seeded = true;
+			m_.rng_seed = (int64_t)o_.seed;
+		}
+		rng_ = m_.rng;
+	}
 	for (;;)
 	{
 		const int global_k = next();
@@ -380,6 +392,7 @@ void Trainer::run(const std::function<int()> &next)
 				cl.oob_acc * 100, (int)cl.snpidx.size(), (int)cl.haplo.h.size());
 		}
 	}
+	if (!o_.per_classifier_seed) m_.rng = rng_;
 	// fold the counters
 	if (scorer_) stats_.add(scorer_->stats);
 	if (rem_)
@@ -798,6 +811,16 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 	int n_lanes = 1;
 	if (opts.per_classifier_seed && !opts.use_legacy_hooks && opts.n_concurrent > 1)
 		n_lanes = std::min(opts.n_concurrent, std::max(opts.nclassifier, 1));
+	else if (opts.n_concurrent > 1 && !opts.use_legacy_hooks)
+	{
+		static bool warned = false;
+		if (!warned)
+		{
+			warned = true;
+			fprintf(stderr, "hibag_b200: n_concurrent = %d ignored: with per_classifier_seed = 0 the classifiers "
+				"consume ONE random stream in order (as R does) and are grown one at a time\n", opts.n_concurrent);
+		}
+	}
 	LaneGroup *g = dynamic_cast<LaneGroup *>(m.tsession.get());
 	if (!g || g->legacy != (opts.use_legacy_hooks != 0) || g->req_threads != opts.n_threads ||
 		g->req_concurrent != opts.n_concurrent || g->mtry != mtry || (int)g->lanes.size() < n_lanes ||

@@ -133,7 +133,10 @@ typedef struct hibag_b200_train_opts {
 	int      prune;             /* src/LibHLA.cpp:2057 */
 	int      n_threads;         /* host threads for candidate-parallel EM (<=0: all cores) */
 	int64_t  seed;              /* R set.seed() value */
-	int      per_classifier_seed; /* 0: one RNG stream over classifiers (what R does);
+	int      per_classifier_seed; /* 0: one RNG stream over classifiers (what R does): the model is
+	                                 seeded when it first sees this seed value; a later train call with
+	                                 the same seed CONTINUES the stream (R: set.seed once, then repeated
+	                                 hlaAttrBagging), a different seed or model_clear re-seeds;
 	                                 1: classifier k is grown after set.seed(seed + k) */
 	int      first_index;       /* global index of the first classifier built by this call */
 	int      index_stride;      /* classifier indices first_index, +stride, ... (multi-GPU shard) */
@@ -142,7 +145,8 @@ typedef struct hibag_b200_train_opts {
 	int      verbose;
 	int      n_concurrent;      /* classifiers grown concurrently on this GPU (host EM of one
 	                               overlaps pair scoring of another); needs per_classifier_seed
-	                               = 1 and is ignored with use_legacy_hooks; <= 1: one */
+	                               = 1 (otherwise ignored, with a warning on stderr) and is ignored
+	                               with use_legacy_hooks; <= 1: one */
 	int      em_on_device;      /* 1: haplotype-pair matching and the candidates' EM run on the
 	                               GPU (bit-identical results); 0: on the
 	                               host thread pool. Ignored with use_legacy_hooks */
@@ -265,6 +269,11 @@ int hibag_b200_bed_decode(const uint8_t *bed_file, size_t n_bytes, int n_samp, i
  * the SNPs to keep (NULL: all), out_dev = int8 [n_samp][n_save]; enqueued on cuda_stream */
 int hibag_b200_bed_decode_device(const uint8_t *payload_dev, int mode, int n_samp, int n_snp,
 	const int32_t *sel_dev, int n_save, int8_t *out_dev, void *cuda_stream);
+
+/* The library recycles device and pinned blocks through a process-wide cache (at most 48 GB of HBM,
+ * 8 GB pinned). This gives every cached block back to the driver, e.g. before another library
+ * needs the memory; returns the bytes released. */
+size_t hibag_b200_trim_cache(void);
 
 /* ---- host-only pieces exposed for the CPU test-suite (no GPU needed) ------------------------- */
 /* R's Mersenne-Twister after set.seed(seed): n draws of unif_rand() */

@@ -458,3 +458,119 @@ def test_bed_decode_matches_oracle(gpu, orc, tmp_path):
     assert np.array_equal(geno["genotype"][np.ix_(si, sj)], np.where((want < 0) | (want > 2), -1, want))
     with pytest.raises(RuntimeError, match="Invalid prefix in the PLINK BED file"):
         gpu.bed_decode(np.array([1, 2, 3, 4, 5], dtype=np.uint8), 2, 2)
+
+
+# ---- the BASELINE-shaped configurations against the compiled reference ------
+
+def _capture_fd2(fn):
+    """run fn() with file descriptor 2 redirected to a file; returns (result, text)"""
+    import os, tempfile
+    fd, path = tempfile.mkstemp(suffix=".log")
+    saved = os.dup(2)
+    os.dup2(fd, 2)
+    try:
+        out = fn()
+    finally:
+        os.dup2(saved, 2)
+        os.close(fd); os.close(saved)
+    text = open(path).read()
+    os.unlink(path)
+    return out, text
+
+
+def _trace_lines(text):
+    """(snp index 0-based, loss string, oob acc string, n_haplo) per accepted SNP from verbose.detail
+    lines -- the reference prints them at src/LibHLA.cpp:2104-2111, the own driver in the same format"""
+    import re
+    pat = re.compile(r"^\s*(\d+), SNP: (\d+), loss: (\S+), oob acc: (\S+)%, # of haplo: (\d+)")
+    out = []
+    for ln in text.splitlines():
+        m = pat.match(ln)
+        if m:
+            out.append((int(m.group(2)) - 1, m.group(3), m.group(4), int(m.group(5))))
+    return out
+
+
+def test_headline_config_classifiers_equal_the_reference(gpu):
+    """configs[1] itself: HLA-A-shaped 5,000 samples x 500 SNPs, bench.py's cohort and seeds. Fixture
+    tests/golden/c2_ref.npz = classifiers trained to completion by the compiled, unmodified reference
+    (tools/make_golden_ref.py; targets base / avx2, 20-40 CPU-minutes each). The B200 path trains the
+    same global indices the way bench.py does -- exact screening, device EM, 24 classifiers in flight --
+    and must reproduce them bit for bit: bootstrap counts, SNP order, haplotypes, fp64 frequencies,
+    out-of-bag accuracy. At this scale the paths the small cohorts never reach are live: uncertified
+    in-bag sums rescored, device-EM host fallbacks, the dense EM shape."""
+    import bench
+    gd = helpers.load_golden("c2_ref.npz")
+    assert (int(gd["n_samp"]), int(gd["n_snp"]), int(gd["mtry"]), int(gd["train_seed"])) == \
+        (bench.N_SAMP, bench.N_SNP, bench.MTRY, bench.TRAIN_SEED)
+    coh = bench.make_cohort()
+    ks = [int(k) for k in gd["ks"] if bool(gd["c%d_finished" % k])]
+    assert len(ks) >= 2
+    m = gpu.HLAModel(bench.N_SNP, coh.n_hla)
+    m.set_training(np.ascontiguousarray(coh.geno, dtype=np.int8), coh.h1, coh.h2)
+    n = max(24, max(ks) + 1)
+    m.train(n, bench.MTRY, prune=True, seed=bench.TRAIN_SEED, per_classifier_seed=True, first_index=0,
+            n_threads=48, n_concurrent=24)
+    st = m.train_stats()
+    assert st["pair_evals"] < 0.3 * st["pair_evals_nominal"]           # the exact screen was on
+    for k in ks:
+        want = {key: gd["c%d_%s" % (k, key)] for key in ("snpidx", "samp_num", "freq", "hla", "packed")}
+        want["oob_acc"] = float(gd["c%d_oob_acc" % k])
+        d = helpers.classifier_diff(m.classifier(k), want)
+        assert d == "", "classifier %d differs from the reference in '%s'" % (k, d)
+    # one of them again alone, every cell scored, EM on the host pool, with the accepted-SNP trace
+    # (SNP, loss to 6 digits, out-of-bag accuracy, haplotypes) equal line by line
+    k = ks[0]
+    h = gpu.HLAModel(bench.N_SNP, coh.n_hla)
+    h.set_training(np.ascontiguousarray(coh.geno, dtype=np.int8), coh.h1, coh.h2)
+    _, text = _capture_fd2(lambda: h.train(1, bench.MTRY, prune=True, seed=bench.TRAIN_SEED, per_classifier_seed=True,
+                                           first_index=k, screening=False, em_on_device=False, verbose=2))
+    want = {key: gd["c%d_%s" % (k, key)] for key in ("snpidx", "samp_num", "freq", "hla", "packed")}
+    want["oob_acc"] = float(gd["c%d_oob_acc" % k])
+    assert helpers.classifier_diff(h.classifier(0), want) == ""
+    got = _trace_lines(text)
+    ref_trace = list(zip(gd["c%d_trace_snp" % k].tolist(), [str(x) for x in gd["c%d_trace_loss" % k]],
+                         [str(x) for x in gd["c%d_trace_acc" % k]], gd["c%d_trace_n_haplo" % k].tolist()))
+    assert got == ref_trace
+
+
+def test_drb1_scale_prefix_equals_the_reference(gpu):
+    """configs[3]: HLA-DRB1-shaped 10,000 samples x 800 SNPs, 86 alleles (3,741 cells), haplotype lists
+    in the thousands. A full reference classifier is ~10 CPU-hours, so the fixture
+    (tests/golden/c4_ref_prefix.npz, tools/make_golden_ref.py) is the PREFIX of accepted SNPs the
+    compiled reference reached in its budget, with the loss (6 digits), out-of-bag accuracy and
+    haplotype count it printed at each -- every one of them must equal the B200 path's trace."""
+    import os
+    if not os.path.exists(os.path.join(helpers.GOLDEN, "c4_ref_prefix.npz")):
+        pytest.skip("tests/golden/c4_ref_prefix.npz not generated")
+    from hibag_b200 import synth
+    gd = helpers.load_golden("c4_ref_prefix.npz")
+    k = int(gd["ks"][0])
+    coh = synth.make_cohort(int(gd["n_samp"]), int(gd["n_snp"]), int(gd["n_hla_drawn"]), seed=int(gd["cohort_seed"]))
+    m = gpu.HLAModel(coh.n_snp, coh.n_hla)
+    m.set_training(np.ascontiguousarray(coh.geno, dtype=np.int8), coh.h1, coh.h2)
+    _, text = _capture_fd2(lambda: m.train(1, int(gd["mtry"]), prune=True, seed=int(gd["train_seed"]),
+                                           per_classifier_seed=True, first_index=k, verbose=2))
+    got = _trace_lines(text)
+    ref_trace = list(zip(gd["c%d_trace_snp" % k].tolist(), [str(x) for x in gd["c%d_trace_loss" % k]],
+                         [str(x) for x in gd["c%d_trace_acc" % k]], gd["c%d_trace_n_haplo" % k].tolist()))
+    assert len(ref_trace) >= 4
+    assert got[:len(ref_trace)] == ref_trace
+    assert m.classifier(0)["snpidx"][:len(ref_trace)].tolist() == [t[0] for t in ref_trace]
+
+
+def test_single_stream_seed_continues_across_train_calls(gpu):
+    """with per_classifier_seed = 0 a second train() call used to re-seed and append
+    duplicates. The reference continues R's stream (set.seed once, BuildClassifiers repeatedly):
+    2 classifiers in one call == 1 + 1 in two calls; a new seed or clear() re-seeds."""
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    a = gpu.HLAModel(geno.shape[1], len(al)); a.set_training(geno, h1, h2)
+    a.train(3, 17, seed=100)
+    b = gpu.HLAModel(geno.shape[1], len(al)); b.set_training(geno, h1, h2)
+    b.train(1, 17, seed=100); b.train(2, 17, seed=100)
+    assert b.num_classifiers() == 3
+    for k in range(3):
+        assert helpers.classifier_diff(b.classifier(k), a.classifier(k)) == ""
+        helpers.assert_classifier_equals_golden(b.classifier(k), ml, k)
+    b.clear(); b.train(1, 17, seed=100)
+    helpers.assert_classifier_equals_golden(b.classifier(0), ml, 0)

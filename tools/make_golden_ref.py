@@ -62,18 +62,36 @@ def worker(cfg, k, target, out, budget):
     os.dup2(fd, 2)
     if budget > 0:
         ref.set_interrupt(seconds=budget)
+    # wall-clock time at which each accepted-SNP line appears (the ctypes call releases the GIL):
+    # the time profile bench.py's reference arm uses to extrapolate a bounded prefix
+    import threading
+    stamps, stop = [], threading.Event()
+
+    def poll():
+        seen = 0
+        while not stop.is_set():
+            n = len(parse_trace(open(log).read()))
+            while seen < n:
+                stamps.append(time.time()); seen += 1
+            stop.wait(0.05)
+    th = threading.Thread(target=poll, daemon=True)
     t0 = time.time()
+    th.start()
     rc = m.build(1, mtry, prune=True, verbose=2, reseed_base=tseed, first_index=k, allow_interrupt=True)
     dt = time.time() - t0
+    stop.set(); th.join()
     os.dup2(saved, 2)
     os.close(fd)
     trace = parse_trace(open(log).read())
     os.unlink(log)
+    stamps = [x - t0 for x in stamps][:len(trace)]
+    stamps += [dt] * (len(trace) - len(stamps))
     res = dict(config=np.array(cfg), k=np.int64(k), target=np.array(target), cpu=np.array(info),
                seconds=np.float64(dt), finished=np.bool_(rc == 0),
                trace_snp=np.array([t[1] for t in trace], dtype=np.int32),
                trace_loss=np.array([t[2] for t in trace]), trace_acc=np.array([t[3] for t in trace]),
-               trace_n_haplo=np.array([t[4] for t in trace], dtype=np.int32))
+               trace_n_haplo=np.array([t[4] for t in trace], dtype=np.int32),
+               trace_seconds=np.array(stamps, dtype=np.float64))
     if rc == 0:
         c = m.classifier(0)
         for key in ("snpidx", "samp_num", "freq", "hla", "packed"):

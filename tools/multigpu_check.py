@@ -61,35 +61,32 @@ def main():
         for key in ("h1", "h2", "prob", "matching", "postprob"):
             cat = np.concatenate([g[key] for g in gathered])
             ok_samp &= bool(np.array_equal(cat, ref[key], equal_nan=True))
-    # 3. classifier-sharded prediction, one NCCL all-reduce
-    sub = api.HLAModel(coh.n_snp, coh.n_hla)
-    for k in hd.classifier_indices(n_cls, rank, world):
-        c = merged[k]
-        sub.add_classifier(c["snpidx"], c["freq"], c["hla"], c["packed"])
+    # 3. classifier-sharded prediction, one NCCL all-reduce per tile of samples (package helpers)
+    sub = hd.sub_model(full, rank, world)
     n = len(g_all)
     n_cells = full.n_cells
     g_dev = torch.from_numpy(g_all).to(dev)
     wts = torch.from_numpy(full.snp_weights()).to(dev)
-    acc = torch.zeros((n, n_cells + 3), dtype=torch.float64, device=dev)
     torch.cuda.synchronize(); hd.barrier()
     t0 = time.time()
-    sub.predict_partial_device(g_dev.data_ptr(), n, wts.data_ptr(), acc.data_ptr())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    hd.allreduce_partial(acc)
-    e1.record()
+    tm = {}
+    res = hd.predict_classifier_sharded(sub, wts, full.n_hla, g_dev, tile=8192, timing=tm)
     torch.cuda.synchronize()
-    ar_ms = e0.elapsed_time(e1)
-    h1 = torch.zeros(n, dtype=torch.int32, device=dev); h2 = torch.zeros_like(h1)
-    pp = torch.zeros((n, n_cells), dtype=torch.float64, device=dev)
-    mt = torch.zeros(n, dtype=torch.float64, device=dev)
-    out = api.PredictOut(h1.data_ptr(), h2.data_ptr(), None, mt.data_ptr(), None, pp.data_ptr())
-    rc = api.lib().hibag_b200_predict_finalize_device(full.n_hla, n, C.c_void_p(acc.data_ptr()),
-                                                      C.byref(out), None, 1)
-    assert rc == 0
     dt = time.time() - t0
+    ar_ms, ar_bytes = tm["allreduce_ms"], tm["allreduce_bytes"]
+    h1, h2, pp, mt = res["h1"], res["h2"], res["postprob"], res["matching"]
+    # 2b. the sample-sharded helper on device tensors: slices equal the single-rank result
+    b2, e2, part2 = hd.predict_sample_sharded(full, g_dev, n, rank, world)
+    ok_samp_dev = True
     ok_cls, max_rel = True, 0.0
+    mine2 = {k: part2[k].cpu().numpy() for k in ("h1", "h2", "prob", "matching", "postprob")}
+    g2 = [None] * world
+    dist.all_gather_object(g2, (b2, e2, mine2))
     if rank == 0:
+        for (bb, ee, pr) in g2:
+            for key in ("h1", "h2", "prob", "matching", "postprob"):
+                ok_samp_dev &= bool(np.array_equal(pr[key], ref[key][bb:ee], equal_nan=True))
+        ok_samp &= ok_samp_dev
         ok_cls = bool(np.array_equal(h1.cpu().numpy(), ref["h1"]) and np.array_equal(h2.cpu().numpy(), ref["h2"]))
         a, r_ = pp.cpu().numpy(), ref["postprob"]
         den = np.maximum(np.abs(r_), 1e-300)
@@ -98,7 +95,7 @@ def main():
         print(json.dumps({"world": world, "nproc_host": os.cpu_count(), "train_shard_equals_single": ok_train,
                           "sample_sharded_bit_exact": ok_samp, "classifier_sharded_calls_equal": ok_cls,
                           "classifier_sharded_max_rel_err": max_rel, "allreduce_ms": ar_ms,
-                          "allreduce_bytes": int(acc.numel() * 8), "partial+reduce+finalize_s": dt}))
+                          "allreduce_bytes": int(ar_bytes), "partial+reduce+finalize_s": dt}))
     hd.barrier()
     assert ok_train and ok_samp and ok_cls
 
