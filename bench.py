@@ -397,8 +397,9 @@ def compact_line(detail):
         _flat(r, rf.get("out_of_bag_launches"), ("frac", "avg_launch_ms"), "out_of_bag_")
         _flat(r, rf.get("alone"), ("frac", "in_bag_frac"), "alone_")
         _flat(r, rf.get("screening"), ("executed_fraction", "effective_frac_reference_formulation"), "screen_")
-        _flat(r, rf.get("em"), ("frac", "achieved", "peak", "unit", "sm_time_share"), "em_")
+        _flat(r, rf.get("em"), ("frac", "cycles_per_iteration", "longest_chain_mean"), "em_")
         _flat(r, rf.get("sm_time"), ("scoring_share", "em_share", "other_share", "busy"), "sm_time_")
+        _flat(r, rf, ("frac_of_held_sm_time", "frac_of_held_sm_time_in_bag"))
     if detail.get("roofline_unscreened"):
         r["unscreened_frac"] = _short(detail["roofline_unscreened"].get("frac"))
     if pred and pred.get("roofline"):
@@ -511,6 +512,7 @@ def run_b200_arm(args):
     st0 = model.train_stats()
     sampler = ClockSampler(local_rank)
     sync_all()
+    api.sm_time(reset=True)          # held SM-time per kernel class over the timed region
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -525,8 +527,10 @@ def run_b200_arm(args):
     wall = time.time() - t0
     ru1 = resource.getrusage(resource.RUSAGE_SELF)
     host_cpu_s = (ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)
-    ms = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_local = e0.elapsed_time(e1)
+    ms = hd.max_over_ranks(ms_local, dev)
     clocks = sampler.stop() if rank == 0 else None
+    acct = api.sm_time()
     st1 = model.train_stats()
     d = {k: st1[k] - st0[k] for k in st1}
     value = world * args.steps * lanes / (ms / 60000.0)
@@ -630,12 +634,50 @@ def run_b200_arm(args):
         "fp64_frac": pair_rate * 3 / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9),
         "em_kernel_ms": d["em_kernel_ms"],
     }
+    # ---- where the GPU's time went: held SM-time per kernel class (counters inside the kernels) ------
+    sm_clock = info["clock_khz"] * 1e3
+    sm_total = info["sm_count"] * ms_local * 1e-3 * sm_clock             # SM-cycles of the timed region
+    share = {k: v / sm_total for k, v in acct.items() if k != "em_cta_cycles"}
+    popc_per_sm_cycle = popc_peak / (info["sm_count"] * sm_clock)
+    roofline["sm_time"] = {
+        "scoring_share": share["gather_ib"] + share["gather_oob"] + share["cell_pass"],
+        "gather_ib_share": share["gather_ib"], "gather_oob_share": share["gather_oob"],
+        "em_share": share["em"],
+        "other_share": share["screen_bound"] + share["screen_need"] + share["screen_tasks"] + share["reduce_oob"] + share["reduce_ib"],
+        "busy": sum(share.values()),
+        "by_class": {k: round(v, 4) for k, v in share.items()},
+        "note": "share of the GPU's SM-cycles in the timed region HELD by each kernel class: sum over its CTAs of resident "
+                "cycles x the fraction of an SM a CTA of that launch occupies (1 / CTAs that fit an SM by registers, threads "
+                "and shared memory). Kernels of the lanes overlap, so CUDA-event durations (em_kernel_ms, gather ms) are "
+                "NOT exclusive time and do not add up to the step; held SM-time does. Pair preparation (cub sort, "
+                "pair matching) is not instrumented."}
+    if screened and acct["gather_ib"] > 0:
+        held = d["gather_ib_popc32"] / (acct["gather_ib"] * popc_per_sm_cycle)
+        roofline["frac_of_held_sm_time_in_bag"] = held
+        roofline["frac_of_held_sm_time"] = d["popc32_issued"] / ((acct["gather_ib"] + acct["gather_oob"]) * popc_per_sm_cycle)
+    # ---- the EM kernel (time-dominant when serialised) against ITS bound: the latency of the longest
+    # chain of dependent fp64 adds of every M step (16.9 cycles per dependent DADD, profiles/pipe_peaks.json)
+    if d.get("em_chain_adds", 0) > 0 and acct["em_cta_cycles"] > 0:
+        dadd = (peaks or {}).get("dadd_dependent_cycles", 16.9)
+        floor_cycles = d["em_chain_adds"] * dadd
+        roofline["em"] = {
+            "kernel": "em_kernel", "bound": "latency of the dependent fp64 add chain (M step), %.1f cycles per add" % dadd,
+            "achieved": floor_cycles / 1e9, "peak": acct["em_cta_cycles"] / 1e9, "unit": "Gcycles (chain floor / CTA-resident)",
+            "frac": floor_cycles / acct["em_cta_cycles"], "sm_time_share": share["em"],
+            "iterations": int(d["em_iterations"]), "candidates": int(d["n_em"]),
+            "cycles_per_iteration": acct["em_cta_cycles"] / max(d["em_iterations"], 1),
+            "longest_chain_mean": d["em_chain_adds"] / max(d["em_iterations"], 1),
+            "pair_updates_per_iteration": d["em_pair_updates"] / max(d["em_iterations"], 1),
+            "note": "one CTA per candidate SNP; an iteration cannot be shorter than its longest chain of sequential "
+                    "fp64 adds (bit-exact M step). frac = that floor / the CTA's resident cycles; the rest is the three "
+                    "E passes, barriers and L2 latency (DESIGN.md 4.4)"}
     if screened and d["gather_ib_launches"] > 0:
         ib_rate = d["gather_ib_popc32"] / max(d["gather_ib_kernel_ms"] * 1e-3, 1e-12)
         roofline["in_bag_launches"] = {
             "launches": int(d["gather_ib_launches"]), "avg_launch_ms": d["gather_ib_kernel_ms"] / d["gather_ib_launches"],
             "achieved": ib_rate / 1e9, "frac": ib_rate / popc_peak,
             "share_of_gather_ms": d["gather_ib_kernel_ms"] / max(d["gather_kernel_ms"], 1e-12),
+            "share_of_pair_evals": d["gather_ib_popc32"] / max(d["popc32_issued"], 1),
             "note": "the in-bag launches alone (86 of 595 cells per sample survive: full warps); the out-of-bag "
                     "launches (2.5 cells per sample) are latency-bound"}
     # the same kernel timed ALONE: one lane, its launches serialised, nothing else on the GPU

@@ -49,7 +49,8 @@ class TrainStats(C.Structure):
                 ("pair_evals_nominal", C.c_uint64), ("n_screen_fallback", C.c_uint64),
                 ("gather_kernel_ms", C.c_double), ("gather_kernel_launches", C.c_uint64),
                 ("gather_ib_kernel_ms", C.c_double), ("gather_ib_launches", C.c_uint64),
-                ("gather_ib_popc32", C.c_uint64)]
+                ("gather_ib_popc32", C.c_uint64), ("em_iterations", C.c_uint64),
+                ("em_chain_adds", C.c_uint64), ("em_pair_updates", C.c_uint64)]
 
 
 class PredictOut(C.Structure):
@@ -73,7 +74,7 @@ EXPORTS = [
     "hibag_b200_model_train", "hibag_b200_model_train_stats", "hibag_b200_model_train_trace",
     "hibag_b200_model_num_classifiers", "hibag_b200_model_clear",
     "hibag_b200_model_classifier_info", "hibag_b200_model_classifier_get",
-    "hibag_b200_model_classifier_samp_num_len", "hibag_b200_trim_cache",
+    "hibag_b200_model_classifier_samp_num_len", "hibag_b200_trim_cache", "hibag_b200_sm_time",
     "hibag_b200_model_add_classifier", "hibag_b200_model_predict",
     "hibag_b200_model_predict_device", "hibag_b200_model_predict_stats",
     "hibag_b200_model_predict_partial_device", "hibag_b200_predict_finalize_device",
@@ -163,6 +164,17 @@ def device_count():
 
 def set_device(i):
     _chk(lib().hibag_b200_set_device(i))
+
+
+SM_TIME_CLASSES = ["gather_oob", "gather_ib", "em", "screen_bound", "screen_need", "screen_tasks", "reduce_oob",
+                   "reduce_ib", "cell_pass", "em_prep", "em_cta_cycles"]
+
+
+def sm_time(reset=False):
+    """held SM-time per kernel class in SM-cycles (see hibag_b200_sm_time); synchronises the device"""
+    out = np.zeros(16, dtype=np.uint64)
+    _chk(lib().hibag_b200_sm_time(_p(out), int(reset)))
+    return {k: float(out[i]) / 1024.0 for i, k in enumerate(SM_TIME_CLASSES)}
 
 
 def trim_cache():

@@ -198,6 +198,19 @@ int hibag_b200_model_classifier_info(const hibag_b200_model *m, int k, int *n_sn
 	});
 }
 
+int hibag_b200_sm_time(uint64_t *out, int reset)
+{
+	return guarded([&]() {
+		require(out != nullptr, "null argument");
+		unsigned long long *d = hb::device_sm_acct();
+		HB_CUDA(cudaDeviceSynchronize());
+		unsigned long long h[hb::SM_ACCT_N];
+		HB_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+		for (int k = 0; k < hb::SM_ACCT_N; k++) out[k] = (uint64_t)h[k];
+		if (reset) HB_CUDA(cudaMemset(d, 0, sizeof(h)));
+	});
+}
+
 size_t hibag_b200_trim_cache(void)
 {
 	try { return hb::pool_trim(); } catch (...) { return 0; }

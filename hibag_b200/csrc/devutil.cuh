@@ -8,6 +8,26 @@
 namespace hb {
 
 // ---------------------------------------------------------------------------------------
+// SM-time accounting: every CTA adds (cycles it was resident) x (its share of an SM in 1/1024) to a
+// per-class counter. Overlapped CUDA-event durations cannot attribute time between concurrently
+// running kernels; resident SM-time can. Classes: see SM_ACCT_* in kernels.h.
+// ---------------------------------------------------------------------------------------
+struct SmAcct
+{
+	unsigned long long *slot;
+	long long t0;
+	unsigned int w;
+	__device__ __forceinline__ SmAcct(unsigned long long *acct, int cls, unsigned int weight) : slot(nullptr), t0(0), w(weight)
+	{
+		if (acct != nullptr && threadIdx.x == 0 && threadIdx.y == 0) { slot = acct + cls; t0 = clock64(); }
+	}
+	__device__ __forceinline__ ~SmAcct()
+	{
+		if (slot != nullptr) atomicAdd(slot, (unsigned long long)(clock64() - t0) * (unsigned long long)w);
+	}
+};
+
+// ---------------------------------------------------------------------------------------
 // small PTX helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -1,5 +1,7 @@
 // em.cu -- see em.h
 #include "em.h"
+#include "kernels.h"
+#include "devutil.cuh"
 
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
@@ -263,6 +265,8 @@ struct EmArgs
 	double scale;                     // 0.5 / n_samp
 	double em_reltol;                 // sqrt(DBL_EPSILON)
 	unsigned long long *prof;         // [m][8] clock64 ticks per phase (HIBAG_B200_EM_PROF), or null
+	unsigned long long *acct;         // SM-time counters (kernels.h) or null
+	int acct_w;                       // 1024 / EM CTAs that fit an SM
 };
 
 constexpr int MAX_CLUSTER = 8;
@@ -339,6 +343,8 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 	cg::cluster_group cluster = cg::this_cluster();
 	const int C = (int)cluster.num_blocks();
 	const int rank = (int)cluster.block_rank();
+	SmAcct acct_scope(p.acct, SM_ACCT_EM, (unsigned)p.acct_w);
+	SmAcct acct_cta(p.acct, SM_ACCT_EM_CTA, 1024u);          // plain CTA-resident cycles (latency roofline)
 
 	extern __shared__ double em_smem[];
 	const int n2 = 2 * p.n_cur;
@@ -755,7 +761,14 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 		const double *fin = fr0 + (size_t)(iters & 1) * n2;        // written by the last M step
 		double *out = p.out_freq + (size_t)c * n2;
 		for (int u = tid; u < n2; u += EM_THREADS) out[u] = fin[u];
-		if (tid == 0) { status[0] = result; status[1] = iters; }
+		if (tid == 0)
+		{
+			// longest chain of the M step in rows (= dependent fp64 adds per iteration) and the compatible
+			// pairs: the kernel's latency floor and its arithmetic work, for the roofline accounting
+			int longest = 0;
+			for (int g = 0; g < n_groups; g++) longest = max(longest, glen[g]);
+			status[0] = result; status[1] = iters; status[2] = longest; status[3] = coff[p.n_entry];
+		}
 	}
 	if (prof)
 	{
@@ -998,6 +1011,8 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	if (dense && n_dense_lanes_ >= 8) cluster = 1;
 	if (const char *e = getenv("HIBAG_B200_EM_CLUSTER")) cluster = std::max(1, std::min(MAX_CLUSTER, atoi(e)));
 	auto kern = dense ? (ring_rows == 64 ? em_kernel<512, 64> : em_kernel<512, 32>) : em_kernel<1024, 64>;
+	a.acct = device_sm_acct();
+	a.acct_w = (dense && smem <= (size_t)113 * 1024) ? 512 : 1024;
 	HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
 	HB_CUDA(cudaEventRecord(ev0_.e, st));
 	{
@@ -1023,6 +1038,14 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 	kernel_ms += ms;
 	launches++;
+	for (int i = 0; i < m; i++)
+	{
+		const int *stt = h_status_.get() + 4 * i;
+		if (stt[0] == EM_INVALID) continue;
+		sum_iterations += (uint64_t)stt[1];
+		sum_chain_adds += (uint64_t)stt[1] * (uint64_t)stt[2];
+		sum_pair_updates += (uint64_t)stt[1] * (uint64_t)stt[3];
+	}
 	if (want_prof)
 	{
 		std::vector<unsigned long long> hp(8 * (size_t)m);

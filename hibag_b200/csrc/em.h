@@ -54,6 +54,7 @@ public:
 	/// test hook: report candidate i as undecided so that the caller's host fallback runs
 	void force_ambiguous(int i) { if (h_status_.get()[4 * i] == EM_OK) h_status_.get()[4 * i] = EM_AMBIGUOUS; }
 	int iterations(int i) const { return h_status_.get()[4 * i + 1]; }
+	uint64_t sum_iterations = 0, sum_chain_adds = 0, sum_pair_updates = 0;   // over run_em calls (see train stats)
 
 	/// the pair lists as the host algorithm holds them (for the host fallback / tests)
 	void fetch_pairs(RoundPairs &out, const std::vector<int> &inbag, const std::vector<int> &boot,

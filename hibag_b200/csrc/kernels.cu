@@ -60,6 +60,7 @@ cell_pass_kernel(const __grid_constant__ CellBatch p)
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
+	SmAcct acct_scope(p.acct, SM_ACCT_CELL_PASS, (unsigned)p.acct_w);
 
 	if (SMEM && tid == 0)
 	{
@@ -284,15 +285,17 @@ static void launch_cell_variant(const CellBatch &p, int sm_count, cudaStream_t s
 	if (grid > need) grid = need;
 	if (grid < p.n_lists) grid = p.n_lists;
 
+	CellBatch q = p;
+	q.acct_w = 1024 / cta_per_sm;
 	if (in_smem)
 	{
 		auto k = cell_pass_kernel<NW, R, CLAMP, true>;
 		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-		k<<<(unsigned)grid, CELL_THREADS, smem, st>>>(p);
+		k<<<(unsigned)grid, CELL_THREADS, smem, st>>>(q);
 	} else {
 		auto k = cell_pass_kernel<NW, R, CLAMP, false>;
 		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-		k<<<(unsigned)grid, CELL_THREADS, smem, st>>>(p);
+		k<<<(unsigned)grid, CELL_THREADS, smem, st>>>(q);
 	}
 	CUDA_CHECK(cudaGetLastError());
 }
@@ -325,6 +328,7 @@ int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cuda
 	b.task_counters = p.task_counter; b.p_stride = p.p_stride;
 	b.n_dist = p.n_dist; b.n_snp = p.n_snp; b.geno_stride = p.geno_stride; b.n_pos = p.n_pos;
 	b.n_lists = 1; b.max_hap = p.n_hap;
+	b.acct = device_sm_acct();
 	ListDesc &L = b.lists[0];
 	L.hap = p.hap; L.cells = p.cells; L.chunks = p.chunks; L.cand_col = p.cand_col; L.P = p.P;
 	L.n_hap = p.n_hap; L.n_chunks = p.n_chunks; L.cand_bit = p.cand_bit;

@@ -70,6 +70,14 @@ struct ListDesc
 
 static const int MAX_BATCH_LISTS = 32;
 
+/// SM-time accounting classes (devutil.cuh SmAcct; hibag_b200_sm_time in the C ABI)
+enum { SM_ACCT_GATHER_OOB = 0, SM_ACCT_GATHER_IB = 1, SM_ACCT_EM = 2, SM_ACCT_BOUND = 3, SM_ACCT_NEED = 4,
+       SM_ACCT_TASKS = 5, SM_ACCT_REDUCE_OOB = 6, SM_ACCT_REDUCE_IB = 7, SM_ACCT_CELL_PASS = 8,
+       SM_ACCT_EM_PREP = 9, SM_ACCT_EM_CTA = 10, SM_ACCT_N = 16 };
+/// per-device counters [SM_ACCT_N] (device memory, zeroed at first use): sum over CTAs of resident
+/// cycles x (1024 / CTAs of that launch that fit an SM)
+unsigned long long *device_sm_acct();
+
 /// Device-side description of one launch of the pair-scoring kernel: n_lists haplotype lists
 /// (e.g. the candidate SNPs of one selection round) against one list of samples.
 struct CellBatch
@@ -81,6 +89,8 @@ struct CellBatch
 	size_t p_stride;
 	int n_dist, n_snp, geno_stride, n_pos;
 	int n_lists, max_hap;         // max_hap = largest n_hap of the batch (shared-memory sizing)
+	unsigned long long *acct;     // SM-time counters or null
+	int acct_w, pad2;
 	ListDesc lists[MAX_BATCH_LISTS];
 };
 
@@ -168,7 +178,9 @@ struct GatherBatch
 	unsigned int *task_counters;  // [n_lists], zeroed before launch
 	size_t p_stride;
 	int n_dist, n_snp, geno_stride, n_pos;
-	int n_lists, max_hap, n_cells, pad;
+	int n_lists, max_hap, n_cells, acct_cls;
+	unsigned long long *acct;     // SM-time counters or null
+	int acct_w, pad2;
 	GatherList lists[MAX_BATCH_LISTS];
 };
 
@@ -200,6 +212,7 @@ struct ScreenArgs
 	int force_rescue;             // test hook: > 0 rescues every force_rescue-th position
 	int device_rescue;            // 1: uncertified sums are rescued inside the reduction; 0: reported
 	                              // as ratio -1 and rescored by the caller with the plain kernel
+	unsigned long long *acct;     // SM-time counters or null
 };
 struct ScreenList { const void *hap; const CellTask *cells; const int8_t *cand_col; int n_hap, cand_bit; };
 struct ScreenLists { ScreenList l[MAX_BATCH_LISTS]; };

@@ -10,6 +10,9 @@
 // report failure by throwing std::exception like any other plugin of the reference would.
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -22,53 +25,92 @@ namespace hb {
 // ---------------------------------------------------------------------------------------------
 // training hooks
 // ---------------------------------------------------------------------------------------------
+/// One of the two device-side copies of the training state. A candidate SNP is evaluated on the
+/// context the previous candidate did NOT use, so that the speculative in-bag pass of the previous
+/// candidate (see hook_build_acc_oob) may still be running while this one is uploaded and scored.
+struct BuildCtx
+{
+	GenoSet geno;
+	PinBuf<unsigned char> h_aos;      // pinned SHADOW of the TGenotype[] this context's planes were built from
+	DevBuf<unsigned char> d_aos;
+	bool shadow_valid = false;
+	PinBuf<int8_t> h_code;            // [4][n_samp] 2-bit codes of up to four changed SNP columns
+	DevBuf<int8_t> d_code;
+	EvalSlot slot_oob{true, true};    // high-priority stream, spinning sync: the host waits on this one
+	EvalSlot slot_ib{false, true};    // the speculative in-bag pass
+	Event ev_ready{false};            // planes + list of this context are on the device
+	bool ib_pending = false;          // an in-bag pass is enqueued on slot_ib and not yet synchronised
+};
+
 struct BuildState
 {
 	int n_hla = 0, n_samp = 0, n_snp = 0;
-	GenoSet geno;
-	PinBuf<unsigned char> h_aos;      // pinned SHADOW of the TGenotype[] the device planes were built from
-	DevBuf<unsigned char> d_aos;
-	bool shadow_valid = false;
-	PinBuf<int8_t> h_code;            // [4][n_samp] column codes of up to four changed SNP columns
-	DevBuf<int8_t> d_code;
-	uint64_t n_full_uploads = 0, n_column_uploads = 0, n_unchanged = 0;
+	BuildCtx ctx[2];
+	int cur = 0;
+	uint64_t n_full_uploads = 0, n_column_uploads = 0, n_unchanged = 0, n_ib_wasted = 0;
+	double t_set = 0, t_oob = 0, t_ib = 0;        // seconds inside the three hooks
 	std::vector<int> boot;            // bootstrap multiplicities currently on the device
 	std::vector<int> oob, ib;         // ascending sample indices (src/LibHLA.cpp:1858-1874)
 	DevBuf<int> d_oob, d_ib;
 	bool have_lists = false;
 	bool have_list_staged = false;
-	EvalSlot slot;
-	ScoreStats total;
+	bool speculate = true;            // HIBAG_B200_HOOK_SPECULATE=0 turns the speculative in-bag pass off
+	ScoreStats retired;               // stats of slots are folded here
+
+	void drain()
+	{
+		for (BuildCtx &c : ctx)
+		{
+			if (c.ib_pending) { c.slot_ib.sync(); c.ib_pending = false; }
+			HB_CUDA(cudaStreamSynchronize(c.slot_oob.stream()));
+		}
+	}
 
 	void set_bootstrap(const int *cnt)
 	{
+		drain();                          // the sample lists are shared by both contexts
 		boot.assign(cnt, cnt + n_samp);
 		oob.clear(); ib.clear();
 		for (int i = 0; i < n_samp; i++)
 			(cnt[i] > 0 ? ib : oob).push_back(i);
 		d_oob.ensure(n_samp); d_ib.ensure(n_samp);
+		cudaStream_t st = ctx[0].slot_oob.stream();
 		// pageable -> device copies are synchronous with respect to the host buffer
 		if (!oob.empty())
 			HB_CUDA(cudaMemcpyAsync(d_oob.get(), oob.data(), sizeof(int) * oob.size(),
-				cudaMemcpyHostToDevice, slot.stream()));
+				cudaMemcpyHostToDevice, st));
 		if (!ib.empty())
 			HB_CUDA(cudaMemcpyAsync(d_ib.get(), ib.data(), sizeof(int) * ib.size(),
-				cudaMemcpyHostToDevice, slot.stream()));
-		HB_CUDA(cudaStreamSynchronize(slot.stream()));
-		slot.stats.h2d_bytes += sizeof(int) * (size_t)n_samp;
+				cudaMemcpyHostToDevice, st));
+		HB_CUDA(cudaStreamSynchronize(st));
+		ctx[0].slot_oob.stats.h2d_bytes += sizeof(int) * (size_t)n_samp;
 		have_lists = true;
 	}
 
-	GenoView view() const
+	static GenoView view(const BuildCtx &c, int n_samp)
 	{
 		GenoView v;
-		v.s1 = geno.s1.get(); v.s2 = geno.s2.get(); v.stride = n_samp;
-		v.a1 = geno.a1.get(); v.a2 = geno.a2.get();
+		v.s1 = c.geno.s1.get(); v.s2 = c.geno.s2.get(); v.stride = n_samp;
+		v.a1 = c.geno.a1.get(); v.a2 = c.geno.a2.get();
 		return v;
+	}
+
+	ScoreStats stats() const
+	{
+		ScoreStats s = retired;
+		for (const BuildCtx &c : ctx) { s.add(c.slot_oob.stats); s.add(c.slot_ib.stats); }
+		return s;
 	}
 };
 
 static std::unique_ptr<BuildState> g_build;
+
+static double hook_now()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static void hook_build_init(int n_hla, int n_sample)
 {
@@ -77,15 +119,33 @@ static void hook_build_init(int n_hla, int n_sample)
 	g_build.reset(new BuildState());
 	g_build->n_hla = n_hla;
 	g_build->n_samp = n_sample;
-	g_build->geno.ensure(n_sample);
-	g_build->h_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
-	g_build->d_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
-	g_build->h_code.ensure(4 * (size_t)n_sample);
-	g_build->d_code.ensure(4 * (size_t)n_sample);
+	for (BuildCtx &c : g_build->ctx)
+	{
+		c.geno.ensure(n_sample);
+		c.h_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
+		c.d_aos.ensure(sizeof(hibag_genotype) * (size_t)n_sample);
+		c.h_code.ensure(4 * (size_t)n_sample);
+		c.d_code.ensure(4 * (size_t)n_sample);
+		int r = 2;                        // samples per lane of the single-list passes (latency-bound)
+		if (const char *e = getenv("HIBAG_B200_HOOK_R")) r = atoi(e);
+		c.slot_oob.set_samples_per_lane(r);
+		c.slot_ib.set_samples_per_lane(r);
+	}
+	if (const char *e = getenv("HIBAG_B200_HOOK_SPECULATE")) g_build->speculate = atoi(e) != 0;
 }
 
 static void hook_build_done()
 {
+	if (g_build)
+	{
+		try { g_build->drain(); } catch (...) {}
+		if (getenv("HIBAG_B200_HOOK_PROF"))
+			fprintf(stderr, "hooks: set_haplo_geno %.3f s (%llu full, %llu column, %llu unchanged uploads), acc_oob %.3f s, "
+				"acc_ib %.3f s, speculative in-bag passes not asked for: %llu\n", g_build->t_set,
+				(unsigned long long)g_build->n_full_uploads, (unsigned long long)g_build->n_column_uploads,
+				(unsigned long long)g_build->n_unchanged, g_build->t_oob, g_build->t_ib,
+				(unsigned long long)g_build->n_ib_wasted);
+	}
 	g_build.reset();
 }
 
@@ -100,6 +160,7 @@ static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo
 {
 	BuildState *b = g_build.get();
 	if (!b) throw std::runtime_error("build_set_haplo_geno called before build_init");
+	const double t0 = hook_now();
 	// the genotype array carries the bootstrap counts too; (re)build the sample lists when the
 	// host did not call build_set_bootstrap or the counts changed
 	bool same = b->have_lists;
@@ -113,16 +174,22 @@ static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo
 		b->set_bootstrap(cnt.data());
 	}
 	b->n_snp = n_snp;
+	// the other context: whatever the previous candidate left running (its speculative in-bag pass)
+	// is not touched; this context's own in-bag pass is two candidates old
+	b->cur ^= 1;
+	BuildCtx &c = b->ctx[b->cur];
+	if (c.ib_pending) { c.slot_ib.sync(); c.ib_pending = false; b->n_ib_wasted++; }
+	cudaStream_t st = c.slot_oob.stream();
 	const size_t bytes = sizeof(hibag_genotype) * (size_t)b->n_samp;
 	// The reference hands over the whole TGenotype[nSample] with every candidate SNP (240 KB at
 	// 5,000 samples), but between two calls it has only rewritten the candidate's bit column
 	// (CGenotypeList::AddSNP / ReduceSNP, src/LibHLA.cpp:860-881) -- or two columns after an accepted
-	// SNP. The previous evaluation has been synchronised (acc_* return values), so the pinned shadow
-	// is free: diff against it, and when the change is confined to <= 4 bit columns upload those
-	// columns as 2-bit codes (n bytes each) and patch the device planes; otherwise upload everything.
-	hibag_genotype *shadow = (hibag_genotype *)b->h_aos.get();
+	// SNP. This context's previous evaluation has been synchronised, so its pinned shadow is free:
+	// diff against it, and when the change is confined to <= 4 bit columns upload those columns as
+	// 2-bit codes (n bytes each) and patch the device planes; otherwise upload everything.
+	hibag_genotype *shadow = (hibag_genotype *)c.h_aos.get();
 	uint64_t d1[2] = { 0, 0 }, d2[2] = { 0, 0 };
-	bool other = !b->shadow_valid;
+	bool other = !c.shadow_valid;
 	if (!other)
 	{
 		for (int i = 0; i < b->n_samp; i++)
@@ -138,13 +205,12 @@ static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo
 	if (other || n_changed > 4)
 	{
 		memcpy(shadow, geno, bytes);
-		HB_CUDA(cudaMemcpyAsync(b->d_aos.get(), b->h_aos.get(), bytes, cudaMemcpyHostToDevice,
-			b->slot.stream()));
-		b->slot.stats.h2d_bytes += bytes;
-		launch_unpack_genotypes(b->d_aos.get(), b->n_samp, b->geno.s1.get(), b->geno.s2.get(),
-			b->n_samp, b->geno.a1.get(), b->geno.a2.get(), b->geno.boot.get(), b->slot.stream());
-		b->slot.stats.launches++;
-		b->shadow_valid = true;
+		HB_CUDA(cudaMemcpyAsync(c.d_aos.get(), c.h_aos.get(), bytes, cudaMemcpyHostToDevice, st));
+		c.slot_oob.stats.h2d_bytes += bytes;
+		launch_unpack_genotypes(c.d_aos.get(), b->n_samp, c.geno.s1.get(), c.geno.s2.get(),
+			b->n_samp, c.geno.a1.get(), c.geno.a2.get(), c.geno.boot.get(), st);
+		c.slot_oob.stats.launches++;
+		c.shadow_valid = true;
 		b->n_full_uploads++;
 	} else if (n_changed > 0)
 	{
@@ -154,31 +220,33 @@ static void hook_build_set_haplo_geno(const hibag_haplotype haplo[], int n_haplo
 			{
 				const int bit = __builtin_ctzll(m);
 				const uint64_t one = (uint64_t)1 << bit;
-				int8_t *code = b->h_code.get() + (size_t)k * b->n_samp;
+				int8_t *code = c.h_code.get() + (size_t)k * b->n_samp;
 				for (int i = 0; i < b->n_samp; i++)
 				{
-					const uint64_t a = (uint64_t)geno[i].snp1[w] & one, c = (uint64_t)geno[i].snp2[w] & one;
-					code[i] = (int8_t)((a ? 1 : 0) | (c ? 2 : 0));
+					const uint64_t a = (uint64_t)geno[i].snp1[w] & one, cc = (uint64_t)geno[i].snp2[w] & one;
+					code[i] = (int8_t)((a ? 1 : 0) | (cc ? 2 : 0));
 					shadow[i].snp1[w] = (int64_t)(((uint64_t)shadow[i].snp1[w] & ~one) | a);
-					shadow[i].snp2[w] = (int64_t)(((uint64_t)shadow[i].snp2[w] & ~one) | c);
+					shadow[i].snp2[w] = (int64_t)(((uint64_t)shadow[i].snp2[w] & ~one) | cc);
 				}
 			}
-		HB_CUDA(cudaMemcpyAsync(b->d_code.get(), b->h_code.get(), (size_t)k * b->n_samp,
-			cudaMemcpyHostToDevice, b->slot.stream()));
-		b->slot.stats.h2d_bytes += (size_t)k * b->n_samp;
+		HB_CUDA(cudaMemcpyAsync(c.d_code.get(), c.h_code.get(), (size_t)k * b->n_samp,
+			cudaMemcpyHostToDevice, st));
+		c.slot_oob.stats.h2d_bytes += (size_t)k * b->n_samp;
 		k = 0;
 		for (int w = 0; w < 2; w++)
 			for (uint64_t m = u[w]; m; m &= m - 1, k++)
 			{
-				launch_patch_column(b->d_code.get() + (size_t)k * b->n_samp, b->n_samp, b->geno.s1.get(),
-					b->geno.s2.get(), b->n_samp, 64 * w + __builtin_ctzll(m), b->slot.stream());
-				b->slot.stats.launches++;
+				launch_patch_column(c.d_code.get() + (size_t)k * b->n_samp, b->n_samp, c.geno.s1.get(),
+					c.geno.s2.get(), b->n_samp, 64 * w + __builtin_ctzll(m), st);
+				c.slot_oob.stats.launches++;
 			}
 		b->n_column_uploads++;
 	} else
 		b->n_unchanged++;
-	b->slot.stage_list(haplo, n_haplo, b->n_hla, n_snp);
+	c.slot_oob.stage_list(haplo, n_haplo, b->n_hla, n_snp);
+	HB_CUDA(cudaEventRecord(c.ev_ready.e, st));
 	b->have_list_staged = true;
+	b->t_set += hook_now() - t0;
 }
 
 /// optional hook (src/LibHLA.cpp:1014-1072): the host expands every record into the 3-4 doubled
@@ -192,8 +260,20 @@ static uint32_t *hook_build_haplomatch(const hibag_haplotype haplo[], const size
 	std::vector<int> ib;
 	for (int i = 0; i < b->n_samp; i++)
 		if (geno[i].bootstrap_count > 0) ib.push_back(i);
-	b->slot.stats.launches += 3;
+	b->ctx[0].slot_oob.stats.launches += 3;
 	return haplomatch_records(haplo, n_haplo, b->n_hla, n_snp, geno, b->n_samp, ib, out_n);
+}
+
+/// enqueue the in-bag pass of the current context on its in-bag slot (after planes + list landed)
+static void enqueue_ib(BuildState *b, BuildCtx &c)
+{
+	const int n = (int)b->ib.size();
+	const GenoView v = BuildState::view(c, b->n_samp);
+	HB_CUDA(cudaStreamWaitEvent(c.slot_ib.stream(), c.ev_ready.e, 0));
+	c.slot_ib.borrow_list(c.slot_oob);
+	c.slot_ib.enqueue_cells(v, b->d_ib.get(), n);
+	c.slot_ib.enqueue_reduce_ib(v, b->d_ib.get(), n);
+	c.ib_pending = true;
 }
 
 static int hook_build_acc_oob()
@@ -201,13 +281,30 @@ static int hook_build_acc_oob()
 	BuildState *b = g_build.get();
 	if (!b || !b->have_list_staged)
 		throw std::runtime_error("build_acc_oob called before build_set_haplo_geno");
+	const double t0 = hook_now();
+	BuildCtx &c = b->ctx[b->cur];
 	const int n = (int)b->oob.size();
-	if (n == 0) return 0;
-	const GenoView v = b->view();
-	b->slot.enqueue_cells(v, b->d_oob.get(), n);
-	b->slot.enqueue_reduce_oob(v, b->d_oob.get(), n);
-	b->slot.sync();
-	return b->slot.oob_count();
+	int result = 0;
+	if (n > 0)
+	{
+		const GenoView v = BuildState::view(c, b->n_samp);
+		c.slot_oob.enqueue_cells(v, b->d_oob.get(), n);
+		c.slot_oob.enqueue_reduce_oob(v, b->d_oob.get(), n);
+	}
+	// The reference asks for the in-bag loss right after this call whenever the accuracy is not below
+	// its running maximum (src/LibHLA.cpp:2031-2034) -- more than half of the candidates. The hook
+	// protocol is strictly sequential and a single-list pass is bound by the latency of its longest
+	// fp64 chain, not by throughput, so the in-bag pass is started NOW on a second stream beside the
+	// out-of-bag pass; build_acc_ib then only waits for it. An in-bag pass that is never asked for
+	// finishes in the background on this context while the next candidate uses the other one.
+	if (b->speculate && !b->ib.empty()) enqueue_ib(b, c);
+	if (n > 0)
+	{
+		c.slot_oob.sync();
+		result = c.slot_oob.oob_count();
+	}
+	b->t_oob += hook_now() - t0;
+	return result;
 }
 
 static double hook_build_acc_ib()
@@ -215,17 +312,19 @@ static double hook_build_acc_ib()
 	BuildState *b = g_build.get();
 	if (!b || !b->have_list_staged)
 		throw std::runtime_error("build_acc_ib called before build_set_haplo_geno");
+	const double t0 = hook_now();
+	BuildCtx &c = b->ctx[b->cur];
 	const int n = (int)b->ib.size();
-	const GenoView v = b->view();
-	b->slot.enqueue_cells(v, b->d_ib.get(), n);
-	b->slot.enqueue_reduce_ib(v, b->d_ib.get(), n);
-	b->slot.sync();
+	if (!c.ib_pending) enqueue_ib(b, c);
+	c.slot_ib.sync();
+	c.ib_pending = false;
 	// log() and the in-bag-order sum stay on the host (glibc log, sequential order of
 	// src/LibHLA.cpp:1966-1977)
-	const double *ratio = b->slot.ib_ratios();
+	const double *ratio = c.slot_ib.ib_ratios();
 	double loglik = 0;
 	for (int i = 0; i < n; i++)
 		loglik += b->boot[b->ib[i]] * std::log(ratio[i]);
+	b->t_ib += hook_now() - t0;
 	return loglik * -2;
 }
 
@@ -373,7 +472,7 @@ hibag_gpu_ext_proc *plugin_procs_with_haplomatch() { return &g_procs_hm; }
 ScoreStats plugin_build_stats()
 {
 	ScoreStats s;
-	if (g_build) s = g_build->slot.stats;
+	if (g_build) s = g_build->stats();
 	return s;
 }
 

@@ -90,6 +90,21 @@ const double *device_rare_freq_floor_table()
 	return d;
 }
 
+static std::map<int, unsigned long long *> g_dev_acct;
+
+unsigned long long *device_sm_acct()
+{
+	const DeviceInfo &di = current_device();
+	std::lock_guard<std::mutex> lk(g_dev_mutex);
+	auto it = g_dev_acct.find(di.device);
+	if (it != g_dev_acct.end()) return it->second;
+	unsigned long long *d = nullptr;
+	HB_CUDA(cudaMalloc((void **)&d, sizeof(unsigned long long) * SM_ACCT_N));
+	HB_CUDA(cudaMemset(d, 0, sizeof(unsigned long long) * SM_ACCT_N));
+	g_dev_acct[di.device] = d;
+	return d;
+}
+
 int choose_samples_per_lane(int n_pos, int n_chunks, int n_snp, int sm_count)
 {
 	// enough (sample group, chunk) tasks to give every SM sub-partition several warps;
@@ -220,7 +235,7 @@ size_t pool_trim()
 }
 
 // ---- EvalSlot ---------------------------------------------------------------------------------
-EvalSlot::EvalSlot()
+EvalSlot::EvalSlot(bool high_priority, bool spin) : st_(high_priority), ev1_(true, !spin)
 {
 	current_device();
 	counter_.ensure(4);
@@ -237,6 +252,7 @@ void EvalSlot::stage_list(const hibag_haplotype *haplo, int n_hap, int n_hla, in
 	unsigned char *d = d_blob_.ensure(cap);
 	HB_CUDA(cudaMemcpyAsync(d, h, blob_.bytes, cudaMemcpyHostToDevice, st_.s));
 	stats.h2d_bytes += blob_.bytes;
+	ext_blob_ = nullptr;
 }
 
 void EvalSlot::enqueue_cells(const GenoView &g, const int *pos_list, int n_pos)
@@ -247,14 +263,15 @@ void EvalSlot::enqueue_cells(const GenoView &g, const int *pos_list, int n_pos)
 	P_.ensure(p_stride_ * (size_t)blob_.n_cells);
 	CellPass p;
 	memset(&p, 0, sizeof(p));
-	bind_list(blob_, d_blob_.get(), device_rare_freq_table(), p);
+	bind_list(blob_, ext_blob_ ? (const void *)ext_blob_ : (const void *)d_blob_.get(), device_rare_freq_table(), p);
 	p.s1 = g.s1; p.s2 = g.s2; p.geno_stride = g.stride;
 	p.cand_col = g.cand_col; p.cand_bit = g.cand_bit;
 	p.samp_list = pos_list; p.n_pos = n_pos;
 	p.task_counter = counter_.get();
 	p.P = P_.get(); p.p_stride = p_stride_;
 	HB_CUDA(cudaMemsetAsync(counter_.get(), 0, sizeof(unsigned int), st_.s));
-	const int R = choose_samples_per_lane(n_pos, blob_.n_chunks, blob_.n_snp, di.sm_count);
+	int R = choose_samples_per_lane(n_pos, blob_.n_chunks, blob_.n_snp, di.sm_count);
+	if (force_r_ > 0 && force_r_ < R) R = force_r_;
 	HB_CUDA(cudaEventRecord(ev0_.e, st_.s));
 	const int nw = launch_cell_pass(p, R, di.sm_count, st_.s);
 	HB_CUDA(cudaEventRecord(evc_.e, st_.s));
@@ -393,6 +410,7 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 	b.p_stride = p_stride;
 	b.n_snp = n_snp_;
 	b.n_lists = count;
+	b.acct = device_sm_acct();
 	int total_chunks = 0;
 	uint64_t pairs = 0;
 	for (int k = 0; k < count; k++)
@@ -450,6 +468,9 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	a.n_snp = n_snp_; a.geno_stride = g.stride; a.n_pos = n_pos; a.n_hla = n_hla_; a.n_lists = count;
 	a.p_stride = p_stride_;
 	a.K = screen_bound_factor();
+	a.acct = device_sm_acct();
+	gb.acct = a.acct;
+	gb.acct_cls = kind ? SM_ACCT_GATHER_IB : SM_ACCT_GATHER_OOB;
 	a.tau = kind ? screen_tau_ : 1.0;
 	a.U = U_.get() + (size_t)first * n_hla_ * p_stride_;
 	a.xref = xref_.get() + (size_t)first * p_stride_;

@@ -69,9 +69,16 @@ struct GenoView
 class EvalSlot
 {
 public:
-	EvalSlot();
+	/// spin: sync() busy-waits (lowest latency; the sequential hook path) instead of sleeping on a
+	/// blocking event (the trainer's workers, which must free their core)
+	explicit EvalSlot(bool high_priority = false, bool spin = false);
 	/// pack + cut + async upload of a haplotype list (tags must be filled, see tasks.h)
 	void stage_list(const hibag_haplotype *haplo, int n_hap, int n_hla, int n_snp);
+	/// score the list staged on another slot (its device blob must stay untouched until this
+	/// slot's work has finished); the caller orders the streams
+	void borrow_list(const EvalSlot &o) { blob_ = o.blob_; ext_blob_ = o.d_blob_.get(); }
+	/// samples per lane of the following enqueue_cells (0: chosen from the pass size)
+	void set_samples_per_lane(int r) { force_r_ = r; }
 	/// all cells for the positions in pos_list (device int[n_pos], may be null = identity)
 	void enqueue_cells(const GenoView &g, const int *pos_list, int n_pos);
 	/// out-of-bag accuracy over the last enqueue_cells (src/LibHLA.cpp:1934-1955)
@@ -93,8 +100,10 @@ public:
 private:
 	Stream st_;
 	Event ev0_, evc_;            // slot span begin, end of the pair-scoring kernel
-	Event ev1_{true, true};      // slot span end; blocking sync so waiting workers free their core
+	Event ev1_;                  // slot span end; blocking sync (unless spin) so waiting workers free their core
 	bool timing_pending_ = false;
+	const unsigned char *ext_blob_ = nullptr;
+	int force_r_ = 0;
 	PinBuf<unsigned char> h_blob_;
 	DevBuf<unsigned char> d_blob_;
 	ListBlob blob_;

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(128)
 screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 {
 	extern __shared__ int sh_al[];                        // start[n_hla], n[n_hla]
+	SmAcct acct_scope(a.acct, SM_ACCT_BOUND, 64u);        // 128 threads: 16 CTAs fit an SM
 	const int l = blockIdx.y;
 	const ScreenList &L = ls.l[l];
 	int *al_start = sh_al, *al_n = sh_al + a.n_hla;
@@ -328,6 +329,7 @@ screen_need_kernel(const ScreenArgs a)
 	// round trip to L2 per cell.
 	__shared__ unsigned int sh_mask[4][NEED_TILE];
 	__shared__ int sh_base[4][NEED_TILE];
+	SmAcct acct_scope(a.acct, SM_ACCT_NEED, 147u);        // 32 KB of shared memory: 7 CTAs fit an SM
 	const int l = blockIdx.y;
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -411,6 +413,7 @@ void launch_screen_need(const ScreenArgs &a, cudaStream_t st)
 __global__ void __launch_bounds__(64)
 reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 {
+	SmAcct acct_scope(a.acct, SM_ACCT_REDUCE_OOB, 32u);  // 64 threads: 32 CTAs fit an SM
 	const int l = blockIdx.y;
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
 	const int n = a.n_hla;
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(64)
 reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls,
 	double *out_ratio, size_t out_stride)
 {
+	SmAcct acct_scope(a.acct, SM_ACCT_REDUCE_IB, 32u);
 	const int l = blockIdx.y;
 	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
@@ -750,6 +754,7 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
+	SmAcct acct_scope(p.acct, p.acct_cls, (unsigned)p.acct_w);
 
 	if (SMEM && tid == 0)
 	{
@@ -880,15 +885,17 @@ static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream
 	long long grid = (long long)sm_count * cta_per_sm;
 	if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
 	if (grid < p.n_lists) grid = p.n_lists;
+	GatherBatch q = p;
+	q.acct_w = 1024 / cta_per_sm;
 	if (in_smem)
 	{
 		auto k = cell_gather_kernel<NW, CLAMP, true>;
 		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-		k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(p);
+		k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(q);
 	} else {
 		auto k = cell_gather_kernel<NW, CLAMP, false>;
 		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-		k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(p);
+		k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(q);
 	}
 	CUDA_CHECK(cudaGetLastError());
 }

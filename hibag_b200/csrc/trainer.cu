@@ -336,7 +336,11 @@ void Trainer::run(const std::function<int()> &next)
 	built_.clear();
 	trace_.clear();
 	if (scorer_) scorer_->stats = ScoreStats();
-	if (rem_) { rem_->kernel_ms = 0; rem_->launches = 0; rem_->h2d_bytes = 0; rem_->d2h_bytes = 0; }
+	if (rem_)
+	{
+		rem_->kernel_ms = 0; rem_->launches = 0; rem_->h2d_bytes = 0; rem_->d2h_bytes = 0;
+		rem_->sum_iterations = rem_->sum_chain_adds = rem_->sum_pair_updates = 0;
+	}
 	const ScoreStats plugin_before = procs_ ? plugin_build_stats() : ScoreStats();
 	std::fill(em_seconds_.begin(), em_seconds_.end(), 0.0);
 	std::fill(wait_seconds_.begin(), wait_seconds_.end(), 0.0);
@@ -400,6 +404,9 @@ void Trainer::run(const std::function<int()> &next)
 		stats_.launches += rem_->launches; stats_.kernel_ms += rem_->kernel_ms;
 		stats_.h2d_bytes += rem_->h2d_bytes; stats_.d2h_bytes += rem_->d2h_bytes;
 		ts_.em_kernel_ms += rem_->kernel_ms;
+		ts_.em_iterations += rem_->sum_iterations;
+		ts_.em_chain_adds += rem_->sum_chain_adds;
+		ts_.em_pair_updates += rem_->sum_pair_updates;
 	}
 	if (procs_)
 	{
@@ -925,6 +932,8 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts)
 		ts.gather_kernel_ms += a.gather_kernel_ms; ts.gather_kernel_launches += a.gather_kernel_launches;
 		ts.gather_ib_kernel_ms += a.gather_ib_kernel_ms; ts.gather_ib_launches += a.gather_ib_launches;
 		ts.gather_ib_popc32 += a.gather_ib_popc32;
+		ts.em_iterations += a.em_iterations; ts.em_chain_adds += a.em_chain_adds;
+		ts.em_pair_updates += a.em_pair_updates;
 		m.train_trace.insert(m.train_trace.end(), t.trace_.begin(), t.trace_.end());
 		t.built_.clear();
 	}

@@ -189,6 +189,11 @@ typedef struct hibag_b200_train_stats {
 	                                 launches score ~2.5 cells per sample and are latency-bound) */
 	uint64_t gather_ib_launches;
 	uint64_t gather_ib_popc32;    /* POPC.32 issued by the in-bag launches */
+	uint64_t em_iterations;       /* device EM: iterations summed over the candidates */
+	uint64_t em_chain_adds;       /* device EM: sum over candidates of iterations x (longest chain of
+	                                 dependent fp64 adds of its M step) -- the latency floor of the
+	                                 kernel in adds (x 16.9 cycles measured for a dependent DADD) */
+	uint64_t em_pair_updates;     /* device EM: sum over candidates of iterations x compatible pairs */
 } hibag_b200_train_stats;
 int hibag_b200_model_train_stats(const hibag_b200_model *m, hibag_b200_train_stats *out);
 
@@ -274,6 +279,15 @@ int hibag_b200_bed_decode_device(const uint8_t *payload_dev, int mode, int n_sam
  * 8 GB pinned). This gives every cached block back to the driver, e.g. before another library
  * needs the memory; returns the bytes released. */
 size_t hibag_b200_trim_cache(void);
+
+/* SM-time accounting of the current device: out[16] = per kernel class the sum over its CTAs of
+ * (SM cycles the CTA was resident) x 1024 / (CTAs of that launch that fit one SM), i.e. 1/1024
+ * SM-cycles held. Classes: 0 out-of-bag gather, 1 in-bag gather, 2 EM, 3 screen bounds, 4 need lists,
+ * 5 task prefix, 6 / 7 screened out-of-bag / in-bag reduction, 8 plain pair-scoring kernel, 10 the EM
+ * kernel's plain CTA-resident cycles (x 1024).
+ * Concurrent kernels overlap, so CUDA-event durations cannot attribute the GPU's time; held SM-time
+ * can. reset != 0 zeroes the counters after reading. */
+int hibag_b200_sm_time(uint64_t *out, int reset);
 
 /* ---- host-only pieces exposed for the CPU test-suite (no GPU needed) ------------------------- */
 /* R's Mersenne-Twister after set.seed(seed): n draws of unif_rand() */

@@ -22,3 +22,4 @@ print("hooks: %.3f s/classifier (%.1f /min) | per classifier: prepare %.3f candi
           d["h2d_bytes"] / n / 1e6, d["d2h_bytes"] / n / 1e6), flush=True)
 import hashlib
 print("digest", hashlib.sha1(b"".join(m.classifier(k)["freq"].tobytes() + m.classifier(k)["snpidx"].tobytes() for k in range(n + 1))).hexdigest()[:12])
+del m
