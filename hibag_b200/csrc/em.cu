@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 
 #include "kernels.h"
@@ -806,6 +807,33 @@ void EmProf::dump()
 }
 }  // namespace
 
+// HIBAG_B200_EM_GATE=n: at most n EM launches (one per lane and selection round, ~23 CTAs each) in
+// flight per process. Every candidate CTA streams ~0.8 MB of scratch per iteration; with 24 lanes
+// all in EM that is 440 MB -- far beyond the 126 MB L2 -- and the scattered 8-byte stores of the
+// contribution pass go to HBM. 0 (default) = no limit.
+namespace {
+struct EmGate
+{
+	std::mutex mu;
+	std::condition_variable cv;
+	int limit = 0, in_flight = 0;
+	EmGate() { if (const char *e = getenv("HIBAG_B200_EM_GATE")) limit = std::max(0, atoi(e)); }
+	void enter()
+	{
+		if (limit <= 0) return;
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&]() { return in_flight < limit; });
+		in_flight++;
+	}
+	void leave()
+	{
+		if (limit <= 0) return;
+		{ std::lock_guard<std::mutex> lk(mu); in_flight--; }
+		cv.notify_one();
+	}
+} g_em_gate;
+}  // namespace
+
 RoundEM::RoundEM() { current_device(); h_total_.ensure(4); }
 RoundEM::~RoundEM() {}
 
@@ -1014,6 +1042,7 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	a.acct = device_sm_acct();
 	a.acct_w = (dense && smem <= (size_t)113 * 1024) ? 512 : 1024;
 	HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+	g_em_gate.enter();
 	HB_CUDA(cudaEventRecord(ev0_.e, st));
 	{
 		cudaLaunchConfig_t cfg;
@@ -1033,7 +1062,9 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	HB_CUDA(cudaMemcpyAsync(h_status_.get(), d_status_.get(), sizeof(int) * 4 * (size_t)m,
 		cudaMemcpyDeviceToHost, st));
 	HB_CUDA(cudaEventRecord(ev_done_.e, st));
-	HB_CUDA(cudaEventSynchronize(ev_done_.e));
+	const cudaError_t sync_rc = cudaEventSynchronize(ev_done_.e);
+	g_em_gate.leave();
+	HB_CUDA(sync_rc);
 	float ms = 0;
 	HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 	kernel_ms += ms;
