@@ -866,11 +866,21 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
         torch.cuda.synchronize(); hd.barrier()
         ms3 = hd.max_over_ranks(e0.elapsed_time(e1), dev)
         same_cs = bool(torch.equal(res_cs["h1"][b:e], h1) and torch.equal(res_cs["h2"][b:e], h2))
-        rel = float(((res_cs["postprob"][b:e] - pp).abs() / pp.abs().clamp_min(1e-300)).max().item()) if n > 0 else 0.0
+        rel, worst = 0.0, None
+        if n > 0:
+            # relative to the larger of the two values (entries below 1e-290 are in or next to the
+            # denormal range, where fp64 has no relative precision left: compared absolutely)
+            x, y = res_cs["postprob"][b:e], pp
+            den = torch.maximum(x.abs(), y.abs()).clamp_min(1e-290)
+            r = (x - y).abs() / den
+            rel = float(r.max().item())
+            k = int(r.argmax().item())
+            worst = [float(x.flatten()[k].item()), float(y.flatten()[k].item()), k // nc, k % nc]
         out.update({"sharded_by_classifier_value": n_total / (ms3 * 1e-3), "sharded_by_classifier_ms": ms3,
                     "allreduce_ms": tm["allreduce_ms"], "allreduce_bytes": int(tm["allreduce_bytes"]),
                     "allreduce_gbs": tm["allreduce_bytes"] / max(tm["allreduce_ms"] * 1e-3, 1e-12) / 1e9,
                     "sharded_by_classifier_calls_equal": same_cs, "sharded_by_classifier_max_rel_err": rel,
+                    "sharded_by_classifier_worst_entry": worst,
                     "sharded_by_classifier_note": "%d classifiers per rank x all %d samples; one NCCL all-reduce (fp64 sum) of "
                                                   "[65536, %d] per tile; calls equal / posteriors vs the sample-sharded "
                                                   "(sequential classifier order) result on this rank's slice" % (

@@ -783,6 +783,456 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// em_resident_kernel -- the EM of one candidate with its working set in shared memory.
+//
+// em_kernel (above) streams ~2.7 MB per iteration per candidate through L2 (GenoFreq buffer, the
+// scattered 8-byte contribution stores into the ELL rows, the padded ELL rows read back by the M
+// step); with two dozen lanes in EM that working set (0.8 MB x ~550 candidates) is several times the
+// L2, the kernel sits on DRAM latency (233 k cycles per iteration measured inside the 24-lane step,
+// against a floor of ~20 k for its longest chain) and holds 30 % of the GPU's SM-time.
+//
+// Here one CTA (1024 threads, one per SM) keeps, per candidate: both frequency vectors, the
+// per-entry scale factors and the compatible pairs (u | v << 16, 4 bytes a pair, in pair order).
+// No contribution is ever stored: a chain's contribution r = x * (count / sum) is RECOMPUTED by the
+// lane that adds it, from a 4-byte record {partner haplotype, entry, u == v} written once per
+// candidate into the ELL of its group -- the lane owns haplotype h, so x = (2 f_h) f_partner (or
+// f_h f_h). (2 f_u) f_v and (2 f_v) f_u round the same real number once, 2 f being exact: the value is
+// the E step's x bit for bit, whichever side h is on.) The records are the only per-iteration global
+// traffic (read-only, L2-resident) and reach the lanes through per-warp cp.async rings, so the chain
+// runs at fp64-add latency.
+//   E step: one thread per in-bag entry -- x of its pairs from the shared frequencies, summed in
+//           list order; log-likelihood term; scale factor count / sum.
+//   M step: EMR_M_WARPS warps take the groups of 32 chains, longest first; every lane walks ITS
+//           chain in the reference's order.
+// Every accumulator receives the operands em_kernel gives it, in the same order, un-fused: the two
+// kernels are bit-identical (tests/test_gpu_parity.py trains the golden models with either).
+// A candidate whose compatible pairs exceed the shared-memory capacity is reported EM_AMBIGUOUS
+// (the host re-estimates it); run_em only chooses this kernel when that is not expected.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int EMR_M_WARPS = 6;          // warps that run the M step, each with its own ring
+constexpr int EMR_RING_B = 8;           // batches of 4 rows (512 B) a ring holds: 32 rows in flight (cp.async.wait_group
+                                        // with more than ~8 groups pending behaved like wait_all: 119 cycles per row measured)
+constexpr int EMR_LONG = 24;            // entries with more compatible pairs are summed by a whole warp
+constexpr int EMR_LONG_MAX = 1024;      // capacity of the list of such entries
+
+struct EmrArgs
+{
+	int n_entry, n_cur, n_samp, total_pairs, cap;   // cap = compatible pairs the CTA can hold
+	const int *ib, *boot, *off;
+	const int4 *pairs4;
+	const int *hap_sorted, *group_base, *inc_off, *inc_val;
+	const double *cur_freq;
+	size_t n_slots;
+	const int8_t *geno_t;
+	const int *cand_snp;
+	int *coff;                        // [m][n_entry + 1]
+	uint32_t *rec;                    // [m][n_slots] chain records: partner | entry << 16 | (u == v) << 31
+	uint32_t *cuv;                    // [m][total_pairs] compatible pairs (u | v << 16) when they are streamed
+	double *out_freq;
+	int *out_status;
+	double scale, em_reltol;
+	unsigned long long *acct;
+	int acct_w;
+	unsigned long long *prof;         // [m][8]: cycles of set-up, E steps, M steps; iterations (HIBAG_B200_EM_DEBUG)
+};
+
+/// THREADS per CTA; PAIRS_SMEM: the compatible pairs live in shared memory (one CTA per SM: lowest
+/// latency, a single classifier in flight) or are streamed from L2 by the E step (half an SM per
+/// CTA: two candidates, or one and the scoring CTAs of other lanes, share an SM)
+template <int THREADS, bool PAIRS_SMEM>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1) em_resident_kernel(const EmrArgs p)
+{
+	SmAcct acct_scope(p.acct, SM_ACCT_EM, (unsigned)p.acct_w);
+	SmAcct acct_cta(p.acct, SM_ACCT_EM_CTA, 1024u);
+	extern __shared__ double em_smem[];
+	constexpr int N_WARPS = THREADS / 32;
+	const int n2 = 2 * p.n_cur;
+	const int n_groups = (n2 + 31) >> 5;
+	double *fr0 = em_smem;                                   // [2][n2]
+	double *scratch = fr0 + 2 * (size_t)n2;                  // [40]
+	double *sck = scratch + 40;                              // [n_entry]
+	uint32_t *rings = (uint32_t *)(sck + ((p.n_entry + 1) & ~1));   // [EMR_M_WARPS][EMR_RING_B][128] (16-byte aligned)
+	uint32_t *s_uv = rings + EMR_M_WARPS * EMR_RING_B * 128; // [cap] (PAIRS_SMEM)
+	int *eg = (int *)(s_uv + (PAIRS_SMEM ? p.cap : 0));      // [n_entry] bootstrap count << 2 | candidate genotype
+	int *clen = eg + p.n_entry;                              // [n2] compatible contributions per chain (by sorted rank)
+	int *glen = clen + n2;                                   // [n_groups]
+	int *longlist = glen + n_groups;                         // [EMR_LONG_MAX] entries summed by a warp
+	__shared__ int sh_i[6];
+
+	const int c = blockIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int8_t *col = p.geno_t + (size_t)p.cand_snp[c] * p.n_samp;
+	int *coff = p.coff + (size_t)c * (p.n_entry + 1);
+	uint32_t *rec = p.rec + (size_t)c * p.n_slots;
+	uint32_t *pairs = PAIRS_SMEM ? s_uv : (p.cuv + (size_t)c * p.total_pairs);
+	int *status = p.out_status + 4 * c;
+
+	// allele frequency of the new SNP in the bootstrap sample (:1136-1151), integers
+	{
+		int ac = 0, vc = 0;
+		for (int k = tid; k < p.n_entry; k += THREADS)
+		{
+			const int s = p.ib[k];
+			const int g = col[s];
+			const int b = p.boot[s];
+			eg[k] = (b << 2) | ((0 <= g && g <= 2) ? g : 3);
+			if (0 <= g && g <= 2) { ac += g * b; vc += 2 * b; }
+		}
+		if (tid < 6) sh_i[tid] = 0;
+		for (int g = tid; g < n_groups; g += THREADS) glen[g] = 0;
+		__syncthreads();
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			ac += __shfl_xor_sync(0xffffffffu, ac, o);
+			vc += __shfl_xor_sync(0xffffffffu, vc, o);
+		}
+		if (lane == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); }
+		__syncthreads();
+	}
+	const int allele_cnt = sh_i[0], valid_cnt = sh_i[1];
+	if (allele_cnt == 0 || allele_cnt == valid_cnt)
+	{
+		if (tid == 0) { status[0] = EM_INVALID; status[1] = 0; status[2] = 0; status[3] = 0; }
+		return;
+	}
+	// doubled list, initial frequencies (:444-459)
+	{
+		const double af = __ddiv_rn((double)allele_cnt, (double)valid_cnt);
+		const double q0 = __dsub_rn(1.0, af), q1 = af;
+		for (int k = tid; k < p.n_cur; k += THREADS)
+		{
+			const double f = p.cur_freq[k];
+			fr0[2 * k] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
+			fr0[2 * k + 1] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
+		}
+	}
+	// ---- (A) the compatible pairs (:1157-1180), in pair order ---------------------------------------
+	int n_compat;
+	{
+		const int chunk = (p.total_pairs + THREADS - 1) / THREADS;
+		const int tb = min(p.total_pairs, tid * chunk), te = min(p.total_pairs, tb + chunk);
+		int cnt = 0;
+		for (int t = tb; t < te; t += 4)
+		{
+			int4 pr[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) pr[q] = (t + q < te) ? __ldg(p.pairs4 + t + q) : make_int4(0, 0, 0, 0);
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const int u = pr[q].x & 0xffff, v = (int)((unsigned)pr[q].x >> 16);
+				const int g = eg[pr[q].y] & 3;
+				cnt += (t + q < te && (g == 3 || ((u & 1) + (v & 1)) == g)) ? 1 : 0;
+			}
+		}
+		int incl = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int y = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += y;
+		}
+		int *wsum = (int *)scratch;             // [32] ints
+		__syncthreads();
+		if (lane == 31) wsum[warp] = incl;
+		__syncthreads();
+		if (tid < 32)
+		{
+			int w = (tid < N_WARPS) ? wsum[tid] : 0;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const int y = __shfl_up_sync(0xffffffffu, w, o);
+				if (tid >= o) w += y;
+			}
+			wsum[tid] = w;
+		}
+		__syncthreads();
+		n_compat = wsum[31];
+		if (PAIRS_SMEM && n_compat > p.cap)
+		{
+			// does not fit: the host re-estimates this candidate (status[2] = -1 tells why)
+			if (tid == 0) { status[0] = EM_AMBIGUOUS; status[1] = 0; status[2] = -1; status[3] = n_compat; }
+			return;
+		}
+		int j = incl - cnt + (warp ? wsum[warp - 1] : 0);
+		for (int t = tb; t < te; t += 4)
+		{
+			int4 pr[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) pr[q] = (t + q < te) ? __ldg(p.pairs4 + t + q) : make_int4(0, 0, 0, 0);
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				if (t + q < te)
+				{
+					const int u = pr[q].x & 0xffff, v = (int)((unsigned)pr[q].x >> 16);
+					const int g = eg[pr[q].y] & 3;
+					if (t + q == p.off[pr[q].y]) coff[pr[q].y] = j;      // first pair of its entry
+					if (g == 3 || ((u & 1) + (v & 1)) == g) pairs[j++] = (uint32_t)pr[q].x;
+				}
+			}
+		}
+		if (tid == 0) coff[p.n_entry] = n_compat;
+		__syncthreads();
+	}
+	// entries with many compatible pairs (ambiguous samples: every pair at the minimum distance is
+	// kept) are summed by a whole warp in the E step; an overflowing list only costs speed
+	for (int k = tid; k < p.n_entry; k += THREADS)
+		if (coff[k + 1] - coff[k] > EMR_LONG)
+		{
+			const int i = atomicAdd(&sh_i[4], 1);
+			if (i < EMR_LONG_MAX) longlist[i] = k;
+		}
+	// ---- (B) every chain's compatible contributions in the reference's order -- (sample, pair,
+	// H1-before-H2) -- as records in the ELL of its group: a warp takes one haplotype at a time and
+	// walks its incidence list. slot(row i, lane l) = base + 128 (i / 4) + 4 l + (i % 4): four rows of
+	// a lane are 16 contiguous bytes (one cp.async), a warp's batch 512 contiguous bytes ---------------
+	{
+		for (;;)
+		{
+			int r = 0;
+			if (lane == 0) r = atomicAdd(&sh_i[3], 1);
+			r = __shfl_sync(0xffffffffu, r, 0);
+			if (r >= n2) break;
+			const int gi = r >> 5, l = r & 31;
+			const int u = p.hap_sorted[r];
+			const int gbase = p.group_base[gi];
+			const int qb = p.inc_off[u], qe = p.inc_off[u + 1];
+			int n = 0;
+			for (int q0 = qb; q0 < qe; q0 += 128)
+			{
+				int e[4]; int4 pr[4];
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+				{
+					const int q = q0 + w * 32 + lane;
+					e[w] = (q < qe) ? __ldg(p.inc_val + q) : -1;
+				}
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+					pr[w] = (e[w] >= 0) ? __ldg(p.pairs4 + (e[w] >> 1)) : make_int4(0, 0, 0, 0);
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+				{
+					bool ok = false;
+					uint32_t record = 0;
+					if (e[w] >= 0)
+					{
+						const int uu = pr[w].x & 0xffff, vv = (int)((unsigned)pr[w].x >> 16);
+						const int g = eg[pr[w].y] & 3;
+						ok = (g == 3 || ((uu & 1) + (vv & 1)) == g);
+						const int partner = (e[w] & 1) ? uu : vv;      // side 1: this haplotype is H2
+						record = (uint32_t)partner | ((uint32_t)pr[w].y << 16) | ((uu == vv) ? 0x80000000u : 0u);
+					}
+					const unsigned m = __ballot_sync(0xffffffffu, ok);
+					if (ok)
+					{
+						const int rk = n + __popc(m & ((1u << lane) - 1u));
+						rec[gbase + 128 * (rk >> 2) + 4 * l + (rk & 3)] = record;
+					}
+					n += __popc(m);
+				}
+			}
+			if (lane == 0) { clen[r] = n; if (n > 0) atomicMax(&glen[gi], n); }
+		}
+	}
+	__threadfence();           // records (and streamed pairs) are read back through L2 by other warps of this CTA
+	__syncthreads();
+	const int n_long = min(sh_i[4], EMR_LONG_MAX);
+	const bool long_overflow = sh_i[4] > EMR_LONG_MAX;
+	const bool prof = (p.prof != nullptr) && tid == 0;
+	long long t_last = prof ? clock64() : 0, t_e = 0, t_m = 0;
+	if (prof) p.prof[8 * c + 0] = (unsigned long long)(t_last - acct_cta.t0);
+
+	double conv_tol = 0, loglik = -1e+30;
+	int result = EM_OK, iters = 0;
+	for (int iter = 0; iter <= EM_MAX_ITER; iter++)
+	{
+		const double old_loglik = loglik;
+		const double *fr = fr0 + (size_t)(iter & 1) * n2;
+		double *fr_new = fr0 + (size_t)((iter & 1) ^ 1) * n2;
+		auto pair_x = [&](uint32_t uv) -> double
+		{
+			const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
+			return (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v]) : __dmul_rn(fr[u], fr[v]);
+		};
+		// ---- E step (:1204-1222) ------------------------------------------------------------------------
+		double ll = 0;
+		// (a) one thread per entry with few pairs: the pairs of a block of 8 are loaded and multiplied
+		//     first, then added in list order
+		{
+			int k = tid;
+			int b = 0, e = 0;
+			if (k < p.n_entry) { b = coff[k]; e = coff[k + 1]; }
+			while (k < p.n_entry)
+			{
+				const int kn = k + THREADS;
+				int bn = 0, en = 0;
+				if (kn < p.n_entry) { bn = coff[kn]; en = coff[kn + 1]; }
+				if (e - b <= EMR_LONG || long_overflow)
+				{
+					double psum = 0;
+					for (int t = b; t < e; t += 8)
+					{
+						uint32_t uv[8];
+						double x[8];
+#pragma unroll
+						for (int q = 0; q < 8; q++) uv[q] = (t + q < e) ? pairs[t + q] : 0u;
+#pragma unroll
+						for (int q = 0; q < 8; q++) x[q] = (t + q < e) ? pair_x(uv[q]) : 0.0;
+#pragma unroll
+						for (int q = 0; q < 8; q++) if (t + q < e) psum = __dadd_rn(psum, x[q]);
+					}
+					const double bc = (double)(eg[k] >> 2);
+					ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
+					sck[k] = __ddiv_rn(bc, psum);
+				}
+				k = kn; b = bn; e = en;
+			}
+		}
+		// (b) one warp per entry with many pairs: 32 pairs loaded and multiplied in parallel (the next
+		//     32 already in flight), then added in list order through shuffles -- the chain of
+		//     dependent adds is the same, the loads and products leave its critical path
+		if (!long_overflow)
+		{
+			for (int i = warp; i < n_long; i += N_WARPS)
+			{
+				const int k = longlist[i];
+				const int b = coff[k], e = coff[k + 1];
+				double psum = 0;
+				uint32_t uv = (b + lane < e) ? pairs[b + lane] : 0u;
+				for (int t = b; t < e; t += 32)
+				{
+					const uint32_t uv_next = (t + 32 + lane < e) ? pairs[t + 32 + lane] : 0u;
+					const double x = (t + lane < e) ? pair_x(uv) : 0.0;
+					const int n = min(32, e - t);
+					for (int q = 0; q < n; q++) psum = __dadd_rn(psum, __shfl_sync(0xffffffffu, x, q));
+					uv = uv_next;
+				}
+				if (lane == 0)
+				{
+					const double bc = (double)(eg[k] >> 2);
+					ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
+					sck[k] = __ddiv_rn(bc, psum);
+				}
+			}
+		}
+		if (tid == 0) sh_i[2] = 0;                 // group counter of the M step
+		ll = block_sum_f64(ll, scratch);           // (its barriers publish sck and sh_i[2])
+		if (prof) { const long long n_ = clock64(); t_e += n_ - t_last; t_last = n_; }
+		// ---- M step: a warp that owns a ring takes the next-longest group of 32 chains; the records
+		// stream through the ring EMR_RING_B - 1 batches ahead, and the contributions of batch b + 1 are
+		// gathered and multiplied before the adds of batch b, so the chain runs at fp64-add latency -------
+		if (warp < EMR_M_WARPS)
+		{
+			const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(rings + (size_t)warp * EMR_RING_B * 128) +
+				(uint32_t)lane * 16u;
+			for (;;)
+			{
+				int gi = 0;
+				if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
+				gi = __shfl_sync(0xffffffffu, gi, 0);
+				if (gi >= n_groups) break;
+				const int r = 32 * gi + lane;
+				const int my_len = (r < n2) ? clen[r] : 0;
+				const int h = (r < n2) ? p.hap_sorted[r] : 0;
+				const double fh = fr[h];
+				const double fh2 = __dmul_rn(2.0, fh);             // exact
+				const double xhh = __dmul_rn(fh, fh);
+				const int nb = (glen[gi] + 3) >> 2;
+				const char *src = (const char *)(rec + p.group_base[gi]) + lane * 16;     // + 512 per batch
+				auto contrib = [&](const int4 &q4, int row0, double (&rr)[4])
+				{
+					const uint32_t rc[4] = { (uint32_t)q4.x, (uint32_t)q4.y, (uint32_t)q4.z, (uint32_t)q4.w };
+#pragma unroll
+					for (int q = 0; q < 4; q++)
+					{
+						rr[q] = 0.0;
+						if (row0 + q < my_len)
+						{
+							const double x = (rc[q] & 0x80000000u) ? xhh : __dmul_rn(fh2, fr[rc[q] & 0xffffu]);
+							rr[q] = __dmul_rn(x, sck[(rc[q] >> 16) & 0x7fffu]);
+						}
+					}
+				};
+				for (int b = 0; b < EMR_RING_B - 1; b++)
+				{
+					if (b < nb) cp_async16_cg(ring_s + (uint32_t)b * 512u, src + (size_t)b * 512);
+					cp_async_commit();
+				}
+				double acc = 0;
+				double rr[4] = { 0.0, 0.0, 0.0, 0.0 };
+				int rb = 0, rbn = EMR_RING_B - 1;      // ring slots of batch b and of batch b + EMR_RING_B - 1
+				// batch 0
+				if (nb > 0)
+				{
+					cp_async_wait<EMR_RING_B - 2>();
+					contrib(lds_i32x4(ring_s), 0, rr);
+				}
+				for (int b = 0; b < nb; b++)
+				{
+					const int bn = b + EMR_RING_B - 1;
+					if (bn < nb) cp_async16_cg(ring_s + (uint32_t)rbn * 512u, src + (size_t)bn * 512);
+					cp_async_commit();
+					// batch b + 1 has landed when at most EMR_RING_B - 2 younger groups are pending
+					cp_async_wait<EMR_RING_B - 2>();
+					double rn[4] = { 0.0, 0.0, 0.0, 0.0 };
+					const int rb1 = (rb + 1 == EMR_RING_B) ? 0 : rb + 1;
+					if (b + 1 < nb) contrib(lds_i32x4(ring_s + (uint32_t)rb1 * 512u), 4 * (b + 1), rn);
+#pragma unroll
+					for (int q = 0; q < 4; q++) if (4 * b + q < my_len) acc = __dadd_rn(acc, rr[q]);
+#pragma unroll
+					for (int q = 0; q < 4; q++) rr[q] = rn[q];
+					rb = rb1;
+					if (++rbn == EMR_RING_B) rbn = 0;
+				}
+				cp_async_wait<0>();
+				if (r < n2) fr_new[h] = __dmul_rn(acc, p.scale);
+			}
+		}
+		__syncthreads();
+		if (prof) { const long long n_ = clock64(); t_m += n_ - t_last; t_last = n_; }
+		iters = iter + 1;
+		// ---- stopping rule (:1236-1250) with the guard band (em_guard_rel) ---------------------------
+		loglik = ll;
+		int f = 0;
+		if (iter > 0)
+		{
+			const double diff = fabs(__dsub_rn(loglik, old_loglik));
+			if (fabs(__dsub_rn(diff, conv_tol)) <= em_guard_rel(p.n_entry) * fabs(loglik)) f = 2;
+			else if (diff <= conv_tol) f = 1;
+		} else {
+			conv_tol = __dmul_rn(p.em_reltol, __dadd_rn(fabs(loglik), p.em_reltol));
+			if (conv_tol < 0) conv_tol = 0;
+		}
+		if (f == 2) { result = EM_AMBIGUOUS; break; }
+		if (f == 1) break;
+	}
+	{
+		const double *fin = fr0 + (size_t)(iters & 1) * n2;
+		double *out = p.out_freq + (size_t)c * n2;
+		for (int u = tid; u < n2; u += THREADS) out[u] = fin[u];
+		if (tid == 0)
+		{
+			int longest = 0;
+			for (int g = 0; g < n_groups; g++) longest = max(longest, glen[g]);
+			status[0] = result; status[1] = iters; status[2] = longest; status[3] = n_compat;
+			if (prof)
+			{
+				p.prof[8 * c + 1] = (unsigned long long)t_e; p.prof[8 * c + 2] = (unsigned long long)t_m;
+				p.prof[8 * c + 3] = (unsigned long long)iters; p.prof[8 * c + 4] = (unsigned long long)n_long;
+			}
+		}
+	}
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
 // HIBAG_B200_EM_PROF=1: per-phase clock64 totals of the EM kernel over the process, printed at exit
 namespace {
 struct EmProf
@@ -967,6 +1417,130 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	d_cand_.ensure(m);
 	HB_CUDA(cudaMemcpyAsync(d_cand_.get(), hc, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, st));
 	const int n_groups = (n2_ + 31) / 32;
+	d_freq_.ensure((size_t)m * n2_ + 2);
+	d_status_.ensure(4 * (size_t)m);
+	h_freq_.ensure((size_t)m * n2_ + 2);
+	h_status_.ensure(4 * (size_t)m);
+	// ---- the shared-memory-resident kernel (frequencies and scale factors on chip, nothing stored
+	// per contribution): an experiment kept behind HIBAG_B200_EM_RESIDENT=1. It is bit-identical to
+	// em_kernel (tests/test_gpu_parity.py trains the golden models with either) but measured SLOWER at
+	// config 2 (profiles/r02_em_resident_sweep.txt: 566 vs 802 classifiers/min at 24 lanes, 65 vs 150
+	// with one lane): the E step sums the long entries of ambiguous samples (hundreds of compatible
+	// pairs, in list order) by one warp each, 226 k cycles per iteration against 152 k for the whole
+	// iteration of em_kernel, which spreads the products over all threads first ------------------------
+	{
+		int want_resident = 0;                 // read per call: the tests switch kernels inside one process
+		if (const char *e = getenv("HIBAG_B200_EM_RESIDENT")) want_resident = atoi(e);
+		const size_t fixed = sizeof(double) * (2 * (size_t)n2_ + 40 + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
+			sizeof(uint32_t) * (size_t)EMR_M_WARPS * EMR_RING_B * 128 +
+			sizeof(int) * ((size_t)n_entry_ + (size_t)n2_ + (size_t)n_groups + EMR_LONG_MAX) + 64;
+		const size_t budget = (size_t)227 * 1024 - 512;     // the kernel also has a few bytes of static shared memory
+		long long cap = (budget > fixed) ? (long long)((budget - fixed) / 4) : 0;
+		cap &= ~(long long)3;
+		// shape: with many lanes sharing the GPU the SM-time per candidate counts -- 512 threads and the
+		// pairs streamed from L2, so that a CTA takes half an SM (two candidates, or one and the scoring
+		// CTAs of other lanes, per SM); with few lanes the latency counts -- 1024 threads and the pairs
+		// in shared memory too (compatible pairs are 1/4 to 1/2 of the doubled pairs, all of them for a
+		// missing genotype: 45 % covers every candidate of the BASELINE cohorts; one that still overflows
+		// is re-estimated on the host). (chain records hold the entry in 15 bits, the partner in 16)
+		bool half = n_dense_lanes_ >= 8;
+		if (const char *e = getenv("HIBAG_B200_EM_HALF")) half = atoi(e) != 0;
+		const bool pairs_fit = cap > 0 && (double)cap >= 0.45 * (double)total_pairs_ + 64;
+		if (!pairs_fit) half = true;
+		if (want_resident && n_entry_ <= 32767 && n2_ <= 65535 && fixed + 1024 <= budget)
+		{
+			if (cap > (long long)total_pairs_ + 4) cap = ((long long)total_pairs_ + 4) & ~(long long)3;
+			d_coff_.ensure((size_t)m * (n_entry_ + 1));
+			d_idxell_.ensure((size_t)m * n_slots_ + 4);
+			if (half) d_cuv_.ensure((size_t)m * total_pairs_ + 4);
+			EmrArgs a;
+			memset(&a, 0, sizeof(a));
+			a.n_entry = n_entry_; a.n_cur = n_cur_; a.n_samp = n_samp; a.total_pairs = (int)total_pairs_; a.cap = (int)cap;
+			a.ib = ib_; a.boot = boot_; a.off = d_off_.get(); a.pairs4 = (const int4 *)d_pairs4_.get();
+			a.hap_sorted = d_hap_sorted_.get(); a.group_base = d_group_base_.get();
+			a.inc_off = d_inc_off_.get(); a.inc_val = d_val2_.get();
+			a.cur_freq = d_curfreq_.get(); a.n_slots = n_slots_;
+			a.geno_t = geno_t; a.cand_snp = d_cand_.get();
+			a.coff = d_coff_.get(); a.rec = (uint32_t *)d_idxell_.get();
+			a.cuv = half ? (uint32_t *)d_cuv_.get() : nullptr;
+			a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
+			a.scale = 0.5 / n_samp; a.em_reltol = std::sqrt(DBL_EPSILON);
+			a.acct = device_sm_acct();
+			const bool want_prof_r = getenv("HIBAG_B200_EM_DEBUG") != nullptr;
+			if (want_prof_r)
+			{
+				d_prof_.ensure(8 * (size_t)m);
+				HB_CUDA(cudaMemsetAsync(d_prof_.get(), 0, sizeof(unsigned long long) * 8 * (size_t)m, st));
+				a.prof = d_prof_.get();
+			}
+			const size_t smem = fixed - 64 + (half ? 0 : 4 * (size_t)cap) + 16;
+			a.acct_w = (half && smem <= (size_t)113 * 1024) ? 512 : 1024;
+			const int max_dyn = 227 * 1024 - 256;
+			g_em_gate.enter();
+			cudaError_t launch_rc;
+			if (half)
+			{
+				auto kern = em_resident_kernel<512, false>;
+				launch_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+				if (launch_rc == cudaSuccess) launch_rc = cudaEventRecord(ev0_.e, st);
+				if (launch_rc == cudaSuccess) { kern<<<m, 512, smem, st>>>(a); launch_rc = cudaGetLastError(); }
+			} else {
+				auto kern = em_resident_kernel<1024, true>;
+				launch_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+				if (launch_rc == cudaSuccess) launch_rc = cudaEventRecord(ev0_.e, st);
+				if (launch_rc == cudaSuccess) { kern<<<m, 1024, smem, st>>>(a); launch_rc = cudaGetLastError(); }
+			}
+			if (launch_rc != cudaSuccess) { g_em_gate.leave(); HB_CUDA(launch_rc); }
+			HB_CUDA(cudaEventRecord(ev1_.e, st));
+			HB_CUDA(cudaMemcpyAsync(h_freq_.get(), d_freq_.get(), sizeof(double) * (size_t)m * n2_,
+				cudaMemcpyDeviceToHost, st));
+			HB_CUDA(cudaMemcpyAsync(h_status_.get(), d_status_.get(), sizeof(int) * 4 * (size_t)m,
+				cudaMemcpyDeviceToHost, st));
+			HB_CUDA(cudaEventRecord(ev_done_.e, st));
+			const cudaError_t sync_rc = cudaEventSynchronize(ev_done_.e);
+			g_em_gate.leave();
+			HB_CUDA(sync_rc);
+			float ms = 0;
+			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
+			kernel_ms += ms;
+			launches++;
+			resident_launches++;
+			for (int i = 0; i < m; i++)
+			{
+				const int *stt = h_status_.get() + 4 * i;
+				if (stt[0] == EM_INVALID || stt[2] < 0) continue;
+				sum_iterations += (uint64_t)stt[1];
+				sum_chain_adds += (uint64_t)stt[1] * (uint64_t)stt[2];
+				sum_pair_updates += (uint64_t)stt[1] * (uint64_t)stt[3];
+			}
+			if (want_prof_r)
+			{
+				int ovf = 0; long compat = 0; int nv = 0;
+				for (int i = 0; i < m; i++)
+				{
+					const int *stt = h_status_.get() + 4 * i;
+					if (stt[2] < 0) ovf++;
+					else if (stt[0] != EM_INVALID) { compat += stt[3]; nv++; }
+				}
+				std::vector<unsigned long long> hp(8 * (size_t)m);
+				HB_CUDA(cudaMemcpy(hp.data(), d_prof_.get(), sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
+				double su = 0, se = 0, sm = 0, it = 0; int it_max = 0, nl = 0;
+				for (int i = 0; i < m; i++)
+				{
+					su += (double)hp[8 * i]; se += (double)hp[8 * i + 1]; sm += (double)hp[8 * i + 2]; it += (double)hp[8 * i + 3];
+					it_max = std::max(it_max, (int)hp[8 * i + 3]); nl = std::max(nl, (int)hp[8 * i + 4]);
+				}
+				fprintf(stderr, "em resident (%s): kernel %.3f ms, cap %lld, total pairs %zu, compat/cand %.0f, overflowed %d of %d, smem %zu | "
+					"kcycles: set-up %.0f per candidate, E step %.1f and M step %.1f per iteration, iterations mean %.1f max %d, "
+					"longest chain %d, long entries %d\n", half ? "512 threads, pairs streamed" : "1024 threads, pairs in shared memory",
+					ms, cap, total_pairs_, nv ? (double)compat / nv : 0.0, ovf, m, smem, su / m * 1e-3, it > 0 ? se / it * 1e-3 : 0.0,
+					it > 0 ? sm / it * 1e-3 : 0.0, it / m, it_max, h_status_.get()[2], nl);
+			}
+			h2d_bytes += sizeof(int) * (size_t)m;
+			d2h_bytes += sizeof(double) * (size_t)m * n2_ + sizeof(int) * 4 * (size_t)m;
+			return;
+		}
+	}
 	d_pmap_.ensure(4 * (size_t)m * total_pairs_ + 4);
 	d_rinc_.ensure((size_t)m * n_slots_ + 2);
 	// slots without a compatible contribution stay 0.0

@@ -186,6 +186,35 @@ def test_trainer_legacy_hook_mode_and_thread_count_invariance(gpu):
             helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
 
 
+@pytest.mark.parametrize("resident,half", [("1", "0"), ("1", "1"), ("0", "0")])
+def test_both_device_em_kernels_reproduce_the_reference(gpu, monkeypatch, resident, half):
+    """em_resident_kernel (frequencies and scale factors in shared memory; its two shapes: 1024 threads
+    with the pairs on chip too, 512 threads with the pairs streamed) and em_kernel (the streaming form
+    for rounds too large for an SM) are bit-identical to the reference's CAlg_EM: the golden model,
+    and the seeded many-allele cohort whose classifiers the compiled reference trained"""
+    from hibag_b200 import synth
+    monkeypatch.setenv("HIBAG_B200_EM_RESIDENT", resident)
+    monkeypatch.setenv("HIBAG_B200_EM_HALF", half)
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = gpu.HLAModel(geno.shape[1], len(al), al)
+    m.set_training(geno, h1, h2)
+    m.train(12, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), n_threads=4, em_on_device=True)
+    for k in range(12):
+        helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+    assert m.train_stats()["em_iterations"] > 0
+    gd = helpers.load_golden("synth_many_alleles_ref.npz")
+    coh = synth.make_cohort(int(gd["n_samp"]), int(gd["n_snp"]), int(gd["n_hla"]), seed=int(gd["cohort_seed"]))
+    for lanes in (1, 2):
+        s = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        s.set_training(coh.geno, coh.h1, coh.h2)
+        s.train(int(gd["n_cls"]), gpu.default_mtry(coh.n_snp), prune=True, seed=int(gd["train_seed"]),
+                per_classifier_seed=True, n_concurrent=lanes)
+        for k in range(int(gd["n_cls"])):
+            want = dict(snpidx=gd["c%d_snpidx" % k], samp_num=gd["c%d_samp_num" % k], freq=gd["c%d_freq" % k],
+                        hla=gd["c%d_hla" % k], packed=gd["c%d_packed" % k], oob_acc=float(gd["c%d_oob_acc" % k]))
+            assert helpers.classifier_diff(s.classifier(k), want) == "", (resident, lanes, k)
+
+
 def test_device_em_host_fallback_path(gpu, monkeypatch):
     """candidates whose stopping test the device cannot decide are re-estimated on the host:
     force that path for every third candidate and require the golden model all the same"""

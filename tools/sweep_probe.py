@@ -20,10 +20,14 @@ g = np.ascontiguousarray(coh.geno, dtype=np.int8)
 m = api.HLAModel(bench.N_SNP, coh.n_hla); m.set_training(g, coh.h1, coh.h2)
 kw = dict(seed=bench.TRAIN_SEED, per_classifier_seed=True, n_threads=nt, n_concurrent=lanes)
 m.train(lanes, bench.MTRY, first_index=0, **kw)
+api.sm_time(reset=True)
 s0 = m.train_stats(); t0 = time.time()
 for s in range(steps):
     m.train(lanes, bench.MTRY, first_index=(1 + s) * lanes, **kw)
 dt = time.time() - t0; s1 = m.train_stats()
+acct = api.sm_time()
+info = api.device_info()
+sm_total = info["sm_count"] * dt * info["clock_khz"] * 1e3
 d = {k: s1[k] - s0[k] for k in s1}
 peak = json.load(open(bench.PEAKS_JSON))["popc32_per_s"]
 n = steps * lanes
@@ -35,7 +39,10 @@ dig = hashlib.sha1(b"".join(m.classifier(k)["freq"].tobytes() + m.classifier(k)[
 print(json.dumps(dict(per_min=round(60 * n / dt, 1), frac=round(d["popc32_issued"] / (d["gather_kernel_ms"] * 1e-3) / peak, 4),
       ib_frac=round(ib, 4), oob_frac=round(oob, 4), gather_ms_per_cls=round(d["gather_kernel_ms"] / n, 2),
       ib_ms_per_cls=round(d["gather_ib_kernel_ms"] / n, 2), pass_ms_per_cls=round(d["cell_kernel_ms"] / n, 2),
-      em_ms_per_cls=round(d["em_kernel_ms"] / n, 1), wall_ms_per_cls=round(1e3 * dt / n, 2), lanes=lanes, digest=dig)), flush=True)
+      em_ms_per_cls=round(d["em_kernel_ms"] / n, 1), wall_ms_per_cls=round(1e3 * dt / n, 2), lanes=lanes, digest=dig,
+      em_kcyc_per_iter=round(acct["em_cta_cycles"] / max(d["em_iterations"], 1) / 1e3, 1), em_iters_per_cand=round(d["em_iterations"] / max(d["n_em"], 1), 1),
+      share={k: round(v / sm_total, 3) for k, v in acct.items() if k != "em_cta_cycles" and v > 0},
+      em_fallbacks=d["n_em_host_fallback"])), flush=True)
 ''' % ROOT
 for spec in sys.argv[1:]:
     env = dict(os.environ)
