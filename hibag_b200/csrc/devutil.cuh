@@ -125,4 +125,115 @@ struct HapRec
 	}
 };
 
+/// shared address of T[c_i + pc][lane] from the row address of T[c_i][lane]: one IMAD. (Written as
+/// plain C the compiler re-associates it into (c_i + pc) * 256 + base: an extra IADD per pair.)
+__device__ __forceinline__ uint32_t table_row(uint32_t row_ci, int pc)
+{
+	uint32_t a;
+	asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(a) : "r"((uint32_t)pc), "r"(row_ci));
+	return a;
+}
+
+/// The inner loop of the reference's chain (src/LibHLA.cpp:1660-1668 and its _PostProb / _PostProb2
+/// twins): partners j0 .. b_n-1 of row i for the lane's R samples, sum[r] += ((2 f_i) f_j) * T[d].
+/// R >= 3: R independent chains per lane keep the pipes busy; the plain loop (6 instructions per pair
+/// evaluation). R <= 2: the loop is bound by the latency of a whole step (record LDS.128 -> POPC ->
+/// table LDS.64 -> DMUL -> DADD, ~85 cycles: the shared-memory loads are volatile asm and keep their
+/// order), not by the dependent DADD. There the terms of the next 4 / R partners are fetched and
+/// multiplied BEFORE the adds of the current ones are issued, so only the adds stay on the critical
+/// path. Same operands, same order, un-fused.
+template <int NW, int R, bool CLAMP, bool SMEM>
+__device__ __forceinline__ void partner_loop(uint32_t hap_base, const char *hap_g, int b_start, int j0,
+	int b_n, double ff, const uint32_t (&K)[R][NW], const uint32_t (&V)[R][NW], const int (&ci)[R],
+	const uint32_t (&tb)[R], uint32_t tbl_lane, int dmax, double *sum)
+{
+	if (R <= 2)
+	{
+		constexpr int JB = (R <= 2) ? 4 / R : 1;
+		auto terms = [&](int j, double (&x)[JB][R])
+		{
+			HapRec<NW, SMEM> hj[JB];
+#pragma unroll
+			for (int q = 0; q < JB; q++) hj[q].load(hap_base, hap_g, b_start + j + q);
+			uint32_t ad[JB][R];
+#pragma unroll
+			for (int q = 0; q < JB; q++)
+#pragma unroll
+				for (int r = 0; r < R; r++)
+				{
+					int pc = 0;
+#pragma unroll
+					for (int w = 0; w < NW; w++) pc += __popc((hj[q].h[w] ^ K[r][w]) & V[r][w]);
+					ad[q][r] = CLAMP ? (tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u) : table_row(tb[r], pc);
+				}
+#pragma unroll
+			for (int q = 0; q < JB; q++)
+#pragma unroll
+				for (int r = 0; r < R; r++) x[q][r] = lds_f64(ad[q][r]);
+#pragma unroll
+			for (int q = 0; q < JB; q++)
+			{
+				const double pf = __dmul_rn(ff, hj[q].f);
+#pragma unroll
+				for (int r = 0; r < R; r++) x[q][r] = __dmul_rn(pf, x[q][r]);
+			}
+		};
+		int j = j0;
+		if (j + JB <= b_n)
+		{
+			double x0[JB][R];
+			terms(j, x0);
+			for (j += JB; j + JB <= b_n; j += JB)
+			{
+				double x1[JB][R];
+				terms(j, x1);
+#pragma unroll
+				for (int q = 0; q < JB; q++)
+#pragma unroll
+					for (int r = 0; r < R; r++) { sum[r] = __dadd_rn(sum[r], x0[q][r]); x0[q][r] = x1[q][r]; }
+			}
+#pragma unroll
+			for (int q = 0; q < JB; q++)
+#pragma unroll
+				for (int r = 0; r < R; r++) sum[r] = __dadd_rn(sum[r], x0[q][r]);
+		}
+		for (; j < b_n; j++)
+		{
+			HapRec<NW, SMEM> hj;
+			hj.load(hap_base, hap_g, b_start + j);
+			const double pf = __dmul_rn(ff, hj.f);
+#pragma unroll
+			for (int r = 0; r < R; r++)
+			{
+				int pc = 0;
+#pragma unroll
+				for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
+				double t;
+				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
+				else t = lds_f64(table_row(tb[r], pc));
+				sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
+			}
+		}
+	} else {
+#pragma unroll 2
+		for (int j = j0; j < b_n; j++)
+		{
+			HapRec<NW, SMEM> hj;
+			hj.load(hap_base, hap_g, b_start + j);
+			const double pf = __dmul_rn(ff, hj.f);
+#pragma unroll
+			for (int r = 0; r < R; r++)
+			{
+				int pc = 0;
+#pragma unroll
+				for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
+				double t;
+				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
+				else t = lds_f64(table_row(tb[r], pc));
+				sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
+			}
+		}
+	}
+}
+
 }  // namespace hb

@@ -227,25 +227,7 @@ cell_pass_kernel(const __grid_constant__ CellBatch p)
 					}
 					ff = __dmul_rn(2.0, hi.f);    // exact
 
-#pragma unroll 2
-					for (int j = j0; j < b_n; j++)
-					{
-						HapRec<NW, SMEM> hj;
-						hj.load(hap_base, hap_g, b_start + j);
-						const double pf = __dmul_rn(ff, hj.f);
-#pragma unroll
-						for (int r = 0; r < R; r++)
-						{
-							int pc = 0;
-#pragma unroll
-							for (int w = 0; w < NW; w++)
-								pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
-							double t;
-							if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
-							else t = lds_f64(tb[r] + (uint32_t)pc * 256u);
-							sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
-						}
-					}
+					partner_loop<NW, R, CLAMP, SMEM>(hap_base, hap_g, b_start, j0, b_n, ff, K, V, ci, tb, tbl_lane, dmax, sum);
 				}
 
 #pragma unroll

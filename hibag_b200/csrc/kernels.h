@@ -90,7 +90,8 @@ struct CellBatch
 	int n_dist, n_snp, geno_stride, n_pos;
 	int n_lists, max_hap;         // max_hap = largest n_hap of the batch (shared-memory sizing)
 	unsigned long long *acct;     // SM-time counters or null
-	int acct_w, pad2;
+	int acct_w;
+	int flat;                     // bit 0: entry-flat tasks (cell_gather_flat_kernel; task_prefix built with flat = true), bit 1: one list per CTA
 	ListDesc lists[MAX_BATCH_LISTS];
 };
 
@@ -180,7 +181,8 @@ struct GatherBatch
 	int n_dist, n_snp, geno_stride, n_pos;
 	int n_lists, max_hap, n_cells, acct_cls;
 	unsigned long long *acct;     // SM-time counters or null
-	int acct_w, pad2;
+	int acct_w;
+	int flat;                     // bit 0: entry-flat tasks (cell_gather_flat_kernel; task_prefix built with flat = true), bit 1: one list per CTA
 	GatherList lists[MAX_BATCH_LISTS];
 };
 
@@ -223,7 +225,7 @@ void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_
 /// and the pair evaluations those tasks hold (added to evals[l])
 void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
 	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, int target_tasks,
-	int warp_slots, cudaStream_t st);
+	int warp_slots, cudaStream_t st, bool flat = false);
 /// per (list, pos): which cells are needed (appends to entries / count)
 void launch_screen_need(const ScreenArgs &a, cudaStream_t st);
 /// screened reductions (same outputs as launch_reduce_oob / launch_reduce_ib). An in-bag position

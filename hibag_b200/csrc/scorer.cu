@@ -521,6 +521,15 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		if (max_ctas < di.sm_count) max_ctas = di.sm_count;
 	}
 	int nw;
+	// out-of-bag passes: a few hundred tasks of very unequal length per list, so every CTA serves one
+	// list only (no barrier between lists). HIBAG_B200_GATHER_FLAT: 0 (cell, positions) tasks walking
+	// all lists, 2 the same with one list per CTA (default for out-of-bag passes), 1 / 3 entry-flat
+	// tasks (cell_gather_flat_kernel, one list per CTA), +4: also for the in-bag passes
+	int flat_mode = 2;                      // read per call: the tests switch forms inside one process
+	if (const char *e = getenv("HIBAG_B200_GATHER_FLAT")) flat_mode = atoi(e);
+	const int gform = (kind == 0 || (flat_mode & 4)) ? (flat_mode & 3) : 0;
+	const bool flat = (gform & 1) != 0;
+	gb.flat = flat ? 3 : gform;
 	static const int excl = []() { const char *e = getenv("HIBAG_B200_GATHER_EXCL"); return e ? atoi(e) : 0; }();
 	if (excl)
 	{
@@ -535,7 +544,7 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
 		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks,
-			di.sm_count * 32, s);
+			di.sm_count * 32, s, flat);
 		HB_CUDA(cudaEventRecord(ev_up_.e, s));
 		// HIBAG_B200_GATHER_OOB: 0 out-of-bag launches share the exclusive stream, 1 their own exclusive
 		// stream (they are latency-bound and small: they run beside the in-bag launches), 2 the lane's
@@ -573,7 +582,7 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
 		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks,
-			di.sm_count * 32, s);
+			di.sm_count * 32, s, flat);
 		HB_CUDA(cudaEventRecord(ev_g0_.e, s));
 		nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
 		HB_CUDA(cudaEventRecord(ev_g1_.e, s));

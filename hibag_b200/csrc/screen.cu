@@ -225,7 +225,7 @@ void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_
 __global__ void __launch_bounds__(256)
 screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 	const int *__restrict__ count, size_t count_stride, unsigned int *task_prefix,
-	unsigned long long *evals, int target_tasks, int n_lists, int warp_slots)
+	unsigned long long *evals, int target_tasks, int n_lists, int warp_slots, int flat)
 {
 	__shared__ unsigned int seg[256];
 	__shared__ unsigned long long seg_ev[256];
@@ -251,6 +251,28 @@ screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 	}
 	seg[tid] = tot; seg_ev[tid] = ev;
 	__syncthreads();
+	if (flat)
+	{
+		// entry-flat tasks (cell_gather_flat_kernel): the plain exclusive prefix of the counts over the
+		// blob's cell order; a task is 32 consecutive entries of that order, whatever cells they are in
+		if (tid == 0)
+		{
+			unsigned int run = 0;
+			for (int t = 0; t < 256; t++) { const unsigned int v = seg[t]; seg[t] = run; run += v; }
+			pre[n_cells] = (run + 31u) >> 5;
+			pre[n_cells + 1] = run;
+		}
+		__syncthreads();
+		unsigned int run = seg[tid];
+		for (int k = k0; k < k1; k++)
+		{
+			const int4 cb = __ldg((const int4 *)((const char *)(cells + k) + 16));
+			pre[k] = run;
+			run += (unsigned int)__ldg(cnt + cb.x);
+		}
+		if (ev) atomicAdd(evals + l, ev);
+		return;
+	}
 	if (tid == 0)
 	{
 		unsigned int e = 0;
@@ -308,11 +330,11 @@ screen_tasks_kernel(const __grid_constant__ ScreenLists ls, int n_cells,
 
 void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const int *count,
 	size_t count_stride, unsigned int *task_prefix, unsigned long long *evals, int target_tasks,
-	int warp_slots, cudaStream_t st)
+	int warp_slots, cudaStream_t st, bool flat)
 {
 	if (n_lists <= 0) return;
 	screen_tasks_kernel<<<n_lists, 256, 0, st>>>(ls, n_cells, count, count_stride, task_prefix, evals,
-		target_tasks, n_lists, warp_slots);
+		target_tasks, n_lists, warp_slots, flat ? 1 : 0);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -649,15 +671,6 @@ void launch_reduce_ib_screened(const ScreenArgs &a, const ScreenLists &ls, doubl
 // the gather form of the pair-scoring kernel
 // ---------------------------------------------------------------------------------------
 
-/// shared address of T[c_i + pc][lane] from the row address of T[c_i][lane]: one IMAD. (Written as
-/// plain C the compiler re-associates it into (c_i + pc) * 256 + base: an extra IADD per pair.)
-__device__ __forceinline__ uint32_t table_row(uint32_t row_ci, int pc)
-{
-	uint32_t a;
-	asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(a) : "r"((uint32_t)pc), "r"(row_ci));
-	return a;
-}
-
 /// the reference's chain of one cell for R samples per lane (same instruction sequence as the
 /// body of cell_pass_kernel, kernels.cu)
 template <int NW, int R, bool CLAMP, bool SMEM>
@@ -715,24 +728,7 @@ __device__ __forceinline__ void cell_chain(uint32_t hap_base, const char *hap_g,
 			j0 = ii + 1;
 		}
 		const double ff = __dmul_rn(2.0, hi.f);               // exact
-#pragma unroll 2
-		for (int j = j0; j < b_n; j++)
-		{
-			HapRec<NW, SMEM> hj;
-			hj.load(hap_base, hap_g, b_start + j);
-			const double pf = __dmul_rn(ff, hj.f);
-#pragma unroll
-			for (int r = 0; r < R; r++)
-			{
-				int pc = 0;
-#pragma unroll
-				for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[r][w]) & V[r][w]);
-				double t;
-				if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci[r] + pc, dmax) * 256u);
-				else t = lds_f64(table_row(tb[r], pc));
-				sum[r] = __dadd_rn(sum[r], __dmul_rn(pf, t));
-			}
-		}
+		partner_loop<NW, R, CLAMP, SMEM>(hap_base, hap_g, b_start, j0, b_n, ff, K, V, ci, tb, tbl_lane, dmax, sum);
 	}
 }
 
@@ -773,7 +769,12 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 	const int dmax = p.n_dist - 1;
 	uint32_t phase = 0;
 
-	for (int k = 0; k < p.n_lists; k++)
+	// p.flat & 2: a CTA serves ONE list (blockIdx mod n_lists; the grid is a multiple of n_lists). The
+	// lists of an out-of-bag launch hold a few hundred tasks of very unequal length each, and a CTA that
+	// walks the lists in turn waits at every list's barrier for its slowest warp (24 % of the stall
+	// samples of such a launch)
+	const int n_visit = (p.flat & 2) ? 1 : p.n_lists;
+	for (int k = 0; k < n_visit; k++)
 	{
 		int l = (int)(blockIdx.x % (unsigned)p.n_lists) + k;
 		if (l >= p.n_lists) l -= p.n_lists;
@@ -869,6 +870,233 @@ cell_gather_kernel(const __grid_constant__ GatherBatch p)
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------
+// cell_gather_flat_kernel -- the entry-flat form for passes whose cells are needed by a handful of
+// positions each (out-of-bag: ~2.5 of 595 cells per sample survive, ~8 positions per cell). In
+// cell_gather_kernel such a (cell, positions) task fills a quarter of its warp and runs one dependent
+// fp64 chain per lane: the launch is latency-bound (10 % of the POPC peak alone on the GPU). Here a
+// task is 32 consecutive (cell, position) ENTRIES of the cost-sorted cell order and every lane walks
+// the chain of ITS entry -- its own cell bounds and record addresses (plain LDS.128 instead of the
+// uniform-datapath broadcast), its own (i, j) position. The lanes of a warp move in lock step
+// through the inner loop for as many steps as the lane closest to the end of its row has left, then
+// those lanes fetch their next row. The chain is cell_chain's, operation for operation.
+// (Measured, config 2: no faster than the (cell, positions) form -- the lanes of a warp lie in
+// several cells whose rows end at different steps, so the lock-step runs are short; a fully
+// per-lane (i, j) iterator that re-reads the row record with every pair is 2.5 x slower, bound by
+// the bank conflicts of two scattered LDS.128 per pair. Kept behind HIBAG_B200_GATHER_FLAT.)
+// ---------------------------------------------------------------------------------------
+template <int NW, bool CLAMP, bool SMEM>
+__global__ void __launch_bounds__(GATHER_THREADS)
+cell_gather_flat_kernel(const __grid_constant__ GatherBatch p)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// same layout as cell_gather_kernel
+	const uint32_t smem_base = smem_u32(smem_raw);
+	const uint32_t bar = smem_base;
+	volatile int *sh_flag = (volatile int *)(smem_raw + 16);
+	const uint32_t tbl_base = smem_base + 128;
+	const uint32_t pre_off = 128u + (uint32_t)p.n_dist * 256u;
+	const uint32_t pre_bytes = (((uint32_t)p.n_cells + 2u) * 4u + 15u) & ~15u;
+	unsigned int *sh_pre = (unsigned int *)(smem_raw + pre_off);
+	const uint32_t hap_base = smem_base + pre_off + pre_bytes;
+	constexpr int REC = (NW <= 2) ? 16 : 32;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	SmAcct acct_scope(p.acct, p.acct_cls, (unsigned)p.acct_w);
+
+	if (SMEM && tid == 0)
+	{
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	{
+		double *tbl = (double *)(smem_raw + 128);
+		const int n = p.n_dist * 32;
+		for (int k = tid; k < n; k += GATHER_THREADS)
+			tbl[k] = __ldg(p.table + (k >> 5));
+	}
+	__syncthreads();
+
+	const uint32_t tbl_lane = tbl_base + lane * 8;
+	const int dmax = p.n_dist - 1;
+	uint32_t phase = 0;
+
+	// a CTA serves ONE list (blockIdx mod n_lists; the grid is a multiple of n_lists): the lists of an
+	// out-of-bag launch hold a few hundred tasks of very unequal length each, and a CTA that walked the
+	// lists in turn would wait at every list's barrier for its slowest warp (24 % of the stall samples
+	// of such a launch, profiles/r02_gather_oob_before.txt)
+	{
+		const int l = (int)(blockIdx.x % (unsigned)p.n_lists);
+		const GatherList &L = p.lists[l];
+		const unsigned n_tasks = __ldg(L.task_prefix + p.n_cells);
+		unsigned int *counter = p.task_counters + l;
+		if (tid == 0) *sh_flag = (*(volatile unsigned int *)counter < n_tasks) ? 1 : 0;
+		__syncthreads();
+		if (!*sh_flag) return;                                        // (CTA-uniform)
+
+		if (SMEM && tid == 0)
+		{
+			const uint32_t total = (uint32_t)L.n_hap * REC;
+			mbar_expect_tx(bar, total);
+			const char *src = (const char *)L.hap;
+			uint32_t off = 0;
+			while (off < total)
+			{
+				uint32_t nb = total - off;
+				if (nb > 65536u) nb = 65536u;
+				tma_bulk_g2s(hap_base + off, src + off, nb, bar);
+				off += nb;
+			}
+		}
+		for (int q = tid; q < p.n_cells + 2; q += GATHER_THREADS) sh_pre[q] = __ldg(L.task_prefix + q);
+		__syncthreads();
+		if (SMEM)
+		{
+			mbar_wait(bar, phase);
+			phase ^= 1u;
+		}
+
+		const char *hap_g = (const char *)L.hap;
+		double *Pl = L.P;
+		const unsigned n_entries = sh_pre[p.n_cells + 1];
+
+		unsigned task = 0;
+		if (lane == 0) task = atomicAdd(counter, 1u);
+		task = __shfl_sync(0xffffffffu, task, 0);
+
+		while (task < n_tasks)
+		{
+			unsigned next_task = 0;
+			if (lane == 0) next_task = atomicAdd(counter, 1u);
+
+			const unsigned f = task * 32u + (unsigned)lane;
+			bool act = f < n_entries;
+			// this lane's cell: the largest q with prefix[q] <= f (cells nobody needs have empty ranges)
+			int lo = 0, hi = p.n_cells;
+			while (hi - lo > 1)
+			{
+				const int mid = (lo + hi) >> 1;
+				if (sh_pre[mid] <= f) lo = mid; else hi = mid;
+			}
+			const int4 ca = __ldg((const int4 *)(L.cells + lo));
+			const int2 cb = __ldg((const int2 *)((const char *)(L.cells + lo) + 16));
+			int pos = -1, samp = 0;
+			if (act)
+			{
+				pos = __ldg(L.entries + (size_t)__ldg(p.ent_off + cb.x) + (f - sh_pre[lo]));
+				samp = p.samp_list ? __ldg(p.samp_list + pos) : pos;
+			}
+			uint32_t S1[NW], S2[NW], V[NW], K[NW];
+			load_geno<NW>(p.s1, p.s2, p.geno_stride, samp, act, L.cand_col, L.cand_bit, S1, S2);
+#pragma unroll
+			for (int w = 0; w < NW; w++) V[w] = S1[w] | ~S2[w];
+			const bool diag = cb.y != 0;
+			const int a_end = act ? ca.x + ca.y : ca.x;         // records [ca.x, a_end) x [ca.z, ca.z + ca.w)
+			int ri = ca.x;                                      // next row
+			int rj = 0, rj_end = 0;                             // current position / end in the row of partners
+			double sum = 0.0, ff = 0.0;
+			uint32_t tb = tbl_lane;
+			int ci = 0;
+			for (;;)
+			{
+				if (act && rj >= rj_end)
+				{
+					if (ri >= a_end) act = false;
+					else
+					{
+						HapRec<NW, SMEM> hi_;
+						hi_.load(hap_base, hap_g, ri);
+						int c0 = 0;
+#pragma unroll
+						for (int w = 0; w < NW; w++)
+						{
+							K[w] = S1[w] & (S2[w] | ~hi_.h[w]);
+							c0 += __popc((hi_.h[w] ^ (S1[w] & S2[w])) & ~(S1[w] ^ S2[w]));
+						}
+						ci = c0;
+						tb = tbl_lane + (uint32_t)c0 * 256u;
+						rj = ca.z; rj_end = ca.z + ca.w;
+						if (diag)
+						{
+							const double p2 = __dmul_rn(hi_.f, hi_.f);          // src/LibHLA.cpp:1658-1659
+							int pc = 0;
+#pragma unroll
+							for (int w = 0; w < NW; w++) pc += __popc((hi_.h[w] ^ K[w]) & V[w]);
+							double t;
+							if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci + pc, dmax) * 256u);
+							else t = lds_f64(table_row(tb, pc));
+							sum = __dadd_rn(sum, __dmul_rn(p2, t));
+							rj = ri + 1;                                        // (a diagonal cell: ca.z == ca.x)
+						}
+						ff = __dmul_rn(2.0, hi_.f);                            // exact
+						ri++;
+					}
+				}
+				if (!__any_sync(0xffffffffu, act)) break;
+				const int n = __reduce_min_sync(0xffffffffu, act ? (rj_end - rj) : 0x7fffffff);
+				if (act)
+				{
+					// the terms of the next four partners are fetched and multiplied before the adds of the
+					// current four are issued: only the dependent adds stay on the critical path
+					auto terms = [&](int j, double (&x)[4])
+					{
+						HapRec<NW, SMEM> hj[4];
+#pragma unroll
+						for (int q = 0; q < 4; q++) hj[q].load(hap_base, hap_g, j + q);
+						uint32_t ad[4];
+#pragma unroll
+						for (int q = 0; q < 4; q++)
+						{
+							int pc = 0;
+#pragma unroll
+							for (int w = 0; w < NW; w++) pc += __popc((hj[q].h[w] ^ K[w]) & V[w]);
+							ad[q] = CLAMP ? (tbl_lane + (uint32_t)min(ci + pc, dmax) * 256u) : table_row(tb, pc);
+						}
+#pragma unroll
+						for (int q = 0; q < 4; q++) x[q] = lds_f64(ad[q]);
+#pragma unroll
+						for (int q = 0; q < 4; q++) x[q] = __dmul_rn(__dmul_rn(ff, hj[q].f), x[q]);
+					};
+					int t_ = 0;
+					if (n >= 4)
+					{
+						double x0[4];
+						terms(rj, x0);
+						for (t_ = 4; t_ + 4 <= n; t_ += 4)
+						{
+							double x1[4];
+							terms(rj + t_, x1);
+#pragma unroll
+							for (int q = 0; q < 4; q++) { sum = __dadd_rn(sum, x0[q]); x0[q] = x1[q]; }
+						}
+#pragma unroll
+						for (int q = 0; q < 4; q++) sum = __dadd_rn(sum, x0[q]);
+					}
+					for (; t_ < n; t_++)
+					{
+						HapRec<NW, SMEM> hj;
+						hj.load(hap_base, hap_g, rj + t_);
+						const double pf = __dmul_rn(ff, hj.f);
+						int pc = 0;
+#pragma unroll
+						for (int w = 0; w < NW; w++) pc += __popc((hj.h[w] ^ K[w]) & V[w]);
+						double t;
+						if (CLAMP) t = lds_f64(tbl_lane + (uint32_t)min(ci + pc, dmax) * 256u);
+						else t = lds_f64(table_row(tb, pc));
+						sum = __dadd_rn(sum, __dmul_rn(pf, t));
+					}
+					rj += n;
+				}
+			}
+			if (pos >= 0) Pl[(size_t)cb.x * p.p_stride + pos] = sum;
+
+			task = __shfl_sync(0xffffffffu, next_task, 0);
+		}
+	}
+}
+
 template <int NW, bool CLAMP>
 static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream_t st, long long max_ctas)
 {
@@ -885,9 +1113,22 @@ static void launch_gather_variant(const GatherBatch &p, int sm_count, cudaStream
 	long long grid = (long long)sm_count * cta_per_sm;
 	if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
 	if (grid < p.n_lists) grid = p.n_lists;
+	if (p.flat) grid = ((grid + p.n_lists - 1) / p.n_lists) * p.n_lists;   // every list the same number of CTAs
 	GatherBatch q = p;
 	q.acct_w = 1024 / cta_per_sm;
-	if (in_smem)
+	if (p.flat & 1)
+	{
+		if (in_smem)
+		{
+			auto k = cell_gather_flat_kernel<NW, CLAMP, true>;
+			CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+			k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(q);
+		} else {
+			auto k = cell_gather_flat_kernel<NW, CLAMP, false>;
+			CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+			k<<<(unsigned)grid, GATHER_THREADS, smem, st>>>(q);
+		}
+	} else if (in_smem)
 	{
 		auto k = cell_gather_kernel<NW, CLAMP, true>;
 		CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));

@@ -601,7 +601,7 @@ void Trainer::grow(Classifier &cl)
 					host_rp_valid = true;
 				}
 		}
-		pool_->run(m, [&](int i, int w) {
+		const auto em_item = [&](int i, int w) {
 			Candidate &cd = cand[i];
 			cd.snp = pool.at(i);
 			cd.acc = 0; cd.loss = 0;
@@ -619,7 +619,73 @@ void Trainer::grow(Classifier &cl)
 			cd.blob = build_list_blob(cd.list.h.data(), (int)cd.list.h.size(), n_hla_, cd.list.n_snp,
 				scorer_->host_blob(i), 256);
 			scorer_->set_list(i, cd.blob, d_geno_t_.get() + (size_t)cd.snp * n_samp_);
-		});
+		};
+		// ---- legacy hooks: sequential, exactly the reference's call sequence (:2022-2040) -----------
+		int hook_running = global_max_acc;
+		double hook_seconds = 0;
+		const auto hook_item = [&](int i) {
+			Candidate &cd = cand[i];
+			if (!cd.valid) return;
+			const double t_w = now_s();
+			// AddSNP on the TGenotype array the hook receives (:2027, :860-874)
+			const int8_t *col = m_.geno_t.data() + (size_t)cd.snp * n_samp_;
+			const int w = bit >> 6;
+			const uint64_t b = (uint64_t)1 << (bit & 63);
+			for (int s = 0; s < n_samp_; s++)
+			{
+				uint64_t s1 = (uint64_t)aos_[s].snp1[w], s2 = (uint64_t)aos_[s].snp2[w];
+				switch (col[s])
+				{
+				case 0: s1 &= ~b; s2 &= ~b; break;
+				case 1: s1 |= b; s2 &= ~b; break;
+				case 2: s1 |= b; s2 |= b; break;
+				default: s1 &= ~b; s2 |= b;
+				}
+				aos_[s].snp1[w] = (int64_t)s1; aos_[s].snp2[w] = (int64_t)s2;
+			}
+			procs_->build_set_haplo_geno(cd.list.h.data(), (int)cd.list.h.size(), aos_.data(),
+				cd.list.n_snp);
+			cd.acc = procs_->build_acc_oob();
+			ts.n_oob_evals++;
+			if (cd.acc >= hook_running)
+			{
+				cd.loss = procs_->build_acc_ib();
+				ts.n_ib_evals++;
+			}
+			if (cd.acc > hook_running) hook_running = cd.acc;
+			hook_seconds += now_s() - t_w;
+		};
+		bool hooks_done = false;
+		if (procs_ && pool_->size() > 1)
+		{
+			// the host EM of the later candidates runs on the pool WHILE the hooks score the earlier
+			// ones: item 0 is the consumer, it calls the hooks in candidate order as the candidates'
+			// lists become ready (the hook sequence itself stays strictly sequential)
+			std::unique_ptr<std::atomic<int>[]> ready(new std::atomic<int>[m]);
+			for (int i = 0; i < m; i++) ready[i].store(0);
+			std::atomic<int> failed{0};
+			pool_->run(m + 1, [&](int item, int w) {
+				if (item == 0)
+				{
+					for (int i = 0; i < m; i++)
+					{
+						while (!ready[i].load(std::memory_order_acquire))
+						{
+							if (failed.load()) return;
+							std::this_thread::yield();
+						}
+						if (failed.load()) return;
+						hook_item(i);
+					}
+					return;
+				}
+				try { em_item(item - 1, w); }
+				catch (...) { failed.store(1); ready[item - 1].store(1, std::memory_order_release); throw; }
+				ready[item - 1].store(1, std::memory_order_release);
+			});
+			hooks_done = true;
+		} else
+			pool_->run(m, em_item);
 		if (dev_em)
 			for (int i = 0; i < m; i++) if (rem_->status(i) == EM_AMBIGUOUS) ts.n_em_host_fallback++;
 		for (int i = 0; i < m; i++) if (cand[i].valid) { ts.n_em++; }
@@ -653,43 +719,9 @@ void Trainer::grow(Classifier &cl)
 			pool_->run((int)need.size(), [&](int k, int) {
 				cand[need[k]].loss = ib_loss(scorer_->ratios(k));
 			});
-		} else {
-			// ---- legacy hooks: sequential, exactly the reference's call sequence -------------
-			int running = global_max_acc;
-			for (int i = 0; i < m; i++)
-			{
-				Candidate &cd = cand[i];
-				if (!cd.valid) continue;
-				// AddSNP on the TGenotype array the hook receives (:2027, :860-874)
-				const int8_t *col = m_.geno_t.data() + (size_t)cd.snp * n_samp_;
-				const int w = bit >> 6;
-				const uint64_t b = (uint64_t)1 << (bit & 63);
-				for (int s = 0; s < n_samp_; s++)
-				{
-					uint64_t s1 = (uint64_t)aos_[s].snp1[w], s2 = (uint64_t)aos_[s].snp2[w];
-					switch (col[s])
-					{
-					case 0: s1 &= ~b; s2 &= ~b; break;
-					case 1: s1 |= b; s2 &= ~b; break;
-					case 2: s1 |= b; s2 |= b; break;
-					default: s1 &= ~b; s2 |= b;
-					}
-					aos_[s].snp1[w] = (int64_t)s1; aos_[s].snp2[w] = (int64_t)s2;
-				}
-				const double t_w = now_s();
-				procs_->build_set_haplo_geno(cd.list.h.data(), (int)cd.list.h.size(), aos_.data(),
-					cd.list.n_snp);
-				cd.acc = procs_->build_acc_oob();
-				ts.n_oob_evals++;
-				if (cd.acc >= running)
-				{
-					cd.loss = procs_->build_acc_ib();
-					ts.n_ib_evals++;
-				}
-				wait_seconds_[0] += now_s() - t_w;
-				if (cd.acc > running) running = cd.acc;
-			}
-		}
+		} else if (!hooks_done)
+			for (int i = 0; i < m; i++) hook_item(i);
+		if (procs_) wait_seconds_[0] += hook_seconds;
 
 		ts.seconds_phase_ib += now_s() - t_p2;
 		// workload accounting (independent of scheduling): what the reference would evaluate

@@ -347,6 +347,45 @@ def test_trainer_matches_reference_many_snps(gpu):
                 assert st["pair_evals"] < st["pair_evals_nominal"]          # the screen was on
 
 
+@pytest.mark.parametrize("flat", ["0", "1", "2", "7"])
+def test_gather_forms_reproduce_the_reference(gpu, monkeypatch, flat):
+    """the forms of the screened pair-scoring kernel -- (cell, block of positions) tasks with
+    warp-uniform cell bounds, CTAs walking all lists of the launch (0) or serving one list each (2, the
+    default for the out-of-bag passes), and entry-flat tasks where every lane walks the chain of its own
+    (cell, position) entry (1; 7 = for both passes) -- all produce the reference's classifiers.
+    One-, two- and four-word genotypes (golden HapMap model, 37- and 67-SNP cohorts), many alleles."""
+    from hibag_b200 import synth
+    monkeypatch.setenv("HIBAG_B200_GATHER_FLAT", flat)
+    geno, h1, h2, al, ml = helpers.hapmap_a_training()
+    m = gpu.HLAModel(geno.shape[1], len(al), al)
+    m.set_training(geno, h1, h2)
+    m.train(8, int(ml["mtry"]), prune=True, seed=int(ml["seed"]), n_threads=4)
+    for k in range(8):
+        helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
+    st = m.train_stats()
+    assert st["pair_evals"] < st["pair_evals_nominal"]
+    gd = helpers.load_golden("synth_thermo_ref.npz")
+    for i in range(int(gd["n_specs"])):
+        g2, a1, a2 = synth.make_thermo_cohort(int(gd["s%d_n_samp" % i]), int(gd["s%d_n_hla" % i]),
+                                              seed=int(gd["s%d_cohort_seed" % i]), noise=float(gd["s%d_noise" % i]))
+        want = dict(snpidx=gd["s%d_snpidx" % i], samp_num=gd["s%d_samp_num" % i], freq=gd["s%d_freq" % i],
+                    hla=gd["s%d_hla" % i], packed=gd["s%d_packed" % i], oob_acc=float(gd["s%d_oob_acc" % i]))
+        s = gpu.HLAModel(g2.shape[1], int(gd["s%d_n_hla" % i]))
+        s.set_training(g2, a1, a2)
+        s.train(1, g2.shape[1], prune=True, seed=int(gd["s%d_train_seed" % i]), per_classifier_seed=True)
+        assert helpers.classifier_diff(s.classifier(0), want) == "", (flat, i)
+    gm = helpers.load_golden("synth_many_alleles_ref.npz")
+    coh = synth.make_cohort(int(gm["n_samp"]), int(gm["n_snp"]), int(gm["n_hla"]), seed=int(gm["cohort_seed"]))
+    t = gpu.HLAModel(coh.n_snp, coh.n_hla)
+    t.set_training(coh.geno, coh.h1, coh.h2)
+    t.train(int(gm["n_cls"]), gpu.default_mtry(coh.n_snp), prune=True, seed=int(gm["train_seed"]),
+            per_classifier_seed=True, n_concurrent=2)
+    for k in range(int(gm["n_cls"])):
+        want = dict(snpidx=gm["c%d_snpidx" % k], samp_num=gm["c%d_samp_num" % k], freq=gm["c%d_freq" % k],
+                    hla=gm["c%d_hla" % k], packed=gm["c%d_packed" % k], oob_acc=float(gm["c%d_oob_acc" % k]))
+        assert helpers.classifier_diff(t.classifier(k), want) == "", (flat, k)
+
+
 def _golden_model(gpu, ref, n_cls=100):
     geno, h1, h2, al, ml = helpers.hapmap_a_training()
     m = gpu.HLAModel(geno.shape[1], len(al), al)
