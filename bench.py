@@ -44,7 +44,7 @@ N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
 GATHER_NCU_CSV = ("r02_gather_ncu_raw.csv", "r01_gather_final_ncu_raw.csv")   # newest capture first
-LANES = 24           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
+LANES = 40           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
 WORKLOAD_JSON = os.path.join(ROOT, "profiles", "c2_workload.json")

@@ -188,6 +188,12 @@ __global__ void incidence_len_kernel(const int *__restrict__ inc_off, int n2, in
 	hap[u] = u;
 }
 
+__global__ void iota_kernel(int n, int *out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = i;
+}
+
 /// Haplotypes sorted by decreasing contribution count are cut into groups of 32 (one per lane
 /// of a warp); group g stores its contributions interleaved ("ELL"): slot (i, lane) at
 /// group_base[g] + 64*(i/2) + 2*lane + (i&1), i < group_len[g] = the longest chain of the group
@@ -783,53 +789,76 @@ __global__ void __launch_bounds__(EM_THREADS, (EM_THREADS <= 512) ? 2 : 1) em_ke
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// em_resident_kernel -- the EM of one candidate with its working set in shared memory.
+// em_chain_kernel -- the EM of one candidate as two walks over chains of 4-byte records, state in
+// shared memory, 128 threads.
 //
-// em_kernel (above) streams ~2.7 MB per iteration per candidate through L2 (GenoFreq buffer, the
-// scattered 8-byte contribution stores into the ELL rows, the padded ELL rows read back by the M
-// step); with two dozen lanes in EM that working set (0.8 MB x ~550 candidates) is several times the
-// L2, the kernel sits on DRAM latency (233 k cycles per iteration measured inside the 24-lane step,
-// against a floor of ~20 k for its longest chain) and holds 30 % of the GPU's SM-time.
-//
-// Here one CTA (1024 threads, one per SM) keeps, per candidate: both frequency vectors, the
-// per-entry scale factors and the compatible pairs (u | v << 16, 4 bytes a pair, in pair order).
-// No contribution is ever stored: a chain's contribution r = x * (count / sum) is RECOMPUTED by the
-// lane that adds it, from a 4-byte record {partner haplotype, entry, u == v} written once per
-// candidate into the ELL of its group -- the lane owns haplotype h, so x = (2 f_h) f_partner (or
-// f_h f_h). (2 f_u) f_v and (2 f_v) f_u round the same real number once, 2 f being exact: the value is
-// the E step's x bit for bit, whichever side h is on.) The records are the only per-iteration global
-// traffic (read-only, L2-resident) and reach the lanes through per-warp cp.async rings, so the chain
-// runs at fp64-add latency.
-//   E step: one thread per in-bag entry -- x of its pairs from the shared frequencies, summed in
-//           list order; log-likelihood term; scale factor count / sum.
-//   M step: EMR_M_WARPS warps take the groups of 32 chains, longest first; every lane walks ITS
-//           chain in the reference's order.
+// em_kernel (above) streams ~2.7 MB per iteration per candidate through L2 (GenoFreq buffer, 44 k
+// scattered 8-byte contribution stores, the padded ELL rows read back by the M step) with 512
+// threads that mostly wait at barriers: with two dozen lanes in EM the scattered stores saturate
+// the L2 (233 k cycles per iteration inside the 24-lane step against 152 k alone) and the kernel
+// HOLDS 30 % of the GPU's SM-time. What counts once the GPU is full is SM-time per
+// candidate-iteration = (share of an SM the CTA occupies) x (duration); the arithmetic is tiny
+// (22 k products and adds in the E step, 44 k contributions in the M step), everything else is
+// latency. So: few threads, no stores, and both steps in ONE form -- a lane walks a chain of records
+// in the reference's order and adds one recomputed term per record:
+//   E step: chain = an in-bag entry, record = a compatible pair (u, v),
+//           term = (2 f_u) f_v (f_u f_v when u == v); then ll += count log(sum), scale = count / sum;
+//   M step: chain = a doubled haplotype h, record = {partner haplotype, entry, u == v} of a compatible
+//           contribution in (sample, pair, H1-before-H2) order,
+//           term = x * scale[entry] with x = (2 f_h) f_partner (f_h f_h when u == v); at the end
+//           f_new[h] = sum * (0.5 / n).
+// ((2 f_u) f_v and (2 f_v) f_u round the same real number once, 2 f being exact: x is the E step's
+// value bit for bit whichever side h is on; the term is em_kernel's r = x * (count / sum).)
+// Chains are sorted by length and cut into groups of 32 (one per lane), a group's records
+// interleaved so that four rows of a lane are 16 contiguous bytes. A warp takes the next-longest
+// group: long groups stream through a private cp.async ring, the terms of batch b + 1 gathered and
+// multiplied before the adds of batch b are issued; short groups (<= 8 rows) are loaded into registers
+// while the previous group is summed. Haplotypes and entries are addressed by their RANK in that
+// order everywhere (frequencies, scale factors, records), so an iteration reads nothing from global
+// memory but the records: read-only, 4 bytes a term, coalesced.
+// Per round (RoundEM::prepare) every pair and every contribution gets its record with the sum
+// s = (u & 1) + (v & 1) of the new SNP's alleles; per candidate the kernel only FILTERS them -- a
+// record is compatible with an entry's genotype g when g is missing or g == s (:1157-1180) -- in two
+// streaming passes (block scan of the flags, rank inside the chain = prefix - prefix at the chain's
+// first record) that write the compatible records into the chains' columns.
 // Every accumulator receives the operands em_kernel gives it, in the same order, un-fused: the two
 // kernels are bit-identical (tests/test_gpu_parity.py trains the golden models with either).
-// A candidate whose compatible pairs exceed the shared-memory capacity is reported EM_AMBIGUOUS
-// (the host re-estimates it); run_em only chooses this kernel when that is not expected.
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int EMR_M_WARPS = 6;          // warps that run the M step, each with its own ring
-constexpr int EMR_RING_B = 8;           // batches of 4 rows (512 B) a ring holds: 32 rows in flight (cp.async.wait_group
-                                        // with more than ~8 groups pending behaved like wait_all: 119 cycles per row measured)
-constexpr int EMR_LONG = 24;            // entries with more compatible pairs are summed by a whole warp
-constexpr int EMR_LONG_MAX = 1024;      // capacity of the list of such entries
+constexpr int EMC_THREADS = 128;
+constexpr int EMC_WARPS = EMC_THREADS / 32;
+constexpr int EMC_RING_B = 8;           // batches of 4 rows (512 B per warp) a ring holds (cp.async.wait_group
+                                        // with more than ~8 groups pending behaved like wait_all)
+constexpr int EMC_MAX_HAP = 16383;      // 14-bit haplotype ranks, 15-bit entry ranks in the records
+constexpr int EMC_MAX_ENTRY = 32767;
 
-struct EmrArgs
+// E record: rank_u | rank_v << 14 | s << 28.   M record: partner rank | entry rank << 14 | (u == v) << 29 | s << 30
+__host__ __device__ inline uint32_t emc_pair_record(int ru, int rv, int s) { return (uint32_t)ru | ((uint32_t)rv << 14) | ((uint32_t)s << 28); }
+__host__ __device__ inline uint32_t emc_contrib_record(int rp, int re, bool diag, int s)
 {
-	int n_entry, n_cur, n_samp, total_pairs, cap;   // cap = compatible pairs the CTA can hold
-	const int *ib, *boot, *off;
-	const int4 *pairs4;
-	const int *hap_sorted, *group_base, *inc_off, *inc_val;
-	const double *cur_freq;
+	return (uint32_t)rp | ((uint32_t)re << 14) | (diag ? (1u << 29) : 0u) | ((uint32_t)s << 30);
+}
+
+struct EmcArgs
+{
+	int n_entry, n_cur, n_samp, total_pairs;
+	const int *ib, *boot;
+	// haplotype chains (M step): rank order, group bases in record slots, all contributions of the round
+	const int *hap_sorted, *hap_rank, *group_base;
+	const uint32_t *mrec_all;         // [2 * total_pairs] in chain order (by haplotype, stable)
+	const uint16_t *mown;             // [2 * total_pairs] rank of the chain a contribution belongs to
 	size_t n_slots;
+	// entry chains (E step)
+	const int *entry_sorted, *egroup_base;
+	const uint32_t *erec_all;         // [total_pairs] in pair order
+	const uint16_t *eown;             // [total_pairs] rank of the pair's entry
+	size_t n_eslots;
+	const double *cur_freq;
 	const int8_t *geno_t;
 	const int *cand_snp;
-	int *coff;                        // [m][n_entry + 1]
-	uint32_t *rec;                    // [m][n_slots] chain records: partner | entry << 16 | (u == v) << 31
-	uint32_t *cuv;                    // [m][total_pairs] compatible pairs (u | v << 16) when they are streamed
+	uint32_t *rec;                    // [m][n_slots]
+	uint32_t *erec;                   // [m][n_eslots]
 	double *out_freq;
 	int *out_status;
 	double scale, em_reltol;
@@ -838,95 +867,172 @@ struct EmrArgs
 	unsigned long long *prof;         // [m][8]: cycles of set-up, E steps, M steps; iterations (HIBAG_B200_EM_DEBUG)
 };
 
-/// THREADS per CTA; PAIRS_SMEM: the compatible pairs live in shared memory (one CTA per SM: lowest
-/// latency, a single classifier in flight) or are streamed from L2 by the E step (half an SM per
-/// CTA: two candidates, or one and the scoring CTAs of other lanes, share an SM)
-template <int THREADS, bool PAIRS_SMEM>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1) em_resident_kernel(const EmrArgs p)
+/// record slot of row i of lane l in a group that starts at base (32-bit slots)
+__device__ __forceinline__ size_t emc_slot(int base, int i, int l)
 {
-	SmAcct acct_scope(p.acct, SM_ACCT_EM, (unsigned)p.acct_w);
-	SmAcct acct_cta(p.acct, SM_ACCT_EM_CTA, 1024u);
-	extern __shared__ double em_smem[];
-	constexpr int N_WARPS = THREADS / 32;
-	const int n2 = 2 * p.n_cur;
-	const int n_groups = (n2 + 31) >> 5;
-	double *fr0 = em_smem;                                   // [2][n2]
-	double *scratch = fr0 + 2 * (size_t)n2;                  // [40]
-	double *sck = scratch + 40;                              // [n_entry]
-	uint32_t *rings = (uint32_t *)(sck + ((p.n_entry + 1) & ~1));   // [EMR_M_WARPS][EMR_RING_B][128] (16-byte aligned)
-	uint32_t *s_uv = rings + EMR_M_WARPS * EMR_RING_B * 128; // [cap] (PAIRS_SMEM)
-	int *eg = (int *)(s_uv + (PAIRS_SMEM ? p.cap : 0));      // [n_entry] bootstrap count << 2 | candidate genotype
-	int *clen = eg + p.n_entry;                              // [n2] compatible contributions per chain (by sorted rank)
-	int *glen = clen + n2;                                   // [n_groups]
-	int *longlist = glen + n_groups;                         // [EMR_LONG_MAX] entries summed by a warp
-	__shared__ int sh_i[6];
+	return (size_t)base + 128 * (size_t)(i >> 2) + 4 * (size_t)l + (size_t)(i & 3);
+}
 
-	const int c = blockIdx.x;
+/// the term of an E-step record (a compatible pair): GenoFreq (:1208-1213)
+struct EmcPairTerm
+{
+	const double *fr;                 // by rank
+	__device__ __forceinline__ void gather(uint32_t rc, bool valid, double &a, double &b) const
+	{
+		const uint32_t u = valid ? (rc & 0x3fffu) : 0u, v = valid ? ((rc >> 14) & 0x3fffu) : 0u;
+		a = fr[u]; b = fr[v];
+	}
+	__device__ __forceinline__ double combine(uint32_t rc, double a, double b) const
+	{
+		const double t = ((rc & 0x3fffu) != ((rc >> 14) & 0x3fffu)) ? __dmul_rn(2.0, a) : a;      // 2 f_u is exact
+		return __dmul_rn(t, b);
+	}
+};
+
+/// the term of an M-step record: GenoFreq * count / sum (:1224-1232)
+struct EmcContribTerm
+{
+	const double *fr, *sck;           // by rank
+	double fh2, xhh;                  // 2 f_h and f_h f_h of the lane's haplotype
+	__device__ __forceinline__ void gather(uint32_t rc, bool valid, double &a, double &b) const
+	{
+		const uint32_t pt = valid ? (rc & 0x3fffu) : 0u, en = valid ? ((rc >> 14) & 0x7fffu) : 0u;
+		a = fr[pt]; b = sck[en];
+	}
+	__device__ __forceinline__ double combine(uint32_t rc, double a, double b) const
+	{
+		const double x = (rc & (1u << 29)) ? xhh : __dmul_rn(fh2, a);
+		return __dmul_rn(x, b);
+	}
+};
+
+/// terms of four consecutive rows of a lane (rows >= my_len give +0.0: s + 0.0 == s for the
+/// non-negative sums here); branch-free, the eight gathers issued together
+template <class Term>
+__device__ __forceinline__ void emc_terms(const int4 &q4, int row0, int my_len, const Term &term, double (&rr)[4])
+{
+	const uint32_t rc[4] = { (uint32_t)q4.x, (uint32_t)q4.y, (uint32_t)q4.z, (uint32_t)q4.w };
+	double a[4], b[4];
+#pragma unroll
+	for (int q = 0; q < 4; q++) term.gather(rc[q], row0 + q < my_len, a[q], b[q]);
+#pragma unroll
+	for (int q = 0; q < 4; q++)
+	{
+		const double r = term.combine(rc[q], a[q], b[q]);
+		rr[q] = (row0 + q < my_len) ? r : 0.0;
+	}
+}
+
+/// One lane's sequential sum over its chain: my_len rows of the group's nb batches, streamed through
+/// the warp's ring. The terms of batch b + 1 are evaluated before the adds of batch b are issued.
+template <class Term>
+__device__ __forceinline__ double emc_walk(const uint32_t *rec_group, int nb, int my_len, uint32_t ring_s,
+	int lane, const Term &term)
+{
+	const char *src = (const char *)rec_group + lane * 16;     // + 512 per batch
+	for (int b = 0; b < EMC_RING_B - 1; b++)
+	{
+		if (b < nb) cp_async16_cg(ring_s + (uint32_t)b * 512u, src + (size_t)b * 512);
+		cp_async_commit();
+	}
+	double acc = 0;
+	double rr[4] = { 0.0, 0.0, 0.0, 0.0 };
+	int rb = 0, rbn = EMC_RING_B - 1;      // ring slots of batch b and of batch b + EMC_RING_B - 1
+	if (nb > 0)
+	{
+		cp_async_wait<EMC_RING_B - 2>();
+		emc_terms(lds_i32x4(ring_s), 0, my_len, term, rr);
+	}
+	for (int b = 0; b < nb; b++)
+	{
+		const int bn = b + EMC_RING_B - 1;
+		if (bn < nb) cp_async16_cg(ring_s + (uint32_t)rbn * 512u, src + (size_t)bn * 512);
+		cp_async_commit();
+		// batch b + 1 has landed when at most EMC_RING_B - 2 younger groups are pending
+		cp_async_wait<EMC_RING_B - 2>();
+		double rn[4] = { 0.0, 0.0, 0.0, 0.0 };
+		const int rb1 = (rb + 1 == EMC_RING_B) ? 0 : rb + 1;
+		if (b + 1 < nb) emc_terms(lds_i32x4(ring_s + (uint32_t)rb1 * 512u), 4 * (b + 1), my_len, term, rn);
+#pragma unroll
+		for (int q = 0; q < 4; q++) { acc = __dadd_rn(acc, rr[q]); rr[q] = rn[q]; }
+		rb = rb1;
+		if (++rbn == EMC_RING_B) rbn = 0;
+	}
+	cp_async_wait<0>();
+	return acc;
+}
+
+constexpr int EMC_DIRECT_B = 2;         // groups of at most this many batches (8 rows) skip the ring: their
+                                        // records are loaded into registers while the previous group is summed
+
+/// records of a short group straight from global memory (the group's rows are a prefix of its slots)
+__device__ __forceinline__ void emc_direct_load(const uint32_t *rec_group, int nb, int lane, int4 (&q)[EMC_DIRECT_B])
+{
+	const int4 *src = (const int4 *)rec_group + lane;          // + 32 int4 per batch
+#pragma unroll
+	for (int b = 0; b < EMC_DIRECT_B; b++) q[b] = (b < nb) ? __ldcg(src + 32 * b) : make_int4(0, 0, 0, 0);
+}
+
+template <class Term>
+__device__ __forceinline__ double emc_direct_sum(const int4 (&q)[EMC_DIRECT_B], int nb, int my_len, const Term &term)
+{
+	double rr[EMC_DIRECT_B][4];
+#pragma unroll
+	for (int b = 0; b < EMC_DIRECT_B; b++)
+	{
+		if (b < nb) emc_terms(q[b], 4 * b, my_len, term, rr[b]);
+		else { rr[b][0] = rr[b][1] = rr[b][2] = rr[b][3] = 0.0; }
+	}
+	double acc = 0;
+#pragma unroll
+	for (int b = 0; b < EMC_DIRECT_B; b++)
+#pragma unroll
+		for (int k = 0; k < 4; k++) acc = __dadd_rn(acc, rr[b][k]);
+	return acc;
+}
+
+/// Streaming filter of one record array (all pairs, or all contributions, of the round) into the
+/// chains' columns: a record of chain `own` is kept when the genotype of its entry is missing or
+/// equals the record's allele sum; its row is its rank among the kept records of its chain. 1 024
+/// records per step (8 per thread, contiguous), the next step's loads in flight.
+/// pstart [n_chains] ints (scratch), len [n_chains] (zeroed by the caller), glen [n_groups] (zeroed).
+template <bool M_RECORDS>
+__device__ __forceinline__ int emc_filter(const uint32_t *__restrict__ all, const uint16_t *__restrict__ own, int n,
+	const int *eg, const int *gbase, uint32_t *out, int *pstart, uint16_t *len, int *glen, int *wsum)
+{
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int8_t *col = p.geno_t + (size_t)p.cand_snp[c] * p.n_samp;
-	int *coff = p.coff + (size_t)c * (p.n_entry + 1);
-	uint32_t *rec = p.rec + (size_t)c * p.n_slots;
-	uint32_t *pairs = PAIRS_SMEM ? s_uv : (p.cuv + (size_t)c * p.total_pairs);
-	int *status = p.out_status + 4 * c;
-
-	// allele frequency of the new SNP in the bootstrap sample (:1136-1151), integers
+	int running = 0;
+	uint4 it0 = make_uint4(0, 0, 0, 0), it1 = it0, ow = it0;
+	int prev_owner = -1;
+	auto load = [&](int base)
 	{
-		int ac = 0, vc = 0;
-		for (int k = tid; k < p.n_entry; k += THREADS)
+		const int i0 = base + 8 * tid;
+		if (i0 < n)       // (the arrays are padded to a multiple of 8 records)
 		{
-			const int s = p.ib[k];
-			const int g = col[s];
-			const int b = p.boot[s];
-			eg[k] = (b << 2) | ((0 <= g && g <= 2) ? g : 3);
-			if (0 <= g && g <= 2) { ac += g * b; vc += 2 * b; }
+			it0 = __ldg((const uint4 *)(all + i0)); it1 = __ldg((const uint4 *)(all + i0 + 4));
+			ow = __ldg((const uint4 *)(own + i0));
+			prev_owner = (i0 > 0) ? (int)__ldg(own + i0 - 1) : -1;
 		}
-		if (tid < 6) sh_i[tid] = 0;
-		for (int g = tid; g < n_groups; g += THREADS) glen[g] = 0;
-		__syncthreads();
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1)
-		{
-			ac += __shfl_xor_sync(0xffffffffu, ac, o);
-			vc += __shfl_xor_sync(0xffffffffu, vc, o);
-		}
-		if (lane == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); }
-		__syncthreads();
-	}
-	const int allele_cnt = sh_i[0], valid_cnt = sh_i[1];
-	if (allele_cnt == 0 || allele_cnt == valid_cnt)
+	};
+	load(0);
+	for (int base = 0; base < n; base += 8 * EMC_THREADS)
 	{
-		if (tid == 0) { status[0] = EM_INVALID; status[1] = 0; status[2] = 0; status[3] = 0; }
-		return;
-	}
-	// doubled list, initial frequencies (:444-459)
-	{
-		const double af = __ddiv_rn((double)allele_cnt, (double)valid_cnt);
-		const double q0 = __dsub_rn(1.0, af), q1 = af;
-		for (int k = tid; k < p.n_cur; k += THREADS)
-		{
-			const double f = p.cur_freq[k];
-			fr0[2 * k] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
-			fr0[2 * k + 1] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
-		}
-	}
-	// ---- (A) the compatible pairs (:1157-1180), in pair order ---------------------------------------
-	int n_compat;
-	{
-		const int chunk = (p.total_pairs + THREADS - 1) / THREADS;
-		const int tb = min(p.total_pairs, tid * chunk), te = min(p.total_pairs, tb + chunk);
+		const uint32_t rc[8] = { it0.x, it0.y, it0.z, it0.w, it1.x, it1.y, it1.z, it1.w };
+		const uint32_t o2[4] = { ow.x, ow.y, ow.z, ow.w };
+		const int pv = prev_owner;
+		const int i0 = base + 8 * tid;
+		if (base + 8 * EMC_THREADS < n) load(base + 8 * EMC_THREADS);
+		int owner[8];
+		bool keep[8];
 		int cnt = 0;
-		for (int t = tb; t < te; t += 4)
+#pragma unroll
+		for (int q = 0; q < 8; q++)
 		{
-			int4 pr[4];
-#pragma unroll
-			for (int q = 0; q < 4; q++) pr[q] = (t + q < te) ? __ldg(p.pairs4 + t + q) : make_int4(0, 0, 0, 0);
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-			{
-				const int u = pr[q].x & 0xffff, v = (int)((unsigned)pr[q].x >> 16);
-				const int g = eg[pr[q].y] & 3;
-				cnt += (t + q < te && (g == 3 || ((u & 1) + (v & 1)) == g)) ? 1 : 0;
-			}
+			owner[q] = (int)((o2[q >> 1] >> (16 * (q & 1))) & 0xffffu);
+			const int g = eg[M_RECORDS ? (int)((rc[q] >> 14) & 0x7fffu) : owner[q]];
+			const int sg = (int)(rc[q] >> (M_RECORDS ? 30 : 28)) & 3;
+			keep[q] = (i0 + q < n) && (g == 3 || g == sg);
+			cnt += keep[q] ? 1 : 0;
 		}
 		int incl = cnt;
 #pragma unroll
@@ -935,118 +1041,151 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1) em_resident
 			const int y = __shfl_up_sync(0xffffffffu, incl, o);
 			if (lane >= o) incl += y;
 		}
-		int *wsum = (int *)scratch;             // [32] ints
-		__syncthreads();
 		if (lane == 31) wsum[warp] = incl;
 		__syncthreads();
-		if (tid < 32)
-		{
-			int w = (tid < N_WARPS) ? wsum[tid] : 0;
+		int pre = running + incl - cnt;
+		int total = 0;
 #pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
+		for (int w = 0; w < EMC_WARPS; w++) { const int v = wsum[w]; if (w < warp) pre += v; total += v; }
+		// the first record of a chain notes the prefix its chain starts at
+		{
+			int pq = pre, last = pv;
+#pragma unroll
+			for (int q = 0; q < 8; q++)
 			{
-				const int y = __shfl_up_sync(0xffffffffu, w, o);
-				if (tid >= o) w += y;
+				if (i0 + q < n && owner[q] != last) pstart[owner[q]] = pq;
+				last = owner[q];
+				pq += keep[q] ? 1 : 0;
 			}
-			wsum[tid] = w;
 		}
 		__syncthreads();
-		n_compat = wsum[31];
-		if (PAIRS_SMEM && n_compat > p.cap)
 		{
-			// does not fit: the host re-estimates this candidate (status[2] = -1 tells why)
-			if (tid == 0) { status[0] = EM_AMBIGUOUS; status[1] = 0; status[2] = -1; status[3] = n_compat; }
-			return;
-		}
-		int j = incl - cnt + (warp ? wsum[warp - 1] : 0);
-		for (int t = tb; t < te; t += 4)
-		{
-			int4 pr[4];
+			int pq = pre, last = pv;
 #pragma unroll
-			for (int q = 0; q < 4; q++) pr[q] = (t + q < te) ? __ldg(p.pairs4 + t + q) : make_int4(0, 0, 0, 0);
-#pragma unroll
-			for (int q = 0; q < 4; q++)
+			for (int q = 0; q < 8; q++)
 			{
-				if (t + q < te)
+				if (i0 + q < n)
 				{
-					const int u = pr[q].x & 0xffff, v = (int)((unsigned)pr[q].x >> 16);
-					const int g = eg[pr[q].y] & 3;
-					if (t + q == p.off[pr[q].y]) coff[pr[q].y] = j;      // first pair of its entry
-					if (g == 3 || ((u & 1) + (v & 1)) == g) pairs[j++] = (uint32_t)pr[q].x;
+					if (owner[q] != last && last >= 0)
+					{
+						// the previous chain ended just before this record
+						const int l = pq - pstart[last];
+						len[last] = (uint16_t)l;
+						if (l > 0) atomicMax(&glen[last >> 5], l);
+					}
+					if (keep[q])
+						out[emc_slot(gbase[owner[q] >> 5], pq - pstart[owner[q]], owner[q] & 31)] = rc[q];
+					if (i0 + q == n - 1)
+					{
+						const int l = pq + (keep[q] ? 1 : 0) - pstart[owner[q]];
+						len[owner[q]] = (uint16_t)l;
+						if (l > 0) atomicMax(&glen[owner[q] >> 5], l);
+					}
 				}
+				last = owner[q];
+				pq += keep[q] ? 1 : 0;
 			}
 		}
-		if (tid == 0) coff[p.n_entry] = n_compat;
-		__syncthreads();
+		running += total;
 	}
-	// entries with many compatible pairs (ambiguous samples: every pair at the minimum distance is
-	// kept) are summed by a whole warp in the E step; an overflowing list only costs speed
-	for (int k = tid; k < p.n_entry; k += THREADS)
-		if (coff[k + 1] - coff[k] > EMR_LONG)
-		{
-			const int i = atomicAdd(&sh_i[4], 1);
-			if (i < EMR_LONG_MAX) longlist[i] = k;
-		}
-	// ---- (B) every chain's compatible contributions in the reference's order -- (sample, pair,
-	// H1-before-H2) -- as records in the ELL of its group: a warp takes one haplotype at a time and
-	// walks its incidence list. slot(row i, lane l) = base + 128 (i / 4) + 4 l + (i % 4): four rows of
-	// a lane are 16 contiguous bytes (one cp.async), a warp's batch 512 contiguous bytes ---------------
+	return running;
+}
+
+__global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs p)
+{
+	SmAcct acct_scope(p.acct, SM_ACCT_EM, (unsigned)p.acct_w);
+	SmAcct acct_cta(p.acct, SM_ACCT_EM_CTA, 1024u);
+	extern __shared__ double em_smem[];
+	const int n2 = 2 * p.n_cur;
+	const int n_groups = (n2 + 31) >> 5, n_egroups = (p.n_entry + 31) >> 5;
+	double *fr0 = em_smem;                                   // [2][n2] frequencies by rank, double-buffered
+	double *scratch = fr0 + 2 * (size_t)n2;                  // [40]
+	double *sck = scratch + 40;                              // [n_entry] count / sum by rank (set-up: genotypes, prefixes)
+	uint32_t *rings = (uint32_t *)(sck + ((p.n_entry + 1) & ~1));   // [EMC_WARPS][EMC_RING_B][128] (16-byte aligned)
+	int *gbase = (int *)(rings + EMC_WARPS * EMC_RING_B * 128);     // [n_groups] first record slot of the group
+	int *egbase = gbase + n_groups;                          // [n_egroups]
+	int *glen = egbase + n_egroups;                          // [n_groups] longest compatible chain of the group
+	int *eglen = glen + n_groups;                            // [n_egroups]
+	uint16_t *clen = (uint16_t *)(eglen + n_egroups);        // [n2] compatible contributions per chain, by rank
+	uint16_t *elen = clen + ((n2 + 1) & ~1);                 // [n_entry] compatible pairs per entry, by rank
+	uint8_t *ebc = (uint8_t *)(elen + ((p.n_entry + 1) & ~1));      // [n_entry] bootstrap count, by rank
+	int *eg = (int *)sck;                                    // set-up: genotype of the entry (3 = missing), by rank
+	int *pstart_e = eg + p.n_entry;                          // set-up: prefix at the first pair of the entry
+	int *pstart_m = (int *)(fr0 + n2);                       // set-up: the same per haplotype chain (second frequency buffer)
+	__shared__ int sh_i[6];
+	__shared__ int sh_w[EMC_WARPS];
+
+	const int c = blockIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int8_t *col = p.geno_t + (size_t)p.cand_snp[c] * p.n_samp;
+	uint32_t *rec = p.rec + (size_t)c * p.n_slots;
+	uint32_t *erec = p.erec + (size_t)c * p.n_eslots;
+	int *status = p.out_status + 4 * c;
+
+	// allele frequency of the new SNP in the bootstrap sample (:1136-1151), integers
 	{
-		for (;;)
+		int ac = 0, vc = 0, big = 0;
+		for (int r = tid; r < p.n_entry; r += EMC_THREADS)
 		{
-			int r = 0;
-			if (lane == 0) r = atomicAdd(&sh_i[3], 1);
-			r = __shfl_sync(0xffffffffu, r, 0);
-			if (r >= n2) break;
-			const int gi = r >> 5, l = r & 31;
-			const int u = p.hap_sorted[r];
-			const int gbase = p.group_base[gi];
-			const int qb = p.inc_off[u], qe = p.inc_off[u + 1];
-			int n = 0;
-			for (int q0 = qb; q0 < qe; q0 += 128)
-			{
-				int e[4]; int4 pr[4];
+			const int s = p.ib[__ldg(p.entry_sorted + r)];
+			const int g = col[s];
+			const int b = p.boot[s];
+			eg[r] = (0 <= g && g <= 2) ? g : 3;
+			ebc[r] = (uint8_t)b;
+			elen[r] = 0;
+			big |= (b > 255) ? 1 : 0;
+			if (0 <= g && g <= 2) { ac += g * b; vc += 2 * b; }
+		}
+		if (tid < 6) sh_i[tid] = 0;
+		for (int g = tid; g < n_groups; g += EMC_THREADS) { gbase[g] = p.group_base[g]; glen[g] = 0; }
+		for (int g = tid; g < n_egroups; g += EMC_THREADS) { egbase[g] = p.egroup_base[g]; eglen[g] = 0; }
+		for (int r = tid; r < n2; r += EMC_THREADS) clen[r] = 0;
+		__syncthreads();
 #pragma unroll
-				for (int w = 0; w < 4; w++)
-				{
-					const int q = q0 + w * 32 + lane;
-					e[w] = (q < qe) ? __ldg(p.inc_val + q) : -1;
-				}
-#pragma unroll
-				for (int w = 0; w < 4; w++)
-					pr[w] = (e[w] >= 0) ? __ldg(p.pairs4 + (e[w] >> 1)) : make_int4(0, 0, 0, 0);
-#pragma unroll
-				for (int w = 0; w < 4; w++)
-				{
-					bool ok = false;
-					uint32_t record = 0;
-					if (e[w] >= 0)
-					{
-						const int uu = pr[w].x & 0xffff, vv = (int)((unsigned)pr[w].x >> 16);
-						const int g = eg[pr[w].y] & 3;
-						ok = (g == 3 || ((uu & 1) + (vv & 1)) == g);
-						const int partner = (e[w] & 1) ? uu : vv;      // side 1: this haplotype is H2
-						record = (uint32_t)partner | ((uint32_t)pr[w].y << 16) | ((uu == vv) ? 0x80000000u : 0u);
-					}
-					const unsigned m = __ballot_sync(0xffffffffu, ok);
-					if (ok)
-					{
-						const int rk = n + __popc(m & ((1u << lane) - 1u));
-						rec[gbase + 128 * (rk >> 2) + 4 * l + (rk & 3)] = record;
-					}
-					n += __popc(m);
-				}
-			}
-			if (lane == 0) { clen[r] = n; if (n > 0) atomicMax(&glen[gi], n); }
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			ac += __shfl_xor_sync(0xffffffffu, ac, o);
+			vc += __shfl_xor_sync(0xffffffffu, vc, o);
+			big |= __shfl_xor_sync(0xffffffffu, big, o);
+		}
+		if (lane == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); atomicOr(&sh_i[5], big); }
+		__syncthreads();
+	}
+	const int allele_cnt = sh_i[0], valid_cnt = sh_i[1];
+	if (allele_cnt == 0 || allele_cnt == valid_cnt)
+	{
+		if (tid == 0) { status[0] = EM_INVALID; status[1] = 0; status[2] = 0; status[3] = 0; }
+		return;
+	}
+	if (sh_i[5])
+	{
+		// a bootstrap count that does not fit the byte table: the host re-estimates this candidate
+		if (tid == 0) { status[0] = EM_AMBIGUOUS; status[1] = 0; status[2] = -1; status[3] = 0; }
+		return;
+	}
+	// doubled list, initial frequencies (:444-459), stored by rank
+	{
+		const double af = __ddiv_rn((double)allele_cnt, (double)valid_cnt);
+		const double q0 = __dsub_rn(1.0, af), q1 = af;
+		for (int k = tid; k < p.n_cur; k += EMC_THREADS)
+		{
+			const double f = p.cur_freq[k];
+			fr0[__ldg(p.hap_rank + 2 * k)] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
+			fr0[__ldg(p.hap_rank + 2 * k + 1)] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
 		}
 	}
-	__threadfence();           // records (and streamed pairs) are read back through L2 by other warps of this CTA
+	// ---- the compatible pairs (:1157-1180) of every entry and the compatible contributions of every
+	// haplotype, in the reference's order, into the chains' columns ------------------------------------
+	const int n_compat = emc_filter<false>(p.erec_all, p.eown, p.total_pairs, eg, egbase, erec, pstart_e, elen, eglen, sh_w);
 	__syncthreads();
-	const int n_long = min(sh_i[4], EMR_LONG_MAX);
-	const bool long_overflow = sh_i[4] > EMR_LONG_MAX;
+	emc_filter<true>(p.mrec_all, p.mown, 2 * p.total_pairs, eg, gbase, rec, pstart_m, clen, glen, sh_w);
+	__threadfence();           // the records are read back through L2 by other warps of this CTA
+	__syncthreads();
 	const bool prof = (p.prof != nullptr) && tid == 0;
 	long long t_last = prof ? clock64() : 0, t_e = 0, t_m = 0;
 	if (prof) p.prof[8 * c + 0] = (unsigned long long)(t_last - acct_cta.t0);
+	const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(rings + (size_t)warp * EMC_RING_B * 128) +
+		(uint32_t)lane * 16u;
 
 	double conv_tol = 0, loglik = -1e+30;
 	int result = EM_OK, iters = 0;
@@ -1055,145 +1194,118 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1) em_resident
 		const double old_loglik = loglik;
 		const double *fr = fr0 + (size_t)(iter & 1) * n2;
 		double *fr_new = fr0 + (size_t)((iter & 1) ^ 1) * n2;
-		auto pair_x = [&](uint32_t uv) -> double
+		// ---- E step (:1204-1222), pass 1: a warp takes the next-longest group of 32 entries; every lane
+		// sums the GenoFreq of its entry's compatible pairs in list order ---------------------------------
 		{
-			const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
-			return (u != v) ? __dmul_rn(__dmul_rn(2.0, fr[u]), fr[v]) : __dmul_rn(fr[u], fr[v]);
-		};
-		// ---- E step (:1204-1222) ------------------------------------------------------------------------
-		double ll = 0;
-		// (a) one thread per entry with few pairs: the pairs of a block of 8 are loaded and multiplied
-		//     first, then added in list order
-		{
-			int k = tid;
-			int b = 0, e = 0;
-			if (k < p.n_entry) { b = coff[k]; e = coff[k + 1]; }
-			while (k < p.n_entry)
+			const EmcPairTerm term = { fr };
+			int gi = 0;
+			if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
+			gi = __shfl_sync(0xffffffffu, gi, 0);
+			int4 pre[EMC_DIRECT_B];
+			bool have_pre = false;
+			while (gi < n_egroups)
 			{
-				const int kn = k + THREADS;
-				int bn = 0, en = 0;
-				if (kn < p.n_entry) { bn = coff[kn]; en = coff[kn + 1]; }
-				if (e - b <= EMR_LONG || long_overflow)
-				{
-					double psum = 0;
-					for (int t = b; t < e; t += 8)
-					{
-						uint32_t uv[8];
-						double x[8];
-#pragma unroll
-						for (int q = 0; q < 8; q++) uv[q] = (t + q < e) ? pairs[t + q] : 0u;
-#pragma unroll
-						for (int q = 0; q < 8; q++) x[q] = (t + q < e) ? pair_x(uv[q]) : 0.0;
-#pragma unroll
-						for (int q = 0; q < 8; q++) if (t + q < e) psum = __dadd_rn(psum, x[q]);
-					}
-					const double bc = (double)(eg[k] >> 2);
-					ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
-					sck[k] = __ddiv_rn(bc, psum);
-				}
-				k = kn; b = bn; e = en;
-			}
-		}
-		// (b) one warp per entry with many pairs: 32 pairs loaded and multiplied in parallel (the next
-		//     32 already in flight), then added in list order through shuffles -- the chain of
-		//     dependent adds is the same, the loads and products leave its critical path
-		if (!long_overflow)
-		{
-			for (int i = warp; i < n_long; i += N_WARPS)
-			{
-				const int k = longlist[i];
-				const int b = coff[k], e = coff[k + 1];
-				double psum = 0;
-				uint32_t uv = (b + lane < e) ? pairs[b + lane] : 0u;
-				for (int t = b; t < e; t += 32)
-				{
-					const uint32_t uv_next = (t + 32 + lane < e) ? pairs[t + 32 + lane] : 0u;
-					const double x = (t + lane < e) ? pair_x(uv) : 0.0;
-					const int n = min(32, e - t);
-					for (int q = 0; q < n; q++) psum = __dadd_rn(psum, __shfl_sync(0xffffffffu, x, q));
-					uv = uv_next;
-				}
-				if (lane == 0)
-				{
-					const double bc = (double)(eg[k] >> 2);
-					ll = __dadd_rn(ll, __dmul_rn(bc, log(psum)));
-					sck[k] = __ddiv_rn(bc, psum);
-				}
-			}
-		}
-		if (tid == 0) sh_i[2] = 0;                 // group counter of the M step
-		ll = block_sum_f64(ll, scratch);           // (its barriers publish sck and sh_i[2])
-		if (prof) { const long long n_ = clock64(); t_e += n_ - t_last; t_last = n_; }
-		// ---- M step: a warp that owns a ring takes the next-longest group of 32 chains; the records
-		// stream through the ring EMR_RING_B - 1 batches ahead, and the contributions of batch b + 1 are
-		// gathered and multiplied before the adds of batch b, so the chain runs at fp64-add latency -------
-		if (warp < EMR_M_WARPS)
-		{
-			const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(rings + (size_t)warp * EMR_RING_B * 128) +
-				(uint32_t)lane * 16u;
-			for (;;)
-			{
-				int gi = 0;
-				if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
-				gi = __shfl_sync(0xffffffffu, gi, 0);
-				if (gi >= n_groups) break;
+				int gn = 0;
+				if (lane == 0) gn = atomicAdd(&sh_i[2], 1);
+				gn = __shfl_sync(0xffffffffu, gn, 0);
 				const int r = 32 * gi + lane;
-				const int my_len = (r < n2) ? clen[r] : 0;
-				const int h = (r < n2) ? p.hap_sorted[r] : 0;
-				const double fh = fr[h];
-				const double fh2 = __dmul_rn(2.0, fh);             // exact
-				const double xhh = __dmul_rn(fh, fh);
-				const int nb = (glen[gi] + 3) >> 2;
-				const char *src = (const char *)(rec + p.group_base[gi]) + lane * 16;     // + 512 per batch
-				auto contrib = [&](const int4 &q4, int row0, double (&rr)[4])
+				const bool mine = r < p.n_entry;
+				const int my_len = mine ? (int)elen[r] : 0;
+				const int nb = (eglen[gi] + 3) >> 2;
+				const uint32_t *grp = erec + egbase[gi];
+				int4 cur[EMC_DIRECT_B];
+				if (nb <= EMC_DIRECT_B)
 				{
-					const uint32_t rc[4] = { (uint32_t)q4.x, (uint32_t)q4.y, (uint32_t)q4.z, (uint32_t)q4.w };
+					if (have_pre) {
 #pragma unroll
-					for (int q = 0; q < 4; q++)
-					{
-						rr[q] = 0.0;
-						if (row0 + q < my_len)
-						{
-							const double x = (rc[q] & 0x80000000u) ? xhh : __dmul_rn(fh2, fr[rc[q] & 0xffffu]);
-							rr[q] = __dmul_rn(x, sck[(rc[q] >> 16) & 0x7fffu]);
-						}
-					}
-				};
-				for (int b = 0; b < EMR_RING_B - 1; b++)
-				{
-					if (b < nb) cp_async16_cg(ring_s + (uint32_t)b * 512u, src + (size_t)b * 512);
-					cp_async_commit();
+						for (int b = 0; b < EMC_DIRECT_B; b++) cur[b] = pre[b];
+					} else emc_direct_load(grp, nb, lane, cur);
 				}
-				double acc = 0;
-				double rr[4] = { 0.0, 0.0, 0.0, 0.0 };
-				int rb = 0, rbn = EMR_RING_B - 1;      // ring slots of batch b and of batch b + EMR_RING_B - 1
-				// batch 0
-				if (nb > 0)
+				// the next group's records, when it is a short one
+				have_pre = false;
+				if (gn < n_egroups)
 				{
-					cp_async_wait<EMR_RING_B - 2>();
-					contrib(lds_i32x4(ring_s), 0, rr);
+					const int nbn = (eglen[gn] + 3) >> 2;
+					if (nbn <= EMC_DIRECT_B) { emc_direct_load(erec + egbase[gn], nbn, lane, pre); have_pre = true; }
 				}
-				for (int b = 0; b < nb; b++)
-				{
-					const int bn = b + EMR_RING_B - 1;
-					if (bn < nb) cp_async16_cg(ring_s + (uint32_t)rbn * 512u, src + (size_t)bn * 512);
-					cp_async_commit();
-					// batch b + 1 has landed when at most EMR_RING_B - 2 younger groups are pending
-					cp_async_wait<EMR_RING_B - 2>();
-					double rn[4] = { 0.0, 0.0, 0.0, 0.0 };
-					const int rb1 = (rb + 1 == EMR_RING_B) ? 0 : rb + 1;
-					if (b + 1 < nb) contrib(lds_i32x4(ring_s + (uint32_t)rb1 * 512u), 4 * (b + 1), rn);
-#pragma unroll
-					for (int q = 0; q < 4; q++) if (4 * b + q < my_len) acc = __dadd_rn(acc, rr[q]);
-#pragma unroll
-					for (int q = 0; q < 4; q++) rr[q] = rn[q];
-					rb = rb1;
-					if (++rbn == EMR_RING_B) rbn = 0;
-				}
-				cp_async_wait<0>();
-				if (r < n2) fr_new[h] = __dmul_rn(acc, p.scale);
+				const double psum = (nb <= EMC_DIRECT_B) ? emc_direct_sum(cur, nb, my_len, term)
+					: emc_walk(grp, nb, my_len, ring_s, lane, term);
+				if (mine) sck[r] = psum;
+				gi = gn;
 			}
 		}
+		__syncthreads();
+		// pass 2: a thread per entry, four at a time (four independent log / divide sequences):
+		// log-likelihood term and scale factor count / sum
+		double ll = 0;
+		for (int r0 = tid; r0 < p.n_entry; r0 += 4 * EMC_THREADS)
+		{
+			double ps[4], bc[4], lg[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const int r = r0 + q * EMC_THREADS;
+				const bool ok = r < p.n_entry;
+				ps[q] = ok ? sck[r] : 1.0;
+				bc[q] = ok ? (double)ebc[r] : 0.0;
+			}
+#pragma unroll
+			for (int q = 0; q < 4; q++) lg[q] = log(ps[q]);
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				const int r = r0 + q * EMC_THREADS;
+				if (r < p.n_entry)
+				{
+					ll = __dadd_rn(ll, __dmul_rn(bc[q], lg[q]));
+					sck[r] = __ddiv_rn(bc[q], ps[q]);
+				}
+			}
+		}
+		ll = block_sum_f64(ll, scratch);           // (its barriers publish the scale factors)
+		if (tid == 0) sh_i[3] = 0;                 // group counter of the M step (sh_i[2] is reset after it)
+		__syncthreads();
+		if (prof) { const long long n_ = clock64(); t_e += n_ - t_last; t_last = n_; }
+		// ---- M step: a warp takes the next-longest group of 32 haplotype chains ---------------------------
+		{
+			int gi = 0;
+			if (lane == 0) gi = atomicAdd(&sh_i[3], 1);
+			gi = __shfl_sync(0xffffffffu, gi, 0);
+			int4 pre[EMC_DIRECT_B];
+			bool have_pre = false;
+			while (gi < n_groups)
+			{
+				int gn = 0;
+				if (lane == 0) gn = atomicAdd(&sh_i[3], 1);
+				gn = __shfl_sync(0xffffffffu, gn, 0);
+				const int r = 32 * gi + lane;
+				const bool mine = r < n2;
+				const int my_len = mine ? (int)clen[r] : 0;
+				const int nb = (glen[gi] + 3) >> 2;
+				const uint32_t *grp = rec + gbase[gi];
+				int4 cur[EMC_DIRECT_B];
+				if (nb <= EMC_DIRECT_B)
+				{
+					if (have_pre) {
+#pragma unroll
+						for (int b = 0; b < EMC_DIRECT_B; b++) cur[b] = pre[b];
+					} else emc_direct_load(grp, nb, lane, cur);
+				}
+				have_pre = false;
+				if (gn < n_groups)
+				{
+					const int nbn = (glen[gn] + 3) >> 2;
+					if (nbn <= EMC_DIRECT_B) { emc_direct_load(rec + gbase[gn], nbn, lane, pre); have_pre = true; }
+				}
+				const double fh = mine ? fr[r] : 0.0;
+				const EmcContribTerm term = { fr, sck, __dmul_rn(2.0, fh), __dmul_rn(fh, fh) };   // 2 f_h is exact
+				const double acc = (nb <= EMC_DIRECT_B) ? emc_direct_sum(cur, nb, my_len, term)
+					: emc_walk(grp, nb, my_len, ring_s, lane, term);
+				if (mine) fr_new[r] = __dmul_rn(acc, p.scale);
+				gi = gn;
+			}
+		}
+		if (tid == 0) sh_i[2] = 0;                 // group counter of the next E step
 		__syncthreads();
 		if (prof) { const long long n_ = clock64(); t_m += n_ - t_last; t_last = n_; }
 		iters = iter + 1;
@@ -1215,7 +1327,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1) em_resident
 	{
 		const double *fin = fr0 + (size_t)(iters & 1) * n2;
 		double *out = p.out_freq + (size_t)c * n2;
-		for (int u = tid; u < n2; u += THREADS) out[u] = fin[u];
+		for (int r = tid; r < n2; r += EMC_THREADS) out[__ldg(p.hap_sorted + r)] = fin[r];
 		if (tid == 0)
 		{
 			int longest = 0;
@@ -1223,11 +1335,44 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512) ? 2 : 1) em_resident
 			status[0] = result; status[1] = iters; status[2] = longest; status[3] = n_compat;
 			if (prof)
 			{
+				int longest_e = 0;
+				for (int g = 0; g < n_egroups; g++) longest_e = max(longest_e, eglen[g]);
 				p.prof[8 * c + 1] = (unsigned long long)t_e; p.prof[8 * c + 2] = (unsigned long long)t_m;
-				p.prof[8 * c + 3] = (unsigned long long)iters; p.prof[8 * c + 4] = (unsigned long long)n_long;
+				p.prof[8 * c + 3] = (unsigned long long)iters; p.prof[8 * c + 4] = (unsigned long long)longest_e;
 			}
 		}
 	}
+}
+
+/// per round: the record of every pair (pair order) and of every contribution (chain order) with the
+/// ranks of its haplotypes and entry, and the chain each belongs to
+__global__ void emc_pair_records_kernel(const int *__restrict__ p1, const int *__restrict__ p2,
+	const int *__restrict__ off, int n_entry, const int *__restrict__ hap_rank,
+	const int *__restrict__ entry_rank, uint32_t *erec_all, uint16_t *eown)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_entry) return;
+	const int re = entry_rank[k];
+	for (int t = off[k]; t < off[k + 1]; t++)
+	{
+		const int u = p1[t], v = p2[t];
+		erec_all[t] = emc_pair_record(hap_rank[u], hap_rank[v], (u & 1) + (v & 1));
+		eown[t] = (uint16_t)re;
+	}
+}
+
+__global__ void emc_contrib_records_kernel(const int *__restrict__ key_sorted, const int *__restrict__ val_sorted,
+	int n_inc, const int *__restrict__ pairs4, const int *__restrict__ hap_rank,
+	const int *__restrict__ entry_rank, uint32_t *mrec_all, uint16_t *mown)
+{
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n_inc) return;
+	const int h = key_sorted[q], e = val_sorted[q];
+	const int uv = pairs4[4 * (size_t)(e >> 1)], k = pairs4[4 * (size_t)(e >> 1) + 1];
+	const int u = uv & 0xffff, v = (int)((unsigned)uv >> 16);
+	const int partner = (e & 1) ? u : v;           // side 1: this haplotype is H2
+	mrec_all[q] = emc_contrib_record(hap_rank[partner], entry_rank[k], u == v, (u & 1) + (v & 1));
+	mown[q] = (uint16_t)hap_rank[h];
 }
 
 }  // namespace
@@ -1284,7 +1429,7 @@ struct EmGate
 } g_em_gate;
 }  // namespace
 
-RoundEM::RoundEM() { current_device(); h_total_.ensure(4); }
+RoundEM::RoundEM() { current_device(); h_total_.ensure(8); }
 RoundEM::~RoundEM() {}
 
 void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2, int stride,
@@ -1391,12 +1536,47 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 	incidence_slots_kernel<<<(n_inc + 255) / 256, 256, 0, st>>>(d_key2_.get(), d_val2_.get(), n_inc,
 		d_inc_off_.get(), d_rank_.get(), d_group_base_.get(), d_pairs4_.get());
 	HB_CUDA(cudaGetLastError());
+	// entry chains of em_chain_kernel's E step: entries by decreasing pair count, groups of 32, the same
+	// interleaved layout (the per-candidate compatible pairs fill a prefix of every column)
+	const int n_egroups = (n_entry + 31) / 32;
+	d_eid_.ensure(n_entry + 1); d_ecnt_sorted_.ensure(n_entry + 1); d_entry_sorted_.ensure(n_entry + 1);
+	d_erank_.ensure(n_entry + 1); d_egroup_len_.ensure(n_egroups + 1); d_egroup_base_.ensure(n_egroups + 2);
+	iota_kernel<<<(n_entry + 255) / 256, 256, 0, st>>>(n_entry, d_eid_.get());
+	HB_CUDA(cudaGetLastError());
+	tmp_bytes = 0;
+	HB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_cnt_.get(), d_ecnt_sorted_.get(),
+		d_eid_.get(), d_entry_sorted_.get(), n_entry, 0, 32, st));
+	d_tmp_.ensure(tmp_bytes + 16);
+	HB_CUDA(cub::DeviceRadixSort::SortPairsDescending(d_tmp_.get(), tmp_bytes, d_cnt_.get(), d_ecnt_sorted_.get(),
+		d_eid_.get(), d_entry_sorted_.get(), n_entry, 0, 32, st));
+	incidence_groups_kernel<<<1, 1024, 0, st>>>(d_ecnt_sorted_.get(), d_entry_sorted_.get(), n_entry, d_erank_.get(),
+		d_egroup_len_.get(), d_egroup_base_.get());
+	HB_CUDA(cudaGetLastError());
+	// the records of every pair and of every contribution of the round (em_chain_kernel filters them
+	// per candidate); padded to whole 8-record steps
+	if (n2_ <= EMC_MAX_HAP && n_entry <= EMC_MAX_ENTRY)
+	{
+		d_erec_all_.ensure(total_pairs_ + 16); d_eown_.ensure(total_pairs_ + 16);
+		d_mrec_all_.ensure((size_t)n_inc + 16); d_mown_.ensure((size_t)n_inc + 16);
+		emc_pair_records_kernel<<<blocks, 128, 0, st>>>(d_p1_.get(), d_p2_.get(), d_off_.get(), n_entry,
+			d_rank_.get(), d_erank_.get(), (uint32_t *)d_erec_all_.get(), d_eown_.get());
+		HB_CUDA(cudaGetLastError());
+		emc_contrib_records_kernel<<<(n_inc + 255) / 256, 256, 0, st>>>(d_key2_.get(), d_val2_.get(), n_inc,
+			d_pairs4_.get(), d_rank_.get(), d_erank_.get(), (uint32_t *)d_mrec_all_.get(), d_mown_.get());
+		HB_CUDA(cudaGetLastError());
+		launches += 2;
+	}
 	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 1, d_group_base_.get() + n_groups, sizeof(int),
 		cudaMemcpyDeviceToHost, st));
 	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 2, d_group_len_.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 4, d_egroup_base_.get() + n_egroups, sizeof(int),
+		cudaMemcpyDeviceToHost, st));
+	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 5, d_egroup_len_.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
 	HB_CUDA(cudaStreamSynchronize(st));
 	n_slots_ = (size_t)h_total_.get()[1];
 	max_chain_ = h_total_.get()[2];
+	n_eslots_ = (size_t)h_total_.get()[4];
+	max_entry_pairs_ = h_total_.get()[5];
 	if (getenv("HIBAG_B200_EM_DEBUG"))
 	{
 		std::vector<int> c(n_entry);
@@ -1405,8 +1585,8 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 		fprintf(stderr, "pairs/entry: median %d p90 %d p99 %d max %d\n", c[n_entry / 2],
 			c[(size_t)n_entry * 9 / 10], c[(size_t)n_entry * 99 / 100], c[n_entry - 1]);
 	}
-	d2h_bytes += 2 * sizeof(int);
-	launches += 8;
+	d2h_bytes += 4 * sizeof(int);
+	launches += 11;
 }
 
 void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_samp, cudaStream_t st)
@@ -1421,48 +1601,36 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 	d_status_.ensure(4 * (size_t)m);
 	h_freq_.ensure((size_t)m * n2_ + 2);
 	h_status_.ensure(4 * (size_t)m);
-	// ---- the shared-memory-resident kernel (frequencies and scale factors on chip, nothing stored
-	// per contribution): an experiment kept behind HIBAG_B200_EM_RESIDENT=1. It is bit-identical to
-	// em_kernel (tests/test_gpu_parity.py trains the golden models with either) but measured SLOWER at
-	// config 2 (profiles/r02_em_resident_sweep.txt: 566 vs 802 classifiers/min at 24 lanes, 65 vs 150
-	// with one lane): the E step sums the long entries of ambiguous samples (hundreds of compatible
-	// pairs, in list order) by one warp each, 226 k cycles per iteration against 152 k for the whole
-	// iteration of em_kernel, which spreads the products over all threads first ------------------------
+	// ---- em_chain_kernel (128 threads, state in shared memory, records streamed) whenever its working
+	// set fits; HIBAG_B200_EM_CHAIN=0 selects em_kernel (the streaming form, also the one for rounds
+	// too large for an SM) ------------------------------------------------------------------------------
 	{
-		int want_resident = 0;                 // read per call: the tests switch kernels inside one process
-		if (const char *e = getenv("HIBAG_B200_EM_RESIDENT")) want_resident = atoi(e);
-		const size_t fixed = sizeof(double) * (2 * (size_t)n2_ + 40 + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
-			sizeof(uint32_t) * (size_t)EMR_M_WARPS * EMR_RING_B * 128 +
-			sizeof(int) * ((size_t)n_entry_ + (size_t)n2_ + (size_t)n_groups + EMR_LONG_MAX) + 64;
+		int want_chain = 1;                    // read per call: the tests switch kernels inside one process
+		if (const char *e = getenv("HIBAG_B200_EM_CHAIN")) want_chain = atoi(e);
+		const int n_egroups = (n_entry_ + 31) / 32;
+		const size_t smem = sizeof(double) * (2 * (size_t)n2_ + 40 + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
+			sizeof(uint32_t) * (size_t)EMC_WARPS * EMC_RING_B * 128 +
+			sizeof(int) * 2 * ((size_t)n_groups + (size_t)n_egroups) +
+			sizeof(uint16_t) * ((((size_t)n2_ + 1) & ~(size_t)1) + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
+			(size_t)n_entry_ + 16;
 		const size_t budget = (size_t)227 * 1024 - 512;     // the kernel also has a few bytes of static shared memory
-		long long cap = (budget > fixed) ? (long long)((budget - fixed) / 4) : 0;
-		cap &= ~(long long)3;
-		// shape: with many lanes sharing the GPU the SM-time per candidate counts -- 512 threads and the
-		// pairs streamed from L2, so that a CTA takes half an SM (two candidates, or one and the scoring
-		// CTAs of other lanes, per SM); with few lanes the latency counts -- 1024 threads and the pairs
-		// in shared memory too (compatible pairs are 1/4 to 1/2 of the doubled pairs, all of them for a
-		// missing genotype: 45 % covers every candidate of the BASELINE cohorts; one that still overflows
-		// is re-estimated on the host). (chain records hold the entry in 15 bits, the partner in 16)
-		bool half = n_dense_lanes_ >= 8;
-		if (const char *e = getenv("HIBAG_B200_EM_HALF")) half = atoi(e) != 0;
-		const bool pairs_fit = cap > 0 && (double)cap >= 0.45 * (double)total_pairs_ + 64;
-		if (!pairs_fit) half = true;
-		if (want_resident && n_entry_ <= 32767 && n2_ <= 65535 && fixed + 1024 <= budget)
+		// (records hold haplotype ranks in 14 bits and entry ranks in 15; chain lengths in 16 bits)
+		if (want_chain && n_entry_ <= EMC_MAX_ENTRY && n2_ <= EMC_MAX_HAP && max_chain_ <= 65535 &&
+			max_entry_pairs_ <= 65535 && smem <= budget)
 		{
-			if (cap > (long long)total_pairs_ + 4) cap = ((long long)total_pairs_ + 4) & ~(long long)3;
-			d_coff_.ensure((size_t)m * (n_entry_ + 1));
 			d_idxell_.ensure((size_t)m * n_slots_ + 4);
-			if (half) d_cuv_.ensure((size_t)m * total_pairs_ + 4);
-			EmrArgs a;
+			d_erec_.ensure((size_t)m * n_eslots_ + 4);
+			EmcArgs a;
 			memset(&a, 0, sizeof(a));
-			a.n_entry = n_entry_; a.n_cur = n_cur_; a.n_samp = n_samp; a.total_pairs = (int)total_pairs_; a.cap = (int)cap;
-			a.ib = ib_; a.boot = boot_; a.off = d_off_.get(); a.pairs4 = (const int4 *)d_pairs4_.get();
-			a.hap_sorted = d_hap_sorted_.get(); a.group_base = d_group_base_.get();
-			a.inc_off = d_inc_off_.get(); a.inc_val = d_val2_.get();
-			a.cur_freq = d_curfreq_.get(); a.n_slots = n_slots_;
+			a.n_entry = n_entry_; a.n_cur = n_cur_; a.n_samp = n_samp; a.total_pairs = (int)total_pairs_;
+			a.ib = ib_; a.boot = boot_;
+			a.hap_sorted = d_hap_sorted_.get(); a.hap_rank = d_rank_.get(); a.group_base = d_group_base_.get();
+			a.mrec_all = (const uint32_t *)d_mrec_all_.get(); a.mown = d_mown_.get(); a.n_slots = n_slots_;
+			a.entry_sorted = d_entry_sorted_.get(); a.egroup_base = d_egroup_base_.get();
+			a.erec_all = (const uint32_t *)d_erec_all_.get(); a.eown = d_eown_.get(); a.n_eslots = n_eslots_;
+			a.cur_freq = d_curfreq_.get();
 			a.geno_t = geno_t; a.cand_snp = d_cand_.get();
-			a.coff = d_coff_.get(); a.rec = (uint32_t *)d_idxell_.get();
-			a.cuv = half ? (uint32_t *)d_cuv_.get() : nullptr;
+			a.rec = (uint32_t *)d_idxell_.get(); a.erec = (uint32_t *)d_erec_.get();
 			a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
 			a.scale = 0.5 / n_samp; a.em_reltol = std::sqrt(DBL_EPSILON);
 			a.acct = device_sm_acct();
@@ -1473,23 +1641,16 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 				HB_CUDA(cudaMemsetAsync(d_prof_.get(), 0, sizeof(unsigned long long) * 8 * (size_t)m, st));
 				a.prof = d_prof_.get();
 			}
-			const size_t smem = fixed - 64 + (half ? 0 : 4 * (size_t)cap) + 16;
-			a.acct_w = (half && smem <= (size_t)113 * 1024) ? 512 : 1024;
+			// the share of an SM a CTA holds: by shared memory (1 KB reserved per CTA) or by threads
+			int per_sm = (int)((size_t)228 * 1024 / (smem + 1024));
+			per_sm = std::max(1, std::min(per_sm, 2048 / EMC_THREADS));
+			a.acct_w = 1024 / per_sm;
 			const int max_dyn = 227 * 1024 - 256;
 			g_em_gate.enter();
-			cudaError_t launch_rc;
-			if (half)
-			{
-				auto kern = em_resident_kernel<512, false>;
-				launch_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-				if (launch_rc == cudaSuccess) launch_rc = cudaEventRecord(ev0_.e, st);
-				if (launch_rc == cudaSuccess) { kern<<<m, 512, smem, st>>>(a); launch_rc = cudaGetLastError(); }
-			} else {
-				auto kern = em_resident_kernel<1024, true>;
-				launch_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-				if (launch_rc == cudaSuccess) launch_rc = cudaEventRecord(ev0_.e, st);
-				if (launch_rc == cudaSuccess) { kern<<<m, 1024, smem, st>>>(a); launch_rc = cudaGetLastError(); }
-			}
+			auto kern = em_chain_kernel;
+			cudaError_t launch_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+			if (launch_rc == cudaSuccess) launch_rc = cudaEventRecord(ev0_.e, st);
+			if (launch_rc == cudaSuccess) { kern<<<m, EMC_THREADS, smem, st>>>(a); launch_rc = cudaGetLastError(); }
 			if (launch_rc != cudaSuccess) { g_em_gate.leave(); HB_CUDA(launch_rc); }
 			HB_CUDA(cudaEventRecord(ev1_.e, st));
 			HB_CUDA(cudaMemcpyAsync(h_freq_.get(), d_freq_.get(), sizeof(double) * (size_t)m * n2_,
@@ -1504,7 +1665,7 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 			HB_CUDA(cudaEventElapsedTime(&ms, ev0_.e, ev1_.e));
 			kernel_ms += ms;
 			launches++;
-			resident_launches++;
+			chain_launches++;
 			for (int i = 0; i < m; i++)
 			{
 				const int *stt = h_status_.get() + 4 * i;
@@ -1515,26 +1676,25 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 			}
 			if (want_prof_r)
 			{
-				int ovf = 0; long compat = 0; int nv = 0;
+				long compat = 0; int nv = 0;
 				for (int i = 0; i < m; i++)
 				{
 					const int *stt = h_status_.get() + 4 * i;
-					if (stt[2] < 0) ovf++;
-					else if (stt[0] != EM_INVALID) { compat += stt[3]; nv++; }
+					if (stt[0] != EM_INVALID && stt[2] >= 0) { compat += stt[3]; nv++; }
 				}
 				std::vector<unsigned long long> hp(8 * (size_t)m);
 				HB_CUDA(cudaMemcpy(hp.data(), d_prof_.get(), sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost));
-				double su = 0, se = 0, sm = 0, it = 0; int it_max = 0, nl = 0;
+				double su = 0, se = 0, sm = 0, it = 0; int it_max = 0, le = 0;
 				for (int i = 0; i < m; i++)
 				{
 					su += (double)hp[8 * i]; se += (double)hp[8 * i + 1]; sm += (double)hp[8 * i + 2]; it += (double)hp[8 * i + 3];
-					it_max = std::max(it_max, (int)hp[8 * i + 3]); nl = std::max(nl, (int)hp[8 * i + 4]);
+					it_max = std::max(it_max, (int)hp[8 * i + 3]); le = std::max(le, (int)hp[8 * i + 4]);
 				}
-				fprintf(stderr, "em resident (%s): kernel %.3f ms, cap %lld, total pairs %zu, compat/cand %.0f, overflowed %d of %d, smem %zu | "
+				fprintf(stderr, "em chain: kernel %.3f ms, %d candidates, total pairs %zu, compat/cand %.0f, smem %zu (%d per SM) | "
 					"kcycles: set-up %.0f per candidate, E step %.1f and M step %.1f per iteration, iterations mean %.1f max %d, "
-					"longest chain %d, long entries %d\n", half ? "512 threads, pairs streamed" : "1024 threads, pairs in shared memory",
-					ms, cap, total_pairs_, nv ? (double)compat / nv : 0.0, ovf, m, smem, su / m * 1e-3, it > 0 ? se / it * 1e-3 : 0.0,
-					it > 0 ? sm / it * 1e-3 : 0.0, it / m, it_max, h_status_.get()[2], nl);
+					"longest chain %d, longest entry %d\n", ms, m, total_pairs_, nv ? (double)compat / nv : 0.0, smem, per_sm,
+					su / m * 1e-3, it > 0 ? se / it * 1e-3 : 0.0, it > 0 ? sm / it * 1e-3 : 0.0, it / m, it_max,
+					h_status_.get()[2], le);
 			}
 			h2d_bytes += sizeof(int) * (size_t)m;
 			d2h_bytes += sizeof(double) * (size_t)m * n2_ + sizeof(int) * 4 * (size_t)m;

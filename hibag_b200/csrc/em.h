@@ -54,7 +54,7 @@ public:
 	/// test hook: report candidate i as undecided so that the caller's host fallback runs
 	void force_ambiguous(int i) { if (h_status_.get()[4 * i] == EM_OK) h_status_.get()[4 * i] = EM_AMBIGUOUS; }
 	int iterations(int i) const { return h_status_.get()[4 * i + 1]; }
-	uint64_t resident_launches = 0;   // run_em calls served by em_resident_kernel
+	uint64_t chain_launches = 0;      // run_em calls served by em_chain_kernel
 	uint64_t sum_iterations = 0, sum_chain_adds = 0, sum_pair_updates = 0;   // over run_em calls (see train stats)
 
 	/// the pair lists as the host algorithm holds them (for the host fallback / tests)
@@ -95,7 +95,12 @@ private:
 	PinBuf<int> h_cand_;
 	DevBuf<double> d_freq_, d_xbuf_, d_rinc_;
 	DevBuf<int> d_pmap_, d_cuv_, d_coff_, d_glen_;      // per-candidate compaction (em_kernel)
-	DevBuf<int> d_idxell_;                              // per-candidate ELL of pair indices (em_resident_kernel)
+	DevBuf<int> d_idxell_, d_erec_;                     // per-candidate chain records (em_chain_kernel)
+	DevBuf<int> d_eid_, d_ecnt_sorted_, d_entry_sorted_, d_erank_, d_egroup_len_, d_egroup_base_;   // entry chains
+	DevBuf<int> d_erec_all_, d_mrec_all_;               // per-round records of all pairs / contributions
+	DevBuf<uint16_t> d_eown_, d_mown_;                  // ... and the chain (rank) each belongs to
+	size_t n_eslots_ = 0;
+	int max_entry_pairs_ = 0;
 	DevBuf<int> d_status_;
 	DevBuf<unsigned long long> d_prof_;   // HIBAG_B200_EM_PROF
 	PinBuf<double> h_freq_;

@@ -186,15 +186,14 @@ def test_trainer_legacy_hook_mode_and_thread_count_invariance(gpu):
             helpers.assert_classifier_equals_golden(m.classifier(k), ml, k)
 
 
-@pytest.mark.parametrize("resident,half", [("1", "0"), ("1", "1"), ("0", "0")])
-def test_both_device_em_kernels_reproduce_the_reference(gpu, monkeypatch, resident, half):
-    """em_resident_kernel (frequencies and scale factors in shared memory; its two shapes: 1024 threads
-    with the pairs on chip too, 512 threads with the pairs streamed) and em_kernel (the streaming form
-    for rounds too large for an SM) are bit-identical to the reference's CAlg_EM: the golden model,
-    and the seeded many-allele cohort whose classifiers the compiled reference trained"""
+@pytest.mark.parametrize("chain", ["1", "0"])
+def test_both_device_em_kernels_reproduce_the_reference(gpu, monkeypatch, chain):
+    """em_chain_kernel (128 threads, frequencies and scale factors in shared memory, both steps as walks
+    over chains of 4-byte records) and em_kernel (the streaming form, also for rounds too large for an
+    SM) are bit-identical to the reference's CAlg_EM: the golden model, and the seeded many-allele
+    cohort whose classifiers the compiled reference trained"""
     from hibag_b200 import synth
-    monkeypatch.setenv("HIBAG_B200_EM_RESIDENT", resident)
-    monkeypatch.setenv("HIBAG_B200_EM_HALF", half)
+    monkeypatch.setenv("HIBAG_B200_EM_CHAIN", chain)
     geno, h1, h2, al, ml = helpers.hapmap_a_training()
     m = gpu.HLAModel(geno.shape[1], len(al), al)
     m.set_training(geno, h1, h2)
@@ -212,7 +211,7 @@ def test_both_device_em_kernels_reproduce_the_reference(gpu, monkeypatch, reside
         for k in range(int(gd["n_cls"])):
             want = dict(snpidx=gd["c%d_snpidx" % k], samp_num=gd["c%d_samp_num" % k], freq=gd["c%d_freq" % k],
                         hla=gd["c%d_hla" % k], packed=gd["c%d_packed" % k], oob_acc=float(gd["c%d_oob_acc" % k]))
-            assert helpers.classifier_diff(s.classifier(k), want) == "", (resident, lanes, k)
+            assert helpers.classifier_diff(s.classifier(k), want) == "", (chain, lanes, k)
 
 
 def test_device_em_host_fallback_path(gpu, monkeypatch):
