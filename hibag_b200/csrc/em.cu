@@ -830,8 +830,8 @@ constexpr int EMC_THREADS = 128;
 constexpr int EMC_WARPS = EMC_THREADS / 32;
 constexpr int EMC_RING_B = 8;           // batches of 4 rows (512 B per warp) a ring holds (cp.async.wait_group
                                         // with more than ~8 groups pending behaved like wait_all)
-constexpr int EMC_MAX_HAP = 16383;      // 14-bit haplotype ranks, 15-bit entry ranks in the records
-constexpr int EMC_MAX_ENTRY = 32767;
+constexpr int EMC_MAX_HAP = 16382;      // 14-bit haplotype ranks, 15-bit entry ranks in the records; one
+constexpr int EMC_MAX_ENTRY = 32766;    // value of each is the null rank
 
 // E record: rank_u | rank_v << 14 | s << 28.   M record: partner rank | entry rank << 14 | (u == v) << 29 | s << 30
 __host__ __device__ inline uint32_t emc_pair_record(int ru, int rv, int s) { return (uint32_t)ru | ((uint32_t)rv << 14) | ((uint32_t)s << 28); }
@@ -864,6 +864,7 @@ struct EmcArgs
 	double scale, em_reltol;
 	unsigned long long *acct;
 	int acct_w;
+	int len_words;                    // 16-bit words of the chain-length / batch-schedule region (even)
 	unsigned long long *prof;         // [m][8]: cycles of set-up, E steps, M steps; iterations (HIBAG_B200_EM_DEBUG)
 };
 
@@ -873,14 +874,14 @@ __device__ __forceinline__ size_t emc_slot(int base, int i, int l)
 	return (size_t)base + 128 * (size_t)(i >> 2) + 4 * (size_t)l + (size_t)(i & 3);
 }
 
-/// the term of an E-step record (a compatible pair): GenoFreq (:1208-1213)
+/// the term of an E-step record (a compatible pair): GenoFreq (:1208-1213). The null record
+/// (both ranks = n2, where the frequency vector holds 0.0) gives +0.0.
 struct EmcPairTerm
 {
 	const double *fr;                 // by rank
-	__device__ __forceinline__ void gather(uint32_t rc, bool valid, double &a, double &b) const
+	__device__ __forceinline__ void gather(uint32_t rc, double &a, double &b) const
 	{
-		const uint32_t u = valid ? (rc & 0x3fffu) : 0u, v = valid ? ((rc >> 14) & 0x3fffu) : 0u;
-		a = fr[u]; b = fr[v];
+		a = fr[rc & 0x3fffu]; b = fr[(rc >> 14) & 0x3fffu];
 	}
 	__device__ __forceinline__ double combine(uint32_t rc, double a, double b) const
 	{
@@ -889,15 +890,15 @@ struct EmcPairTerm
 	}
 };
 
-/// the term of an M-step record: GenoFreq * count / sum (:1224-1232)
+/// the term of an M-step record: GenoFreq * count / sum (:1224-1232). The null record (partner rank
+/// n2, entry rank n_entry, where the tables hold 0.0) gives +0.0.
 struct EmcContribTerm
 {
 	const double *fr, *sck;           // by rank
 	double fh2, xhh;                  // 2 f_h and f_h f_h of the lane's haplotype
-	__device__ __forceinline__ void gather(uint32_t rc, bool valid, double &a, double &b) const
+	__device__ __forceinline__ void gather(uint32_t rc, double &a, double &b) const
 	{
-		const uint32_t pt = valid ? (rc & 0x3fffu) : 0u, en = valid ? ((rc >> 14) & 0x7fffu) : 0u;
-		a = fr[pt]; b = sck[en];
+		a = fr[rc & 0x3fffu]; b = sck[(rc >> 14) & 0x7fffu];
 	}
 	__device__ __forceinline__ double combine(uint32_t rc, double a, double b) const
 	{
@@ -906,89 +907,96 @@ struct EmcContribTerm
 	}
 };
 
-/// terms of four consecutive rows of a lane (rows >= my_len give +0.0: s + 0.0 == s for the
-/// non-negative sums here); branch-free, the eight gathers issued together
+/// terms of four consecutive rows of a lane, branch-free, in two halves: the eight shared-memory
+/// gathers, then the products. (Rows past the end of a lane's chain hold null records: +0.0, and
+/// s + 0.0 == s for the non-negative sums here.)
 template <class Term>
-__device__ __forceinline__ void emc_terms(const int4 &q4, int row0, int my_len, const Term &term, double (&rr)[4])
+__device__ __forceinline__ void emc_gather4(const int4 &q4, const Term &term, double (&a)[4], double (&b)[4])
 {
 	const uint32_t rc[4] = { (uint32_t)q4.x, (uint32_t)q4.y, (uint32_t)q4.z, (uint32_t)q4.w };
-	double a[4], b[4];
 #pragma unroll
-	for (int q = 0; q < 4; q++) term.gather(rc[q], row0 + q < my_len, a[q], b[q]);
-#pragma unroll
-	for (int q = 0; q < 4; q++)
-	{
-		const double r = term.combine(rc[q], a[q], b[q]);
-		rr[q] = (row0 + q < my_len) ? r : 0.0;
-	}
+	for (int q = 0; q < 4; q++) term.gather(rc[q], a[q], b[q]);
 }
 
-/// One lane's sequential sum over its chain: my_len rows of the group's nb batches, streamed through
-/// the warp's ring. The terms of batch b + 1 are evaluated before the adds of batch b are issued.
 template <class Term>
-__device__ __forceinline__ double emc_walk(const uint32_t *rec_group, int nb, int my_len, uint32_t ring_s,
-	int lane, const Term &term)
+__device__ __forceinline__ void emc_combine4(const int4 &q4, const Term &term, const double (&a)[4],
+	const double (&b)[4], double (&rr)[4])
 {
-	const char *src = (const char *)rec_group + lane * 16;     // + 512 per batch
-	for (int b = 0; b < EMC_RING_B - 1; b++)
-	{
-		if (b < nb) cp_async16_cg(ring_s + (uint32_t)b * 512u, src + (size_t)b * 512);
-		cp_async_commit();
-	}
-	double acc = 0;
-	double rr[4] = { 0.0, 0.0, 0.0, 0.0 };
-	int rb = 0, rbn = EMC_RING_B - 1;      // ring slots of batch b and of batch b + EMC_RING_B - 1
-	if (nb > 0)
-	{
-		cp_async_wait<EMC_RING_B - 2>();
-		emc_terms(lds_i32x4(ring_s), 0, my_len, term, rr);
-	}
-	for (int b = 0; b < nb; b++)
-	{
-		const int bn = b + EMC_RING_B - 1;
-		if (bn < nb) cp_async16_cg(ring_s + (uint32_t)rbn * 512u, src + (size_t)bn * 512);
-		cp_async_commit();
-		// batch b + 1 has landed when at most EMC_RING_B - 2 younger groups are pending
-		cp_async_wait<EMC_RING_B - 2>();
-		double rn[4] = { 0.0, 0.0, 0.0, 0.0 };
-		const int rb1 = (rb + 1 == EMC_RING_B) ? 0 : rb + 1;
-		if (b + 1 < nb) emc_terms(lds_i32x4(ring_s + (uint32_t)rb1 * 512u), 4 * (b + 1), my_len, term, rn);
+	const uint32_t rc[4] = { (uint32_t)q4.x, (uint32_t)q4.y, (uint32_t)q4.z, (uint32_t)q4.w };
 #pragma unroll
-		for (int q = 0; q < 4; q++) { acc = __dadd_rn(acc, rr[q]); rr[q] = rn[q]; }
-		rb = rb1;
-		if (++rbn == EMC_RING_B) rbn = 0;
+	for (int q = 0; q < 4; q++) rr[q] = term.combine(rc[q], a[q], b[q]);
+}
+
+/// The groups of one step dealt to this warp (list, longest first), as ONE stream of record batches
+/// through the warp's ring (sched: where every batch of the stream lies): batch k goes to ring slot k mod 8 and is requested seven
+/// batches before it is consumed, whatever groups the batches in between belong to -- a group of two
+/// batches does not wait for L2 any more than the middle of a long one. Inside a group three stages
+/// are in flight: the records of batch j + 2 are read from the ring and the terms of batch j + 1
+/// gathered and multiplied while the adds of batch j -- the only dependent chain -- are issued.
+/// done(group, chain sum) is called for every group of the list, also the empty ones.
+template <class TermOf, class Done>
+__device__ __forceinline__ void emc_stream(const uint16_t *list, int cnt, const uint16_t *sched, int n_sched,
+	const uint32_t *records, const int *glen, uint32_t ring_s, int lane, TermOf term_of, Done done)
+{
+	// issuer: batch ki of the warp's schedule (the batch's first record slot / 128) goes to ring slot ki mod 8
+	int ki = 0;
+	const char *lane_src = (const char *)records + lane * 16;
+	auto issue = [&]()
+	{
+		if (ki < n_sched)
+			cp_async16_cg(ring_s + (uint32_t)(ki & (EMC_RING_B - 1)) * 512u, lane_src + (size_t)sched[ki] * 512);
+		ki++;
+		cp_async_commit();                  // (an empty group when the stream has ended: the count stays uniform)
+	};
+#pragma unroll 1
+	for (int b = 0; b < EMC_RING_B - 1; b++) issue();
+	cp_async_wait<EMC_RING_B - 4>();       // stream batches 0, 1 and 2 have landed
+	int4 q4 = lds_i32x4(ring_s);           // records of the next batch to be turned into terms
+	int slot_n = 1;                        // ring slot of the stream batch after that one
+#pragma unroll 1
+	for (int idx = 0; idx < cnt; idx++)
+	{
+		const int g = (int)list[idx];
+		const int nb = (glen[g] + 3) >> 2;
+		double acc = 0;
+		if (nb > 0)
+		{
+			const auto term = term_of(g);
+			double rr[4];
+			{
+				double ga[4], gb[4];
+				emc_gather4(q4, term, ga, gb);
+				emc_combine4(q4, term, ga, gb, rr);
+			}
+			q4 = lds_i32x4(ring_s + (uint32_t)slot_n * 512u);
+			slot_n = (slot_n + 1) & (EMC_RING_B - 1);
+			// all batches but the last. The ring read of the batch after next and the gathers of the next
+			// batch go first: the asm statements below are memory barriers for the compiler, and loads
+			// placed after them would wait behind the adds
+#pragma unroll 1
+			for (int b = 0; b + 1 < nb; b++)
+			{
+				const int4 q4n = lds_i32x4(ring_s + (uint32_t)slot_n * 512u);      // (landed: see the wait below)
+				slot_n = (slot_n + 1) & (EMC_RING_B - 1);
+				double ga[4], gb[4];
+				emc_gather4(q4, term, ga, gb);
+				issue();
+				cp_async_wait<EMC_RING_B - 4>();               // the stream batch three ahead has landed
+				double rn[4];
+				emc_combine4(q4, term, ga, gb, rn);
+#pragma unroll
+				for (int q = 0; q < 4; q++) { acc = __dadd_rn(acc, rr[q]); rr[q] = rn[q]; }
+				q4 = q4n;
+			}
+			// the last batch: q4 already holds the first records of the next group
+			issue();
+			cp_async_wait<EMC_RING_B - 4>();
+#pragma unroll
+			for (int q = 0; q < 4; q++) acc = __dadd_rn(acc, rr[q]);
+		}
+		done(g, acc);
 	}
 	cp_async_wait<0>();
-	return acc;
-}
-
-constexpr int EMC_DIRECT_B = 2;         // groups of at most this many batches (8 rows) skip the ring: their
-                                        // records are loaded into registers while the previous group is summed
-
-/// records of a short group straight from global memory (the group's rows are a prefix of its slots)
-__device__ __forceinline__ void emc_direct_load(const uint32_t *rec_group, int nb, int lane, int4 (&q)[EMC_DIRECT_B])
-{
-	const int4 *src = (const int4 *)rec_group + lane;          // + 32 int4 per batch
-#pragma unroll
-	for (int b = 0; b < EMC_DIRECT_B; b++) q[b] = (b < nb) ? __ldcg(src + 32 * b) : make_int4(0, 0, 0, 0);
-}
-
-template <class Term>
-__device__ __forceinline__ double emc_direct_sum(const int4 (&q)[EMC_DIRECT_B], int nb, int my_len, const Term &term)
-{
-	double rr[EMC_DIRECT_B][4];
-#pragma unroll
-	for (int b = 0; b < EMC_DIRECT_B; b++)
-	{
-		if (b < nb) emc_terms(q[b], 4 * b, my_len, term, rr[b]);
-		else { rr[b][0] = rr[b][1] = rr[b][2] = rr[b][3] = 0.0; }
-	}
-	double acc = 0;
-#pragma unroll
-	for (int b = 0; b < EMC_DIRECT_B; b++)
-#pragma unroll
-		for (int k = 0; k < 4; k++) acc = __dadd_rn(acc, rr[b][k]);
-	return acc;
 }
 
 /// Streaming filter of one record array (all pairs, or all contributions, of the round) into the
@@ -1097,23 +1105,31 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 	SmAcct acct_cta(p.acct, SM_ACCT_EM_CTA, 1024u);
 	extern __shared__ double em_smem[];
 	const int n2 = 2 * p.n_cur;
+	const int nf = (n2 + 2) & ~1;                            // stride of a frequency buffer: n2 ranks + the null slot
 	const int n_groups = (n2 + 31) >> 5, n_egroups = (p.n_entry + 31) >> 5;
-	double *fr0 = em_smem;                                   // [2][n2] frequencies by rank, double-buffered
-	double *scratch = fr0 + 2 * (size_t)n2;                  // [40]
-	double *sck = scratch + 40;                              // [n_entry] count / sum by rank (set-up: genotypes, prefixes)
-	uint32_t *rings = (uint32_t *)(sck + ((p.n_entry + 1) & ~1));   // [EMC_WARPS][EMC_RING_B][128] (16-byte aligned)
+	double *fr0 = em_smem;                                   // [2][nf] frequencies by rank, double-buffered; [n2] = 0.0
+	double *scratch = fr0 + 2 * (size_t)nf;                  // [40]
+	double *sck = scratch + 40;                              // [n_entry + 1] count / sum by rank, [n_entry] = 0.0 (set-up: genotypes, prefixes)
+	uint32_t *rings = (uint32_t *)(sck + ((p.n_entry + 2) & ~1));   // [EMC_WARPS][EMC_RING_B][128] (16-byte aligned)
 	int *gbase = (int *)(rings + EMC_WARPS * EMC_RING_B * 128);     // [n_groups] first record slot of the group
 	int *egbase = gbase + n_groups;                          // [n_egroups]
 	int *glen = egbase + n_egroups;                          // [n_groups] longest compatible chain of the group
 	int *eglen = glen + n_groups;                            // [n_egroups]
-	uint16_t *clen = (uint16_t *)(eglen + n_egroups);        // [n2] compatible contributions per chain, by rank
-	uint16_t *elen = clen + ((n2 + 1) & ~1);                 // [n_entry] compatible pairs per entry, by rank
-	uint8_t *ebc = (uint8_t *)(elen + ((p.n_entry + 1) & ~1));      // [n_entry] bootstrap count, by rank
+	uint16_t *mlist = (uint16_t *)(eglen + n_egroups);       // [n_groups] the M step's groups, warp by warp
+	uint16_t *elist = mlist + ((n_groups + 1) & ~1);         // [n_egroups] the E step's
+	// set-up: chain lengths by rank; afterwards the same words hold the warps' batch schedules
+	uint16_t *clen = elist + ((n_egroups + 1) & ~1);         // [n2] compatible contributions per chain
+	uint16_t *elen = clen + ((n2 + 1) & ~1);                 // [n_entry] compatible pairs per entry
+	uint16_t *sched_m = clen;                                // [<= n_slots / 128] first slot / 128 of every batch, warp by warp
+	uint16_t *sched_e = sched_m + p.n_slots / 128;           // [<= n_eslots / 128]
+	uint8_t *ebc = (uint8_t *)(clen + p.len_words);          // [n_entry] bootstrap count, by rank
 	int *eg = (int *)sck;                                    // set-up: genotype of the entry (3 = missing), by rank
 	int *pstart_e = eg + p.n_entry;                          // set-up: prefix at the first pair of the entry
-	int *pstart_m = (int *)(fr0 + n2);                       // set-up: the same per haplotype chain (second frequency buffer)
+	int *pstart_m = (int *)(fr0 + nf);                       // set-up: the same per haplotype chain (second frequency buffer)
 	__shared__ int sh_i[6];
 	__shared__ int sh_w[EMC_WARPS];
+	__shared__ int sh_cnt[2][EMC_WARPS + 1];                 // first group of every warp in mlist / elist
+	__shared__ int sh_sch[2][EMC_WARPS + 1];                 // first batch of every warp in sched_m / sched_e
 
 	const int c = blockIdx.x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1173,16 +1189,82 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 			fr0[__ldg(p.hap_rank + 2 * k)] = __dadd_rn(__dmul_rn(q0, f), EM_INIT_VAL_FRAC);
 			fr0[__ldg(p.hap_rank + 2 * k + 1)] = __dadd_rn(__dmul_rn(q1, f), EM_INIT_VAL_FRAC);
 		}
+		if (tid == 0) fr0[n2] = 0.0;            // the null slot of the first buffer (the second one: after the set-up)
 	}
 	// ---- the compatible pairs (:1157-1180) of every entry and the compatible contributions of every
 	// haplotype, in the reference's order, into the chains' columns ------------------------------------
 	const int n_compat = emc_filter<false>(p.erec_all, p.eown, p.total_pairs, eg, egbase, erec, pstart_e, elen, eglen, sh_w);
 	__syncthreads();
 	emc_filter<true>(p.mrec_all, p.mown, 2 * p.total_pairs, eg, gbase, rec, pstart_m, clen, glen, sh_w);
+	__syncthreads();
+	// null records behind the end of every chain, up to the last row of its group's last batch
+	{
+		const uint32_t null_e = emc_pair_record(n2, n2, 0), null_m = emc_contrib_record(n2, p.n_entry, false, 0);
+		for (int r = tid; r < 32 * n_egroups; r += EMC_THREADS)
+		{
+			const int end = ((eglen[r >> 5] + 3) >> 2) << 2;
+			for (int i = (r < p.n_entry) ? (int)elen[r] : 0; i < end; i++) erec[emc_slot(egbase[r >> 5], i, r & 31)] = null_e;
+		}
+		for (int r = tid; r < 32 * n_groups; r += EMC_THREADS)
+		{
+			const int end = ((glen[r >> 5] + 3) >> 2) << 2;
+			for (int i = (r < n2) ? (int)clen[r] : 0; i < end; i++) rec[emc_slot(gbase[r >> 5], i, r & 31)] = null_m;
+		}
+	}
+	// the groups of either step dealt to the warps: in rank order (longest first) each group goes to the
+	// warp with the fewest batches so far
+	if (tid < 2)
+	{
+		const int ng = tid ? n_egroups : n_groups;
+		const int *len_g = tid ? eglen : glen;
+		uint16_t *lst = tid ? elist : mlist;
+		int load[EMC_WARPS], cnt[EMC_WARPS];
+		for (int w = 0; w < EMC_WARPS; w++) { load[w] = 0; cnt[w] = 0; }
+		// first pass: sizes; second pass: positions (the lists are stored warp after warp)
+		for (int pass = 0; pass < 2; pass++)
+		{
+			int pos[EMC_WARPS];
+			if (pass)
+			{
+				int run = 0;
+				for (int w = 0; w < EMC_WARPS; w++) { sh_cnt[tid][w] = run; pos[w] = run; run += cnt[w]; load[w] = 0; }
+				sh_cnt[tid][EMC_WARPS] = run;
+			}
+			for (int g = 0; g < ng; g++)
+			{
+				int best = 0;
+				for (int w = 1; w < EMC_WARPS; w++) if (load[w] < load[best]) best = w;
+				load[best] += ((len_g[g] + 3) >> 2) + 1;         // (+1: a group costs about a batch by itself)
+				if (pass) lst[pos[best]++] = (uint16_t)g; else cnt[best]++;
+			}
+		}
+	}
+	if (tid == 0) { sck[p.n_entry] = 0.0; fr0[nf + n2] = 0.0; }
 	__threadfence();           // the records are read back through L2 by other warps of this CTA
 	__syncthreads();
+	// the warps' batch schedules (over the chain lengths, which nobody reads any more)
+	if (tid < 2)
+	{
+		const int *len_g = tid ? eglen : glen;
+		const int *base_g = tid ? egbase : gbase;
+		const uint16_t *lst = tid ? elist : mlist;
+		uint16_t *sch = tid ? sched_e : sched_m;
+		int k = 0;
+		for (int w = 0; w < EMC_WARPS; w++)
+		{
+			sh_sch[tid][w] = k;
+			for (int idx = sh_cnt[tid][w]; idx < sh_cnt[tid][w + 1]; idx++)
+			{
+				const int g = (int)lst[idx];
+				const int nb = (len_g[g] + 3) >> 2, b0 = base_g[g] >> 7;
+				for (int b = 0; b < nb; b++) sch[k++] = (uint16_t)(b0 + b);
+			}
+		}
+		sh_sch[tid][EMC_WARPS] = k;
+	}
+	__syncthreads();
 	const bool prof = (p.prof != nullptr) && tid == 0;
-	long long t_last = prof ? clock64() : 0, t_e = 0, t_m = 0;
+	long long t_last = prof ? clock64() : 0, t_e = 0, t_m = 0, t_e1 = 0;
 	if (prof) p.prof[8 * c + 0] = (unsigned long long)(t_last - acct_cta.t0);
 	const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(rings + (size_t)warp * EMC_RING_B * 128) +
 		(uint32_t)lane * 16u;
@@ -1192,49 +1274,16 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 	for (int iter = 0; iter <= EM_MAX_ITER; iter++)
 	{
 		const double old_loglik = loglik;
-		const double *fr = fr0 + (size_t)(iter & 1) * n2;
-		double *fr_new = fr0 + (size_t)((iter & 1) ^ 1) * n2;
+		const double *fr = fr0 + (size_t)(iter & 1) * nf;
+		double *fr_new = fr0 + (size_t)((iter & 1) ^ 1) * nf;
 		// ---- E step (:1204-1222), pass 1: a warp takes the next-longest group of 32 entries; every lane
 		// sums the GenoFreq of its entry's compatible pairs in list order ---------------------------------
-		{
-			const EmcPairTerm term = { fr };
-			int gi = 0;
-			if (lane == 0) gi = atomicAdd(&sh_i[2], 1);
-			gi = __shfl_sync(0xffffffffu, gi, 0);
-			int4 pre[EMC_DIRECT_B];
-			bool have_pre = false;
-			while (gi < n_egroups)
-			{
-				int gn = 0;
-				if (lane == 0) gn = atomicAdd(&sh_i[2], 1);
-				gn = __shfl_sync(0xffffffffu, gn, 0);
-				const int r = 32 * gi + lane;
-				const bool mine = r < p.n_entry;
-				const int my_len = mine ? (int)elen[r] : 0;
-				const int nb = (eglen[gi] + 3) >> 2;
-				const uint32_t *grp = erec + egbase[gi];
-				int4 cur[EMC_DIRECT_B];
-				if (nb <= EMC_DIRECT_B)
-				{
-					if (have_pre) {
-#pragma unroll
-						for (int b = 0; b < EMC_DIRECT_B; b++) cur[b] = pre[b];
-					} else emc_direct_load(grp, nb, lane, cur);
-				}
-				// the next group's records, when it is a short one
-				have_pre = false;
-				if (gn < n_egroups)
-				{
-					const int nbn = (eglen[gn] + 3) >> 2;
-					if (nbn <= EMC_DIRECT_B) { emc_direct_load(erec + egbase[gn], nbn, lane, pre); have_pre = true; }
-				}
-				const double psum = (nb <= EMC_DIRECT_B) ? emc_direct_sum(cur, nb, my_len, term)
-					: emc_walk(grp, nb, my_len, ring_s, lane, term);
-				if (mine) sck[r] = psum;
-				gi = gn;
-			}
-		}
+		emc_stream(elist + sh_cnt[1][warp], sh_cnt[1][warp + 1] - sh_cnt[1][warp], sched_e + sh_sch[1][warp],
+			sh_sch[1][warp + 1] - sh_sch[1][warp], erec, eglen, ring_s, lane,
+			[&](int) { return EmcPairTerm{ fr }; },
+			[&](int g, double psum) { const int r = 32 * g + lane; if (r < p.n_entry) sck[r] = psum; });
 		__syncthreads();
+		if (prof) { const long long n_ = clock64(); t_e1 += n_ - t_last; }
 		// pass 2: a thread per entry, four at a time (four independent log / divide sequences):
 		// log-likelihood term and scale factor count / sum
 		double ll = 0;
@@ -1263,49 +1312,16 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 			}
 		}
 		ll = block_sum_f64(ll, scratch);           // (its barriers publish the scale factors)
-		if (tid == 0) sh_i[3] = 0;                 // group counter of the M step (sh_i[2] is reset after it)
-		__syncthreads();
 		if (prof) { const long long n_ = clock64(); t_e += n_ - t_last; t_last = n_; }
 		// ---- M step: a warp takes the next-longest group of 32 haplotype chains ---------------------------
-		{
-			int gi = 0;
-			if (lane == 0) gi = atomicAdd(&sh_i[3], 1);
-			gi = __shfl_sync(0xffffffffu, gi, 0);
-			int4 pre[EMC_DIRECT_B];
-			bool have_pre = false;
-			while (gi < n_groups)
-			{
-				int gn = 0;
-				if (lane == 0) gn = atomicAdd(&sh_i[3], 1);
-				gn = __shfl_sync(0xffffffffu, gn, 0);
-				const int r = 32 * gi + lane;
-				const bool mine = r < n2;
-				const int my_len = mine ? (int)clen[r] : 0;
-				const int nb = (glen[gi] + 3) >> 2;
-				const uint32_t *grp = rec + gbase[gi];
-				int4 cur[EMC_DIRECT_B];
-				if (nb <= EMC_DIRECT_B)
-				{
-					if (have_pre) {
-#pragma unroll
-						for (int b = 0; b < EMC_DIRECT_B; b++) cur[b] = pre[b];
-					} else emc_direct_load(grp, nb, lane, cur);
-				}
-				have_pre = false;
-				if (gn < n_groups)
-				{
-					const int nbn = (glen[gn] + 3) >> 2;
-					if (nbn <= EMC_DIRECT_B) { emc_direct_load(rec + gbase[gn], nbn, lane, pre); have_pre = true; }
-				}
-				const double fh = mine ? fr[r] : 0.0;
-				const EmcContribTerm term = { fr, sck, __dmul_rn(2.0, fh), __dmul_rn(fh, fh) };   // 2 f_h is exact
-				const double acc = (nb <= EMC_DIRECT_B) ? emc_direct_sum(cur, nb, my_len, term)
-					: emc_walk(grp, nb, my_len, ring_s, lane, term);
-				if (mine) fr_new[r] = __dmul_rn(acc, p.scale);
-				gi = gn;
-			}
-		}
-		if (tid == 0) sh_i[2] = 0;                 // group counter of the next E step
+		emc_stream(mlist + sh_cnt[0][warp], sh_cnt[0][warp + 1] - sh_cnt[0][warp], sched_m + sh_sch[0][warp],
+			sh_sch[0][warp + 1] - sh_sch[0][warp], rec, glen, ring_s, lane,
+			[&](int g) {
+				const int r = 32 * g + lane;
+				const double fh = (r < n2) ? fr[r] : 0.0;
+				return EmcContribTerm{ fr, sck, __dmul_rn(2.0, fh), __dmul_rn(fh, fh) };      // 2 f_h is exact
+			},
+			[&](int g, double acc) { const int r = 32 * g + lane; if (r < n2) fr_new[r] = __dmul_rn(acc, p.scale); });
 		__syncthreads();
 		if (prof) { const long long n_ = clock64(); t_m += n_ - t_last; t_last = n_; }
 		iters = iter + 1;
@@ -1325,7 +1341,7 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 		if (f == 1) break;
 	}
 	{
-		const double *fin = fr0 + (size_t)(iters & 1) * n2;
+		const double *fin = fr0 + (size_t)(iters & 1) * nf;
 		double *out = p.out_freq + (size_t)c * n2;
 		for (int r = tid; r < n2; r += EMC_THREADS) out[__ldg(p.hap_sorted + r)] = fin[r];
 		if (tid == 0)
@@ -1339,6 +1355,11 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 				for (int g = 0; g < n_egroups; g++) longest_e = max(longest_e, eglen[g]);
 				p.prof[8 * c + 1] = (unsigned long long)t_e; p.prof[8 * c + 2] = (unsigned long long)t_m;
 				p.prof[8 * c + 3] = (unsigned long long)iters; p.prof[8 * c + 4] = (unsigned long long)longest_e;
+				unsigned long long se = 0, sm_ = 0, le = 0, lm = 0;
+				for (int g = 0; g < n_egroups; g++) { const int nb = (eglen[g] + 3) >> 2; se += nb; le += nb > 4; }
+				for (int g = 0; g < n_groups; g++) { const int nb = (glen[g] + 3) >> 2; sm_ += nb; lm += nb > 4; }
+				p.prof[8 * c + 5] = se | (le << 32); p.prof[8 * c + 6] = sm_ | (lm << 32);
+				p.prof[8 * c + 7] = (unsigned long long)t_e1;
 			}
 		}
 	}
@@ -1608,15 +1629,19 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 		int want_chain = 1;                    // read per call: the tests switch kernels inside one process
 		if (const char *e = getenv("HIBAG_B200_EM_CHAIN")) want_chain = atoi(e);
 		const int n_egroups = (n_entry_ + 31) / 32;
-		const size_t smem = sizeof(double) * (2 * (size_t)n2_ + 40 + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
+		// chain lengths during the set-up, the warps' batch schedules afterwards (at most one 16-bit word per
+		// 128 record slots)
+		const size_t len_words = (std::max((((size_t)n2_ + 1) & ~(size_t)1) + (((size_t)n_entry_ + 1) & ~(size_t)1),
+			n_slots_ / 128 + n_eslots_ / 128) + 1) & ~(size_t)1;
+		const size_t smem = sizeof(double) * (2 * (((size_t)n2_ + 2) & ~(size_t)1) + 40 + (((size_t)n_entry_ + 2) & ~(size_t)1)) +
 			sizeof(uint32_t) * (size_t)EMC_WARPS * EMC_RING_B * 128 +
 			sizeof(int) * 2 * ((size_t)n_groups + (size_t)n_egroups) +
-			sizeof(uint16_t) * ((((size_t)n2_ + 1) & ~(size_t)1) + (((size_t)n_entry_ + 1) & ~(size_t)1)) +
+			sizeof(uint16_t) * ((((size_t)n_groups + 1) & ~(size_t)1) + (((size_t)n_egroups + 1) & ~(size_t)1) + len_words) +
 			(size_t)n_entry_ + 16;
 		const size_t budget = (size_t)227 * 1024 - 512;     // the kernel also has a few bytes of static shared memory
 		// (records hold haplotype ranks in 14 bits and entry ranks in 15; chain lengths in 16 bits)
 		if (want_chain && n_entry_ <= EMC_MAX_ENTRY && n2_ <= EMC_MAX_HAP && max_chain_ <= 65535 &&
-			max_entry_pairs_ <= 65535 && smem <= budget)
+			max_entry_pairs_ <= 65535 && (n_slots_ + n_eslots_) / 128 <= 65535 && smem <= budget)
 		{
 			d_idxell_.ensure((size_t)m * n_slots_ + 4);
 			d_erec_.ensure((size_t)m * n_eslots_ + 4);
@@ -1634,6 +1659,7 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 			a.out_freq = d_freq_.get(); a.out_status = d_status_.get();
 			a.scale = 0.5 / n_samp; a.em_reltol = std::sqrt(DBL_EPSILON);
 			a.acct = device_sm_acct();
+			a.len_words = (int)len_words;
 			const bool want_prof_r = getenv("HIBAG_B200_EM_DEBUG") != nullptr;
 			if (want_prof_r)
 			{
@@ -1690,6 +1716,10 @@ void RoundEM::run_em(const int *cand_snp, int m, const int8_t *geno_t, int n_sam
 					su += (double)hp[8 * i]; se += (double)hp[8 * i + 1]; sm += (double)hp[8 * i + 2]; it += (double)hp[8 * i + 3];
 					it_max = std::max(it_max, (int)hp[8 * i + 3]); le = std::max(le, (int)hp[8 * i + 4]);
 				}
+				fprintf(stderr, "emc groups (candidate 0): E %d groups, %llu batches, %llu long; M %d groups, %llu batches, %llu long; "
+					"E pass 1 %.1f kcycles per iteration\n",
+					n_egroups, hp[5] & 0xffffffffull, hp[5] >> 32, n_groups, hp[6] & 0xffffffffull, hp[6] >> 32,
+					hp[3] ? (double)hp[7] / (double)hp[3] * 1e-3 : 0.0);
 				fprintf(stderr, "em chain: kernel %.3f ms, %d candidates, total pairs %zu, compat/cand %.0f, smem %zu (%d per SM) | "
 					"kcycles: set-up %.0f per candidate, E step %.1f and M step %.1f per iteration, iterations mean %.1f max %d, "
 					"longest chain %d, longest entry %d\n", ms, m, total_pairs_, nv ? (double)compat / nv : 0.0, smem, per_sm,
