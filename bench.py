@@ -43,7 +43,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 N_SAMP, N_SNP, N_HLA_REQ, COHORT_SEED = 5000, 500, 40, 1
 TRAIN_SEED = 2024
 MTRY = 23
-GATHER_NCU_CSV = ("r02_gather_ncu_raw.csv", "r01_gather_final_ncu_raw.csv")   # newest capture first
+GATHER_NCU_CSV = ("r02_gather_cellform_ncu_raw.csv", "r01_gather_final_ncu_raw.csv")   # newest capture first
 LANES = 40           # classifiers in flight per GPU (one step = LANES classifiers per GPU)
 N_PREDICT = 200000
 N_PREDICT_CLS = 100
@@ -399,7 +399,7 @@ def compact_line(detail):
         _flat(r, rf.get("screening"), ("executed_fraction", "effective_frac_reference_formulation"), "screen_")
         _flat(r, rf.get("em"), ("frac", "cycles_per_iteration", "longest_chain_mean"), "em_")
         _flat(r, rf.get("sm_time"), ("scoring_share", "em_share", "other_share", "busy"), "sm_time_")
-        _flat(r, rf, ("frac_of_held_sm_time", "frac_of_held_sm_time_in_bag"))
+        _flat(r, rf, ("frac_launch_events", "frac_of_held_sm_time_in_bag"))
     if detail.get("roofline_unscreened"):
         r["unscreened_frac"] = _short(detail["roofline_unscreened"].get("frac"))
     if pred and pred.get("roofline"):
@@ -613,16 +613,13 @@ def run_b200_arm(args):
                     "passes / the summed durations of the whole screened passes (bounds, need lists, gather "
                     "launch, reduction)"},
         "note": "achieved = POPC.32 the pair-scoring kernel issues (1 per executed pair evaluation per 32 "
-                "SNPs: the one-popcount distance) / its summed launch durations (CUDA events around the "
-                "kernel on its stream). POPC (XU pipe) and the lane-private LDS.64 table lookup co-bind at the "
-                "same 16 /clk/SM. *_reference_formulation counts the 4 POPC.32 per pair evaluation of the "
-                "reference's hamm_d (SURVEY.md 8d). The lanes' passes run on six streams and share the SMs "
-                "with each other and with other lanes' EM CTAs (two of them take an SM's whole register file), so a "
-                "launch's CUDA-event duration is an upper bound of its kernel time: frac is conservative -- "
-                "'alone' holds the same launches with one classifier in flight (every launch alone on the GPU), "
-                "'in_bag_launches' the launches that carry the work. The gather form is ragged (a warp's "
-                "lanes are the samples that need the cell) and latency-bound on the small passes; the plain "
-                "kernel's fraction (every cell, full warps) is under roofline_unscreened and predict.roofline.",
+                "SNPs: the one-popcount distance) / the time its launches hold the GPU (see timing). POPC (XU pipe) "
+                "and the lane-private LDS.64 table lookup co-bind at the same 16 /clk/SM. *_reference_formulation "
+                "counts the 4 POPC.32 per pair evaluation of the reference's hamm_d (SURVEY.md 8d). 'alone' holds "
+                "the same launches with one classifier in flight (every launch alone on the GPU, CUDA events), "
+                "'in_bag_launches' the launches that carry the work, 'launch_events' the overlapped CUDA-event "
+                "figure. The plain kernel's fraction (every cell, full warps) is under roofline_unscreened and "
+                "predict.roofline.",
         "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum of one in-bag launch (ncu --set full,
         # profiles/r01_gather_r2_ncu_raw.csv): the surviving entries of the cell matrix written once and
@@ -652,16 +649,39 @@ def run_b200_arm(args):
                 "NOT exclusive time and do not add up to the step; held SM-time does. Pair preparation (cub sort, "
                 "pair matching) is not instrumented."}
     if screened and acct["gather_ib"] > 0:
+        # ---- the headline fraction: POPC issued / the SM-time the kernel's CTAs HELD in the timed region.
+        # 40 lanes overlap their launches on six streams and share every SM with other lanes' EM CTAs, so a
+        # launch's CUDA-event duration is not its kernel time ("CUDA-event sums are not
+        # exclusive time ... measure SM-time"): the kernels count their own resident cycles (devutil.cuh:
+        # SmAcct), weighted by the share of an SM a CTA occupies (1/8: 128 threads x 64 registers).
+        held_cycles = acct["gather_ib"] + acct["gather_oob"]                 # SM-cycles
+        held_s = held_cycles / (info["sm_count"] * sm_clock)                 # seconds of the WHOLE GPU
         held = d["gather_ib_popc32"] / (acct["gather_ib"] * popc_per_sm_cycle)
         roofline["frac_of_held_sm_time_in_bag"] = held
-        roofline["frac_of_held_sm_time"] = d["popc32_issued"] / ((acct["gather_ib"] + acct["gather_oob"]) * popc_per_sm_cycle)
+        roofline["frac_of_held_sm_time"] = d["popc32_issued"] / (held_cycles * popc_per_sm_cycle)
+        roofline["launch_events"] = {
+            "achieved": roofline["achieved"], "frac": roofline["frac"], "avg_launch_ms": roofline["avg_launch_ms"],
+            "pair_evals_per_s": roofline["pair_evals_per_s"],
+            "note": "the same POPC count / the summed CUDA-event durations of the launches (events on the launching "
+                    "stream): every overlapped launch is charged the whole time it shares the GPU, so this is a lower "
+                    "bound of the kernel's efficiency, not a roofline fraction"}
+        roofline["achieved"] = d["popc32_issued"] / held_s / 1e9
+        roofline["frac"] = roofline["frac_of_held_sm_time"]
+        roofline["avg_launch_ms"] = held_s * 1e3 / n_l
+        roofline["pair_evals_per_s"] = d["pair_evals"] / held_s
+        roofline["frac_reference_formulation"] = d["pair_evals"] * 4 / held_s / popc_peak
+        roofline["fp64_frac"] = d["pair_evals"] * 3 / held_s / (peaks or {}).get("fp64_ops_per_s", 148 * 64 * 1.965e9)
+        roofline["frac_launch_events"] = roofline["launch_events"]["frac"]
+        roofline["timing"] = ("sm_time: avg_launch_ms = SM-cycles the kernel's CTAs held in the timed region (in-kernel clock64 "
+                              "counters, x 1/8 SM per CTA) / (SMs x clock) / launches, i.e. the duration a launch would have "
+                              "with the GPU to itself at the same efficiency; CUDA-event durations overlap (launch_events)")
     # ---- the EM kernel (time-dominant when serialised) against ITS bound: the latency of the longest
     # chain of dependent fp64 adds of every M step (16.9 cycles per dependent DADD, profiles/pipe_peaks.json)
     if d.get("em_chain_adds", 0) > 0 and acct["em_cta_cycles"] > 0:
         dadd = (peaks or {}).get("dadd_dependent_cycles", 16.9)
         floor_cycles = d["em_chain_adds"] * dadd
         roofline["em"] = {
-            "kernel": "em_kernel", "bound": "latency of the dependent fp64 add chain (M step), %.1f cycles per add" % dadd,
+            "kernel": "em_chain_kernel", "bound": "latency of the dependent fp64 add chain (M step), %.1f cycles per add" % dadd,
             "achieved": floor_cycles / 1e9, "peak": acct["em_cta_cycles"] / 1e9, "unit": "Gcycles (chain floor / CTA-resident)",
             "frac": floor_cycles / acct["em_cta_cycles"], "sm_time_share": share["em"],
             "iterations": int(d["em_iterations"]), "candidates": int(d["n_em"]),
@@ -699,7 +719,7 @@ def run_b200_arm(args):
             "in_bag_avg_launch_ms": sa["gather_ib_kernel_ms"] / max(sa["gather_ib_launches"], 1),
             "in_bag_achieved": a_ib / 1e9, "in_bag_frac": a_ib / popc_peak,
             "note": "same kernel, same workload, ONE classifier in flight: every gather launch has the GPU to "
-                    "itself, so launch duration = kernel time (the burst figure). In the timed region 24 lanes "
+                    "itself, so launch duration = kernel time (the burst figure). In the timed region the lanes "
                     "overlap their launches on six streams and share the SMs with the EM CTAs of other lanes."}
         del m3
     # one step with screening off: the plain pair-scoring kernel alone on its stream
