@@ -1502,7 +1502,7 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 	HB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp_.get(), tmp_bytes, d_cnt_.get(), d_off_.get(), n_entry + 1, st));
 	HB_CUDA(cudaMemcpyAsync(h_total_.get(), d_off_.get() + n_entry, sizeof(int), cudaMemcpyDeviceToHost, st));
 	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 3, d_cnt_.get() + n_entry + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-	HB_CUDA(cudaStreamSynchronize(st));
+	stream_sync_blocking(st);
 	total_pairs_ = (size_t)h_total_.get()[0];
 	has_empty_entry_ = h_total_.get()[3] != 0;
 	d2h_bytes += sizeof(int);
@@ -1593,7 +1593,7 @@ void RoundEM::prepare(const HapList &cur, const uint32_t *s1, const uint32_t *s2
 	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 4, d_egroup_base_.get() + n_egroups, sizeof(int),
 		cudaMemcpyDeviceToHost, st));
 	HB_CUDA(cudaMemcpyAsync(h_total_.get() + 5, d_egroup_len_.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
-	HB_CUDA(cudaStreamSynchronize(st));
+	stream_sync_blocking(st);
 	n_slots_ = (size_t)h_total_.get()[1];
 	max_chain_ = h_total_.get()[2];
 	n_eslots_ = (size_t)h_total_.get()[4];
@@ -1888,7 +1888,7 @@ void RoundEM::fetch_pairs(RoundPairs &out, const std::vector<int> &inbag,
 		HB_CUDA(cudaMemcpyAsync(out.p1.data(), d_p1_.get(), sizeof(int) * total_pairs_, cudaMemcpyDeviceToHost, st));
 		HB_CUDA(cudaMemcpyAsync(out.p2.data(), d_p2_.get(), sizeof(int) * total_pairs_, cudaMemcpyDeviceToHost, st));
 	}
-	HB_CUDA(cudaStreamSynchronize(st));
+	stream_sync_blocking(st);
 	for (int k = 0; k < n; k++)
 	{
 		out.samp[k] = inbag[k];

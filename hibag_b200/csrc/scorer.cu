@@ -389,7 +389,7 @@ void BatchScorer::set_sample_sets(const std::vector<int> &oob, const std::vector
 		for (int c = 0; c < n_cells; c++) eoff[c] = (int)((size_t)c * stride);
 		ent_off_[kind].ensure(n_cells);
 		HB_CUDA(cudaMemcpyAsync(ent_off_[kind].get(), eoff.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, st_.s));
-		HB_CUDA(cudaStreamSynchronize(st_.s));       // the host vector goes out of scope
+		stream_sync_blocking(st_.s);                 // the host vector goes out of scope
 		stats.h2d_bytes += sizeof(int) * (size_t)n_cells;
 		evals_per_list_[kind] = 0;
 	}
@@ -773,7 +773,7 @@ void BatchScorer::rescore_uncertified(const GenoView &g, int cand_bit, const std
 	h_ratio_fb_.ensure((size_t)nl * stride);
 	HB_CUDA(cudaMemcpyAsync(d_fb_samp_.get(), fb_samp.data(), sizeof(int) * (size_t)nf,
 		cudaMemcpyHostToDevice, st_.s));
-	HB_CUDA(cudaStreamSynchronize(st_.s));
+	stream_sync_blocking(st_.s);
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
 	std::vector<int> which_fb(nl);
 	for (int j = 0; j < nl; j++) which_fb[j] = which[lists_fb[j]];

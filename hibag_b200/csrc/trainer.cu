@@ -300,7 +300,7 @@ void Trainer::upload_base_geno()
 	}
 	HB_CUDA(cudaMemcpyAsync(d_s1_.get(), h, sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice, main_st_.s));
 	HB_CUDA(cudaMemcpyAsync(d_s2_.get(), h + 4 * n, sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice, main_st_.s));
-	HB_CUDA(cudaStreamSynchronize(main_st_.s));
+	stream_sync_blocking(main_st_.s);
 	stats_.h2d_bytes += sizeof(uint32_t) * 8 * n;
 }
 

@@ -21,10 +21,14 @@ m = api.HLAModel(bench.N_SNP, coh.n_hla); m.set_training(g, coh.h1, coh.h2)
 kw = dict(seed=bench.TRAIN_SEED, per_classifier_seed=True, n_threads=nt, n_concurrent=lanes)
 m.train(lanes, bench.MTRY, first_index=0, **kw)
 api.sm_time(reset=True)
+import resource
+ru0 = resource.getrusage(resource.RUSAGE_SELF)
 s0 = m.train_stats(); t0 = time.time()
 for s in range(steps):
     m.train(lanes, bench.MTRY, first_index=(1 + s) * lanes, **kw)
 dt = time.time() - t0; s1 = m.train_stats()
+ru1 = resource.getrusage(resource.RUSAGE_SELF)
+host_cores = ((ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)) / dt
 acct = api.sm_time()
 info = api.device_info()
 sm_total = info["sm_count"] * dt * info["clock_khz"] * 1e3
@@ -42,7 +46,7 @@ print(json.dumps(dict(per_min=round(60 * n / dt, 1), frac=round(d["popc32_issued
       em_ms_per_cls=round(d["em_kernel_ms"] / n, 1), wall_ms_per_cls=round(1e3 * dt / n, 2), lanes=lanes, digest=dig,
       em_kcyc_per_iter=round(acct["em_cta_cycles"] / max(d["em_iterations"], 1) / 1e3, 1), em_iters_per_cand=round(d["em_iterations"] / max(d["n_em"], 1), 1),
       share={k: round(v / sm_total, 3) for k, v in acct.items() if k != "em_cta_cycles" and v > 0},
-      em_fallbacks=d["n_em_host_fallback"])), flush=True)
+      em_fallbacks=d["n_em_host_fallback"], host_cores=round(host_cores, 2))), flush=True)
 ''' % ROOT
 for spec in sys.argv[1:]:
     env = dict(os.environ)
