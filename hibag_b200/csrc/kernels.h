@@ -215,6 +215,14 @@ struct ScreenArgs
 	int device_rescue;            // 1: uncertified sums are rescued inside the reduction; 0: reported
 	                              // as ratio -1 and rescored by the caller with the plain kernel
 	unsigned long long *acct;     // SM-time counters or null
+	// second level of the in-bag screen (null / 0: off): per-allele sums split by the haplotypes' alleles
+	// at the sample's first two heterozygous SNPs, and the compacted need lists the gather launch uses
+	double *U2;                   // [n_lists][n_hla][p_stride][4]
+	int *hetk;                    // [n_lists][p_stride] heterozygous SNPs used (0..2) | true cell << 2
+	int *count2;                  // [n_lists][n_cells]
+	int *entries2;                // [n_lists][n_cells][p_stride]
+	double K2;                    // bound factor of the second level
+	double tf[3];                 // T'[0], T'[1], T'[2]
 };
 struct ScreenList { const void *hap; const CellTask *cells; const int8_t *cand_col; int n_hap, cand_bit; };
 struct ScreenLists { ScreenList l[MAX_BATCH_LISTS]; };
@@ -228,6 +236,9 @@ void launch_screen_tasks(const ScreenLists &ls, int n_lists, int n_cells, const 
 	int warp_slots, cudaStream_t st, bool flat = false);
 /// per (list, pos): which cells are needed (appends to entries / count)
 void launch_screen_need(const ScreenArgs &a, cudaStream_t st);
+/// second level: every (cell, position) entry of the need lists is tested against the class bound;
+/// survivors go to entries2 / count2, the others get minus their bound into P (the reduction adds it)
+void launch_screen_refine(const ScreenArgs &a, cudaStream_t st);
 /// screened reductions (same outputs as launch_reduce_oob / launch_reduce_ib). An in-bag position
 /// whose sum is not certified is rescued inside the reduction: the lanes of its warp score its
 /// skipped cells one by one, then the plain sequential sum is taken. (ratio -1 = not certified

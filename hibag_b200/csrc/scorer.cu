@@ -450,6 +450,17 @@ void BatchScorer::run_cells(const GenoView &g, int cand_bit, const std::vector<i
 	stats.popc32 += pairs * (uint64_t)n_pos * (uint64_t)nw;
 }
 
+/// second level of the in-bag screen: HIBAG_B200_SCREEN_REFINE=1 turns it on (read per
+/// call: the tests switch it inside one process). Off by default: it removes 25-30 % of the in-bag pair
+/// evaluations (8 % of the GPU's SM-time at config 2) and costs 3.5 % in its own kernel, but the
+/// classifiers/min of the 40-lane step do not move beyond the run-to-run spread
+/// (profiles/r02_screen_refine.txt), and it needs a second set of need lists (170 MB per lane)
+static bool screen_refine()
+{
+	const char *e = getenv("HIBAG_B200_SCREEN_REFINE");
+	return e ? atoi(e) != 0 : false;
+}
+
 /// One sub-batch of a screened pass, all on one of the device's scoring streams: per-allele
 /// bounds and x_ref, the need lists, their tasks, the surviving cells (gather launch) and the
 /// screened reduction. kind: 0 out-of-bag, 1 in-bag.
@@ -481,6 +492,17 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	a.evals = d_evals_.get() + first;
 	a.rescued = d_evals_.get() + which.size();
 	a.al_tab = al_tab_.get() + 2 * (size_t)first * n_hla_;
+	const bool refine = kind == 1 && screen_refine();
+	if (refine)
+	{
+		a.U2 = U2_.get() + (size_t)first * n_hla_ * 4 * p_stride_;
+		a.hetk = hetk_.get() + (size_t)first * p_stride_;
+		a.count2 = cnt2_.get() + (size_t)first * n_cells;
+		a.entries2 = ent2_.get() + (size_t)first * n_cells * p_stride_;
+		a.K2 = screen_bound_factor2();
+		const double *tf = host_rare_freq_floor_table();
+		a.tf[0] = tf[0]; a.tf[1] = tf[1]; a.tf[2] = tf[2];
+	}
 	if (const char *e = getenv("HIBAG_B200_SCREEN_FORCE_RESCUE")) a.force_rescue = std::max(0, atoi(e));
 	if (const char *e = getenv("HIBAG_B200_SCREEN_DEVICE_RESCUE")) a.device_rescue = atoi(e) != 0;
 	gb.table = a.table;
@@ -503,8 +525,8 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		L.P = a.P + (size_t)k * n_cells * p_stride_;
 		L.n_hap = lb.n_hap; L.cand_bit = cand_bit;
 		L.task_prefix = a.task_prefix + (size_t)k * (n_cells + 2);
-		L.count = a.count + (size_t)k * n_cells;
-		L.entries = a.entries + (size_t)k * n_cells * p_stride_;
+		L.count = (refine ? a.count2 : a.count) + (size_t)k * n_cells;
+		L.entries = (refine ? a.entries2 : a.entries) + (size_t)k * n_cells * p_stride_;
 		a.n_dist = gb.n_dist = lb.n_dist;
 		if (lb.n_hap > gb.max_hap) gb.max_hap = lb.n_hap;
 		pairs += lb.pairs_per_sample;
@@ -543,7 +565,8 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		HB_CUDA(cudaEventRecord(ev0_.e, s));
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
-		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks,
+		if (refine) launch_screen_refine(a, s);
+		launch_screen_tasks(ls, count, n_cells_, refine ? a.count2 : a.count, n_cells, a.task_prefix, a.evals, target_tasks,
 			di.sm_count * 32, s, flat);
 		HB_CUDA(cudaEventRecord(ev_up_.e, s));
 		// HIBAG_B200_GATHER_OOB: 0 out-of-bag launches share the exclusive stream, 1 their own exclusive
@@ -581,7 +604,8 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		HB_CUDA(cudaEventRecord(ev0_.e, s));
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
-		launch_screen_tasks(ls, count, n_cells_, a.count, n_cells, a.task_prefix, a.evals, target_tasks,
+		if (refine) launch_screen_refine(a, s);
+		launch_screen_tasks(ls, count, n_cells_, refine ? a.count2 : a.count, n_cells, a.task_prefix, a.evals, target_tasks,
 			di.sm_count * 32, s, flat);
 		HB_CUDA(cudaEventRecord(ev_g0_.e, s));
 		nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
@@ -692,6 +716,13 @@ void BatchScorer::score_ib(const GenoView &g, int cand_bit, const std::vector<in
 		cnt_.ensure((size_t)n * n_cells_);
 		ent_.ensure((size_t)n * n_cells_ * p_stride_);
 		prefix_.ensure((size_t)n * (n_cells_ + 2));
+		if (screen_refine())
+		{
+			U2_.ensure((size_t)n * n_hla_ * 4 * p_stride_);
+			hetk_.ensure((size_t)n * p_stride_);
+			cnt2_.ensure((size_t)n * n_cells_);
+			ent2_.ensure((size_t)n * n_cells_ * p_stride_);
+		}
 		HB_CUDA(cudaMemsetAsync(d_evals_.get(), 0, sizeof(unsigned long long) * (size_t)(n + 1), st_.s));
 	}
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));

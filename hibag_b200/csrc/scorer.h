@@ -174,6 +174,8 @@ private:
 	DevBuf<double> U_, xref_;
 	double evals_per_list_[2] = { 0, 0 };        // executed by the previous pass of the kind
 	DevBuf<int> cnt_, ent_, al_tab_;
+	DevBuf<double> U2_;                          // second level of the in-bag screen: class sums
+	DevBuf<int> hetk_, cnt2_, ent2_;             // ... heterozygous SNPs used, compacted need lists
 	DevBuf<unsigned int> prefix_;
 	DevBuf<unsigned long long> d_evals_;
 	PinBuf<unsigned long long> h_evals_;

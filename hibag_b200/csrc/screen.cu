@@ -118,6 +118,30 @@ screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 	const int dmax = a.n_dist - 1;
 	const char *hap_g = (const char *)L.hap;
 	double *U = a.U + (size_t)l * a.n_hla * a.p_stride;
+	// second level: the sample's first two heterozygous SNPs (word, bit); a haplotype's class = its
+	// alleles there. (A SNP the sample is heterozygous at adds a mismatch to every pair of haplotypes
+	// that AGREE on it: the distance the product bound ignores.)
+	const bool lvl2 = a.U2 != nullptr;
+	int hw0 = 0, hw1 = 0, k_eff = 0;
+	uint32_t hb0 = 0u, hb1 = 0u;
+	if (lvl2)
+	{
+#pragma unroll
+		for (int w = 0; w < NW; w++)
+		{
+			uint32_t het = S1[w] & ~S2[w];
+			while (het && k_eff < 2)
+			{
+				const uint32_t bit = het & (0u - het);
+				if (k_eff == 0) { hw0 = w; hb0 = bit; } else { hw1 = w; hb1 = bit; }
+				k_eff++;
+				het ^= bit;
+			}
+		}
+		// (the true cell of the position rides in the upper bits: one load in screen_refine_kernel)
+		if (ok) a.hetk[(size_t)l * a.p_stride + pos] = k_eff | (true_cell_index(t1, t2, a.n_hla) << 2);
+	}
+	double *U2 = lvl2 ? a.U2 + (size_t)l * a.n_hla * 4 * a.p_stride : nullptr;
 	// the haplotype of each true allele with the largest f * T'[c] (first one on ties)
 	int best1 = -1, best2 = -1;
 	double bu1 = -1.0, bu2 = -1.0;
@@ -125,21 +149,40 @@ screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 	{
 		const int i0 = al_start[al], i1 = i0 + al_n[al];
 		double acc = 0.0;
+		double ac0 = 0.0, ac1 = 0.0, ac2 = 0.0, ac3 = 0.0;
 #pragma unroll 4
 		for (int i = i0; i < i1; i++)
 		{
 			HapRec<NW, false> h;
 			h.load(0u, hap_g, i);
 			int c = 0;
+			uint32_t x0 = 0u, x1 = 0u;
 #pragma unroll
-			for (int w = 0; w < NW; w++) c += __popc((h.h[w] ^ G2[w]) & HOM[w]);
+			for (int w = 0; w < NW; w++)
+			{
+				c += __popc((h.h[w] ^ G2[w]) & HOM[w]);
+				if (w == hw0) x0 = h.h[w] & hb0;
+				if (w == hw1) x1 = h.h[w] & hb1;
+			}
 			const double t = __ldg(a.table_floor + min(c, dmax));
 			const double u = __dmul_rn(h.f, t);
 			acc = __dadd_rn(acc, u);
+			if (lvl2)
+			{
+				const int cls = (x0 ? 1 : 0) | (x1 ? 2 : 0);
+				ac0 = __dadd_rn(ac0, cls == 0 ? u : 0.0); ac1 = __dadd_rn(ac1, cls == 1 ? u : 0.0);
+				ac2 = __dadd_rn(ac2, cls == 2 ? u : 0.0); ac3 = __dadd_rn(ac3, cls == 3 ? u : 0.0);
+			}
 			if (al == t1 && u > bu1) { bu1 = u; best1 = i; }
 			if (al == t2 && u > bu2) { bu2 = u; best2 = i; }
 		}
 		if (ok) U[(size_t)al * a.p_stride + pos] = acc;
+		if (ok && lvl2)
+		{
+			// [allele][position][class]: the four classes of a (allele, position) are one 32-byte sector
+			double2 *u2 = (double2 *)(U2 + ((size_t)al * a.p_stride + pos) * 4);
+			u2[0] = make_double2(ac0, ac1); u2[1] = make_double2(ac2, ac3);
+		}
 	}
 	// ---- x_ref: ONE term of the true cell's chain, evaluated exactly as the chain does (kernels.cu)
 	// -- a sum of non-negative terms is at least each term, so x_ref <= the true cell's value <= the
@@ -430,6 +473,98 @@ void launch_screen_need(const ScreenArgs &a, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------
+// second level of the in-bag screen. The product bound U_a U_b K ignores the heterozygous SNPs:
+// d(g,i,j) = c_i + c_j + #{het SNPs on which h_i and h_j AGREE}. With the haplotypes of an allele
+// split by their alleles at the sample's first k_eff <= 2 heterozygous SNPs (class s, U_a[s] from
+// screen_bound_kernel), a pair of classes (s, t) agrees on k_eff - popc(s ^ t) of them, hence
+//     P(a,b) <= bound2(a,b) = K2 * sum_{s,t} U_a[s] U_b[t] T'[k_eff - popc(s ^ t)]
+// (K2: the factor 2, the table's rounding over THREE factors, the chains' rounding and this sum's).
+// One thread per (cell, position) entry of the first level's need lists -- no divergence: a sample's
+// survivors are its own entries. A survivor is appended to entries2; a discarded entry leaves
+// MINUS its bound in the cell matrix, where the reduction finds it and adds it to the upper sum of
+// its certificate, exactly as it adds the product bound of the cells the first level skipped.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double screen_bound2(const double *ua, const double *ub, int k_eff,
+	double K2, const double (&tf)[3])
+{
+	// w[j] = T'[k_eff - j] for j = popc(s ^ t) disagreements (classes that do not occur have U = 0)
+	const double w0 = tf[k_eff], w1 = tf[max(k_eff - 1, 0)], w2 = tf[max(k_eff - 2, 0)];
+	const double2 a01 = __ldg((const double2 *)ua), a23 = __ldg((const double2 *)ua + 1);
+	const double2 b01 = __ldg((const double2 *)ub), b23 = __ldg((const double2 *)ub + 1);
+	const double a4[4] = { a01.x, a01.y, a23.x, a23.y }, b4[4] = { b01.x, b01.y, b23.x, b23.y };
+	double sum = 0.0;
+#pragma unroll
+	for (int sI = 0; sI < 4; sI++)
+#pragma unroll
+		for (int tI = 0; tI < 4; tI++)
+		{
+			const int j = __popc(sI ^ tI);
+			const double w = (j == 0) ? w0 : ((j == 1) ? w1 : w2);
+			sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(a4[sI], b4[tI]), w));
+		}
+	return __dmul_rn(sum, K2);
+}
+
+__global__ void __launch_bounds__(128)
+screen_refine_kernel(const ScreenArgs a)
+{
+	SmAcct acct_scope(a.acct, SM_ACCT_NEED, 64u);         // 128 threads: 16 CTAs fit an SM
+	__shared__ int sh_keep, sh_ab[2];
+	const int l = blockIdx.y, c = blockIdx.x;
+	const int n = a.n_hla;
+	const int n_cells = n * (n + 1) / 2;
+	const int tid = threadIdx.x, lane = tid & 31;
+	if (tid == 0)
+	{
+		sh_keep = 0;
+		int row = 0, row0 = 0;                                // cell index -> (al, bl), bl >= al
+		while (c >= row0 + (n - row)) { row0 += n - row; row++; }
+		sh_ab[0] = row; sh_ab[1] = row + (c - row0);
+	}
+	__syncthreads();
+	const int al = sh_ab[0], bl = sh_ab[1];
+	const int cnt = a.count[(size_t)l * n_cells + c];
+	const int *ent = a.entries + ((size_t)l * n_cells + c) * a.p_stride;
+	int *ent2 = a.entries2 + ((size_t)l * n_cells + c) * a.p_stride;
+	double *P = a.P + ((size_t)l * n_cells + c) * a.p_stride;
+	const double *U2a = a.U2 + ((size_t)l * n + al) * 4 * a.p_stride;
+	const double *U2b = a.U2 + ((size_t)l * n + bl) * 4 * a.p_stride;
+	const int *hk = a.hetk + (size_t)l * a.p_stride;
+	const double *xr = a.xref + (size_t)l * a.p_stride;
+	for (int e0 = 0; e0 < cnt; e0 += 128)
+	{
+		const int e = e0 + tid;
+		bool keep = false;
+		int pos = 0;
+		if (e < cnt)
+		{
+			pos = ent[e];
+			const int hv = __ldg(hk + pos);
+			const double thr = __dmul_rn(__ldg(xr + pos), a.tau);
+			const double bd2 = screen_bound2(U2a + (size_t)pos * 4, U2b + (size_t)pos * 4, hv & 3, a.K2, a.tf);
+			keep = (c == (hv >> 2)) || (bd2 >= thr && bd2 > 0.0);
+			if (!keep) P[pos] = -((bd2 > 0.0) ? bd2 : 1e-300);      // (negative = skipped, with this bound)
+		}
+		const unsigned m = __ballot_sync(0xffffffffu, keep);
+		int base = 0;
+		if (lane == 0 && m) base = atomicAdd(&sh_keep, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (keep) ent2[base + __popc(m & ((1u << lane) - 1u))] = pos;
+	}
+	__syncthreads();
+	if (tid == 0) a.count2[(size_t)l * n_cells + c] = sh_keep;
+}
+
+void launch_screen_refine(const ScreenArgs &a, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0 || a.U2 == nullptr) return;
+	const int n_cells = a.n_hla * (a.n_hla + 1) / 2;
+	dim3 grid(n_cells, a.n_lists);
+	screen_refine_kernel<<<grid, 128, 0, st>>>(a);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
 // screened reductions
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64)
@@ -589,8 +724,13 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 				{
 					if (nd[q])
 					{
-						lo = __dadd_rn(lo, v[q]);
-						hi = __dadd_rn(hi, v[q]);
+						if (v[q] < 0.0)
+							hi = __dadd_rn(hi, -v[q]);         // skipped by the second level: minus its bound
+						else
+						{
+							lo = __dadd_rn(lo, v[q]);
+							hi = __dadd_rn(hi, v[q]);
+						}
 					} else if (q < nb)
 						hi = __dadd_rn(hi, bd[q]);
 				}
@@ -628,7 +768,8 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 				const int al = row, bl = row + (idx - row0);
 				const double bd = screen_bound(U[(size_t)al * a.p_stride + fpos],
 					U[(size_t)bl * a.p_stride + fpos], a.K);
-				if (idx == ftrue || (bd >= fthr && bd > 0.0)) continue;      // already scored
+				// already scored? (a cell the second level skipped holds minus its bound)
+				if ((idx == ftrue || (bd >= fthr && bd > 0.0)) && !(P[(size_t)idx * a.p_stride + fpos] < 0.0)) continue;
 				double x = 0.0;
 				if (bd > 0.0)
 					x = rescue_chain((const char *)L.hap, nw, a.table, dmax, al_tab[2 * al], al_tab[2 * al + 1],

@@ -14,7 +14,7 @@ static int g_first_zero = 0;
 static std::once_flag g_table_once;
 
 static double g_floor_table[2 * HIBAG_B200_MAX_SNP + 1];
-static double g_bound_factor = 0;
+static double g_bound_factor = 0, g_bound_factor2 = 0;
 
 static void init_table()
 {
@@ -42,6 +42,17 @@ static void init_table()
 			if (r > kappa) kappa = r;
 		}
 	g_bound_factor = 2.0 * kappa * (1.0 + 1e-12) * (1.0 + 1e-8);
+	// second level (classes of the first two heterozygous SNPs, screen.cu: screen_refine_kernel):
+	// T[d] <= kappa3 * T'[p] T'[q] T'[r] for every d >= p + q + r, r <= 2
+	double kappa3 = 1.0;
+	for (int p = 0; p <= n; p++)
+		for (int q = 0; p + q <= n; q++)
+			for (int r = 0; r <= 2 && p + q + r <= n; r++)
+			{
+				const double v = suffix_max[p + q + r] / (g_floor_table[p] * g_floor_table[q] * g_floor_table[r]);
+				if (v > kappa3) kappa3 = v;
+			}
+	g_bound_factor2 = 2.0 * kappa3 * (1.0 + 1e-12) * (1.0 + 1e-8);
 }
 
 const double *host_rare_freq_floor_table()
@@ -54,6 +65,12 @@ double screen_bound_factor()
 {
 	std::call_once(g_table_once, init_table);
 	return g_bound_factor;
+}
+
+double screen_bound_factor2()
+{
+	std::call_once(g_table_once, init_table);
+	return g_bound_factor2;
 }
 
 const double *host_rare_freq_table()

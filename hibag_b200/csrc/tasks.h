@@ -24,6 +24,8 @@ int table_rows_for(int n_snp);
 /// of the chains (< 4e7 terms) and of the bound's own arithmetic.
 const double *host_rare_freq_floor_table();
 double screen_bound_factor();
+/// the same for the second-level bound over the classes of two heterozygous SNPs (three table factors)
+double screen_bound_factor2();
 
 /// A haplotype list laid out for one H2D copy: [records | cells | chunks]
 struct ListBlob

@@ -3,6 +3,7 @@ the compiled reference and the reference's golden model. Integers are bit-exact;
 are required to agree within 1e-10 relative (north_star) and in practice are bit-identical, which
 is asserted too where the operation order is the reference's."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -291,6 +292,19 @@ def test_exact_screening_changes_nothing_but_the_work(gpu, monkeypatch):
     assert sp["pair_evals"] == sp["pair_evals_nominal"] == ss["pair_evals_nominal"]
     assert 0 < ss["pair_evals"] < sp["pair_evals"]
     assert sp["n_screen_fallback"] == 0
+    # the second level of the in-bag screen (class bound over two heterozygous SNPs; opt-in) only removes
+    # work, also with the rescue path of the reduction forced
+    monkeypatch.setenv("HIBAG_B200_SCREEN_REFINE", "1")
+    lvl2 = run(screening=True)
+    monkeypatch.setenv("HIBAG_B200_SCREEN_FORCE_RESCUE", "5")
+    lvl2r = run(screening=True, n_concurrent=2)
+    monkeypatch.delenv("HIBAG_B200_SCREEN_FORCE_RESCUE")
+    monkeypatch.delenv("HIBAG_B200_SCREEN_REFINE")
+    for k in range(3):
+        assert helpers.classifier_diff(lvl2.classifier(k), plain.classifier(k)) == "", k
+        assert helpers.classifier_diff(lvl2r.classifier(k), plain.classifier(k)) == "", k
+    assert np.array_equal(lvl2.train_trace(), plain.train_trace())
+    assert lvl2.train_stats()["pair_evals"] < ss["pair_evals"] < sp["pair_evals"]
     # uncertified sums: rescued inside the reduction (every 5th position forced), or -- the host's
     # safety net for a ratio the device reports as uncertified -- rescored with the plain kernel
     for var in ("HIBAG_B200_SCREEN_FORCE_RESCUE", "HIBAG_B200_SCREEN_FORCE_FALLBACK"):
@@ -585,6 +599,20 @@ def test_headline_config_classifiers_equal_the_reference(gpu):
         want["oob_acc"] = float(gd["c%d_oob_acc" % k])
         d = helpers.classifier_diff(m.classifier(k), want)
         assert d == "", "classifier %d differs from the reference in '%s'" % (k, d)
+    # the same with the opt-in second level of the in-bag screen
+    os.environ["HIBAG_B200_SCREEN_REFINE"] = "1"
+    try:
+        m2 = gpu.HLAModel(bench.N_SNP, coh.n_hla)
+        m2.set_training(np.ascontiguousarray(coh.geno, dtype=np.int8), coh.h1, coh.h2)
+        m2.train(n, bench.MTRY, prune=True, seed=bench.TRAIN_SEED, per_classifier_seed=True, first_index=0,
+                 n_threads=48, n_concurrent=24)
+    finally:
+        del os.environ["HIBAG_B200_SCREEN_REFINE"]
+    assert m2.train_stats()["pair_evals"] < st["pair_evals"]
+    for k in ks:
+        want = {key: gd["c%d_%s" % (k, key)] for key in ("snpidx", "samp_num", "freq", "hla", "packed")}
+        want["oob_acc"] = float(gd["c%d_oob_acc" % k])
+        assert helpers.classifier_diff(m2.classifier(k), want) == "", k
     # one of them again alone, every cell scored, EM on the host pool, with the accepted-SNP trace
     # (SNP, loss to 6 digits, out-of-bag accuracy, haplotypes) equal line by line
     k = ks[0]
