@@ -562,9 +562,11 @@ def run_b200_arm(args):
                       "(new model, cohort H2D, per-round list uploads, accuracy/ratio/frequency downloads)"}
         # the reference-facing plugin struct, driven with the reference's own call sequence
         n_hook = max(1, min(3, args.steps))
+        hook_threads = max(2, (os.cpu_count() or 2) // max(world, 1))    # the host EM pool: one thread per core
+
         def run_hooks(first, count):
             m = api.hlaAttrBagging((coh.h1, coh.h2), geno, nclassifier=count, mtry=MTRY, prune=True,
-                                   mono_rm=False, seed=TRAIN_SEED, nthread=n_threads,
+                                   mono_rm=False, seed=TRAIN_SEED, nthread=hook_threads,
                                    per_classifier_seed=True, use_legacy_hooks=True,
                                    first_index=rank + world * first, index_stride=world)
             return m.train_stats()
