@@ -1126,7 +1126,7 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 	int *eg = (int *)sck;                                    // set-up: genotype of the entry (3 = missing), by rank
 	int *pstart_e = eg + p.n_entry;                          // set-up: prefix at the first pair of the entry
 	int *pstart_m = (int *)(fr0 + nf);                       // set-up: the same per haplotype chain (second frequency buffer)
-	__shared__ int sh_i[6];
+	__shared__ int sh_i[3];                                  // allele count, valid count, oversized bootstrap count
 	__shared__ int sh_w[EMC_WARPS];
 	__shared__ int sh_cnt[2][EMC_WARPS + 1];                 // first group of every warp in mlist / elist
 	__shared__ int sh_sch[2][EMC_WARPS + 1];                 // first batch of every warp in sched_m / sched_e
@@ -1152,7 +1152,7 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 			big |= (b > 255) ? 1 : 0;
 			if (0 <= g && g <= 2) { ac += g * b; vc += 2 * b; }
 		}
-		if (tid < 6) sh_i[tid] = 0;
+		if (tid < 3) sh_i[tid] = 0;
 		for (int g = tid; g < n_groups; g += EMC_THREADS) { gbase[g] = p.group_base[g]; glen[g] = 0; }
 		for (int g = tid; g < n_egroups; g += EMC_THREADS) { egbase[g] = p.egroup_base[g]; eglen[g] = 0; }
 		for (int r = tid; r < n2; r += EMC_THREADS) clen[r] = 0;
@@ -1164,7 +1164,7 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 			vc += __shfl_xor_sync(0xffffffffu, vc, o);
 			big |= __shfl_xor_sync(0xffffffffu, big, o);
 		}
-		if (lane == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); atomicOr(&sh_i[5], big); }
+		if (lane == 0) { atomicAdd(&sh_i[0], ac); atomicAdd(&sh_i[1], vc); atomicOr(&sh_i[2], big); }
 		__syncthreads();
 	}
 	const int allele_cnt = sh_i[0], valid_cnt = sh_i[1];
@@ -1173,7 +1173,7 @@ __global__ void __launch_bounds__(EMC_THREADS, 4) em_chain_kernel(const EmcArgs 
 		if (tid == 0) { status[0] = EM_INVALID; status[1] = 0; status[2] = 0; status[3] = 0; }
 		return;
 	}
-	if (sh_i[5])
+	if (sh_i[2])
 	{
 		// a bootstrap count that does not fit the byte table: the host re-estimates this candidate
 		if (tid == 0) { status[0] = EM_AMBIGUOUS; status[1] = 0; status[2] = -1; status[3] = 0; }
