@@ -13,6 +13,7 @@ oracle/_ref); the GPU tests only read the committed outputs.
       fixture is the accepted-SNP PREFIX reached inside BUDGET_S.
   python tools/make_golden_ref.py merge c2 OUT1.npz OUT2.npz ...  -> tests/golden/c2_ref.npz
   python tools/make_golden_ref.py merge c4 OUT.npz               -> tests/golden/c4_ref_prefix.npz
+  python tools/make_golden_ref.py extend c2 OUT7.npz ...         -> adds classifiers to the committed c2_ref.npz
 
 Targets: `base` is the parity oracle; `avx2` is bit-identical to it (checked again
 by merge: classifiers present under both targets must be equal); `max` only for timing.
@@ -102,11 +103,20 @@ def worker(cfg, k, target, out, budget):
         cfg, k, target, "finished" if rc == 0 else "interrupted", dt, len(trace), [t[1] for t in trace]), flush=True)
 
 
-def merge(cfg, paths):
+def merge(cfg, paths, extend=False):
     parts = [np.load(p) for p in paths]
     n_samp, n_snp, n_hla, cseed, mtry, tseed = CONFIGS[cfg]
     out = dict(n_samp=np.int64(n_samp), n_snp=np.int64(n_snp), n_hla_drawn=np.int64(n_hla), cohort_seed=np.int64(cseed),
                mtry=np.int64(mtry), train_seed=np.int64(tseed))
+    old_ks = []
+    if extend:
+        # keep the classifiers of the committed fixture, add the new parts
+        name = "c2_ref.npz" if cfg == "c2" else "c4_ref_prefix.npz"
+        old = np.load(os.path.join(ROOT, "tests", "golden", name))
+        old_ks = [int(k) for k in old["ks"]]
+        for key in old.files:
+            if key.startswith("c") and key.split("_")[0][1:].isdigit():
+                out[key] = old[key]
     by_k = {}
     for p in parts:
         if str(p["target"]) == "max":
@@ -128,7 +138,7 @@ def merge(cfg, paths):
         for key in a.files:
             if key not in ("config", "k", "cpu"):
                 out[pre + key] = a[key]
-    out["ks"] = np.array(sorted(by_k), dtype=np.int64)
+    out["ks"] = np.array(sorted(set(by_k) | set(old_ks)), dtype=np.int64)
     name = "c2_ref.npz" if cfg == "c2" else "c4_ref_prefix.npz"
     path = os.path.join(ROOT, "tests", "golden", name)
     np.savez_compressed(path, **out)
@@ -138,5 +148,7 @@ def merge(cfg, paths):
 if __name__ == "__main__":
     if sys.argv[1] == "worker":
         worker(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5], float(sys.argv[6]) if len(sys.argv) > 6 else 0.0)
+    elif sys.argv[1] == "extend":
+        merge(sys.argv[2], sys.argv[3:], extend=True)
     else:
         merge(sys.argv[2], sys.argv[3:])
