@@ -973,7 +973,7 @@ __device__ __forceinline__ void emc_stream(const uint16_t *list, int cnt, const 
 			// all batches but the last. The ring read of the batch after next and the gathers of the next
 			// batch go first: the asm statements below are memory barriers for the compiler, and loads
 			// placed after them would wait behind the adds
-#pragma unroll 1
+#pragma unroll 2
 			for (int b = 0; b + 1 < nb; b++)
 			{
 				const int4 q4n = lds_i32x4(ring_s + (uint32_t)slot_n * 512u);      // (landed: see the wait below)
