@@ -928,7 +928,7 @@ __device__ __forceinline__ void emc_combine4(const int4 &q4, const Term &term, c
 }
 
 /// The groups of one step dealt to this warp (list, longest first), as ONE stream of record batches
-/// through the warp's ring (sched: where every batch of the stream lies): batch k goes to ring slot k mod 8 and is requested seven
+/// through the warp's ring (sched: where every batch of the stream lies): batch k goes to ring slot k mod 8 and is requested nine
 /// batches before it is consumed, whatever groups the batches in between belong to -- a group of two
 /// batches does not wait for L2 any more than the middle of a long one. Inside a group three stages
 /// are in flight: the records of batch j + 2 are read from the ring and the terms of batch j + 1
@@ -948,11 +948,15 @@ __device__ __forceinline__ void emc_stream(const uint16_t *list, int cnt, const 
 		ki++;
 		cp_async_commit();                  // (an empty group when the stream has ended: the count stays uniform)
 	};
+	// Three batches live in registers (terms of batch j, records of batches j + 1 and j + 2), so the
+	// 8-slot ring can run NINE batches ahead: batch j + 9 goes into the slot of batch j + 1, which has
+	// been read. Step j waits until at most 6 groups are pending = batch j + 3 has landed.
 #pragma unroll 1
-	for (int b = 0; b < EMC_RING_B - 1; b++) issue();
-	cp_async_wait<EMC_RING_B - 4>();       // stream batches 0, 1 and 2 have landed
+	for (int b = 0; b < EMC_RING_B; b++) issue();
+	cp_async_wait<EMC_RING_B - 3>();       // stream batches 0, 1 and 2 have landed
 	int4 q4 = lds_i32x4(ring_s);           // records of the next batch to be turned into terms
 	int slot_n = 1;                        // ring slot of the stream batch after that one
+	issue();                               // batch 8 into the slot batch 0 was just read from
 #pragma unroll 1
 	for (int idx = 0; idx < cnt; idx++)
 	{
@@ -981,7 +985,7 @@ __device__ __forceinline__ void emc_stream(const uint16_t *list, int cnt, const 
 				double ga[4], gb[4];
 				emc_gather4(q4, term, ga, gb);
 				issue();
-				cp_async_wait<EMC_RING_B - 4>();               // the stream batch three ahead has landed
+				cp_async_wait<EMC_RING_B - 2>();               // the stream batch three ahead has landed
 				double rn[4];
 				emc_combine4(q4, term, ga, gb, rn);
 #pragma unroll
@@ -990,7 +994,7 @@ __device__ __forceinline__ void emc_stream(const uint16_t *list, int cnt, const 
 			}
 			// the last batch: q4 already holds the first records of the next group
 			issue();
-			cp_async_wait<EMC_RING_B - 4>();
+			cp_async_wait<EMC_RING_B - 2>();
 #pragma unroll
 			for (int q = 0; q < 4; q++) acc = __dadd_rn(acc, rr[q]);
 		}
