@@ -50,7 +50,9 @@ def _stub_detail(steps=20, warmup=5, lanes=24, world=1):
             "alone": {"frac": 0.47, "in_bag_frac": 0.6, "note": long},
             "screening": {"executed_fraction": 0.135, "effective_frac_reference_formulation": 3.1, "note": long},
             "em": {"frac": 0.4, "achieved": 1.0, "peak": 2.5, "unit": "Gadd/s", "sm_time_share": 0.28, "note": long},
-            "sm_time": {"scoring_share": 0.5, "em_share": 0.3, "other_share": 0.2, "busy": 0.8}}
+            "sm_time": {"scoring_share": 0.5, "em_share": 0.3, "other_share": 0.2, "busy": 0.8},
+            "frac_launch_events": 0.23, "frac_of_held_sm_time_in_bag": 0.66,
+            "launch_events": {"frac": 0.23, "avg_launch_ms": 1.0, "note": long}}
     return {
         "metric": "classifiers/min trained (HLA-A 5k x 500 SNP)", "value": 861.123, "unit": "classifiers/min",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1672.5, "higher_is_better": True,
@@ -66,13 +68,13 @@ def _stub_detail(steps=20, warmup=5, lanes=24, world=1):
                          "parity_prefix_ok": True, "parity_prefix_snps": 13, "per_process": [{"a": 1}] * 16},
         "predict": {"value": 137000.0, "unit": "samples/s", "e2e": {"value": 90000.0}, "roofline": {"frac": 0.73},
                     "sharded_by_classifier_value": 1e5, "allreduce_ms": 3.0, "allreduce_bytes": 1316800000},
-        "bed_decode": {"ms": 0.227, "note": long},
+        "bed_decode": {"ms": 0.227, "note": long}, "large_list": {"frac": 0.58, "note": long},
         "train_detail": {"classifiers": {"count": (steps + warmup) * lanes}, "note": long},
         "device": {"name": "NVIDIA B200", "sm_count": 148, "clock_khz": 1965000},
     }
 
 
-@pytest.mark.parametrize("steps,warmup,lanes,world", [(20, 5, 24, 1), (20, 5, 24, 8), (200, 50, 64, 8)])
+@pytest.mark.parametrize("steps,warmup,lanes,world", [(20, 5, 40, 1), (20, 5, 40, 8), (200, 50, 64, 8)])
 def test_b200_line_is_bounded_and_complete(steps, warmup, lanes, world):
     """The driver parses ONE stdout line; round 1's grew with steps x lanes and was cut. The line is
     < 4 KB whatever the step count and carries the contract's keys as flat scalars."""
@@ -87,7 +89,8 @@ def test_b200_line_is_bounded_and_complete(steps, warmup, lanes, world):
         assert key in back, key
     assert back["value"] > 0 and back["steps"] == steps and back["warmup"] == warmup
     assert back["config"]["lanes"] == lanes and "workload" in back["config"]
-    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "timing", "frac_launch_events", "alone_frac",
+                "em_frac", "sm_time_busy", "global_operand_frac", "predict_frac"):
         assert key in back["roofline"], key
     for key in ("value", "unit", "cores", "kind", "sample"):
         assert key in back["cpu_baseline"], key
