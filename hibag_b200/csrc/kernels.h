@@ -223,6 +223,7 @@ struct ScreenArgs
 	int *entries2;                // [n_lists][n_cells][p_stride]
 	double K2;                    // bound factor of the second level
 	double tf[3];                 // T'[0], T'[1], T'[2]
+	int u_smem;                   // 1: the need / reduction kernels keep a position's per-allele sums in shared memory
 };
 struct ScreenList { const void *hap; const CellTask *cells; const int8_t *cand_col; int n_hap, cand_bit; };
 struct ScreenLists { ScreenList l[MAX_BATCH_LISTS]; };

@@ -479,6 +479,11 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 	a.n_snp = n_snp_; a.geno_stride = g.stride; a.n_pos = n_pos; a.n_hla = n_hla_; a.n_lists = count;
 	a.p_stride = p_stride_;
 	a.K = screen_bound_factor();
+	{
+		// (read per call: an experiment switch) a tile of per-allele sums fits shared memory up to ~150 alleles
+		const char *e = getenv("HIBAG_B200_SCREEN_USMEM");
+		a.u_smem = ((e ? atoi(e) != 0 : true) && (size_t)n_hla_ * 128 * sizeof(double) <= 120 * 1024) ? 1 : 0;
+	}
 	a.acct = device_sm_acct();
 	gb.acct = a.acct;
 	gb.acct_cls = kind ? SM_ACCT_GATHER_IB : SM_ACCT_GATHER_OOB;

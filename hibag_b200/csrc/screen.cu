@@ -406,6 +406,15 @@ screen_need_kernel(const ScreenArgs a)
 	int *ent = a.entries + (size_t)l * n_cells * a.p_stride;
 	unsigned int *wm = sh_mask[wid];
 	int *wb = sh_base[wid];
+	// the position's per-allele sums: n loads into shared memory instead of n (n + 1) / 2 from L1/L2
+	extern __shared__ double sU[];
+	const bool us = a.u_smem != 0;
+	if (us)
+	{
+		for (int al = 0; al < n; al++) sU[al * 128 + threadIdx.x] = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
+		__syncthreads();
+	}
+	auto Uat = [&](int al) -> double { return us ? sU[al * 128 + threadIdx.x] : U[(size_t)al * a.p_stride + pos]; };
 	int true_idx = -1;
 	double thr = 0.0;
 	if (ok)
@@ -439,14 +448,14 @@ screen_need_kernel(const ScreenArgs a)
 	int idx = 0, t0 = 0;
 	for (int al = 0; al < n; al++)
 	{
-		const double ua = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
+		const double ua = ok ? Uat(al) : 0.0;
 		for (int bl = al; bl < n; bl += 8)
 		{
 			const int nb = min(8, n - bl);
 			if (idx - t0 + nb > NEED_TILE) { flush(t0, idx - t0); t0 = idx; }
 			double ub[8];
 #pragma unroll
-			for (int q = 0; q < 8; q++) ub[q] = (ok && q < nb) ? U[(size_t)(bl + q) * a.p_stride + pos] : 0.0;
+			for (int q = 0; q < 8; q++) ub[q] = (ok && q < nb) ? Uat(bl + q) : 0.0;
 #pragma unroll
 			for (int q = 0; q < 8; q++)
 			{
@@ -468,7 +477,10 @@ void launch_screen_need(const ScreenArgs &a, cudaStream_t st)
 {
 	if (a.n_pos <= 0 || a.n_lists <= 0) return;
 	dim3 grid((a.n_pos + 127) / 128, a.n_lists);
-	screen_need_kernel<<<grid, 128, 0, st>>>(a);
+	const size_t smem = a.u_smem ? sizeof(double) * 128 * (size_t)a.n_hla : 0;
+	if (smem > 16 * 1024)
+		CUDA_CHECK(cudaFuncSetAttribute(screen_need_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+	screen_need_kernel<<<grid, 128, smem, st>>>(a);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -576,9 +588,18 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 	const int n = a.n_hla;
 	const int n_cells = n * (n + 1) / 2;
 	int cnt = 0;
+	extern __shared__ double sU[];
+	const bool us = a.u_smem != 0;
+	if (us)
+	{
+		const double *Ug = a.U + (size_t)l * n * a.p_stride + pos;
+		for (int al = 0; al < n; al++) sU[al * 64 + threadIdx.x] = (pos < a.n_pos) ? Ug[(size_t)al * a.p_stride] : 0.0;
+		__syncthreads();
+	}
 	if (pos < a.n_pos)
 	{
 		const double *U = a.U + (size_t)l * n * a.p_stride + pos;
+		auto Uat = [&](int al) -> double { return us ? sU[al * 64 + threadIdx.x] : U[(size_t)al * a.p_stride]; };
 		const double *P = a.P + (size_t)l * n_cells * a.p_stride + pos;
 		const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
 		int t1 = __ldg(a.a1 + samp), t2 = __ldg(a.a2 + samp);
@@ -591,7 +612,7 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 		int idx = 0;
 		for (int al = 0; al < n; al++)
 		{
-			const double ua = U[(size_t)al * a.p_stride];
+			const double ua = Uat(al);
 			for (int bl = al; bl < n; bl += 8, idx += 8)       // 8 cells per step: the loads overlap
 			{
 				const int nb = min(8, n - bl);
@@ -600,7 +621,7 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 #pragma unroll
 				for (int q = 0; q < 8; q++)
 				{
-					const double ub = (q < nb) ? U[(size_t)(bl + q) * a.p_stride] : 0.0;
+					const double ub = (q < nb) ? Uat(bl + q) : 0.0;
 					const double bd = screen_bound(ua, ub, a.K);
 					nd[q] = (q < nb) && ((idx + q) == true_idx || (bd >= thr && bd > 0.0));
 				}
@@ -626,7 +647,10 @@ void launch_reduce_oob_screened(const ScreenArgs &a, int *out_count, cudaStream_
 {
 	if (a.n_pos <= 0 || a.n_lists <= 0) return;
 	dim3 grid((a.n_pos + 63) / 64, a.n_lists);
-	reduce_oob_screened_kernel<<<grid, 64, 0, st>>>(a, out_count);
+	const size_t smem = a.u_smem ? sizeof(double) * 64 * (size_t)a.n_hla : 0;
+	if (smem > 40 * 1024)
+		CUDA_CHECK(cudaFuncSetAttribute(reduce_oob_screened_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+	reduce_oob_screened_kernel<<<grid, 64, smem, st>>>(a, out_count);
 	CUDA_CHECK(cudaGetLastError());
 }
 
@@ -691,6 +715,13 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 	double *P = a.P + (size_t)l * n_cells * a.p_stride;
 	int samp = 0, true_idx = 0;
 	double x_true = 0.0, thr = 0.0, lo = 0.0, hi = 0.0;
+	extern __shared__ double sU[];
+	const bool us = a.u_smem != 0;
+	if (us)
+	{
+		for (int al = 0; al < n; al++) sU[al * 64 + threadIdx.x] = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
+		__syncthreads();
+	}
 	if (ok)
 	{
 		samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
@@ -701,10 +732,11 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 		// cell: addition is monotone, so lo <= (the full chain) <= hi, and lo == hi certifies it
 		const double *Up = U + pos;
 		const double *Pp = P + pos;
+		auto Uat = [&](int al) -> double { return us ? sU[al * 64 + threadIdx.x] : Up[(size_t)al * a.p_stride]; };
 		int idx = 0;
 		for (int al = 0; al < n; al++)
 		{
-			const double ua = Up[(size_t)al * a.p_stride];
+			const double ua = Uat(al);
 			for (int bl = al; bl < n; bl += 8, idx += 8)           // 8 cells per step: the loads overlap
 			{
 				const int nb = min(8, n - bl);
@@ -713,7 +745,7 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 #pragma unroll
 				for (int q = 0; q < 8; q++)
 				{
-					const double ub = (q < nb) ? Up[(size_t)(bl + q) * a.p_stride] : 0.0;
+					const double ub = (q < nb) ? Uat(bl + q) : 0.0;
 					bd[q] = screen_bound(ua, ub, a.K);
 					nd[q] = (q < nb) && ((idx + q) == true_idx || (bd[q] >= thr && bd[q] > 0.0));
 				}
@@ -804,7 +836,10 @@ void launch_reduce_ib_screened(const ScreenArgs &a, const ScreenLists &ls, doubl
 {
 	if (a.n_pos <= 0 || a.n_lists <= 0) return;
 	dim3 grid((a.n_pos + 63) / 64, a.n_lists);
-	reduce_ib_screened_kernel<<<grid, 64, 0, st>>>(a, ls, out_ratio, out_stride);
+	const size_t smem = a.u_smem ? sizeof(double) * 64 * (size_t)a.n_hla : 0;
+	if (smem > 40 * 1024)
+		CUDA_CHECK(cudaFuncSetAttribute(reduce_ib_screened_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+	reduce_ib_screened_kernel<<<grid, 64, smem, st>>>(a, ls, out_ratio, out_stride);
 	CUDA_CHECK(cudaGetLastError());
 }
 
