@@ -82,6 +82,7 @@ EXPORTS = [
     "hibag_b200_host_unif_rand", "hibag_b200_host_build_tasks", "hibag_b200_host_screen_constants",
     "hibag_b200_bed_decode", "hibag_b200_bed_decode_device",
     "hibag_b200_get_procs_ex", "hibag_b200_haplomatch", "hibag_b200_free",
+    "hibag_b200_host_alloc", "hibag_b200_host_free",
 ]
 
 _lib = None
@@ -145,6 +146,9 @@ def lib():
     L.hibag_b200_bed_decode_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                                C.c_void_p, C.c_void_p]
     L.hibag_b200_pipe_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.hibag_b200_host_alloc.restype = C.c_void_p
+    L.hibag_b200_host_alloc.argtypes = [C.c_size_t]
+    L.hibag_b200_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -181,6 +185,20 @@ def trim_cache():
     """release the library's cached device / pinned blocks; returns the bytes given back"""
     lib().hibag_b200_trim_cache.restype = C.c_size_t
     return int(lib().hibag_b200_trim_cache())
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over a page-locked block of the library's cache (hibag_b200_host_alloc); the
+    block goes back to the cache when the array (and every view of it) is garbage-collected"""
+    import weakref
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = lib().hibag_b200_host_alloc(max(n, 1))
+    if not p:
+        raise RuntimeError(lib().hibag_b200_last_error().decode())
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    weakref.finalize(buf, lib().hibag_b200_host_free, C.c_void_p(p))
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
 
 
 def device_info():
@@ -356,10 +374,12 @@ class HLAModel:
         g = np.ascontiguousarray(geno, dtype=np.int8)
         assert g.ndim == 2 and g.shape[1] == self.n_snp
         n = g.shape[0]
+        # large results land in page-locked memory (D2H at PCIe rate behind the next tile's scoring)
+        new = pinned_empty if n * self.n_cells * 8 >= (8 << 20) else np.empty
         h1 = np.zeros(n, dtype=np.int32); h2 = np.zeros(n, dtype=np.int32)
         mp = np.zeros(n); mt = np.zeros(n)
-        ds = np.zeros((n, self.n_hla)) if want_dosage else None
-        pr = np.zeros((n, self.n_cells)) if want_prob else None
+        ds = new((n, self.n_hla), np.float64) if want_dosage else None
+        pr = new((n, self.n_cells), np.float64) if want_prob else None
         out = PredictOut(_p(h1).value, _p(h2).value, _p(mp).value, _p(mt).value,
                          None if ds is None else _p(ds).value, None if pr is None else _p(pr).value)
         _chk(lib().hibag_b200_model_predict(self._h, _p(g), n, C.byref(out)))

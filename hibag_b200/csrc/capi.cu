@@ -5,6 +5,8 @@
 #include <string>
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "em.h"
@@ -214,6 +216,38 @@ int hibag_b200_sm_time(uint64_t *out, int reset)
 size_t hibag_b200_trim_cache(void)
 {
 	try { return hb::pool_trim(); } catch (...) { return 0; }
+}
+
+namespace {
+std::mutex g_host_mu;
+std::map<void *, size_t> g_host_blocks;          // blocks handed out by hibag_b200_host_alloc
+}
+
+void *hibag_b200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	const int rc = guarded([&]() {
+		hb::current_device();
+		size_t got = 0;
+		p = hb::pool_alloc(true, bytes ? bytes : 1, &got);
+		std::lock_guard<std::mutex> lk(g_host_mu);
+		g_host_blocks[p] = got;
+	});
+	return rc == 0 ? p : nullptr;
+}
+
+void hibag_b200_host_free(void *p)
+{
+	if (!p) return;
+	size_t bytes = 0;
+	{
+		std::lock_guard<std::mutex> lk(g_host_mu);
+		auto it = g_host_blocks.find(p);
+		if (it == g_host_blocks.end()) return;      // not ours: ignore
+		bytes = it->second;
+		g_host_blocks.erase(it);
+	}
+	try { hb::pool_free(true, p, bytes); } catch (...) {}
 }
 
 int hibag_b200_model_classifier_samp_num_len(const hibag_b200_model *m, int k)

@@ -855,6 +855,17 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(int iters, uint32_t seed
 				d1 += lds_f64(lane_addr + ((x1 + u) & 63u) * 256u);
 				d2 += lds_f64(lane_addr + ((x2 + u) & 63u) * 256u);
 				d3 += lds_f64(lane_addr + ((x3 + u) & 63u) * 256u);
+			} else if (WHICH == 8 || WHICH == 9 || WHICH == 10)
+			{
+				// LDS.64 from a COMPACT table (8-byte stride, no lane replication), data-dependent
+				// row: 8 -- rows spread over a window of 8 (distinct banks); 9 -- all lanes one row;
+				// 10 -- rows spread over 32 (row d and d + 16 share their banks)
+				const uint32_t msk = (WHICH == 8) ? 7u : (WHICH == 9) ? 0u : 31u;
+				const uint32_t base = smem_u32(tbl);
+				d0 += lds_f64(base + (((x0 & msk) + u) & 63u) * 8u);
+				d1 += lds_f64(base + (((x1 & msk) + u) & 63u) * 8u);
+				d2 += lds_f64(base + (((x2 & msk) + u) & 63u) * 8u);
+				d3 += lds_f64(base + (((x3 & msk) + u) & 63u) * 8u);
 			} else if (WHICH == 6)   // one dependent DADD chain per thread (latency)
 			{
 				d0 = __dadd_rn(d0, m0);
@@ -878,9 +889,10 @@ double run_pipe_peak(int which, int sm_count, double *out_ms)
 	CUDA_CHECK(cudaMalloc(&sink, 4));
 	const int iters = 4096;
 	// 6, 7: dependent-chain latency -- one warp on one SM
-	const int grid = (which >= 6) ? 1 : sm_count * 8, block = (which >= 6) ? 32 : 256;
+	const bool lat = (which == 6 || which == 7);
+	const int grid = lat ? 1 : sm_count * 8, block = lat ? 32 : 256;
 	// lane-operations of the measured kind per thread per inner iteration (16x unrolled)
-	static const int ops_per_u[8] = { 8, 8, 8, 8, 4, 8, 1, 1 };
+	static const int ops_per_u[11] = { 8, 8, 8, 8, 4, 8, 1, 1, 4, 4, 4 };
 	cudaEvent_t e0, e1;
 	CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
 	float best = 1e30f;
@@ -894,6 +906,9 @@ double run_pipe_peak(int which, int sm_count, double *out_ms)
 		case 2: pipe_peak_kernel<2><<<grid, block>>>(iters, 1u + rep, sink); break;
 		case 3: pipe_peak_kernel<3><<<grid, block>>>(iters, 1u + rep, sink); break;
 		case 4: pipe_peak_kernel<4><<<grid, block>>>(iters, 1u + rep, sink); break;
+		case 8: pipe_peak_kernel<8><<<grid, block>>>(iters, 1u + rep, sink); break;
+		case 9: pipe_peak_kernel<9><<<grid, block>>>(iters, 1u + rep, sink); break;
+		case 10: pipe_peak_kernel<10><<<grid, block>>>(iters, 1u + rep, sink); break;
 		default: pipe_peak_kernel<5><<<grid, block>>>(iters, 1u + rep, sink); break;
 		}
 		CUDA_CHECK(cudaEventRecord(e1));
@@ -904,7 +919,7 @@ double run_pipe_peak(int which, int sm_count, double *out_ms)
 	}
 	CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
 	CUDA_CHECK(cudaFree(sink));
-	const int w = (which < 0 || which > 7) ? 5 : which;
+	const int w = (which < 0 || which > 10) ? 5 : which;
 	const double ops = (double)grid * block * (double)iters * 16.0 * ops_per_u[w];
 	if (out_ms) *out_ms = best;
 	return ops / (best * 1e-3);

@@ -280,6 +280,14 @@ int hibag_b200_bed_decode_device(const uint8_t *payload_dev, int mode, int n_sam
  * needs the memory; returns the bytes released. */
 size_t hibag_b200_trim_cache(void);
 
+/* Page-locked host buffers from that cache, for the host-array entry points: results copied into
+ * them leave the GPU at PCIe rate while the next tile is scored (a pageable destination is staged
+ * by the driver and page-faults on first touch: 1 GB of posterior rows per 200,000 samples).
+ * The reference has no counterpart (its hlaPredict fills an R matrix column by column,
+ * src/HIBAG.cpp:680-741). NULL on failure (hibag_b200_last_error). */
+void *hibag_b200_host_alloc(size_t bytes);
+void hibag_b200_host_free(void *p);
+
 /* SM-time accounting of the current device: out[16] = per kernel class the sum over its CTAs of
  * (SM cycles the CTA was resident) x 1024 / (CTAs of that launch that fit one SM), i.e. 1/1024
  * SM-cycles held. Classes: 0 out-of-bag gather, 1 in-bag gather, 2 EM, 3 screen bounds, 4 need lists,

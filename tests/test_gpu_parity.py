@@ -629,29 +629,62 @@ def test_headline_config_classifiers_equal_the_reference(gpu):
     assert got == ref_trace
 
 
+def test_reference_host_with_gpu_hooks_at_headline_config(gpu, ref):
+    """The drop-in itself at configs[1]: the reference's own BuildClassifiers (compiled, unmodified:
+    CVariableSelection::Search src/LibHLA.cpp:1981-2122 with its sequential CAlg_EM on the host)
+    calling OUR ten hooks per candidate SNP on the 5,000 x 500 cohort must build the classifier the
+    reference's CPU path built (tests/golden/c2_ref.npz) bit for bit. Prints the seconds per
+    classifier of that pairing (the CPU path alone: 590-610 s, profiles/ref_full_classifier.json)."""
+    import time
+    import bench
+    gd = helpers.load_golden("c2_ref.npz")
+    coh = bench.make_cohort()
+    k = [int(k) for k in gd["ks"] if bool(gd["c%d_finished" % k])][0]
+    m = ref.new_model()
+    m.init_training(coh.geno, coh.h1, coh.h2, coh.n_hla)
+    ref.set_gpu_procs(gpu.get_procs())
+    try:
+        t0 = time.time()
+        m.build(1, bench.MTRY, prune=True, reseed_base=bench.TRAIN_SEED, first_index=k)
+        dt = time.time() - t0
+    finally:
+        ref.set_gpu_procs(None)
+    want = {key: gd["c%d_%s" % (k, key)] for key in ("snpidx", "samp_num", "freq", "hla", "packed")}
+    want["oob_acc"] = float(gd["c%d_oob_acc" % k])
+    assert helpers.classifier_diff(m.classifier(0), want) == ""
+    print("\nreference host + B200 hooks, configs[1], classifier %d: %.2f s (reference CPU path: %.0f s)"
+          % (k, dt, float(gd["c%d_seconds" % k])))
+
+
 def test_drb1_scale_prefix_equals_the_reference(gpu):
     """configs[3]: HLA-DRB1-shaped 10,000 samples x 800 SNPs, 86 alleles (3,741 cells), haplotype lists
-    in the thousands. A full reference classifier is ~10 CPU-hours, so the fixture
-    (tests/golden/c4_ref_prefix.npz, tools/make_golden_ref.py) is the PREFIX of accepted SNPs the
-    compiled reference reached in its budget, with the loss (6 digits), out-of-bag accuracy and
-    haplotype count it printed at each -- every one of them must equal the B200 path's trace."""
+    up to 1,800. After its last accepted SNP the reference scores every remaining SNP at full list
+    size (src/LibHLA.cpp:2113-2119): ~80 CPU-minutes to the last accepted SNP, many hours to the end.
+    The fixture (tests/golden/c4_ref_prefix.npz, tools/make_golden_ref.py) is therefore the trace of
+    accepted SNPs the compiled reference printed -- SNP, loss (6 digits), out-of-bag accuracy and
+    haplotype count at each -- and every line must equal the B200 path's trace; a classifier the
+    reference did finish is compared whole, bit for bit."""
     import os
     if not os.path.exists(os.path.join(helpers.GOLDEN, "c4_ref_prefix.npz")):
         pytest.skip("tests/golden/c4_ref_prefix.npz not generated")
     from hibag_b200 import synth
     gd = helpers.load_golden("c4_ref_prefix.npz")
-    k = int(gd["ks"][0])
     coh = synth.make_cohort(int(gd["n_samp"]), int(gd["n_snp"]), int(gd["n_hla_drawn"]), seed=int(gd["cohort_seed"]))
-    m = gpu.HLAModel(coh.n_snp, coh.n_hla)
-    m.set_training(np.ascontiguousarray(coh.geno, dtype=np.int8), coh.h1, coh.h2)
-    _, text = _capture_fd2(lambda: m.train(1, int(gd["mtry"]), prune=True, seed=int(gd["train_seed"]),
-                                           per_classifier_seed=True, first_index=k, verbose=2))
-    got = _trace_lines(text)
-    ref_trace = list(zip(gd["c%d_trace_snp" % k].tolist(), [str(x) for x in gd["c%d_trace_loss" % k]],
-                         [str(x) for x in gd["c%d_trace_acc" % k]], gd["c%d_trace_n_haplo" % k].tolist()))
-    assert len(ref_trace) >= 4
-    assert got[:len(ref_trace)] == ref_trace
-    assert m.classifier(0)["snpidx"][:len(ref_trace)].tolist() == [t[0] for t in ref_trace]
+    for k in [int(k) for k in gd["ks"]]:
+        m = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        m.set_training(np.ascontiguousarray(coh.geno, dtype=np.int8), coh.h1, coh.h2)
+        _, text = _capture_fd2(lambda: m.train(1, int(gd["mtry"]), prune=True, seed=int(gd["train_seed"]),
+                                               per_classifier_seed=True, first_index=k, verbose=2))
+        got = _trace_lines(text)
+        ref_trace = list(zip(gd["c%d_trace_snp" % k].tolist(), [str(x) for x in gd["c%d_trace_loss" % k]],
+                             [str(x) for x in gd["c%d_trace_acc" % k]], gd["c%d_trace_n_haplo" % k].tolist()))
+        assert len(ref_trace) >= 4
+        assert got[:len(ref_trace)] == ref_trace
+        assert m.classifier(0)["snpidx"][:len(ref_trace)].tolist() == [t[0] for t in ref_trace]
+        if bool(gd["c%d_finished" % k]):
+            want = {key: gd["c%d_%s" % (k, key)] for key in ("snpidx", "samp_num", "freq", "hla", "packed")}
+            want["oob_acc"] = float(gd["c%d_oob_acc" % k])
+            assert helpers.classifier_diff(m.classifier(0), want) == "", k
 
 
 def test_single_stream_seed_continues_across_train_calls(gpu):

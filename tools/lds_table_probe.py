@@ -1,0 +1,7 @@
+import sys; sys.path.insert(0, '/root/repo')
+from hibag_b200 import api
+api.set_device(0)
+clk = api.device_info()["clock_khz"]*1e3; sm = api.device_info()["sm_count"]
+for w, name in ((0,'popc32'),(4,'lds64 lane-replicated'),(8,'lds64 compact window8'),(9,'lds64 compact same row'),(10,'lds64 compact window32')):
+    ops, ms = api.pipe_peak(w)
+    print("%-28s %.3e /s  %.2f /clk/SM  %.3f ms" % (name, ops, ops/clk/sm, ms))

@@ -11,6 +11,10 @@ oracle/_ref); the GPU tests only read the committed outputs.
       the same on config 4 = tools/c4_probe.py's cohort (10,000 x 800, 100 alleles drawn,
       cohort seed 2, mtry 29, train seed 7 + K); a full classifier is ~10 CPU-hours, so the
       fixture is the accepted-SNP PREFIX reached inside BUDGET_S.
+  python tools/make_golden_ref.py fromlog c4 K TARGET TRACE.log OUT.npz SECONDS
+      the same prefix from the captured stderr of a worker that is still running: after its last
+      accepted SNP the reference scores every remaining SNP (LibHLA.cpp:2113-2119), hours at this
+      scale, and reaches CheckInterrupt only at an accepted one (:2112)
   python tools/make_golden_ref.py merge c2 OUT1.npz OUT2.npz ...  -> tests/golden/c2_ref.npz
   python tools/make_golden_ref.py merge c4 OUT.npz               -> tests/golden/c4_ref_prefix.npz
   python tools/make_golden_ref.py extend c2 OUT7.npz ...         -> adds classifiers to the committed c2_ref.npz
@@ -103,6 +107,18 @@ def worker(cfg, k, target, out, budget):
         cfg, k, target, "finished" if rc == 0 else "interrupted", dt, len(trace), [t[1] for t in trace]), flush=True)
 
 
+def fromlog(cfg, k, target, log, out, seconds):
+    trace = parse_trace(open(log).read())
+    res = dict(config=np.array(cfg), k=np.int64(k), target=np.array(target), cpu=np.array("build container"),
+               seconds=np.float64(seconds), finished=np.bool_(False),
+               trace_snp=np.array([t[1] for t in trace], dtype=np.int32),
+               trace_loss=np.array([t[2] for t in trace]), trace_acc=np.array([t[3] for t in trace]),
+               trace_n_haplo=np.array([t[4] for t in trace], dtype=np.int32),
+               trace_seconds=np.zeros(len(trace)))
+    np.savez_compressed(out, **res)
+    print("%s k=%d target=%s: %d accepted SNPs from %s" % (cfg, k, target, len(trace), log))
+
+
 def merge(cfg, paths, extend=False):
     parts = [np.load(p) for p in paths]
     n_samp, n_snp, n_hla, cseed, mtry, tseed = CONFIGS[cfg]
@@ -148,6 +164,8 @@ def merge(cfg, paths, extend=False):
 if __name__ == "__main__":
     if sys.argv[1] == "worker":
         worker(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5], float(sys.argv[6]) if len(sys.argv) > 6 else 0.0)
+    elif sys.argv[1] == "fromlog":
+        fromlog(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5], sys.argv[6], float(sys.argv[7]))
     elif sys.argv[1] == "extend":
         merge(sys.argv[2], sys.argv[3:], extend=True)
     else:
