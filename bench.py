@@ -384,7 +384,7 @@ def compact_line(detail):
         e["predict_value"] = _short(pred.get("value"))
         e["predict_e2e_value"] = _short((pred.get("e2e") or {}).get("value"))
         e["predict_unit"] = pred.get("unit")
-        for k in ("sharded_by_classifier_value", "allreduce_ms", "allreduce_bytes"):
+        for k in ("distinct_genotype_fraction", "sharded_by_classifier_value", "allreduce_ms", "allreduce_bytes"):
             if pred.get(k) is not None:
                 e["predict_" + k] = _short(pred[k])
     line["e2e"] = e or None
@@ -869,6 +869,10 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
         "e2e": {"value": n_total / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes": int(host.nbytes),
                 "d2h_bytes": int(n * (8 + 16 + 8 * coh.n_hla + 8 * nc)), "api": "HLAModel.predict (host numpy in, page-locked numpy out; 1 warm-up call)"},
         "model": "100 classifiers = the %d classifiers trained above, cycled" % n_src,
+        # each distinct packed genotype of a tile is scored once per classifier (exact: equal inputs,
+        # equal bits); the roofline below counts EXECUTED pair evaluations only
+        "distinct_genotype_fraction": d["positions_scored"] / max(d["positions_total"], 1),
+        "pair_evals_executed": int(d["pair_evals"]), "pair_evals_reference": int(d["pair_evals_nominal"]),
         "calls_equal_between_paths": same,
         "roofline": {"bound": "popc", "kernel": "cell_pass_kernel",
                      "achieved": d["popc32_issued"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12) / 1e9,

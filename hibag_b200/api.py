@@ -62,7 +62,9 @@ class PredictStats(C.Structure):
     _fields_ = [("gpu_kernel_ms", C.c_double), ("cell_kernel_ms", C.c_double),
                 ("pair_evals", C.c_uint64), ("popc32_issued", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("cell_kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("pair_evals_nominal", C.c_uint64), ("positions_scored", C.c_uint64),
+                ("positions_total", C.c_uint64)]
 
 
 # every symbol include/hibag_b200.h declares (tests check the library exports all of them)

@@ -77,7 +77,8 @@ cell_pass_kernel(const __grid_constant__ CellBatch p)
 	__syncthreads();
 
 	const uint32_t tbl_lane = tbl_base + lane * 8;
-	const int n_groups = (p.n_pos + 32 * R - 1) / (32 * R);
+	const int n_pos = p.n_pos_dev ? min(__ldg(p.n_pos_dev), p.n_pos) : p.n_pos;
+	const int n_groups = (n_pos + 32 * R - 1) / (32 * R);
 	const int dmax = p.n_dist - 1;
 	uint32_t phase = 0;
 
@@ -141,7 +142,7 @@ cell_pass_kernel(const __grid_constant__ CellBatch p)
 			for (int r = 0; r < R; r++)
 			{
 				pos[r] = group * (32 * R) + r * 32 + lane;
-				const bool ok = pos[r] < p.n_pos;
+				const bool ok = pos[r] < n_pos;
 				int samp = 0;
 				if (ok) samp = p.samp_list ? __ldg(p.samp_list + pos[r]) : pos[r];
 #pragma unroll
@@ -232,7 +233,7 @@ cell_pass_kernel(const __grid_constant__ CellBatch p)
 
 #pragma unroll
 				for (int r = 0; r < R; r++)
-					if (pos[r] < p.n_pos)
+					if (pos[r] < n_pos)
 						Pl[(size_t)cb.x * p.p_stride + pos[r]] = sum[r];
 			}
 
@@ -309,6 +310,7 @@ int launch_cell_pass(const CellPass &p, int samples_per_lane, int sm_count, cuda
 	b.table = p.table; b.s1 = p.s1; b.s2 = p.s2; b.samp_list = p.samp_list;
 	b.task_counters = p.task_counter; b.p_stride = p.p_stride;
 	b.n_dist = p.n_dist; b.n_snp = p.n_snp; b.geno_stride = p.geno_stride; b.n_pos = p.n_pos;
+	b.n_pos_dev = p.n_pos_dev;
 	b.n_lists = 1; b.max_hap = p.n_hap;
 	b.acct = device_sm_acct();
 	ListDesc &L = b.lists[0];
@@ -658,6 +660,128 @@ void launch_predict_accumulate(const double *P, size_t p_stride, int n_cells, in
 	if (n_tile <= 0) return;
 	predict_accumulate_kernel<<<(n_tile + 63) / 64, 64, 0, st>>>(P, p_stride, n_cells, n_tile,
 		weight, acc, acc_stride, aux);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- exact de-duplication of a tile's packed genotypes (see kernels.h) ---------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256) dedup_insert_kernel(const uint32_t *__restrict__ s1,
+	const uint32_t *__restrict__ s2, int stride, int n_tile, int *table, unsigned mask, int *repof,
+	int *uid, int *rep_list, int *n_unique)
+{
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos >= n_tile) return;
+	uint32_t a[NW], b[NW];
+	uint64_t h = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+	for (int w = 0; w < NW; w++)
+	{
+		a[w] = s1[(size_t)w * stride + pos];
+		b[w] = s2[(size_t)w * stride + pos];
+		h = mix64(h ^ (((uint64_t)a[w] << 32) | b[w]));
+	}
+	unsigned slot = (unsigned)h & mask;
+	for (;;)
+	{
+		int r = *(volatile int *)(table + slot);
+		if (r < 0)
+		{
+			r = atomicCAS(table + slot, -1, pos);
+			if (r < 0)
+			{
+				// this sample represents its genotype: the next dense number is its own
+				const int u = atomicAdd(n_unique, 1);
+				repof[pos] = pos;
+				uid[pos] = u;
+				rep_list[u] = pos;
+				return;
+			}
+		}
+		bool same = true;
+#pragma unroll
+		for (int w = 0; w < NW; w++)
+			same = same && (s1[(size_t)w * stride + r] == a[w]) && (s2[(size_t)w * stride + r] == b[w]);
+		if (same) { repof[pos] = r; return; }
+		slot = (slot + 1) & mask;
+	}
+}
+
+__global__ void dedup_resolve_kernel(const int *__restrict__ repof, int n_tile, int *uid)
+{
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos >= n_tile) return;
+	const int r = repof[pos];
+	if (r != pos) uid[pos] = uid[r];        // uid[r] was written by the insert launch
+}
+
+void launch_dedup_genotypes(const uint32_t *s1, const uint32_t *s2, int stride, int nw, int n_tile,
+	int *table, int table_size, int *repof, int *uid, int *rep_list, int *n_unique, cudaStream_t st)
+{
+	if (n_tile <= 0) return;
+	if (table_size < 2 * n_tile || (table_size & (table_size - 1)))
+		throw std::runtime_error("launch_dedup_genotypes: table size must be a power of two >= 2 * n_tile");
+	CUDA_CHECK(cudaMemsetAsync(table, 0xff, sizeof(int) * (size_t)table_size, st));
+	CUDA_CHECK(cudaMemsetAsync(n_unique, 0, sizeof(int), st));
+	const int grid = (n_tile + 255) / 256;
+	const unsigned mask = (unsigned)table_size - 1u;
+	if (nw == 1) dedup_insert_kernel<1><<<grid, 256, 0, st>>>(s1, s2, stride, n_tile, table, mask, repof, uid, rep_list, n_unique);
+	else if (nw == 2) dedup_insert_kernel<2><<<grid, 256, 0, st>>>(s1, s2, stride, n_tile, table, mask, repof, uid, rep_list, n_unique);
+	else dedup_insert_kernel<4><<<grid, 256, 0, st>>>(s1, s2, stride, n_tile, table, mask, repof, uid, rep_list, n_unique);
+	CUDA_CHECK(cudaGetLastError());
+	dedup_resolve_kernel<<<grid, 256, 0, st>>>(repof, n_tile, uid);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+/// per distinct genotype: PostProb2's sum and its reciprocal (src/LibHLA.cpp:1823-1829)
+__global__ void predict_unique_norm_kernel(const double *__restrict__ P, size_t p_stride, int n_cells,
+	const int *__restrict__ n_unique, int cap, double *norm, size_t u_stride)
+{
+	const int u = blockIdx.x * blockDim.x + threadIdx.x;
+	if (u >= min(__ldg(n_unique), cap)) return;
+	const double s = seqsum_cells(P + u, p_stride, n_cells);
+	norm[u] = __ddiv_rn(1.0, s);
+	norm[u_stride + u] = s;
+}
+
+/// predict_accumulate_kernel reading the cell matrix through uid[]
+__global__ void predict_accumulate_dedup_kernel(const double *__restrict__ P, size_t p_stride,
+	int n_cells, int n_tile, const int *__restrict__ uid, const double *__restrict__ norm,
+	size_t u_stride, const double *__restrict__ weight, double *acc, size_t acc_stride, double *aux)
+{
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos >= n_tile) return;
+	const double w = weight[pos];
+	if (w <= 0) return;
+	const int u = __ldg(uid + pos);
+	const double ff = norm[u], s = norm[u_stride + u];
+	const double *Pu = P + u;
+	for (int c = 0; c < n_cells; c++)
+	{
+		const double pr = __dmul_rn(__ldg(Pu + (size_t)c * p_stride), ff);
+		double *a = acc + (size_t)c * acc_stride + pos;
+		*a = __dadd_rn(*a, __dmul_rn(pr, w));
+	}
+	aux[pos] = __dadd_rn(aux[pos], w);                                        // sum of weights
+	aux[(size_t)n_tile + pos] = __dadd_rn(aux[(size_t)n_tile + pos], __dmul_rn(s, w));
+	aux[2 * (size_t)n_tile + pos] += 1.0;
+}
+
+void launch_predict_accumulate_dedup(const double *P, size_t p_stride, int n_cells, int n_tile,
+	const int *uid, const int *n_unique, double *norm, size_t u_stride, const double *weight,
+	double *acc, size_t acc_stride, double *aux, cudaStream_t st)
+{
+	if (n_tile <= 0) return;
+	predict_unique_norm_kernel<<<(n_tile + 63) / 64, 64, 0, st>>>(P, p_stride, n_cells, n_unique,
+		n_tile, norm, u_stride);
+	CUDA_CHECK(cudaGetLastError());
+	predict_accumulate_dedup_kernel<<<(n_tile + 63) / 64, 64, 0, st>>>(P, p_stride, n_cells, n_tile,
+		uid, norm, u_stride, weight, acc, acc_stride, aux);
 	CUDA_CHECK(cudaGetLastError());
 }
 

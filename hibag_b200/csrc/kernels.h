@@ -45,6 +45,9 @@ struct CellPass
 	// samples to score: sample index = samp_list ? samp_list[pos] : pos, pos in [0, n_pos)
 	const int *samp_list;
 	int n_pos;
+	// optional: the number of positions is read from device memory (<= n_pos, which then only
+	// sizes the launch) -- the distinct genotypes of a prediction tile are counted on the device
+	const int *n_pos_dev;
 	// work list
 	const CellTask *cells;
 	const Chunk *chunks;
@@ -91,6 +94,7 @@ struct CellBatch
 	int n_lists, max_hap;         // max_hap = largest n_hap of the batch (shared-memory sizing)
 	unsigned long long *acct;     // SM-time counters or null
 	int acct_w;
+	const int *n_pos_dev;         // if set: positions = min(*n_pos_dev, n_pos)
 	int flat;                     // bit 0: entry-flat tasks (cell_gather_flat_kernel; task_prefix built with flat = true), bit 1: one list per CTA
 	ListDesc lists[MAX_BATCH_LISTS];
 };
@@ -264,6 +268,24 @@ void launch_pack_classifier(const int8_t *geno_t, size_t n_samp_total, int samp_
 /// acc layout: acc[cell * acc_stride + pos]; aux[0..2][pos] = sum_w, sum_w*match, n_used
 void launch_predict_accumulate(const double *P, size_t p_stride, int n_cells, int n_tile,
 	const double *weight, double *acc, size_t acc_stride, double *aux, cudaStream_t st);
+
+/// Exact de-duplication of a tile's packed genotypes (prediction). A sample's cell sums depend only
+/// on its packed genotype at the classifier's SNPs, and cohorts repeat them (the haplotypes of a
+/// population are few: 22 % of the 200,000 x 100 (sample, classifier) genotypes of configs[2] are
+/// distinct), so each distinct genotype is scored ONCE and its column of the cell matrix is shared.
+/// table: int [table_size] (power of two >= 2 * n_tile) open-addressing set keyed by the full
+/// genotype words; uid[pos] = dense number of the sample's genotype, rep_list[u] = one sample that
+/// carries genotype u, *n_unique = how many there are. Which of the equal samples becomes the
+/// representative is a race and does not matter: equal inputs, equal bits.
+void launch_dedup_genotypes(const uint32_t *s1, const uint32_t *s2, int stride, int nw, int n_tile,
+	int *table, int table_size, int *repof, int *uid, int *rep_list, int *n_unique, cudaStream_t st);
+
+/// predict_accumulate over a de-duplicated cell matrix: P[cell * p_stride + u], u = uid[pos];
+/// norm[2 * u_stride]: scratch for the per-genotype 1/sum and sum. Same operations per sample, in
+/// the same order, as launch_predict_accumulate.
+void launch_predict_accumulate_dedup(const double *P, size_t p_stride, int n_cells, int n_tile,
+	const int *uid, const int *n_unique, double *norm, size_t u_stride, const double *weight,
+	double *acc, size_t acc_stride, double *aux, cudaStream_t st);
 
 /// finalisation of a tile: normalise by sum_w, matching, best guess, max prob, dosage,
 /// posterior rows. Outputs are indexed by global sample (samp_begin + pos); any may be NULL.

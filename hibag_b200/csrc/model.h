@@ -59,6 +59,8 @@ void train_model(hibag_b200_model &m, const hibag_b200_train_opts &opts);
 void predict_device(hibag_b200_model &m, const int8_t *geno_dev, int n_samp,
 	const hibag_b200_predict_out &out_dev, const int32_t *snp_weight_dev_or_null,
 	double *partial_dev_or_null, cudaStream_t st, bool sync);
+/// fold the distinct-genotype counts of finished asynchronous predict calls into m.predict_stats (waits)
+void predict_collect_stats(hibag_b200_model &m);
 void predict_host(hibag_b200_model &m, const int8_t *geno, int n_samp,
 	const hibag_b200_predict_out &out);
 void snp_weights(const hibag_b200_model &m, std::vector<int> &w);

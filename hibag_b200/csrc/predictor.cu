@@ -11,6 +11,7 @@
 // genotype matrix, which crosses PCIe once.
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -36,7 +37,53 @@ struct PredictCache
 	DevBuf<int8_t> geno_t;
 	Event ev_begin, ev_end;
 	std::vector<std::unique_ptr<Event> > cell_ev;   // begin/end pair per cell-kernel launch
+	// exact de-duplication of a tile's genotypes per classifier (kernels.h: launch_dedup_genotypes)
+	DevBuf<int> dd_table, dd_repof, dd_uid, dd_rep;
+	DevBuf<int> dd_count;                           // distinct genotypes per (tile, classifier) of a call
+	DevBuf<double> dd_norm;
+	// executed-work accounting of calls whose counts have not come back yet
+	struct Pending
+	{
+		Event done{false};
+		PinBuf<int> host;
+		std::vector<uint64_t> pairs_per_sample;     // per count entry
+		std::vector<int> nw;
+	};
+	std::vector<std::unique_ptr<Pending> > pending;
 };
+
+/// PREDICT_DEDUP: score each distinct packed genotype of a tile once per classifier (default on;
+/// HIBAG_B200_PREDICT_DEDUP=0 scores every sample as the reference does -- same bits either way)
+static bool predict_dedup_enabled()
+{
+	const char *e = getenv("HIBAG_B200_PREDICT_DEDUP");      // read per call: tests switch it
+	return !(e && e[0] == '0');
+}
+
+/// fold the distinct-genotype counts that have arrived into the model's statistics
+static void collect_pending(hibag_b200_model &m, PredictCache &pc, bool wait)
+{
+	hibag_b200_predict_stats &ps = m.predict_stats;
+	for (size_t k = 0; k < pc.pending.size();)
+	{
+		PredictCache::Pending &pd = *pc.pending[k];
+		if (wait) HB_CUDA(cudaEventSynchronize(pd.done.e));
+		else if (cudaEventQuery(pd.done.e) != cudaSuccess) { cudaGetLastError(); k++; continue; }
+		for (size_t i = 0; i < pd.pairs_per_sample.size(); i++)
+		{
+			const uint64_t n = (uint64_t)pd.host.get()[i];
+			ps.pair_evals += pd.pairs_per_sample[i] * n;
+			ps.popc32_issued += pd.pairs_per_sample[i] * n * (uint64_t)pd.nw[i];
+			ps.positions_scored += n;
+		}
+		pc.pending.erase(pc.pending.begin() + k);
+	}
+}
+
+void predict_collect_stats(hibag_b200_model &m)
+{
+	if (m.pcache) collect_pending(m, *m.pcache, true);
+}
 
 void snp_weights(const hibag_b200_model &m, std::vector<int> &w)
 {
@@ -94,8 +141,11 @@ static PredictCache &get_cache(hibag_b200_model &m)
 
 static int pick_tile(int n_samp, int n_cells)
 {
-	// cell matrix + accumulator of one tile: 2 * 8 * n_cells * tile bytes; keep under ~6 GB
-	long long t = 65536;
+	// cell matrix + accumulator of one tile: 2 * 8 * n_cells * tile bytes; keep under ~6 GB.
+	// Large tiles: the more samples a tile holds, the smaller its share of distinct genotypes.
+	const char *e = getenv("HIBAG_B200_PREDICT_TILE");
+	const long long v = e ? atoll(e) : 0;
+	long long t = (v >= 1024) ? v : 262144LL;
 	while (t > 1024 && 16LL * n_cells * t > (6LL << 30)) t >>= 1;
 	if (t > n_samp) t = ((n_samp + 127) / 128) * 128;
 	return (int)t;
@@ -118,6 +168,21 @@ void predict_device(hibag_b200_model &m, const int8_t *geno_dev, int n_samp,
 	pc.acc.ensure((size_t)n_cells * tile);
 	pc.aux.ensure((size_t)3 * tile);
 	pc.geno_t.ensure((size_t)m.n_snp * n_samp);
+	const bool dedup = predict_dedup_enabled();
+	const int n_tiles = (n_samp + tile - 1) / tile;
+	int table_size = 1024;
+	while (table_size < 2 * tile) table_size <<= 1;
+	std::unique_ptr<PredictCache::Pending> pd;
+	if (dedup)
+	{
+		pc.dd_table.ensure((size_t)table_size);
+		pc.dd_repof.ensure(tile); pc.dd_uid.ensure(tile); pc.dd_rep.ensure(tile);
+		pc.dd_norm.ensure((size_t)2 * tile);
+		pc.dd_count.ensure((size_t)n_tiles * nc + 1);
+		collect_pending(m, pc, false);
+		pd.reset(new PredictCache::Pending());
+		pd->host.ensure((size_t)n_tiles * nc + 1);
+	}
 	const double *tbl = device_rare_freq_table();
 	const int *snp_w = snp_weight_dev ? snp_weight_dev : pc.d_snp_weight.get();
 	hibag_b200_predict_stats &ps = m.predict_stats;
@@ -128,9 +193,11 @@ void predict_device(hibag_b200_model &m, const int8_t *geno_dev, int n_samp,
 	ps.kernel_launches++;
 
 	size_t n_cell_ev = 0;
+	int tile_idx = -1;
 	for (int begin = 0; begin < n_samp; begin += tile)
 	{
 		const int nt = std::min(tile, n_samp - begin);
+		tile_idx++;
 		HB_CUDA(cudaMemsetAsync(pc.acc.get(), 0, sizeof(double) * (size_t)n_cells * tile, st));
 		HB_CUDA(cudaMemsetAsync(pc.aux.get(), 0, sizeof(double) * 3 * (size_t)tile, st));
 		HB_CUDA(cudaMemsetAsync(pc.counters.get(), 0, sizeof(unsigned int) * (size_t)(nc + 1), st));
@@ -146,6 +213,21 @@ void predict_device(hibag_b200_model &m, const int8_t *geno_dev, int n_samp,
 			bind_list(pc.blobs[c], pc.d_blobs.get() + pc.blob_off[c], tbl, p);
 			p.s1 = pc.s1.get(); p.s2 = pc.s2.get(); p.geno_stride = tile;
 			p.samp_list = nullptr; p.n_pos = nt;
+			int *n_unique = nullptr;
+			if (dedup)
+			{
+				// distinct genotypes of the tile at this classifier's SNPs: the kernel scores position
+				// u < *n_unique = sample rep[u]; every other sample shares a column of the cell matrix
+				n_unique = pc.dd_count.get() + (size_t)tile_idx * nc + c;
+				launch_dedup_genotypes(pc.s1.get(), pc.s2.get(), tile, geno_words(n_snp_c), nt,
+					pc.dd_table.get(), table_size, pc.dd_repof.get(), pc.dd_uid.get(), pc.dd_rep.get(),
+					n_unique, st);
+				p.samp_list = pc.dd_rep.get();
+				p.n_pos_dev = n_unique;
+				pd->pairs_per_sample.push_back(pc.blobs[c].pairs_per_sample);
+				pd->nw.push_back(0);
+				ps.kernel_launches += 2;
+			}
 			p.task_counter = pc.counters.get() + c;
 			p.P = pc.P.get(); p.p_stride = (size_t)tile;
 			const int R = choose_samples_per_lane(nt, pc.blobs[c].n_chunks, n_snp_c, di.sm_count);
@@ -155,11 +237,23 @@ void predict_device(hibag_b200_model &m, const int8_t *geno_dev, int n_samp,
 			const int nw = launch_cell_pass(p, R, di.sm_count, st);
 			HB_CUDA(cudaEventRecord(pc.cell_ev[n_cell_ev + 1]->e, st));
 			n_cell_ev += 2;
-			launch_predict_accumulate(pc.P.get(), (size_t)tile, n_cells, nt, pc.weight.get(),
-				pc.acc.get(), (size_t)tile, pc.aux.get(), st);
+			if (dedup)
+			{
+				launch_predict_accumulate_dedup(pc.P.get(), (size_t)tile, n_cells, nt, pc.dd_uid.get(),
+					n_unique, pc.dd_norm.get(), (size_t)tile, pc.weight.get(), pc.acc.get(), (size_t)tile,
+					pc.aux.get(), st);
+				pd->nw.back() = nw;
+				ps.kernel_launches++;
+			} else {
+				launch_predict_accumulate(pc.P.get(), (size_t)tile, n_cells, nt, pc.weight.get(),
+					pc.acc.get(), (size_t)tile, pc.aux.get(), st);
+				ps.pair_evals += pc.blobs[c].pairs_per_sample * (uint64_t)nt;
+				ps.popc32_issued += pc.blobs[c].pairs_per_sample * (uint64_t)nt * (uint64_t)nw;
+				ps.positions_scored += (uint64_t)nt;
+			}
 			ps.kernel_launches += 3; ps.cell_kernel_launches++;
-			ps.pair_evals += pc.blobs[c].pairs_per_sample * (uint64_t)nt;
-			ps.popc32_issued += pc.blobs[c].pairs_per_sample * (uint64_t)nt * (uint64_t)nw;
+			ps.pair_evals_nominal += pc.blobs[c].pairs_per_sample * (uint64_t)nt;
+			ps.positions_total += (uint64_t)nt;
 		}
 		if (partial_dev)
 		{
@@ -172,10 +266,23 @@ void predict_device(hibag_b200_model &m, const int8_t *geno_dev, int n_samp,
 			ps.kernel_launches += out.post_prob ? 2 : 1;
 		}
 	}
+	if (dedup)
+	{
+		// the counts of this call come back behind its kernels; they are folded into the statistics
+		// once they have arrived (at once for a synchronous call)
+		const size_t n_cnt = pd->pairs_per_sample.size();
+		if (tile_idx + 1 != n_tiles || n_cnt != (size_t)n_tiles * nc)
+			throw std::runtime_error("predict: internal count mismatch");
+		HB_CUDA(cudaMemcpyAsync(pd->host.get(), pc.dd_count.get(), sizeof(int) * n_cnt,
+			cudaMemcpyDeviceToHost, st));
+		HB_CUDA(cudaEventRecord(pd->done.e, st));
+		pc.pending.emplace_back(std::move(pd));
+	}
 	HB_CUDA(cudaEventRecord(pc.ev_end.e, st));
 	if (sync)
 	{
 		HB_CUDA(cudaStreamSynchronize(st));
+		collect_pending(m, pc, true);
 		float ms = 0;
 		HB_CUDA(cudaEventElapsedTime(&ms, pc.ev_begin.e, pc.ev_end.e));
 		ps.gpu_kernel_ms += ms;
@@ -254,6 +361,7 @@ void predict_host(hibag_b200_model &m, const int8_t *geno, int n_samp,
 	}
 	HB_CUDA(cudaStreamSynchronize(st.s));
 	HB_CUDA(cudaStreamSynchronize(st_copy.s));
+	predict_collect_stats(m);
 	m.predict_stats.h2d_bytes += (size_t)n_samp * m.n_snp;
 	m.predict_stats.d2h_bytes += d2h;
 }

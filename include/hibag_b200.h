@@ -246,6 +246,11 @@ typedef struct hibag_b200_predict_stats {
 	uint64_t popc32_issued;
 	uint64_t kernel_launches, cell_kernel_launches;
 	uint64_t h2d_bytes, d2h_bytes;
+	/* pair_evals / popc32_issued count EXECUTED work: each distinct packed genotype of a tile is
+	 * scored once per classifier. Nominal = what the reference's loop nest evaluates
+	 * (samples x classifiers x pairs, src/LibHLA.cpp:2451-2464); positions = (sample, classifier). */
+	uint64_t pair_evals_nominal;
+	uint64_t positions_scored, positions_total;
 } hibag_b200_predict_stats;
 int hibag_b200_model_predict_stats(const hibag_b200_model *m, hibag_b200_predict_stats *out);
 

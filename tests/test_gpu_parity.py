@@ -448,6 +448,50 @@ def test_predict_on_synthetic_model_matches_reference(gpu, ref):
     assert acc > 0.5          # sanity: the ensemble actually predicts
 
 
+@pytest.mark.parametrize("n_snp", [20, 50, 100])
+def test_predict_scores_each_distinct_genotype_once_and_exactly(gpu, ref, monkeypatch, n_snp):
+    """Prediction scores every DISTINCT packed genotype of a tile once per classifier and shares its
+    column of the cell matrix (kernels.h: launch_dedup_genotypes). Same bits as scoring every sample
+    (HIBAG_B200_PREDICT_DEDUP=0) and as the reference's per-sample loop (src/LibHLA.cpp:2451-2464),
+    for 1-, 2- and 4-word genotypes, duplicates inside and across tiles, missing and all-missing rows."""
+    rng = np.random.default_rng(100 + n_snp)
+    n_hla, n_total_snp = 7, n_snp + 9
+    m = gpu.HLAModel(n_total_snp, n_hla)
+    r = ref.new_model(); r.init_predict(n_total_snp, 1, n_hla)
+    for k in range(3):
+        haplo, _, _ = helpers.random_haplo_list(rng, n_hla=n_hla, n_snp=n_snp, max_per_allele=5)
+        idx = np.sort(rng.choice(n_total_snp, size=n_snp, replace=False)).astype(np.int32)
+        m.add_classifier(idx, haplo["freq"], haplo["hla"], haplo["packed"])
+        r.add_classifier(idx, haplo["freq"], haplo["hla"], haplo["packed"])
+    base = rng.integers(0, 3, size=(60, n_total_snp)).astype(np.int8)
+    test = base[rng.integers(0, 60, size=3000)]                      # ~50 copies of each row
+    test[rng.random(test.shape) < 0.002] = -1                        # a few near-duplicates
+    test[17, :] = -1
+    test[2500:2520] = rng.integers(0, 3, size=(20, n_total_snp))      # rows seen nowhere else
+    want = r.predict(test.astype(np.int32))
+    outs, stats = {}, {}
+    for name, env in (("dedup", {}), ("every sample", {"HIBAG_B200_PREDICT_DEDUP": "0"}),
+                      ("dedup, tiles of 1024", {"HIBAG_B200_PREDICT_TILE": "1024"})):
+        for k in ("HIBAG_B200_PREDICT_DEDUP", "HIBAG_B200_PREDICT_TILE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s0 = m.predict_stats()
+        outs[name] = m.predict(test)
+        s1 = m.predict_stats()
+        stats[name] = {k: s1[k] - s0[k] for k in s1}
+    for name, got in outs.items():
+        assert np.array_equal(want["h1"], got["h1"]) and np.array_equal(want["h2"], got["h2"]), name
+        for key in ("prob", "matching", "dosage", "postprob"):
+            assert np.array_equal(want[key], got[key], equal_nan=True), (name, key)
+    d, e, t = stats["dedup"], stats["every sample"], stats["dedup, tiles of 1024"]
+    assert e["positions_scored"] == e["positions_total"] == 3 * 3000
+    assert e["pair_evals"] == e["pair_evals_nominal"] == d["pair_evals_nominal"]
+    assert d["positions_total"] == 3 * 3000 and d["positions_scored"] < 0.2 * d["positions_total"]
+    assert d["pair_evals"] < 0.2 * d["pair_evals_nominal"]
+    assert d["positions_scored"] <= t["positions_scored"] < 0.5 * t["positions_total"]
+
+
 def test_classifier_sharded_predict_agrees_within_tolerance(gpu, ref):
     """classifiers split over two 'ranks', partial sums added (what the NCCL all-reduce does), then
     finalised: calls equal, posteriors within 1e-10 of the single-rank result"""
