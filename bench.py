@@ -887,7 +887,7 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
     if world > 1:
         # the other multi-GPU mode (SURVEY.md 8e, config 5's shape of work): classifiers sharded, every
         # rank scores ALL samples with its share of the classifiers, one NCCL all-reduce of the
-        # [tile, n_cells + 3] fp64 partial posterior sums per tile of 65,536 samples, then finalise
+        # [tile, n_cells + 3] fp64 partial posterior sums per tile of up to 262,144 samples, then finalise
         sub = hd.sub_model(big, rank, world)
         wts = torch.from_numpy(big.snp_weights()).to(dev)
         g_all = torch.from_numpy(all_host).to(dev)
@@ -916,7 +916,7 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
                     "sharded_by_classifier_calls_equal": same_cs, "sharded_by_classifier_max_rel_err": rel,
                     "sharded_by_classifier_worst_entry": worst,
                     "sharded_by_classifier_note": "%d classifiers per rank x all %d samples; one NCCL all-reduce (fp64 sum) of "
-                                                  "[65536, %d] per tile; calls equal / posteriors vs the sample-sharded "
+                                                  "[min(n, 262144), %d] per tile; calls equal / posteriors vs the sample-sharded "
                                                   "(sequential classifier order) result on this rank's slice" % (
                                                       sub.num_classifiers(), n_total, nc + 3)})
     return out

@@ -14,6 +14,8 @@ there is no CPU fallback.
 import ctypes as C
 import math
 import os
+import sys
+import time
 
 import numpy as np
 
@@ -373,6 +375,7 @@ class HLAModel:
 
     def predict(self, geno, want_prob=True, want_dosage=True):
         """Host-buffer prediction: H2D of the raw genotypes and D2H of the results inside."""
+        t0 = time.time()
         g = np.ascontiguousarray(geno, dtype=np.int8)
         assert g.ndim == 2 and g.shape[1] == self.n_snp
         n = g.shape[0]
@@ -384,7 +387,11 @@ class HLAModel:
         pr = new((n, self.n_cells), np.float64) if want_prob else None
         out = PredictOut(_p(h1).value, _p(h2).value, _p(mp).value, _p(mt).value,
                          None if ds is None else _p(ds).value, None if pr is None else _p(pr).value)
+        t1 = time.time()
         _chk(lib().hibag_b200_model_predict(self._h, _p(g), n, C.byref(out)))
+        if os.environ.get("HIBAG_B200_PREDICT_DEBUG"):
+            print("HLAModel.predict: result buffers %.1f ms, library call %.1f ms" % (
+                1e3 * (t1 - t0), 1e3 * (time.time() - t1)), file=sys.stderr)
         return dict(h1=h1, h2=h2, prob=mp, matching=mt, dosage=ds, postprob=pr)
 
     def predict_device(self, geno_ptr, n_samp, h1=0, h2=0, max_prob=0, matching=0, dosage=0,

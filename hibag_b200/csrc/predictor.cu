@@ -11,6 +11,8 @@
 // genotype matrix, which crosses PCIe once.
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -299,6 +301,9 @@ void predict_host(hibag_b200_model &m, const int8_t *geno, int n_samp,
 {
 	if (n_samp <= 0) return;
 	current_device();
+	const bool dbg = getenv("HIBAG_B200_PREDICT_DEBUG") != nullptr;
+	const auto t_begin = std::chrono::steady_clock::now();
+	auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
 	const int n_hla = m.n_hla;
 	const size_t n_cells = (size_t)n_hla * (n_hla + 1) / 2;
 	// Chunks of one tile: chunk c+1 is enqueued on the compute stream before the outputs of
@@ -353,14 +358,20 @@ void predict_host(hibag_b200_model &m, const int8_t *geno, int n_samp,
 		back(out.post_prob ? out.post_prob + (size_t)b * n_cells : nullptr,
 			dev.post_prob + (size_t)b * n_cells, sizeof(double) * (size_t)n * n_cells);
 	};
+	const double t_alloc = since();
 	enqueue(0);
 	for (int c = 0; c < n_chunks; c++)
 	{
 		if (c + 1 < n_chunks) enqueue(c + 1);
 		fetch(c);
 	}
+	const double t_enq = since();
 	HB_CUDA(cudaStreamSynchronize(st.s));
+	const double t_comp = since();
 	HB_CUDA(cudaStreamSynchronize(st_copy.s));
+	if (dbg)
+		fprintf(stderr, "predict_host: %d samples, %d chunk(s): buffers %.1f ms, enqueued at %.1f, computed at %.1f, "
+			"copied back at %.1f\n", n_samp, n_chunks, t_alloc, t_enq, t_comp, since());
 	predict_collect_stats(m);
 	m.predict_stats.h2d_bytes += (size_t)n_samp * m.n_snp;
 	m.predict_stats.d2h_bytes += d2h;

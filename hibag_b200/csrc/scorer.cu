@@ -131,7 +131,7 @@ struct BlockPool
 };
 BlockPool g_pool[2];                                 // [0] device (per current device), [1] pinned
 std::map<void *, int> g_block_device;                // device blocks: which device owns them
-const size_t POOL_LIMIT[2] = { (size_t)48 << 30, (size_t)8 << 30 };   // of 180 GB HBM / host RAM
+const size_t POOL_LIMIT[2] = { (size_t)48 << 30, (size_t)24 << 30 };  // of 180 GB HBM / host RAM
 }
 
 void *pool_alloc(bool pinned, size_t bytes, size_t *got_bytes)

@@ -122,7 +122,7 @@ def predict_sample_sharded(model, geno_dev, n_total, rank, world, want_prob=True
     return b, e, out
 
 
-def predict_classifier_sharded(sub, snp_weight_dev, n_hla, geno_dev, tile=65536, want_prob=True, timing=None):
+def predict_classifier_sharded(sub, snp_weight_dev, n_hla, geno_dev, tile=262144, want_prob=True, timing=None):
     """Prediction with the CLASSIFIERS sharded over ranks: `sub` holds this
     rank's classifiers (sub_model), snp_weight_dev the WHOLE model's per-SNP weights (int32 device
     tensor, reference _GetSNPWeights src/LibHLA.cpp:2484-2496). Per tile of samples every rank

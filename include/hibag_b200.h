@@ -281,7 +281,7 @@ int hibag_b200_bed_decode_device(const uint8_t *payload_dev, int mode, int n_sam
 	const int32_t *sel_dev, int n_save, int8_t *out_dev, void *cuda_stream);
 
 /* The library recycles device and pinned blocks through a process-wide cache (at most 48 GB of HBM,
- * 8 GB pinned). This gives every cached block back to the driver, e.g. before another library
+ * 24 GB pinned). This gives every cached block back to the driver, e.g. before another library
  * needs the memory; returns the bytes released. */
 size_t hibag_b200_trim_cache(void);
 
