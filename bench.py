@@ -644,7 +644,7 @@ def run_b200_arm(args):
         "scoring_share": share["gather_ib"] + share["gather_oob"] + share["cell_pass"],
         "gather_ib_share": share["gather_ib"], "gather_oob_share": share["gather_oob"],
         "em_share": share["em"],
-        "other_share": share["screen_bound"] + share["screen_need"] + share["screen_tasks"] + share["reduce_oob"] + share["reduce_ib"],
+        "other_share": share["screen_bound"] + share["screen_need"] + share["screen_tasks"] + share["reduce_oob"] + share["reduce_ib"] + share.get("screen_dedup", 0.0),
         "busy": sum(share.values()),
         "by_class": {k: round(v, 4) for k, v in share.items()},
         "note": "share of the GPU's SM-cycles in the timed region HELD by each kernel class: sum over its CTAs of resident "

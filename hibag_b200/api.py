@@ -175,7 +175,7 @@ def set_device(i):
 
 
 SM_TIME_CLASSES = ["gather_oob", "gather_ib", "em", "screen_bound", "screen_need", "screen_tasks", "reduce_oob",
-                   "reduce_ib", "cell_pass", "em_prep", "em_cta_cycles"]
+                   "reduce_ib", "cell_pass", "em_prep", "em_cta_cycles", "screen_dedup"]
 
 
 def sm_time(reset=False):

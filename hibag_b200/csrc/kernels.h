@@ -76,7 +76,7 @@ static const int MAX_BATCH_LISTS = 32;
 /// SM-time accounting classes (devutil.cuh SmAcct; hibag_b200_sm_time in the C ABI)
 enum { SM_ACCT_GATHER_OOB = 0, SM_ACCT_GATHER_IB = 1, SM_ACCT_EM = 2, SM_ACCT_BOUND = 3, SM_ACCT_NEED = 4,
        SM_ACCT_TASKS = 5, SM_ACCT_REDUCE_OOB = 6, SM_ACCT_REDUCE_IB = 7, SM_ACCT_CELL_PASS = 8,
-       SM_ACCT_EM_PREP = 9, SM_ACCT_EM_CTA = 10, SM_ACCT_N = 16 };
+       SM_ACCT_EM_PREP = 9, SM_ACCT_EM_CTA = 10, SM_ACCT_DEDUP = 11, SM_ACCT_N = 16 };
 /// per-device counters [SM_ACCT_N] (device memory, zeroed at first use): sum over CTAs of resident
 /// cycles x (1024 / CTAs of that launch that fit an SM)
 unsigned long long *device_sm_acct();
@@ -228,10 +228,26 @@ struct ScreenArgs
 	double K2;                    // bound factor of the second level
 	double tf[3];                 // T'[0], T'[1], T'[2]
 	int u_smem;                   // 1: the need / reduction kernels keep a position's per-allele sums in shared memory
+	// position classes (null: off): positions of a list whose sample has the same packed genotype (candidate
+	// SNP patched in) and the same true type get the same bounds, need list, cell values and reduction --
+	// only one REPRESENTATIVE of each class is screened and scored, the others copy its result
+	const int *rep;               // [n_lists][p_stride] representative position of every position
+	const int *rep_list;          // [n_lists][p_stride] the representatives, compacted
+	const int *n_rep;             // [n_lists] how many
+	int *pos_res;                 // [n_lists][p_stride] out-of-bag: correct alleles per representative
 };
 struct ScreenList { const void *hap; const CellTask *cells; const int8_t *cand_col; int n_hap, cand_bit; };
 struct ScreenLists { ScreenList l[MAX_BATCH_LISTS]; };
 
+/// position classes of every list of the launch: table = int [n_lists][table_size] (power of two >=
+/// 2 * n_pos) followed by int [n_lists] counters, ALL ZEROED by the caller; fills rep, rep_list and the
+/// counters (= a.n_rep)
+void launch_screen_dedup(const ScreenArgs &a, const ScreenLists &ls, int *table, int table_size, int *rep,
+	int *rep_list, int *n_rep, cudaStream_t st);
+/// every position takes its representative's result: out-of-bag -- sum of pos_res into out_count[l];
+/// in-bag -- ratio copied
+void launch_screen_broadcast_oob(const ScreenArgs &a, int *out_count, cudaStream_t st);
+void launch_screen_broadcast_ib(const ScreenArgs &a, double *out_ratio, size_t out_stride, cudaStream_t st);
 /// U[l][a][pos] and xref[l][pos]
 void launch_screen_bound(const ScreenArgs &a, const ScreenLists &ls, cudaStream_t st);
 /// per list: task prefix over the blob's cell order from count (stride 0: one shared count array)

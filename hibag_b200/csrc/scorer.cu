@@ -461,6 +461,15 @@ static bool screen_refine()
 	return e ? atoi(e) != 0 : false;
 }
 
+/// Position classes (kernels.h ScreenArgs::rep): the positions of a list that carry the same packed
+/// genotype and the same true type are screened and scored once. HIBAG_B200_TRAIN_DEDUP=0 turns it
+/// off (read per call: the tests switch it inside one process); the trained model is the same bit for bit.
+static bool train_dedup()
+{
+	const char *e = getenv("HIBAG_B200_TRAIN_DEDUP");
+	return e ? atoi(e) != 0 : true;
+}
+
 /// One sub-batch of a screened pass, all on one of the device's scoring streams: per-allele
 /// bounds and x_ref, the need lists, their tasks, the surviving cells (gather launch) and the
 /// screened reduction. kind: 0 out-of-bag, 1 in-bag.
@@ -507,6 +516,22 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		a.K2 = screen_bound_factor2();
 		const double *tf = host_rare_freq_floor_table();
 		a.tf[0] = tf[0]; a.tf[1] = tf[1]; a.tf[2] = tf[2];
+	}
+	const bool dedup = train_dedup();
+	int table_size = 1024;
+	while (table_size < 2 * n_pos) table_size <<= 1;
+	int *dd_table = nullptr, *dd_n_rep = nullptr;
+	size_t dd_bytes = 0;
+	if (dedup)
+	{
+		// [MAX_BATCH_LISTS][table_size] hash sets, then [MAX_BATCH_LISTS] counters: one memset
+		dd_bytes = sizeof(int) * ((size_t)count * table_size + MAX_BATCH_LISTS);
+		dd_table = dd_table_.ensure((size_t)MAX_BATCH_LISTS * table_size + MAX_BATCH_LISTS);
+		dd_n_rep = dd_table + (size_t)count * table_size;
+		a.rep = rep_.ensure((size_t)MAX_BATCH_LISTS * p_stride_);
+		a.rep_list = rep_list_.ensure((size_t)MAX_BATCH_LISTS * p_stride_);
+		a.n_rep = dd_n_rep;
+		a.pos_res = pos_res_.ensure((size_t)MAX_BATCH_LISTS * p_stride_);
 	}
 	if (const char *e = getenv("HIBAG_B200_SCREEN_FORCE_RESCUE")) a.force_rescue = std::max(0, atoi(e));
 	if (const char *e = getenv("HIBAG_B200_SCREEN_DEVICE_RESCUE")) a.device_rescue = atoi(e) != 0;
@@ -567,7 +592,9 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		cudaStream_t s = st_.s;
 		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * MAX_BATCH_LISTS, s));
 		HB_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * (size_t)count * n_cells, s));
+		if (dedup) HB_CUDA(cudaMemsetAsync(dd_table, 0, dd_bytes, s));
 		HB_CUDA(cudaEventRecord(ev0_.e, s));
+		if (dedup) launch_screen_dedup(a, ls, dd_table, table_size, (int *)a.rep, (int *)a.rep_list, dd_n_rep, s);
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
 		if (refine) launch_screen_refine(a, s);
@@ -593,9 +620,13 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 			HB_CUDA(cudaStreamWaitEvent(s, ev_g1_.e, 0));
 		}
 		if (kind == 0)
+		{
 			launch_reduce_oob_screened(a, d_counts_.get() + first, s);
-		else
+			if (dedup) launch_screen_broadcast_oob(a, d_counts_.get() + first, s);
+		} else {
 			launch_reduce_ib_screened(a, ls, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+			if (dedup) launch_screen_broadcast_ib(a, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+		}
 		HB_CUDA(cudaEventRecord(ev1_.e, s));
 		HB_CUDA(cudaEventRecord(ev_up_.e, s));
 	} else {
@@ -606,7 +637,9 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		HB_CUDA(cudaStreamWaitEvent(s, ev_up_.e, 0));
 		HB_CUDA(cudaMemsetAsync(counters_.get(), 0, sizeof(unsigned int) * MAX_BATCH_LISTS, s));
 		HB_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * (size_t)count * n_cells, s));
+		if (dedup) HB_CUDA(cudaMemsetAsync(dd_table, 0, dd_bytes, s));
 		HB_CUDA(cudaEventRecord(ev0_.e, s));
+		if (dedup) launch_screen_dedup(a, ls, dd_table, table_size, (int *)a.rep, (int *)a.rep_list, dd_n_rep, s);
 		launch_screen_bound(a, ls, s);
 		launch_screen_need(a, s);
 		if (refine) launch_screen_refine(a, s);
@@ -616,15 +649,19 @@ void BatchScorer::run_cells_screened(const GenoView &g, int cand_bit, const std:
 		nw = launch_cell_gather(gb, di.sm_count, s, max_ctas);
 		HB_CUDA(cudaEventRecord(ev_g1_.e, s));
 		if (kind == 0)
+		{
 			launch_reduce_oob_screened(a, d_counts_.get() + first, s);
-		else
+			if (dedup) launch_screen_broadcast_oob(a, d_counts_.get() + first, s);
+		} else {
 			launch_reduce_ib_screened(a, ls, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+			if (dedup) launch_screen_broadcast_ib(a, d_ratio_.get() + (size_t)first * ratio_stride_, ratio_stride_, s);
+		}
 		HB_CUDA(cudaEventRecord(ev1_.e, s));
 	}
 	HB_CUDA(cudaStreamWaitEvent(st_.s, ev1_.e, 0));
 	HB_CUDA(cudaEventRecord(ev_up_.e, st_.s));
 	}
-	stats.launches += 5; stats.cell_launches += 1;
+	stats.launches += dedup ? 7 : 5; stats.cell_launches += 1;
 	stats.pair_evals_nominal += pairs * (uint64_t)n_pos;
 	(void)nw;
 }

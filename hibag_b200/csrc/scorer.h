@@ -176,6 +176,9 @@ private:
 	DevBuf<int> cnt_, ent_, al_tab_;
 	DevBuf<double> U2_;                          // second level of the in-bag screen: class sums
 	DevBuf<int> hetk_, cnt2_, ent2_;             // ... heterozygous SNPs used, compacted need lists
+	// position classes of a screened pass (kernels.h ScreenArgs::rep): hash sets + counters, the
+	// representative of every position, the compacted representatives, out-of-bag results
+	DevBuf<int> dd_table_, rep_, rep_list_, pos_res_;
 	DevBuf<unsigned int> prefix_;
 	DevBuf<unsigned long long> d_evals_;
 	PinBuf<unsigned long long> h_evals_;

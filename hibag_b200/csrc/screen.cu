@@ -70,6 +70,141 @@ __device__ __forceinline__ int true_cell_index(int t1, int t2, int n_hla)
 	return t2 + t1 * (2 * n_hla - t1 - 1) / 2;           // src/LibHLA.cpp:1712, t1 <= t2
 }
 
+/// the position thread k of a launch works on: k itself, or the k-th representative of list l when
+/// position classes are on (ok = there is one)
+__device__ __forceinline__ int screen_pos(const ScreenArgs &a, int l, int k, bool &ok)
+{
+	if (a.rep_list == nullptr) { ok = k < a.n_pos; return k; }
+	ok = k < __ldg(a.n_rep + l);
+	return ok ? __ldg(a.rep_list + (size_t)l * a.p_stride + k) : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// position classes: equal packed genotype (candidate patched in) and equal true type
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64s(uint64_t x)
+{
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256)
+screen_dedup_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls, int *table, unsigned mask,
+	int *rep, int *rep_list, int *n_rep)
+{
+	SmAcct acct_scope(a.acct, SM_ACCT_DEDUP, 128u);       // 256 threads: 8 CTAs fit an SM
+	__shared__ int sh_cnt[8];
+	__shared__ int sh_base;
+	const int l = blockIdx.y;
+	const ScreenList &L = ls.l[l];
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	int *tab = table + (size_t)l * ((size_t)mask + 1);
+	bool is_rep = false;
+	if (pos < a.n_pos)
+	{
+		const int samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;
+		const int t1 = __ldg(a.a1 + samp), t2 = __ldg(a.a2 + samp);
+		uint32_t S1[NW], S2[NW];
+		load_geno<NW>(a.s1, a.s2, a.geno_stride, samp, true, L.cand_col, L.cand_bit, S1, S2);
+		uint64_t h = mix64s(((uint64_t)(uint32_t)t1 << 32) | (uint32_t)t2);
+#pragma unroll
+		for (int w = 0; w < NW; w++) h = mix64s(h ^ (((uint64_t)S1[w] << 32) | S2[w]));
+		unsigned slot = (unsigned)h & mask;
+		for (;;)
+		{
+			int r = *(volatile int *)(tab + slot);             // position + 1; 0 = free
+			if (r == 0)
+			{
+				r = atomicCAS(tab + slot, 0, pos + 1);
+				if (r == 0) { is_rep = true; rep[(size_t)l * a.p_stride + pos] = pos; break; }
+			}
+			const int rp = r - 1;
+			const int rs = a.samp_list ? __ldg(a.samp_list + rp) : rp;
+			bool same = (__ldg(a.a1 + rs) == t1) && (__ldg(a.a2 + rs) == t2);
+			if (same)
+			{
+				uint32_t R1[NW], R2[NW];
+				load_geno<NW>(a.s1, a.s2, a.geno_stride, rs, true, L.cand_col, L.cand_bit, R1, R2);
+#pragma unroll
+				for (int w = 0; w < NW; w++) same = same && (R1[w] == S1[w]) && (R2[w] == S2[w]);
+			}
+			if (same) { rep[(size_t)l * a.p_stride + pos] = rp; break; }
+			slot = (slot + 1) & mask;
+		}
+	}
+	// the representatives of the block, compacted in position order (neighbouring threads of the
+	// later kernels then touch neighbouring columns of U and P)
+	const unsigned m = __ballot_sync(0xffffffffu, is_rep);
+	if (lane == 0) sh_cnt[wid] = __popc(m);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		int tot = 0;
+		for (int w = 0; w < 8; w++) { const int c = sh_cnt[w]; sh_cnt[w] = tot; tot += c; }
+		sh_base = tot ? atomicAdd(n_rep + l, tot) : 0;
+	}
+	__syncthreads();
+	if (is_rep)
+		rep_list[(size_t)l * a.p_stride + sh_base + sh_cnt[wid] + __popc(m & ((1u << lane) - 1u))] = pos;
+}
+
+void launch_screen_dedup(const ScreenArgs &a, const ScreenLists &ls, int *table, int table_size, int *rep,
+	int *rep_list, int *n_rep, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	if (table_size < 2 * a.n_pos || (table_size & (table_size - 1)))
+		throw std::runtime_error("launch_screen_dedup: table size must be a power of two >= 2 * n_pos");
+	dim3 grid((a.n_pos + 255) / 256, a.n_lists);
+	const unsigned mask = (unsigned)table_size - 1u;
+	switch (geno_words(a.n_snp))
+	{
+	case 1: screen_dedup_kernel<1><<<grid, 256, 0, st>>>(a, ls, table, mask, rep, rep_list, n_rep); break;
+	case 2: screen_dedup_kernel<2><<<grid, 256, 0, st>>>(a, ls, table, mask, rep, rep_list, n_rep); break;
+	default: screen_dedup_kernel<4><<<grid, 256, 0, st>>>(a, ls, table, mask, rep, rep_list, n_rep); break;
+	}
+	CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+screen_broadcast_oob_kernel(const ScreenArgs a, int *out_count)
+{
+	const int l = blockIdx.y;
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	int cnt = 0;
+	if (pos < a.n_pos) cnt = a.pos_res[(size_t)l * a.p_stride + __ldg(a.rep + (size_t)l * a.p_stride + pos)];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out_count + l, cnt);
+}
+
+void launch_screen_broadcast_oob(const ScreenArgs &a, int *out_count, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	dim3 grid((a.n_pos + 255) / 256, a.n_lists);
+	screen_broadcast_oob_kernel<<<grid, 256, 0, st>>>(a, out_count);
+	CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+screen_broadcast_ib_kernel(const ScreenArgs a, double *out_ratio, size_t out_stride)
+{
+	const int l = blockIdx.y;
+	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos >= a.n_pos) return;
+	const int rp = __ldg(a.rep + (size_t)l * a.p_stride + pos);
+	if (rp != pos) out_ratio[(size_t)l * out_stride + pos] = out_ratio[(size_t)l * out_stride + rp];
+}
+
+void launch_screen_broadcast_ib(const ScreenArgs &a, double *out_ratio, size_t out_stride, cudaStream_t st)
+{
+	if (a.n_pos <= 0 || a.n_lists <= 0) return;
+	dim3 grid((a.n_pos + 255) / 256, a.n_lists);
+	screen_broadcast_ib_kernel<<<grid, 256, 0, st>>>(a, out_ratio, out_stride);
+	CUDA_CHECK(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------------------
 // U[l][a][pos] = sum_{i in allele a} f_i * T'[min(c_i, dmax)],  c_i = mismatches of h_i on the
 // sample's homozygous SNPs (the c_i of cell_pass_kernel's one-popcount distance)
@@ -100,8 +235,9 @@ screen_bound_kernel(const ScreenArgs a, const __grid_constant__ ScreenLists ls)
 	}
 	__syncthreads();
 
-	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool ok = pos < a.n_pos;
+	bool ok;
+	const int pos = screen_pos(a, l, blockIdx.x * blockDim.x + threadIdx.x, ok);
+	if (!__any_sync(0xffffffffu, ok)) return;             // (no barrier below)
 	int samp = 0, t1 = -1, t2 = -1;
 	if (ok)
 	{
@@ -396,9 +532,9 @@ screen_need_kernel(const ScreenArgs a)
 	__shared__ int sh_base[4][NEED_TILE];
 	SmAcct acct_scope(a.acct, SM_ACCT_NEED, 147u);        // 32 KB of shared memory: 7 CTAs fit an SM
 	const int l = blockIdx.y;
-	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	bool ok;
+	const int pos = screen_pos(a, l, blockIdx.x * blockDim.x + threadIdx.x, ok);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const bool ok = pos < a.n_pos;
 	const int n = a.n_hla;
 	const int n_cells = n * (n + 1) / 2;
 	const double *U = a.U + (size_t)l * n * a.p_stride;
@@ -414,6 +550,7 @@ screen_need_kernel(const ScreenArgs a)
 		for (int al = 0; al < n; al++) sU[al * 128 + threadIdx.x] = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
 		__syncthreads();
 	}
+	if (!__any_sync(0xffffffffu, ok)) return;             // (warp-level synchronisation only from here on)
 	auto Uat = [&](int al) -> double { return us ? sU[al * 128 + threadIdx.x] : U[(size_t)al * a.p_stride + pos]; };
 	int true_idx = -1;
 	double thr = 0.0;
@@ -584,7 +721,8 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 {
 	SmAcct acct_scope(a.acct, SM_ACCT_REDUCE_OOB, 32u);  // 64 threads: 32 CTAs fit an SM
 	const int l = blockIdx.y;
-	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	bool ok;
+	const int pos = screen_pos(a, l, blockIdx.x * blockDim.x + threadIdx.x, ok);
 	const int n = a.n_hla;
 	const int n_cells = n * (n + 1) / 2;
 	int cnt = 0;
@@ -593,10 +731,11 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 	if (us)
 	{
 		const double *Ug = a.U + (size_t)l * n * a.p_stride + pos;
-		for (int al = 0; al < n; al++) sU[al * 64 + threadIdx.x] = (pos < a.n_pos) ? Ug[(size_t)al * a.p_stride] : 0.0;
+		for (int al = 0; al < n; al++) sU[al * 64 + threadIdx.x] = ok ? Ug[(size_t)al * a.p_stride] : 0.0;
 		__syncthreads();
 	}
-	if (pos < a.n_pos)
+	if (!__any_sync(0xffffffffu, ok)) return;
+	if (ok)
 	{
 		const double *U = a.U + (size_t)l * n * a.p_stride + pos;
 		auto Uat = [&](int al) -> double { return us ? sU[al * 64 + threadIdx.x] : U[(size_t)al * a.p_stride]; };
@@ -637,6 +776,12 @@ reduce_oob_screened_kernel(const ScreenArgs a, int *out_count)
 		if (p1 == t1) { cnt = 1; t1 = -1; }
 		else if (p1 == t2) { cnt = 1; t2 = -1; }
 		if (p2 == t1 || p2 == t2) cnt++;
+	}
+	if (a.rep != nullptr)
+	{
+		// position classes: kept per representative, summed over ALL positions by the broadcast kernel
+		if (ok) a.pos_res[(size_t)l * a.p_stride + pos] = cnt;
+		return;
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -706,9 +851,9 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 {
 	SmAcct acct_scope(a.acct, SM_ACCT_REDUCE_IB, 32u);
 	const int l = blockIdx.y;
-	const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	bool ok;
+	const int pos = screen_pos(a, l, blockIdx.x * blockDim.x + threadIdx.x, ok);
 	const int lane = threadIdx.x & 31;
-	const bool ok = pos < a.n_pos;
 	const int n = a.n_hla;
 	const int n_cells = n * (n + 1) / 2;
 	const double *U = a.U + (size_t)l * n * a.p_stride;
@@ -722,6 +867,7 @@ reduce_ib_screened_kernel(const ScreenArgs a, const __grid_constant__ ScreenList
 		for (int al = 0; al < n; al++) sU[al * 64 + threadIdx.x] = ok ? U[(size_t)al * a.p_stride + pos] : 0.0;
 		__syncthreads();
 	}
+	if (!__any_sync(0xffffffffu, ok)) return;             // (warp-level synchronisation only from here on)
 	if (ok)
 	{
 		samp = a.samp_list ? __ldg(a.samp_list + pos) : pos;

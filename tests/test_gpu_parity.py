@@ -316,6 +316,55 @@ def test_exact_screening_changes_nothing_but_the_work(gpu, monkeypatch):
         assert forced.train_stats()["n_screen_fallback"] > ss["n_screen_fallback"], var
 
 
+def test_position_classes_change_nothing_but_the_work(gpu, monkeypatch):
+    """Positions of a candidate list whose samples carry the same packed genotype (candidate SNP
+    included) and the same true type are screened and scored ONCE (kernels.h ScreenArgs::rep): same
+    classifiers and search trace as with every position scored (HIBAG_B200_TRAIN_DEDUP=0) and as
+    without screening, fewer pair evaluations -- also with the second screen level, the rescue path of
+    the reduction and the host's rescoring fallback forced, and for two-word genotypes."""
+    from hibag_b200 import synth
+    coh = synth.make_cohort(900, 140, 12, seed=6, noise=0.002, missing=0.002)    # few founders: many repeats
+    mtry = gpu.default_mtry(coh.n_snp)
+
+    def run(**kw):
+        m = gpu.HLAModel(coh.n_snp, coh.n_hla)
+        m.set_training(coh.geno, coh.h1, coh.h2)
+        m.train(3, mtry, prune=True, seed=78, per_classifier_seed=True, n_threads=6, **kw)
+        return m
+
+    plain = run(screening=False)
+    monkeypatch.setenv("HIBAG_B200_TRAIN_DEDUP", "0")
+    every = run(screening=True)
+    monkeypatch.delenv("HIBAG_B200_TRAIN_DEDUP")
+    cls = run(screening=True, n_concurrent=3)
+    for k in range(3):
+        assert helpers.classifier_diff(every.classifier(k), plain.classifier(k)) == "", k
+        assert helpers.classifier_diff(cls.classifier(k), plain.classifier(k)) == "", k
+    assert np.array_equal(cls.train_trace(), plain.train_trace())
+    assert 0 < cls.train_stats()["pair_evals"] < 0.8 * every.train_stats()["pair_evals"]
+    for env in ({"HIBAG_B200_SCREEN_REFINE": "1"}, {"HIBAG_B200_SCREEN_FORCE_RESCUE": "3"},
+                {"HIBAG_B200_SCREEN_FORCE_FALLBACK": "1"}, {"HIBAG_B200_SCREEN_DEVICE_RESCUE": "1"},
+                {"HIBAG_B200_GATHER_FLAT": "7"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        m = run(screening=True, n_concurrent=2)
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        for k in range(3):
+            assert helpers.classifier_diff(m.classifier(k), plain.classifier(k)) == "", (env, k)
+    # two-word genotypes (37 SNPs): the thermometer cohort of the reference fixture, every position vs classes
+    gd = helpers.load_golden("synth_thermo_ref.npz")
+    geno, h1, h2 = synth.make_thermo_cohort(int(gd["s0_n_samp"]), int(gd["s0_n_hla"]),
+                                            seed=int(gd["s0_cohort_seed"]), noise=float(gd["s0_noise"]))
+    want = dict(snpidx=gd["s0_snpidx"], samp_num=gd["s0_samp_num"], freq=gd["s0_freq"],
+                hla=gd["s0_hla"], packed=gd["s0_packed"], oob_acc=float(gd["s0_oob_acc"]))
+    m = gpu.HLAModel(geno.shape[1], int(gd["s0_n_hla"]))
+    m.set_training(geno, h1, h2)
+    m.train(1, geno.shape[1], prune=True, seed=int(gd["s0_train_seed"]), per_classifier_seed=True)
+    assert helpers.classifier_diff(m.classifier(0), want) == ""
+    assert m.train_stats()["pair_evals"] < m.train_stats()["pair_evals_nominal"]
+
+
 def test_trainer_matches_reference_many_alleles(gpu):
     """DRB1-like shape (many alleles, long haplotype lists, EM clusters of several CTAs):
     bit-identical classifiers vs the reference's base target (fixture generated from the compiled
