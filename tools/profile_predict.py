@@ -23,4 +23,4 @@ for rep in range(2):
     s1 = m.predict_stats(); dt = time.time() - t0
     d = {k: s1[k] - s0[k] for k in s1}
     print("rep %d: %.3f s, %.0f samples/s, cell kernel %.1f ms of %.1f ms, %.3e pair-evals/s" % (
-        rep, dt, n / dt, d["cell_kernel_ms"], d["gpu_kernel_ms"], d["pair_evals"] / (d["cell_kernel_ms"] * 1e-3)))
+        rep, dt, n / dt, d["cell_kernel_ms"], d["gpu_kernel_ms"], d["pair_evals"] / max(d["cell_kernel_ms"] * 1e-3, 1e-12)))
