@@ -891,7 +891,7 @@ def bench_predict(api, hd, synth, torch, model, coh, rank, world, dev, args):
         sub = hd.sub_model(big, rank, world)
         wts = torch.from_numpy(big.snp_weights()).to(dev)
         g_all = torch.from_numpy(all_host).to(dev)
-        hd.predict_classifier_sharded(sub, wts, coh.n_hla, g_all[:4096])          # warm-up (buffers, NCCL)
+        hd.predict_classifier_sharded(sub, wts, coh.n_hla, g_all)                 # full-size warm-up (tile buffers, NCCL)
         torch.cuda.synchronize(); hd.barrier()
         tm = {}
         e0.record()

@@ -106,6 +106,12 @@ def test_compute_fails_loudly_without_gpu(built):
     m.set_training(np.zeros((6, 10), dtype=np.int8), np.zeros(6, dtype=np.int32), np.ones(6, dtype=np.int32))
     with pytest.raises(RuntimeError, match="no usable CUDA device"):
         m.train(1, 3)
+    # page-locked result buffers come from the CUDA runtime: no device, no buffer (and no pageable stand-in)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        api.pinned_empty((4, 4))
+    m.add_classifier(np.arange(3, dtype=np.int32), h["freq"], h["hla"], h["packed"])
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        m.predict(np.zeros((2, 10), dtype=np.int8))
 
 
 def test_default_mtry_rule():
