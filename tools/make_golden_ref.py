@@ -97,14 +97,18 @@ def worker(cfg, k, target, out, budget):
                trace_loss=np.array([t[2] for t in trace]), trace_acc=np.array([t[3] for t in trace]),
                trace_n_haplo=np.array([t[4] for t in trace], dtype=np.int32),
                trace_seconds=np.array(stamps, dtype=np.float64))
-    if rc == 0:
+    # BuildClassifiers checks for an interrupt once more AFTER a classifier is complete (LibHLA.cpp:2300):
+    # a run that ends there reports "interrupted" with the finished classifier in the model -- keep it
+    done = rc == 0 or m.num_classifiers() == 1
+    res["finished"] = np.bool_(done)
+    if done:
         c = m.classifier(0)
         for key in ("snpidx", "samp_num", "freq", "hla", "packed"):
             res[key] = np.asarray(c[key])
         res["oob_acc"] = np.float64(c["oob_acc"])
     np.savez_compressed(out, **res)
     print("%s k=%d target=%s: %s in %.1f s, %d accepted SNPs %s" % (
-        cfg, k, target, "finished" if rc == 0 else "interrupted", dt, len(trace), [t[1] for t in trace]), flush=True)
+        cfg, k, target, "finished" if done else "interrupted", dt, len(trace), [t[1] for t in trace]), flush=True)
 
 
 def fromlog(cfg, k, target, log, out, seconds):
