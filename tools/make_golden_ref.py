@@ -87,7 +87,8 @@ def worker(cfg, k, target, out, budget):
     stop.set(); th.join()
     os.dup2(saved, 2)
     os.close(fd)
-    trace = parse_trace(open(log).read())
+    log_text = open(log).read()
+    trace = parse_trace(log_text)
     os.unlink(log)
     stamps = [x - t0 for x in stamps][:len(trace)]
     stamps += [dt] * (len(trace) - len(stamps))
@@ -99,7 +100,8 @@ def worker(cfg, k, target, out, budget):
                trace_seconds=np.array(stamps, dtype=np.float64))
     # BuildClassifiers checks for an interrupt once more AFTER a classifier is complete (LibHLA.cpp:2300):
     # a run that ends there reports "interrupted" with the finished classifier in the model -- keep it
-    done = rc == 0 or m.num_classifiers() == 1
+    # (the summary line "[k] date, oob acc: ..., # of SNPs: n, # of haplo: m" is printed just before that check)
+    done = rc == 0 or re.search(r"^\[\d+\] .*# of SNPs: \d+, # of haplo: \d+", log_text, re.M) is not None
     res["finished"] = np.bool_(done)
     if done:
         c = m.classifier(0)
