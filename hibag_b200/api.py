@@ -380,7 +380,13 @@ class HLAModel:
         assert g.ndim == 2 and g.shape[1] == self.n_snp
         n = g.shape[0]
         # large results land in page-locked memory (D2H at PCIe rate behind the next tile's scoring)
-        new = pinned_empty if n * self.n_cells * 8 >= (8 << 20) else np.empty
+        def new(shape, dtype):
+            if n * self.n_cells * 8 >= (8 << 20):
+                try:
+                    return pinned_empty(shape, dtype)
+                except RuntimeError:              # host cannot page-lock that much: pageable (slower copy back)
+                    pass
+            return np.empty(shape, dtype)
         h1 = np.zeros(n, dtype=np.int32); h2 = np.zeros(n, dtype=np.int32)
         mp = np.zeros(n); mt = np.zeros(n)
         ds = new((n, self.n_hla), np.float64) if want_dosage else None
