@@ -52,6 +52,11 @@ struct PredictCache
 		std::vector<int> nw;
 	};
 	std::vector<std::unique_ptr<Pending> > pending;
+	~PredictCache()
+	{
+		// counts still on their way back land in page-locked blocks that return to the cache here
+		for (auto &p : pending) cudaEventSynchronize(p->done.e);
+	}
 };
 
 /// PREDICT_DEDUP: score each distinct packed genotype of a tile once per classifier (default on;
