@@ -180,3 +180,51 @@ def test_bed_decode_both_modes_and_ragged_sizes(orc):
             assert np.array_equal(np.where(got == np.iinfo(np.int32).min, -1, got), want), (mode, n_samp, n_snp)
     with pytest.raises(RuntimeError, match="Invalid prefix"):
         orc.bed_decode(np.array([1, 2, 3, 4], dtype=np.uint8), 2, 2)
+
+
+@pytest.mark.parametrize("n_snp", [9, 40, 100])
+def test_reference_scores_depend_on_the_packed_genotype_and_true_type_only(ref, n_snp):
+    """The premise of DESIGN.md 4.7 (each distinct genotype scored once), checked on the compiled
+    reference itself: its per-sample outputs -- BestGuess, PostProb of the true type, the PostProb2
+    posterior row -- are the same bits for two samples with the same SNP words (and, for PostProb, the
+    same true type), wherever they sit in the array and whatever their bootstrap count; and the
+    out-of-bag / in-bag totals are the sums over samples (in-bag: count x log ratio in array order,
+    src/LibHLA.cpp:1966-1977), so a copied per-sample result changes nothing."""
+    rng = np.random.default_rng(4700 + n_snp)
+    h, n_hla, _ = helpers.random_haplo_list(rng, 9, n_snp)
+    rows = rng.integers(0, 3, size=(12, n_snp)).astype(np.int32)
+    rows[rng.random(rows.shape) < 0.05] = -1
+    t1 = rng.integers(0, n_hla, 12); t2 = rng.integers(0, n_hla, 12)
+    pick = rng.integers(0, 12, size=90)                     # every row ~7 times, scattered
+    boot = rng.integers(0, 4, size=90)
+    g = refpy.pack_geno(rows[pick], boot=boot, a1=t1[pick], a2=t2[pick])
+    a1, a2 = ref.best_guess(h, n_hla, n_snp, g)
+    pp = ref.post_prob(h, n_hla, n_snp, g)
+    p2, s2 = ref.post_prob2(h, n_hla, n_snp, g)
+    first = {}
+    for i, k in enumerate(pick):
+        j = first.setdefault(int(k), i)
+        assert (a1[i], a2[i]) == (a1[j], a2[j])
+        assert pp[i].tobytes() == pp[j].tobytes()
+        assert p2[i].tobytes() == p2[j].tobytes() and s2[i].tobytes() == s2[j].tobytes()
+    # the totals from one representative per distinct (genotype, type)
+    oob = g[boot == 0]
+    cnt = 0
+    for i in np.flatnonzero(boot == 0):
+        j = first[int(pick[i])]
+        lo, hi = sorted((int(t1[pick[i]]), int(t2[pick[i]])))
+        x, y = int(a1[j]), int(a2[j])
+        c = 0
+        if x == lo: c, lo = 1, -1
+        elif x == hi: c, hi = 1, -1
+        if y in (lo, hi): c += 1
+        cnt += c
+    assert ref.acc_oob(h, n_hla, n_snp, oob) == cnt
+    ib = np.flatnonzero(boot > 0)
+    if n_snp == 40:
+        assert np.all(pp[ib] > 0)                           # (this case does take the in-bag branch)
+    if np.all(pp[ib] > 0):
+        ll = 0.0
+        for i in ib:
+            ll += int(boot[i]) * np.log(pp[first[int(pick[i])]])
+        assert ref.acc_ib(h, n_hla, n_snp, g[ib]) == ll * -2
