@@ -1,4 +1,6 @@
-import sys; sys.path.insert(0, '/root/repo')
+"""GPU probe: LDS.64 rate of the lane-replicated rare-frequency table against compact layouts."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hibag_b200 import api
 api.set_device(0)
 clk = api.device_info()["clock_khz"]*1e3; sm = api.device_info()["sm_count"]
